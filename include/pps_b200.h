@@ -1,0 +1,234 @@
+/*
+ * pps_b200.h — C ABI of libpps_b200.so: the B200 (sm_100a) retrieval hot path of
+ * shenyunhang/PPS (part-power-set pooling + distance / ranking / CMC / mAP).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns 0 or a
+ * negative PPS_ERR_* code, never allocates device memory behind the caller's back
+ * (scratch is passed in as `workspace` whose size the matching *_workspace_bytes()
+ * call reports) and never synchronises the stream unless its name ends in `_host`.
+ * `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   pooling   detectron/modeling/bpm_heads.py:18-55   add_uniform_partition
+ *             detectron/modeling/pps_heads.py:38-80   add_pps_part_head_
+ *             detectron/modeling/pps_heads.py:83-142  add_pps_part_head (pyramid)
+ *             (a Caffe2 sub-graph of Split/AveragePool/MaxPool/Mean/Max/Add; the op
+ *             idiom a custom op would follow is detectron/ops/pairwise_distance_op.h:10-21)
+ *   distance  detectron/datasets/reid_dataset_evaluator.py:244-272  compute_dist
+ *   masks     detectron/datasets/reid_dataset_evaluator.py:327-328,427-428
+ *   mAP       detectron/datasets/reid_dataset_evaluator.py:366-439  mean_ap
+ *   CMC       detectron/datasets/reid_dataset_evaluator.py:283-363  cmc
+ *   evaluate  detectron/datasets/reid_dataset_evaluator.py:29-125   evaluate (single query)
+ */
+#ifndef PPS_B200_H_
+#define PPS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPS_ABI_VERSION 1
+
+/* ---- error codes (the Python mirror turns every non-zero code into RuntimeError,
+ * like CAFFE_ENFORCE does: detectron/tests/test_zero_even_op.py:50-53) ---- */
+#define PPS_OK                   0
+#define PPS_ERR_INVALID_ARG     -1  /* null pointer, negative size, unknown enum   */
+#define PPS_ERR_SHAPE           -2  /* sum(split) != H, n_parts out of range, ...  */
+#define PPS_ERR_ALIGN           -3  /* pointer / leading dimension alignment       */
+#define PPS_ERR_CUDA            -4  /* a CUDA call failed: pps_last_cuda_error()   */
+#define PPS_ERR_UNSUPPORTED     -5  /* valid request this build does not implement */
+#define PPS_ERR_WORKSPACE       -6  /* workspace too small                         */
+#define PPS_ERR_NO_VALID_QUERY  -7  /* reid_dataset_evaluator.py:358-359           */
+
+int         pps_abi_version(void);
+const char* pps_strerror(int code);
+const char* pps_last_cuda_error(void);   /* thread-local text of the last CUDA failure */
+
+/* ------------------------------------------------------------------------------------
+ * Part 1 — part-power-set pooling          (bpm_heads.py:18-55 + pps_heads.py:38-80)
+ *
+ * x : [N, C, H, W] fp32, NCHW, contiguous (a conv5 map, e.g. [N,2048,24,8]).
+ * split[n_parts] : rows per horizontal strip, sum == H   (bpm_heads.py:25-45).
+ * mode : PPS_POOL_AVG_MAX  y[m] = max_{j in S_m} avg_j                (pps_heads.py:69-76)
+ *        PPS_POOL_MAX_AVE  y[m] = mean_{j in S_m} avg_j + max_{j in S_m} max_j  (:58-68)
+ *        where S_m = { j : bit j of m set } and avg_j / max_j are the global average /
+ *        max pool of strip j.
+ * combos : NULL -> all masks m = 1 .. 2^n_parts - 1 in ascending order (pps_heads.py:47-52);
+ *          otherwise n_combos explicit masks (e.g. the 21 contiguous `pyramid_combs`,
+ *          pps_heads.py:22-25) emitted in the given order.
+ * y : element (n, k, c) of output k (k-th emitted combo) at y[n*y_stride_n + k*y_stride_k + c].
+ *     [N, K, C] layout: y_stride_n = K*C, y_stride_k = C.  The reference's list of K blobs
+ *     [N,C,1,1] is the [K, N, C] layout: y_stride_n = C, y_stride_k = N*C.
+ * ---------------------------------------------------------------------------------- */
+#define PPS_POOL_AVG_MAX 0
+#define PPS_POOL_MAX_AVE 1
+#define PPS_POOL_MAX_PARTS 10
+
+int pps_pool_fwd(const float* x, int N, int C, int H, int W,
+                 int n_parts, const int* split, int mode,
+                 const int* combos, int n_combos,
+                 float* y, long long y_stride_n, long long y_stride_k,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2a — operand preparation for the tensor-core distance.
+ *
+ * Splits fp32 rows into `planes` bf16 planes (x = p0 + p1 [+ p2], each plane the bf16
+ * rounding of the remaining residual), K zero-padded to a multiple of 64, and computes
+ * the fp32 squared norm of every row (reid_dataset_evaluator.py:266-268) accumulated in
+ * fp64.  out_planes : [planes][rows][kpad] bf16 with kpad = pps_kpad(dim).
+ * For PPS_DTYPE_F16 input there is no split: planes must be 1 and the rows are copied
+ * (padded) as fp16.
+ * ---------------------------------------------------------------------------------- */
+#define PPS_DTYPE_F32 0
+#define PPS_DTYPE_F16 1
+
+int       pps_kpad(int dim);
+long long pps_split_bytes(long long rows, int dim, int planes);
+int pps_split_rows(const void* feats, int dtype, long long rows, int dim, long long ld,
+                   int planes, void* out_planes, float* out_sqnorm, void* stream);
+/* same, for rows [row0, row0+nrows) of a [total_rows, dim] array whose base is `feats`
+ * (lets a host->device upload in slabs overlap the split of the slabs already there). */
+int pps_split_rows_slab(const void* feats, int dtype, long long row0, long long nrows,
+                        long long total_rows, int dim, long long ld, int planes,
+                        void* out_planes, float* out_sqnorm, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2b — distance matrix        (reid_dataset_evaluator.py:244-272, 'euclidean')
+ *
+ * dist[i*ldd + j] = sqrt(max(0, |a_i|^2 + |b_j|^2 - 2 a_i.b_j)).
+ * precision selects how a.b is formed:
+ *   PPS_PREC_BF16X1  one tcgen05 pass on the leading bf16 plane       (not parity grade)
+ *   PPS_PREC_BF16X3  p0.p0 + p0.p1 + p1.p0, fp32 accumulate in TMEM   (default; ~3e-7 rel)
+ *   PPS_PREC_BF16X6  all products down to 2^-24                       (fp32-exact grade)
+ *   PPS_PREC_F16X1   operands are fp16 planes (dtype F16), one pass, exact products
+ *   PPS_PREC_FP32    CUDA-core fp32 FMA kernel on the original fp32 rows (a_f32/b_f32)
+ * a_planes/b_planes come from pps_split_rows (need >= the planes the precision uses).
+ * flags: PPS_DIST_SQUARED returns the clamped squared distance (no sqrt);
+ *        PPS_DIST_DOT returns a.b only (the reference's 'cosine' branch at :259-263
+ *        once rows are L2-normalised).
+ * ---------------------------------------------------------------------------------- */
+#define PPS_PREC_BF16X1 1
+#define PPS_PREC_BF16X3 3
+#define PPS_PREC_BF16X6 6
+#define PPS_PREC_F16X1  16
+#define PPS_PREC_FP32   32
+
+#define PPS_DIST_SQUARED 1
+#define PPS_DIST_DOT     2
+
+int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
+                const void* b_planes, const float* b_sqnorm, long long m2, int b_planes_n,
+                int dim, int precision, int flags,
+                float* dist, long long ldd, void* stream);
+
+int pps_dist_fp32(const float* a, long long lda, const float* a_sqnorm, long long m1,
+                  const float* b, long long ldb, const float* b_sqnorm, long long m2,
+                  int dim, int flags, float* dist, long long ldd, void* stream);
+
+/* row squared norms only (fp64 accumulate, fp32 result) */
+int pps_row_sqnorm(const void* feats, int dtype, long long rows, int dim, long long ld,
+                   float* out_sqnorm, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2c — same-id pair lists (host side; reid_dataset_evaluator.py:320,327-328,421,427-428)
+ *
+ * For query i the gallery items with gallery_ids == query_ids[i] are its "pairs":
+ * positives (camera differs -> valid match) and junk (same camera -> filtered out).
+ * Everything else in the gallery is a valid non-match and needs no per-item mask.
+ * Two-call pattern: pps_pairs_count() -> total E, then pps_pairs_fill().
+ *   pair_off[nq+1] CSR offsets, pair_q[E] query index, pair_g[E] gallery index
+ *   (ascending inside a query), pair_pos[E] 1 = positive, 0 = junk.
+ * ---------------------------------------------------------------------------------- */
+long long pps_pairs_count(const int64_t* query_ids, long long nq,
+                          const int64_t* gallery_ids, long long ng);
+int pps_pairs_fill(const int64_t* query_ids, const int64_t* query_cams, long long nq,
+                   const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
+                   int32_t* pair_off, int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2d — ranking on a materialised block of the distance matrix.
+ *
+ * dist : [nq, ncols] block (row stride ldd) holding gallery columns col0 .. col0+ncols-1.
+ * Step 1  pps_rank_gather : pair_d[e] = dist[pair_q[e], pair_g[e]-col0] for pairs whose
+ *         gallery item lies in the block (others untouched; zero pair_d first, then a
+ *         sum-allreduce over gallery shards completes it).
+ * Step 2  pps_rank_count  : for every positive pair e, cnt_le[e] += #{columns j of the
+ *         block : dist[q,j] <= pair_d[e]}; cnt_first[q] += #{j : (dist[q,j], j) <
+ *         (d*, g*)} with (d*, g*) the query's nearest positive (ties by gallery index,
+ *         i.e. the order a stable argsort gives).  No id/camera arrays are read: junk
+ *         and positives are subtracted in step 3 from their own pair distances.
+ *         Counters are exact integers, so summing them over gallery shards / chunks
+ *         gives the unsharded result bit for bit.
+ * Step 3  pps_rank_finalize : ap[q] (float64, sklearn >= 0.19 tie-grouped step-wise AP:
+ *         (1/P) sum_p tp(d<=d_p)/n_valid(d<=d_p)), is_valid[q], first_rank[q] = 0-based
+ *         position of the first correct match in the valid-filtered ranking (-1 if the
+ *         query has no valid match), and optionally neg_before[e] = number of valid
+ *         non-matches ranked before positive e (what cmc(first_match_break=False) needs).
+ * ---------------------------------------------------------------------------------- */
+int pps_rank_gather(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                    const int32_t* pair_q, const int32_t* pair_g, long long n_pairs,
+                    float* pair_d, void* stream);
+
+int pps_rank_count(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                   const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                   const float* pair_d, int max_pairs_per_query,
+                   uint32_t* cnt_le, uint32_t* cnt_first, void* stream);
+
+int pps_rank_finalize(long long nq,
+                      const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                      const float* pair_d, const uint32_t* cnt_le, const uint32_t* cnt_first,
+                      double* ap, uint8_t* is_valid, int32_t* first_rank, int32_t* neg_before,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2e — per-query top-k (smallest distance first, ties by gallery index).
+ *
+ * Streams a block of the distance matrix once and merges it into the running state
+ * topk_key[nq*k] (uint64 = float bits << 32 | global gallery index; initialise to all
+ * ones with pps_topk_init).  exclude_* (optional, CSR per query, global gallery indices)
+ * lists items to skip — pass the junk pairs to rank the valid-filtered gallery.
+ * pps_topk_unpack splits the state into distances / indices (-1 = fewer than k items).
+ * ---------------------------------------------------------------------------------- */
+#define PPS_TOPK_MAX 128
+int pps_topk_init(uint64_t* topk_key, long long nq, int k, void* stream);
+int pps_topk_update(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                    const int32_t* excl_off, const int32_t* excl_g,
+                    uint64_t* topk_key, int k, void* stream);
+int pps_topk_unpack(const uint64_t* topk_key, long long nq, int k,
+                    float* out_dist, int32_t* out_index, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2f — the whole single-query evaluation from HOST buffers
+ *           (reid_dataset_evaluator.py:104-122: compute_dist -> mean_ap + cmc(topk,
+ *           first_match_break=True); the call bench.py times as `e2e`).
+ *
+ * Copies features to the device (gallery in chunks, overlapped with compute), runs
+ * split -> tcgen05 distance -> gather -> count -> finalize [-> top-k], copies the small
+ * results back and synchronises.  Uses `device` and allocates/free its own scratch
+ * (this is the one entry point that owns memory, because its buffers are host buffers).
+ *   out_ap[nq] float64, out_valid[nq], out_first_rank[nq]; out_cmc[cmc_topk] float64 and
+ *   *out_map follow the reference's averaging (:360-362, :437-438).
+ *   out_topk_index / out_topk_dist [nq, topk] may be NULL (topk = 0).
+ * Returns PPS_ERR_NO_VALID_QUERY if no query has a valid match.
+ * ---------------------------------------------------------------------------------- */
+int pps_evaluate_host(const float* q_feats, long long nq,
+                      const float* g_feats, long long ng, int dim,
+                      const int64_t* query_ids, const int64_t* query_cams,
+                      const int64_t* gallery_ids, const int64_t* gallery_cams,
+                      int precision, int cmc_topk, int topk, int device,
+                      double* out_map, double* out_cmc,
+                      double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,
+                      int32_t* out_topk_index, float* out_topk_dist);
+
+/* instrumentation: number of kernels this library has launched in this process
+ * (bench.py reports the delta over the timed region as `gpu_launches`). */
+unsigned long long pps_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPS_B200_H_ */

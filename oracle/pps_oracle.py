@@ -1,0 +1,269 @@
+"""CPU oracle for the PPS retrieval hot path — TEST INFRASTRUCTURE, not product code.
+
+A NumPy restatement of the reference's algorithm, used only as the checker by ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.
+Nothing under ``pps_b200/`` imports it.
+
+Pinning status
+  * ranking (compute_dist / cmc / mean_ap): the reference ships NO golden vectors or tests for
+    these functions.  The restatement is pinned instead against outputs of
+    the unmodified reference functions run in the authoring container (oracle/ref_loader.py,
+    fixtures in tests/golden/ made by oracle/make_golden.py): numpy 2.3.5, scikit-learn 1.9.0.
+  * pooling: **parity unpinned** — the reference's pooling exists only as a Caffe2 graph
+    (pytorch v1.0.1 `Split/AveragePool/MaxPool/Mean/Max/Add`, not vendored, not importable here),
+    so this restates the published semantics of those ops at the call sites
+    bpm_heads.py:45-55 and pps_heads.py:58-76.
+
+Third-party arithmetic the reference leans on: scikit-learn ``average_precision_score``
+(reid_dataset_evaluator.py:434; the code asks for 0.18.1 at :398-407, the installed 1.9.0
+computes the step-wise AP; both definitions are restated below), NumPy ``matmul``/``argsort``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# ------------------------------------------------------------------------------------
+# pooling  (bpm_heads.py:18-55, pps_heads.py:38-80)
+# ------------------------------------------------------------------------------------
+
+
+def uniform_partition_split(strip_num, scale_h=384, spatial_scale=1.0 / 16):
+    """Rows per strip.  bpm_heads.py:25-43: fixed tables for 5/7/9/10 strips on a 384-row crop
+    (scaled by 16*spatial_scale for pyramid levels), else int(H*scale/strip_num) each."""
+    tables = {
+        7: [3, 3, 4, 4, 4, 3, 3],
+        5: [5, 5, 4, 5, 5],
+        9: [2, 3, 3, 3, 3, 3, 3, 2, 2],
+        10: [2, 2, 2, 3, 3, 3, 3, 2, 2, 2],
+    }
+    if strip_num in tables and scale_h == 16 * 24:
+        return [int(s * (16 * spatial_scale)) for s in tables[strip_num]]
+    return [int(scale_h * spatial_scale / strip_num)] * strip_num
+
+
+def strip_pools(x, split, dtype=np.float32):
+    """Split(axis=2) then global AveragePool / MaxPool per strip (bpm_heads.py:45-55).
+    x: [N, C, H, W] -> avg [n, N, C], max [n, N, C]."""
+    x = np.asarray(x)
+    assert x.ndim == 4 and sum(split) == x.shape[2], "Split: sum(split) must equal H"
+    avgs, maxs, r = [], [], 0
+    for h in split:
+        s = x[:, :, r:r + h, :].astype(dtype)
+        avgs.append(s.mean(axis=(2, 3), dtype=dtype))
+        maxs.append(s.max(axis=(2, 3)))
+        r += h
+    return np.stack(avgs), np.stack(maxs)
+
+
+def pps_pool(x, n_parts=6, split=None, mode="max_ave", combos=None, dtype=np.float32):
+    """All part-combination features, ascending mask order (pps_heads.py:47-76) -> [N, K, C].
+
+    max_ave (:58-68): Caffe2 ``Mean`` = inputs summed in order then scaled by 1/count;
+                      ``Max`` = elementwise max; ``Add``.
+    avg_max (:69-76): ``Max`` over the strip averages.
+    """
+    x = np.asarray(x)
+    if split is None:
+        split = [x.shape[2] // n_parts] * n_parts
+    avg, mx = strip_pools(x, split, dtype)
+    masks = list(combos) if combos is not None else list(range(1, 1 << n_parts))
+    out = np.empty((x.shape[0], len(masks), x.shape[1]), dtype=dtype)
+    for k, m in enumerate(masks):
+        parts = [j for j in range(n_parts) if m & (1 << j)]
+        if mode == "max_ave":
+            s = avg[parts[0]].copy()
+            for j in parts[1:]:
+                s = s + avg[j]
+            if len(parts) > 1:
+                s = s * dtype(1.0 / len(parts))
+            top = mx[parts[0]]
+            for j in parts[1:]:
+                top = np.maximum(top, mx[j])
+            out[:, k, :] = s + top
+        elif mode == "avg_max":
+            top = avg[parts[0]]
+            for j in parts[1:]:
+                top = np.maximum(top, avg[j])
+            out[:, k, :] = top
+        else:
+            raise ValueError(mode)
+    return out
+
+
+# ------------------------------------------------------------------------------------
+# distance  (reid_dataset_evaluator.py:244-272)
+# ------------------------------------------------------------------------------------
+
+
+def compute_dist(array1, array2, type="euclidean"):
+    """:266-271: |a|^2 + |b|^2 - 2 a.b^T, negatives clamped to 0, sqrt.  dtype follows the input.
+    'cosine' (:259-263) in the reference dies on an undefined ``normalize``; the helper it means is
+    test_engine.py:52-55 (row L2 normalisation), and the result is the similarity a.b^T."""
+    assert type in ["cosine", "euclidean"]
+    if type == "cosine":
+        a = array1 / (np.linalg.norm(array1, ord=2, axis=1, keepdims=True) + 1e-12)
+        b = array2 / (np.linalg.norm(array2, ord=2, axis=1, keepdims=True) + 1e-12)
+        return np.matmul(a, b.T)
+    sq1 = np.sum(np.square(array1), axis=1)[:, np.newaxis]
+    sq2 = np.sum(np.square(array2), axis=1)[np.newaxis, :]
+    d2 = -2 * np.matmul(array1, array2.T) + sq1 + sq2
+    d2[d2 < 0] = 0
+    return np.sqrt(d2)
+
+
+# ------------------------------------------------------------------------------------
+# masks / ranking  (reid_dataset_evaluator.py:283-439)
+# ------------------------------------------------------------------------------------
+
+
+def valid_mask(query_id, query_cam, gallery_ids, gallery_cams):
+    """:327-328 / :427-428: drop gallery items with the query's id AND camera."""
+    return (gallery_ids != query_id) | (gallery_cams != query_cam)
+
+
+def average_precision_step(y_true, y_score):
+    """scikit-learn >= 0.19 ``average_precision_score`` for one binary ranking: thresholds are the
+    distinct scores; AP = sum_k (R_k - R_{k-1}) P_k  (tie-grouped, no interpolation)."""
+    y_true = np.asarray(y_true).astype(bool)
+    y_score = np.asarray(y_score)
+    order = np.argsort(-y_score, kind="stable")
+    ys, yt = y_score[order], y_true[order]
+    last_of_group = np.r_[np.nonzero(np.diff(ys))[0], len(ys) - 1]
+    tps = np.cumsum(yt)[last_of_group].astype(np.float64)
+    fps = (1 + last_of_group) - tps
+    precision = tps / (tps + fps)
+    recall = tps / tps[-1]
+    return float(np.sum(np.diff(np.r_[0.0, recall]) * precision))
+
+
+def average_precision_trapezoid(y_true, y_score):
+    """scikit-learn 0.18.1 ``average_precision_score`` (what :398-407 asks for): area under the
+    precision-recall curve by the trapezoidal rule, curve starting at (recall 0, precision 1)."""
+    y_true = np.asarray(y_true).astype(bool)
+    y_score = np.asarray(y_score)
+    order = np.argsort(-y_score, kind="stable")
+    ys, yt = y_score[order], y_true[order]
+    last_of_group = np.r_[np.nonzero(np.diff(ys))[0], len(ys) - 1]
+    tps = np.cumsum(yt)[last_of_group].astype(np.float64)
+    fps = (1 + last_of_group) - tps
+    precision = tps / (tps + fps)
+    recall = tps / tps[-1]
+    # precision_recall_curve stops at full recall and prepends the (0, 1) end point
+    stop = int(np.searchsorted(tps, tps[-1]))
+    precision = np.r_[1.0, precision[:stop + 1]]
+    recall = np.r_[0.0, recall[:stop + 1]]
+    trapezoid = getattr(np, "trapezoid", None) or np.trapz
+    return float(trapezoid(precision, recall))
+
+
+def mean_ap(distmat, query_ids, gallery_ids, query_cams, gallery_cams, average=True, ap_fn=None):
+    """:366-439.  ``ap_fn`` defaults to scikit-learn's installed ``average_precision_score`` exactly
+    as the reference calls it; pass ``average_precision_step`` / ``average_precision_trapezoid`` for
+    the restated definitions."""
+    if ap_fn is None:
+        from sklearn.metrics import average_precision_score as ap_fn
+    m, n = distmat.shape
+    order = np.argsort(distmat, axis=1)
+    aps = np.zeros(m)
+    is_valid_query = np.zeros(m)
+    for i in range(m):
+        idx = order[i]
+        keep = valid_mask(query_ids[i], query_cams[i], gallery_ids[idx], gallery_cams[idx])
+        y_true = (gallery_ids[idx] == query_ids[i])[keep]
+        if not np.any(y_true):
+            continue
+        y_score = -distmat[i][idx][keep]
+        is_valid_query[i] = 1
+        aps[i] = ap_fn(y_true, y_score)
+    if len(aps) == 0:
+        raise RuntimeError("No valid query")
+    if average:
+        return float(np.sum(aps)) / np.sum(is_valid_query)
+    return aps, is_valid_query
+
+
+def cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk=100, first_match_break=False,
+        average=True, stable=False):
+    """:283-363 for the flag combination the evaluator uses (separate_camera_set=False,
+    single_gallery_shot=False).  ``stable=True`` sorts ties by gallery index (the reference's
+    np.argsort is unstable, so tie order there is implementation-defined)."""
+    m, n = distmat.shape
+    order = np.argsort(distmat, axis=1, kind="stable" if stable else None)
+    ret = np.zeros([m, topk])
+    is_valid_query = np.zeros(m)
+    num_valid = 0
+    for i in range(m):
+        idx = order[i]
+        keep = valid_mask(query_ids[i], query_cams[i], gallery_ids[idx], gallery_cams[idx])
+        hits = (gallery_ids[idx] == query_ids[i])[keep]
+        if not np.any(hits):
+            continue
+        is_valid_query[i] = 1
+        where = np.nonzero(hits)[0]
+        delta = 1.0 / len(where)
+        for j, k in enumerate(where):
+            if k - j >= topk:
+                break
+            if first_match_break:
+                ret[i, k - j] += 1
+                break
+            ret[i, k - j] += delta
+        num_valid += 1
+    if num_valid == 0:
+        raise RuntimeError("No valid query")
+    ret = ret.cumsum(axis=1)
+    if average:
+        return np.sum(ret, axis=0) / num_valid
+    return ret, is_valid_query
+
+
+# ------------------------------------------------------------------------------------
+# count-based restatement (what the GPU kernels compute) — an independent cross-check
+# ------------------------------------------------------------------------------------
+
+
+def rank_counts(distmat, query_ids, gallery_ids, query_cams, gallery_cams):
+    """Per query: AP from <=-counts, 0-based rank of the first match under (distance, index)
+    order, and for every positive the number of valid non-matches at distance <= its own.
+    Returns (ap[m], is_valid[m], first_rank[m], neg_before: list of arrays in gallery-index order)."""
+    m, n = distmat.shape
+    ap = np.zeros(m)
+    valid_q = np.zeros(m, dtype=np.uint8)
+    first = np.full(m, -1, dtype=np.int32)
+    neg_before = []
+    gidx = np.arange(n)
+    for i in range(m):
+        same = gallery_ids == query_ids[i]
+        pos = same & (gallery_cams != query_cams[i])
+        keep = ~(same & ~pos)
+        if not pos.any():
+            neg_before.append(np.zeros(0, dtype=np.int64))
+            continue
+        d = distmat[i]
+        dv = np.sort(d[keep])
+        dp = d[pos]
+        n_le = np.searchsorted(dv, dp, side="right")
+        p_le = np.searchsorted(np.sort(dp), dp, side="right")
+        ap[i] = float(np.mean(p_le / n_le))
+        valid_q[i] = 1
+        neg_before.append((n_le - p_le).astype(np.int64))
+        pidx = gidx[pos]
+        best = np.lexsort((pidx, dp))[0]
+        dstar, gstar = dp[best], pidx[best]
+        before = keep & ((d < dstar) | ((d == dstar) & (gidx < gstar)))
+        first[i] = int(before.sum())
+    return ap, valid_q, first, neg_before
+
+
+def topk_filtered(distmat, query_ids, gallery_ids, query_cams, gallery_cams, k):
+    """k nearest valid gallery items per query, ties by gallery index -> (index [m,k], dist [m,k])."""
+    m, n = distmat.shape
+    idx_out = np.full((m, k), -1, dtype=np.int32)
+    d_out = np.full((m, k), np.inf, dtype=np.float32)
+    for i in range(m):
+        keep = valid_mask(query_ids[i], query_cams[i], gallery_ids, gallery_cams)
+        cand = np.nonzero(keep)[0]
+        order = cand[np.argsort(distmat[i][cand], kind="stable")][:k]
+        idx_out[i, :len(order)] = order
+        d_out[i, :len(order)] = distmat[i][order]
+    return idx_out, d_out

@@ -1,0 +1,270 @@
+// Part-power-set pooling, fused: strip average/max pooling + all subset combinations.
+//
+// Replaces the Caffe2 sub-graph the reference emits per image
+//   Split(axis=2) -> n x {AveragePool, MaxPool}(global)          bpm_heads.py:41-55
+//   for m in 1..2^n-1: Mean(avg_j, j in S_m) / Max(max_j) / Add     pps_heads.py:47-76
+// (~200 tiny launches for n = 6) with one persistent kernel that reads every conv5 plane
+// once and writes every combination once: 4*C*H*W bytes in + 4*K*C bytes out per image.
+//
+// Data movement (HBM-bound kernel, no tensor cores):
+//   * a "unit" is one image x 32 consecutive channels: its planes are one contiguous run of
+//     32*H*W floats in NCHW, so a producer thread fetches them with 1-D bulk TMA copies
+//     (cp.async.bulk, completion on an mbarrier) into a 4-stage shared-memory ring;
+//   * 8 consumer warps reduce (plane, strip) pairs out of shared memory with 128-bit loads
+//     (lane-rotated start so a quarter-warp touches 32 distinct banks), leave avg/max in a
+//     double-buffered [strip][channel] table, and
+//   * combine: lane = channel, warp = subset mask, so every output row is one coalesced
+//     128-byte streaming store.
+#include "common.cuh"
+
+#include <cfloat>
+
+namespace pps {
+
+constexpr int kCB = 32;                  // channels per unit
+constexpr int kPoolStages = 4;           // shared-memory ring depth
+constexpr int kStageBytes = 32 * 1024;   // bytes per ring slot
+constexpr int kConsumerWarps = 8;
+constexpr int kPoolThreads = 32 * (1 + kConsumerWarps);
+constexpr int kMaxComboList = 512;
+
+struct PoolArgs {
+  const float* x;
+  float* y;
+  int N, C, H, W;
+  int n_parts, mode;
+  int n_out;            // combinations emitted
+  int use_list;         // 1: masks come from combos[]
+  int planes_per_stage;
+  long long ysn, ysk;
+  int row0[PPS_POOL_MAX_PARTS + 1];
+  float inv_cnt[PPS_POOL_MAX_PARTS + 1];   // 1.0f / k  (Caffe2 Mean scales the sum by 1.0f/InputSize())
+  int combos[kMaxComboList];
+};
+
+// one output row (combination `idx`) for the 32 channels of a unit; lane = channel
+__device__ __forceinline__ void combine_store(const PoolArgs& a, const float* pavg, const float* pmax, int idx,
+                                              int lane, int nch, float* ybase) {
+  int m = a.use_list ? a.combos[idx] : idx + 1;
+  float s = 0.f, mxa = -FLT_MAX, mxm = -FLT_MAX;
+  int cnt = 0;
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1;
+    const float av = pavg[j * kCB + lane];
+    s = cnt ? s + av : av;   // ascending-j sequential sum, like Caffe2 Mean
+    mxa = fmaxf(mxa, av);
+    mxm = fmaxf(mxm, pmax[j * kCB + lane]);
+    ++cnt;
+  }
+  float val;
+  if (a.mode == PPS_POOL_MAX_AVE) {
+    const float mean = cnt > 1 ? s * a.inv_cnt[cnt] : s;
+    val = mean + mxm;
+  } else {
+    val = mxa;
+  }
+  if (lane < nch) st_stream_f32(ybase + (long long)idx * a.ysk + lane, val);
+}
+
+// ------------------------------------------------------------------------------------
+// fast path: W % 4 == 0, 16-byte aligned x, one plane fits a ring slot
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPoolThreads, 1) pool_tma_kernel(const __grid_constant__ PoolArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage = reinterpret_cast<float*>(smem_raw);                               // [stages][kStageBytes/4]
+  float* pavg = reinterpret_cast<float*>(smem_raw + kPoolStages * kStageBytes);    // [2][MAXP][kCB]
+  float* pmax = pavg + 2 * PPS_POOL_MAX_PARTS * kCB;                               // [2][MAXP][kCB]
+  uint64_t* full = reinterpret_cast<uint64_t*>(pmax + 2 * PPS_POOL_MAX_PARTS * kCB);
+  uint64_t* empty = full + kPoolStages;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int HW = a.H * a.W;
+  const int cblocks = (a.C + kCB - 1) / kCB;
+  const long long units = (long long)a.N * cblocks;
+  const int P = a.planes_per_stage;
+
+  if (tid == 0) {
+    for (int s = 0; s < kPoolStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsumerWarps);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ===== producer: one thread streams the planes of this CTA's units into the ring =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const long long n = u / cblocks;
+        const int c0 = (int)(u % cblocks) * kCB;
+        const int nch = min(kCB, a.C - c0);
+        const float* src = a.x + (n * a.C + c0) * (long long)HW;
+        for (int p0 = 0; p0 < nch; p0 += P, ++it) {
+          const int npl = min(P, nch - p0);
+          const uint32_t s = it % kPoolStages, ph = (it / kPoolStages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          const uint32_t bytes = (uint32_t)npl * (uint32_t)HW * 4u;
+          mbar_expect_tx(&full[s], bytes);
+          bulk_load_1d(stage + (size_t)s * (kStageBytes / 4), src + (long long)p0 * HW, bytes, &full[s]);
+        }
+      }
+    }
+  } else {
+    // ===== consumers =====
+    const int ctid = tid - 32;
+    const int cw = warp - 1;
+    uint32_t it = 0;
+    int ubuf = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const long long n = u / cblocks;
+      const int c0 = (int)(u % cblocks) * kCB;
+      const int nch = min(kCB, a.C - c0);
+      float* ua = pavg + ubuf * PPS_POOL_MAX_PARTS * kCB;
+      float* um = pmax + ubuf * PPS_POOL_MAX_PARTS * kCB;
+      for (int p0 = 0; p0 < nch; p0 += P, ++it) {
+        const int npl = min(P, nch - p0);
+        const uint32_t s = it % kPoolStages, ph = (it / kPoolStages) & 1u;
+        mbar_wait(&full[s], ph);
+        const float* sbase = stage + (size_t)s * (kStageBytes / 4);
+        const int tasks = npl * a.n_parts;
+        for (int t = ctid; t < tasks; t += 32 * kConsumerWarps) {
+          const int pl = t / a.n_parts, j = t - pl * a.n_parts;
+          const int r0 = a.row0[j], r1 = a.row0[j + 1];
+          const int L4 = ((r1 - r0) * a.W) >> 2;
+          const float4* b4 = reinterpret_cast<const float4*>(sbase + pl * HW + r0 * a.W);
+          int idx = lane % L4;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+#pragma unroll 4
+          for (int q = 0; q < L4; ++q) {
+            const float4 v = b4[idx];
+            idx = (idx + 1 == L4) ? 0 : idx + 1;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+          }
+          const float sum = (acc.x + acc.y) + (acc.z + acc.w);
+          ua[j * kCB + p0 + pl] = __fdiv_rn(sum, (float)((r1 - r0) * a.W));
+          um[j * kCB + p0 + pl] = fmaxf(fmaxf(mx.x, mx.y), fmaxf(mx.z, mx.w));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);   // slot may be refilled
+      }
+      // all strip results of this unit are in ua/um
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * kConsumerWarps) : "memory");
+      float* ybase = a.y + n * a.ysn + c0;
+      for (int idx = cw; idx < a.n_out; idx += kConsumerWarps) combine_store(a, ua, um, idx, lane, nch, ybase);
+      ubuf ^= 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// generic path: any W / alignment / plane size. One CTA per unit, plain global loads.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_generic_kernel(const __grid_constant__ PoolArgs a) {
+  __shared__ float pavg[PPS_POOL_MAX_PARTS * kCB];
+  __shared__ float pmax[PPS_POOL_MAX_PARTS * kCB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = a.H * a.W;
+  const int cblocks = (a.C + kCB - 1) / kCB;
+  const long long u = blockIdx.x;
+  const long long n = u / cblocks;
+  const int c0 = (int)(u % cblocks) * kCB;
+  const int nch = min(kCB, a.C - c0);
+  for (int pl = warp; pl < nch; pl += 8) {
+    const float* plane = a.x + (n * a.C + c0 + pl) * (long long)HW;
+    for (int j = 0; j < a.n_parts; ++j) {
+      const int e0 = a.row0[j] * a.W, e1 = a.row0[j + 1] * a.W;
+      float s = 0.f, mx = -FLT_MAX;
+      for (int e = e0 + lane; e < e1; e += 32) {
+        const float v = __ldg(plane + e);
+        s += v;
+        mx = fmaxf(mx, v);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (lane == 0) {
+        pavg[j * kCB + pl] = __fdiv_rn(s, (float)(e1 - e0));
+        pmax[j * kCB + pl] = mx;
+      }
+    }
+  }
+  __syncthreads();
+  float* ybase = a.y + n * a.ysn + c0;
+  for (int idx = warp; idx < a.n_out; idx += 8) combine_store(a, pavg, pmax, idx, lane, nch, ybase);
+}
+
+}  // namespace pps
+
+using namespace pps;
+
+extern "C" int pps_pool_fwd(const float* x, int N, int C, int H, int W, int n_parts, const int* split, int mode,
+                            const int* combos, int n_combos, float* y, long long y_stride_n, long long y_stride_k,
+                            void* stream) {
+  if (N < 0 || C <= 0 || H <= 0 || W <= 0 || !split) return PPS_ERR_INVALID_ARG;
+  if (mode != PPS_POOL_AVG_MAX && mode != PPS_POOL_MAX_AVE) return PPS_ERR_INVALID_ARG;
+  if (n_parts < 1 || n_parts > PPS_POOL_MAX_PARTS) return PPS_ERR_SHAPE;
+  PoolArgs a;
+  a.row0[0] = 0;
+  for (int j = 0; j < n_parts; ++j) {
+    if (split[j] <= 0) return PPS_ERR_SHAPE;
+    a.row0[j + 1] = a.row0[j] + split[j];
+  }
+  if (a.row0[n_parts] != H) return PPS_ERR_SHAPE;   // Caffe2 Split enforces sum(split) == dim
+  for (int j = n_parts + 1; j <= PPS_POOL_MAX_PARTS; ++j) a.row0[j] = H;
+  a.inv_cnt[0] = 0.f;
+  for (int k = 1; k <= PPS_POOL_MAX_PARTS; ++k) a.inv_cnt[k] = 1.0f / (float)k;
+  const int full_mask = (1 << n_parts) - 1;
+  if (combos) {
+    if (n_combos < 1 || n_combos > kMaxComboList) return PPS_ERR_SHAPE;
+    for (int i = 0; i < n_combos; ++i) {
+      if (combos[i] < 1 || combos[i] > full_mask) return PPS_ERR_SHAPE;
+      a.combos[i] = combos[i];
+    }
+    a.use_list = 1;
+    a.n_out = n_combos;
+  } else {
+    a.use_list = 0;
+    a.n_out = full_mask;
+  }
+  if (N == 0) return PPS_OK;
+  if (!x || !y) return PPS_ERR_INVALID_ARG;
+  a.x = x; a.y = y; a.N = N; a.C = C; a.H = H; a.W = W;
+  a.n_parts = n_parts; a.mode = mode;
+  a.ysn = y_stride_n; a.ysk = y_stride_k;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const long long plane_bytes = (long long)H * W * 4;
+  const int cblocks = (C + kCB - 1) / kCB;
+  const long long units = (long long)N * cblocks;
+  const bool fast = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && plane_bytes <= kStageBytes;
+  if (fast) {
+    a.planes_per_stage = (int)((kStageBytes / plane_bytes) < kCB ? (kStageBytes / plane_bytes) : kCB);
+    const size_t smem = (size_t)kPoolStages * kStageBytes + 4 * PPS_POOL_MAX_PARTS * kCB * sizeof(float) +
+                        2 * kPoolStages * sizeof(uint64_t);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    PPS_CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+      PPS_CUDA_TRY(cudaFuncSetAttribute(pool_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_dev = dev;
+    }
+    const int sms = sm_count();
+    const int grid = (int)(units < sms ? units : sms);
+    pool_tma_kernel<<<grid, kPoolThreads, smem, st>>>(a);
+    PPS_LAUNCH_CHECK("pool_tma_kernel");
+  } else {
+    if (units > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+    a.planes_per_stage = 0;
+    pool_generic_kernel<<<(int)units, 256, 0, st>>>(a);
+    PPS_LAUNCH_CHECK("pool_generic_kernel");
+  }
+  return PPS_OK;
+}

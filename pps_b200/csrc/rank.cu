@@ -1,0 +1,407 @@
+// Ranking without a sort (replaces the two np.argsort calls and the per-query Python loops of
+// mean_ap / cmc, reid_dataset_evaluator.py:319-357 and :420-434).
+//
+// For a query, the only gallery items whose identity matters are the ones with the same
+// person id ("pairs": positives = other camera, junk = same camera, :327-328/:427-428).
+// Everything the metrics need follows from integer counts against the positives' distances:
+//   n_le(p)   = #{gallery j : d(q,j) <= d(q,p)}                         (this file, count kernel)
+//   AP(q)     = (1/P) sum_p  #{p' : d_p' <= d_p} / (n_le(p) - #{junk j : d_j <= d_p})
+//               == sklearn.metrics.average_precision_score (>= 0.19, tie-grouped step AP)
+//   first(q)  = #{valid j ranked before the nearest positive}  -> CMC with first_match_break
+// The count kernel is a single HBM-bound sweep of the distance block: per element one
+// branch-free binary search into the (<= 63 per pass) sorted positive distances held in shared
+// memory and one increment of a lane-private histogram column (bank = lane, so no atomics
+// and no conflicts).  It reads no id / camera arrays.  Counters are exact integers: adding
+// them across gallery chunks or shards reproduces the unsharded ranking bit for bit.
+#include "common.cuh"
+
+#include <cfloat>
+
+namespace pps {
+
+constexpr int kCntThreads = 128;
+constexpr int kCntWarps = kCntThreads / 32;
+constexpr int kWin = 63;            // thresholds per pass (slot 63 is a +inf sentinel)
+
+// ------------------------------------------------------------------------------------
+// step 1: gather the pair distances out of the block
+// ------------------------------------------------------------------------------------
+__global__ void rank_gather_kernel(const float* __restrict__ dist, long long ldd, long long ncols, long long col0,
+                                   const int32_t* __restrict__ pair_q, const int32_t* __restrict__ pair_g,
+                                   long long n_pairs, float* __restrict__ pair_d) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pairs) return;
+  const long long c = (long long)pair_g[e] - col0;
+  if (c < 0 || c >= ncols) return;
+  pair_d[e] = dist[(long long)pair_q[e] * ldd + c];
+}
+
+// ------------------------------------------------------------------------------------
+// step 2: counts.  grid = (nq, splits); CTA (q, s) sweeps columns [s*seg, (s+1)*seg).
+// dynamic smem: thr[maxp] (sorted positive distances), tpair[maxp] (pair index of each),
+//               hist[kCntWarps][64][32]
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCntThreads) rank_count_kernel(const float* __restrict__ dist, long long ldd,
+                                                                  long long ncols, long long col0, long long seg,
+                                                                  const int32_t* __restrict__ pair_off,
+                                                                  const int32_t* __restrict__ pair_g,
+                                                                  const uint8_t* __restrict__ pair_pos,
+                                                                  const float* __restrict__ pair_d, int maxp,
+                                                                  uint32_t* __restrict__ cnt_le,
+                                                                  uint32_t* __restrict__ cnt_first) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* thr = reinterpret_cast<float*>(smem_raw);                          // [maxp]
+  int32_t* tpair = reinterpret_cast<int32_t*>(thr + maxp);                  // [maxp]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(tpair + maxp);               // [warps][64][32]
+  __shared__ float win[64];
+  __shared__ uint32_t wsum[64];
+  __shared__ int s_np;
+  __shared__ unsigned long long s_first_key;   // (d*, g*) of the nearest positive
+  __shared__ uint32_t s_first_cnt;
+
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int e0 = pair_off[q], e1 = pair_off[q + 1];
+
+  // --- positives of this query, rank-sorted by (distance, gallery index) into thr[] ---
+  if (tid == 0) { s_np = 0; s_first_cnt = 0; s_first_key = ~0ull; }
+  __syncthreads();
+  for (int e = e0 + tid; e < e1; e += kCntThreads) {
+    if (!pair_pos[e]) continue;
+    const float d = pair_d[e];
+    const int g = pair_g[e];
+    int pos = 0;
+    for (int f = e0; f < e1; ++f) {
+      if (!pair_pos[f]) continue;
+      const float df = pair_d[f];
+      pos += (df < d) || (df == d && pair_g[f] < g);
+    }
+    thr[pos] = d;
+    tpair[pos] = e;
+    atomicAdd(&s_np, 1);
+  }
+  __syncthreads();
+  const int np = s_np;
+  if (np == 0) return;                                     // query without a valid match: nothing to count
+  const float dstar = thr[0];
+  const int gstar = pair_g[tpair[0]];
+
+  const long long c_begin = (long long)blockIdx.y * seg;
+  const long long c_end = min(ncols, c_begin + seg);
+  if (c_begin >= c_end) return;
+  const float* drow = dist + (long long)q * ldd;
+  const bool vec = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dist) & 15u) == 0) && ((c_begin & 3) == 0);
+  uint32_t* myhist = hist + warp * (64 * 32) + lane;       // column `lane` of this warp's table
+  uint32_t first_local = 0;
+  uint32_t carry = 0;                                      // elements counted in earlier windows
+
+  for (int w0 = 0; w0 < np; w0 += kWin) {
+    const int wn = min(kWin, np - w0);
+    __syncthreads();                                       // previous window fully consumed
+    if (tid < 64) win[tid] = tid < wn ? thr[w0 + tid] : FLT_MAX;
+    for (int i = tid; i < kCntWarps * 64 * 32; i += kCntThreads) hist[i] = 0;
+    __syncthreads();
+    const float lo = w0 ? thr[w0 - 1] : -FLT_MAX;          // elements <= lo belong to earlier windows
+    const float hi = win[wn - 1];
+    const bool do_first = (w0 == 0);
+
+    auto visit = [&](float d, long long col) {
+      if (do_first) first_local += (d < dstar) || (d == dstar && (col0 + col) < (long long)gstar);
+      if (d <= hi && (w0 == 0 || d > lo)) {
+        int b = 0;                                          // b = #{window thresholds < d}
+#pragma unroll
+        for (int s = 32; s > 0; s >>= 1) b += (win[b + s - 1] < d) ? s : 0;
+        myhist[b * 32] += 1;
+      }
+    };
+
+    if (vec) {
+      const long long c4_end = c_begin + ((c_end - c_begin) & ~3LL);
+      for (long long c = c_begin + 4LL * tid; c < c4_end; c += 4LL * kCntThreads) {
+        const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(drow + c));
+        visit(v.x, c); visit(v.y, c + 1); visit(v.z, c + 2); visit(v.w, c + 3);
+      }
+      for (long long c = c4_end + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
+    } else {
+      for (long long c = c_begin + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
+    }
+    __syncthreads();
+    // reduce the lane-private columns: thread t < 64 owns bucket t
+    if (tid < 64) {
+      uint32_t s = 0;
+      for (int w = 0; w < kCntWarps; ++w) {
+        const uint32_t* hb = hist + w * (64 * 32) + tid * 32;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) s += hb[(l + tid) & 31];
+      }
+      wsum[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t run = carry;
+      for (int b = 0; b < wn; ++b) {
+        run += wsum[b];
+        if (run) atomicAdd(&cnt_le[tpair[w0 + b]], run);
+      }
+      wsum[0] = run;
+    }
+    __syncthreads();
+    carry = wsum[0];
+  }
+  // first-match counter
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first_local += __shfl_xor_sync(0xffffffffu, first_local, o);
+  if (lane == 0 && first_local) atomicAdd(&s_first_cnt, first_local);
+  __syncthreads();
+  if (tid == 0 && s_first_cnt) atomicAdd(&cnt_first[q], s_first_cnt);
+}
+
+// ------------------------------------------------------------------------------------
+// step 3: finalize (one warp per query; pair lists are short)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rank_finalize_kernel(long long nq, const int32_t* __restrict__ pair_off,
+                                                            const int32_t* __restrict__ pair_g,
+                                                            const uint8_t* __restrict__ pair_pos,
+                                                            const float* __restrict__ pair_d,
+                                                            const uint32_t* __restrict__ cnt_le,
+                                                            const uint32_t* __restrict__ cnt_first,
+                                                            double* __restrict__ ap, uint8_t* __restrict__ is_valid,
+                                                            int32_t* __restrict__ first_rank,
+                                                            int32_t* __restrict__ neg_before) {
+  const int lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const int e0 = pair_off[q], e1 = pair_off[q + 1];
+  double acc = 0.0;
+  int np = 0;
+  float dstar = FLT_MAX;
+  int gstar = 0x7fffffff;
+  for (int e = e0 + lane; e < e1; e += 32) {
+    if (!pair_pos[e]) continue;
+    const float d = pair_d[e];
+    const int g = pair_g[e];
+    int c_pos = 0, c_junk = 0;
+    for (int f = e0; f < e1; ++f) {
+      const bool le = pair_d[f] <= d;
+      if (pair_pos[f]) c_pos += le; else c_junk += le;
+    }
+    const int n_valid = (int)cnt_le[e] - c_junk;           // valid items with d <= d_p (includes p)
+    acc += (double)c_pos / (double)n_valid;
+    if (neg_before) neg_before[e] = n_valid - c_pos;
+    ++np;
+    if (d < dstar || (d == dstar && g < gstar)) { dstar = d; gstar = g; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    np += __shfl_xor_sync(0xffffffffu, np, o);
+    const float od = __shfl_xor_sync(0xffffffffu, dstar, o);
+    const int og = __shfl_xor_sync(0xffffffffu, gstar, o);
+    if (od < dstar || (od == dstar && og < gstar)) { dstar = od; gstar = og; }
+  }
+  // junk items ranked before the nearest positive
+  int jb = 0;
+  if (np > 0) {
+    for (int e = e0 + lane; e < e1; e += 32) {
+      if (pair_pos[e]) continue;
+      const float d = pair_d[e];
+      jb += (d < dstar) || (d == dstar && pair_g[e] < gstar);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) jb += __shfl_xor_sync(0xffffffffu, jb, o);
+  }
+  if (lane == 0) {
+    ap[q] = np > 0 ? acc / (double)np : 0.0;
+    is_valid[q] = np > 0 ? 1 : 0;
+    first_rank[q] = np > 0 ? (int32_t)cnt_first[q] - jb : -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// top-k: one CTA per query keeps <= 2048 candidate keys in shared memory, admits a column
+// only if its key beats the current k-th best, and re-selects by bitonic sort when full.
+// key = (float bits << 32) | global gallery index: unsigned order == (distance, index) order
+// for the non-negative distances this path produces.
+// ------------------------------------------------------------------------------------
+constexpr int kTopkThreads = 256;
+constexpr int kCand = 2048;
+
+__device__ __forceinline__ void bitonic_sort_smem(unsigned long long* a, int n /*pow2*/, int tid, int nthreads) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n; i += nthreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = a[i], y = a[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTopkThreads) topk_update_kernel(const float* __restrict__ dist, long long ldd,
+                                                                    long long ncols, long long col0,
+                                                                    const int32_t* __restrict__ excl_off,
+                                                                    const int32_t* __restrict__ excl_g,
+                                                                    unsigned long long* __restrict__ topk_key, int k) {
+  __shared__ unsigned long long cand[kCand];
+  __shared__ int s_n;
+  __shared__ unsigned long long s_bound;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  unsigned long long* state = topk_key + (long long)q * k;
+  for (int i = tid; i < kCand; i += kTopkThreads) cand[i] = i < k ? state[i] : ~0ull;
+  if (tid == 0) { s_n = k; s_bound = state[k - 1]; }
+  __syncthreads();
+  const float* drow = dist + (long long)q * ldd;
+  const int x0 = excl_off ? excl_off[q] : 0, x1 = excl_off ? excl_off[q + 1] : 0;
+  const long long tile = 4LL * kTopkThreads;
+  for (long long c0 = 0; c0 < ncols; c0 += tile) {
+    const unsigned long long bound = s_bound;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long c = c0 + (long long)u * kTopkThreads + tid;
+      if (c < ncols) {
+        const float d = ld_stream_f32(drow + c);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(uint32_t)(col0 + c);
+        if (key < bound) {
+          bool skip = false;
+          for (int x = x0; x < x1; ++x) skip |= ((long long)excl_g[x] == col0 + c);
+          if (!skip) {
+            const int slot = atomicAdd(&s_n, 1);
+            cand[slot] = key;        // s_n <= kCand - tile at tile start, so slot < kCand
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (s_n > kCand - (int)tile) {
+      bitonic_sort_smem(cand, kCand, tid, kTopkThreads);
+      for (int i = k + tid; i < kCand; i += kTopkThreads) cand[i] = ~0ull;
+      if (tid == 0) { s_n = k; s_bound = cand[k - 1]; }
+      __syncthreads();
+    }
+  }
+  bitonic_sort_smem(cand, kCand, tid, kTopkThreads);
+  for (int i = tid; i < k; i += kTopkThreads) state[i] = cand[i];
+}
+
+__global__ void topk_fill_kernel(unsigned long long* p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = ~0ull;
+}
+
+__global__ void topk_unpack_kernel(const unsigned long long* __restrict__ key, long long n, float* __restrict__ od,
+                                   int32_t* __restrict__ oi) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long kk = key[i];
+  const bool none = kk == ~0ull;
+  if (od) od[i] = none ? __int_as_float(0x7f800000) : __uint_as_float((uint32_t)(kk >> 32));
+  if (oi) oi[i] = none ? -1 : (int32_t)(uint32_t)(kk & 0xffffffffu);
+}
+
+}  // namespace pps
+
+using namespace pps;
+
+extern "C" int pps_rank_gather(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                               const int32_t* pair_q, const int32_t* pair_g, long long n_pairs, float* pair_d,
+                               void* stream) {
+  if (nq < 0 || ncols < 0 || n_pairs < 0 || ldd < ncols) return PPS_ERR_INVALID_ARG;
+  if (n_pairs == 0 || ncols == 0 || nq == 0) return PPS_OK;
+  if (!dist || !pair_q || !pair_g || !pair_d) return PPS_ERR_INVALID_ARG;
+  const long long blocks = (n_pairs + 255) / 256;
+  if (blocks > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  rank_gather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dist, ldd, ncols, col0, pair_q,
+                                                                                      pair_g, n_pairs, pair_d);
+  PPS_LAUNCH_CHECK("rank_gather_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_rank_count(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                              const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                              const float* pair_d, int max_pairs_per_query, uint32_t* cnt_le, uint32_t* cnt_first,
+                              void* stream) {
+  if (nq < 0 || ncols < 0 || ldd < ncols || max_pairs_per_query < 0) return PPS_ERR_INVALID_ARG;
+  if (nq == 0 || ncols == 0) return PPS_OK;
+  if (!dist || !pair_off || !cnt_first) return PPS_ERR_INVALID_ARG;
+  if (max_pairs_per_query == 0) return PPS_OK;               // no query has any same-id gallery item
+  if (!pair_g || !pair_pos || !pair_d || !cnt_le) return PPS_ERR_INVALID_ARG;
+  if (nq > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  const int maxp = (max_pairs_per_query + 3) & ~3;
+  const size_t smem = (size_t)maxp * 8 + (size_t)kCntWarps * 64 * 32 * 4;
+  if (smem > 200 * 1024) return PPS_ERR_UNSUPPORTED;          // > ~21k same-id items for one query
+  // column splits: enough CTAs to fill the GPU when there are few queries
+  const int sms = sm_count();
+  long long splits = 1;
+  if (nq < 4LL * sms) splits = (4LL * sms + nq - 1) / nq;
+  long long seg = (ncols + splits - 1) / splits;
+  seg = (seg + 1023) & ~1023LL;                               // keeps 16-byte alignment of segment starts
+  splits = (ncols + seg - 1) / seg;
+  if (splits > 65535) return PPS_ERR_UNSUPPORTED;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  PPS_CUDA_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    PPS_CUDA_TRY(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured_dev = dev;
+  }
+  rank_count_kernel<<<dim3((unsigned)nq, (unsigned)splits), kCntThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      dist, ldd, ncols, col0, seg, pair_off, pair_g, pair_pos, pair_d, maxp, cnt_le, cnt_first);
+  PPS_LAUNCH_CHECK("rank_count_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_rank_finalize(long long nq, const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                                 const float* pair_d, const uint32_t* cnt_le, const uint32_t* cnt_first, double* ap,
+                                 uint8_t* is_valid, int32_t* first_rank, int32_t* neg_before, void* stream) {
+  if (nq < 0) return PPS_ERR_INVALID_ARG;
+  if (nq == 0) return PPS_OK;
+  if (!pair_off || !cnt_first || !ap || !is_valid || !first_rank) return PPS_ERR_INVALID_ARG;
+  const long long blocks = (nq + 3) / 4;
+  if (blocks > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  rank_finalize_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      nq, pair_off, pair_g, pair_pos, pair_d, cnt_le, cnt_first, ap, is_valid, first_rank, neg_before);
+  PPS_LAUNCH_CHECK("rank_finalize_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_topk_init(uint64_t* topk_key, long long nq, int k, void* stream) {
+  if (nq < 0 || k < 1 || k > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
+  if (nq == 0) return PPS_OK;
+  if (!topk_key) return PPS_ERR_INVALID_ARG;
+  const long long n = nq * k, blocks = (n + 255) / 256;
+  topk_fill_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<unsigned long long*>(topk_key), n);
+  PPS_LAUNCH_CHECK("topk_fill_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_topk_update(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                               const int32_t* excl_off, const int32_t* excl_g, uint64_t* topk_key, int k,
+                               void* stream) {
+  if (nq < 0 || ncols < 0 || ldd < ncols || k < 1 || k > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
+  if (nq == 0 || ncols == 0) return PPS_OK;
+  if (!dist || !topk_key) return PPS_ERR_INVALID_ARG;
+  if (excl_off && !excl_g) return PPS_ERR_INVALID_ARG;
+  if (nq > 0x7fffffffLL || col0 + ncols > 0xffffffffLL) return PPS_ERR_UNSUPPORTED;
+  topk_update_kernel<<<(unsigned)nq, kTopkThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      dist, ldd, ncols, col0, excl_off, excl_g, reinterpret_cast<unsigned long long*>(topk_key), k);
+  PPS_LAUNCH_CHECK("topk_update_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_topk_unpack(const uint64_t* topk_key, long long nq, int k, float* out_dist, int32_t* out_index,
+                               void* stream) {
+  if (nq < 0 || k < 1 || k > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
+  if (nq == 0) return PPS_OK;
+  if (!topk_key) return PPS_ERR_INVALID_ARG;
+  const long long n = nq * k, blocks = (n + 255) / 256;
+  topk_unpack_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(topk_key), n, out_dist, out_index);
+  PPS_LAUNCH_CHECK("topk_unpack_kernel");
+  return PPS_OK;
+}

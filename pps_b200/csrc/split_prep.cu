@@ -1,0 +1,128 @@
+// Operand preparation for the tensor-core distance: fp32 rows -> bf16 residual planes
+// (x = p0 + p1 + p2, each the bf16 round-to-nearest of what is left) with K zero-padded to
+// a multiple of 64, plus the row squared norms |x|^2 of compute_dist
+// (reid_dataset_evaluator.py:266-268) accumulated in fp64 and rounded once to fp32.
+// HBM-bound: reads 4*dim bytes per row, writes 2*kpad bytes per plane. One warp per row.
+#include "common.cuh"
+
+namespace pps {
+
+constexpr int kSplitWarps = 8;
+
+template <int PLANES, bool F16IN>
+__global__ void __launch_bounds__(32 * kSplitWarps) split_rows_kernel(const void* __restrict__ feats, long long row_begin,
+                                                                       long long row_end, long long rows, int dim,
+                                                                       long long ld, int kpad,
+                                                                       void* __restrict__ out_planes,
+                                                                       float* __restrict__ out_sqnorm) {
+  const int lane = threadIdx.x & 31;
+  const long long row = row_begin + (long long)blockIdx.x * kSplitWarps + (threadIdx.x >> 5);
+  if (row >= row_end) return;
+  double acc = 0.0;
+  const long long plane_stride = rows * (long long)kpad;   // elements
+  if constexpr (F16IN) {
+    const __half* src = reinterpret_cast<const __half*>(feats) + row * ld;
+    __half* dst = out_planes ? reinterpret_cast<__half*>(out_planes) + row * (long long)kpad : nullptr;
+    for (int k = lane; k < kpad; k += 32) {
+      const __half h = k < dim ? src[k] : __float2half(0.f);
+      const float v = __half2float(h);
+      acc += (double)v * (double)v;
+      if (dst) dst[k] = h;
+    }
+  } else {
+    const float* src = reinterpret_cast<const float*>(feats) + row * ld;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out_planes);
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15u) == 0);
+    for (int k = lane * 4; k < kpad; k += 128) {
+      float v[4];
+      if (vec && k + 3 < dim) {
+        const float4 t = ld_stream_f4(reinterpret_cast<const float4*>(src + k));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (k + e < dim) ? src[k + e] : 0.f;
+      }
+      __nv_bfloat16 p[3][4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc += (double)v[e] * (double)v[e];
+        float r = v[e];
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl) {
+          p[pl][e] = __float2bfloat16_rn(r);
+          r -= __bfloat162float(p[pl][e]);   // exact in fp32
+        }
+      }
+      if (dst) {
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl) {
+          uint2 w;
+          w.x = (uint32_t)__bfloat16_as_ushort(p[pl][0]) | ((uint32_t)__bfloat16_as_ushort(p[pl][1]) << 16);
+          w.y = (uint32_t)__bfloat16_as_ushort(p[pl][2]) | ((uint32_t)__bfloat16_as_ushort(p[pl][3]) << 16);
+          *reinterpret_cast<uint2*>(dst + pl * plane_stride + row * (long long)kpad + k) = w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && out_sqnorm) out_sqnorm[row] = (float)acc;
+}
+
+}  // namespace pps
+
+using namespace pps;
+
+extern "C" int pps_kpad(int dim) { return dim <= 0 ? 0 : ((dim + 63) / 64) * 64; }
+
+extern "C" long long pps_split_bytes(long long rows, int dim, int planes) {
+  if (rows < 0 || dim <= 0 || planes < 1 || planes > 3) return PPS_ERR_INVALID_ARG;
+  return rows * (long long)pps_kpad(dim) * 2 * planes;
+}
+
+static int split_dispatch(const void* feats, int dtype, long long row0, long long nrows, long long rows, int dim,
+                          long long ld, int planes, void* out_planes, float* out_sqnorm, void* stream) {
+  if (rows < 0 || dim <= 0 || ld < dim || row0 < 0 || nrows < 0 || row0 + nrows > rows) return PPS_ERR_INVALID_ARG;
+  if (nrows == 0) return PPS_OK;
+  if (!feats) return PPS_ERR_INVALID_ARG;
+  if (out_planes && (reinterpret_cast<uintptr_t>(out_planes) & 15u)) return PPS_ERR_ALIGN;
+  const int kpad = pps_kpad(dim);
+  const long long blocks = (nrows + kSplitWarps - 1) / kSplitWarps;
+  if (blocks > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid((unsigned)blocks), block(32 * kSplitWarps);
+  if (dtype == PPS_DTYPE_F16) {
+    if (planes != 1) return PPS_ERR_INVALID_ARG;
+    split_rows_kernel<1, true><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm);
+  } else if (dtype == PPS_DTYPE_F32) {
+    switch (planes) {
+      case 1: split_rows_kernel<1, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm); break;
+      case 2: split_rows_kernel<2, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm); break;
+      case 3: split_rows_kernel<3, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm); break;
+      default: return PPS_ERR_INVALID_ARG;
+    }
+  } else {
+    return PPS_ERR_INVALID_ARG;
+  }
+  PPS_LAUNCH_CHECK("split_rows_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_split_rows(const void* feats, int dtype, long long rows, int dim, long long ld, int planes,
+                              void* out_planes, float* out_sqnorm, void* stream) {
+  if (!out_planes && rows > 0) return PPS_ERR_INVALID_ARG;
+  return split_dispatch(feats, dtype, 0, rows, rows, dim, ld, planes, out_planes, out_sqnorm, stream);
+}
+
+extern "C" int pps_split_rows_slab(const void* feats, int dtype, long long row0, long long nrows, long long total_rows,
+                                   int dim, long long ld, int planes, void* out_planes, float* out_sqnorm,
+                                   void* stream) {
+  if (!out_planes && nrows > 0) return PPS_ERR_INVALID_ARG;
+  return split_dispatch(feats, dtype, row0, nrows, total_rows, dim, ld, planes, out_planes, out_sqnorm, stream);
+}
+
+extern "C" int pps_row_sqnorm(const void* feats, int dtype, long long rows, int dim, long long ld, float* out_sqnorm,
+                              void* stream) {
+  if (!out_sqnorm && rows > 0) return PPS_ERR_INVALID_ARG;
+  return split_dispatch(feats, dtype, 0, rows, rows, dim, ld, 1, nullptr, out_sqnorm, stream);
+}

@@ -1,0 +1,603 @@
+"""Test-time ranking: host-side mirror of detectron/datasets/reid_dataset_evaluator.py.
+
+Same entry points, argument order and error behaviour as the reference:
+  compute_dist(array1, array2, type='euclidean')                                  (:244-272)
+  cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk=100, ...)   (:283-363)
+  mean_ap(distmat, query_ids, gallery_ids, query_cams, gallery_cams, average)     (:366-439)
+  evaluate(json_dataset, all_feats, output_dir) -> (mAP, cmc, mq_mAP, mq_cmc)     (:29-209)
+plus ``rank_eval`` — the fused path from features to AP / first-match ranks / top-k that never
+needs more than one gallery chunk of the distance matrix — and ``evaluate_host`` (the C ABI's
+pps_evaluate_host: host buffers in, metrics out).
+
+All arithmetic runs in the CUDA library (tcgen05 distance GEMM, counting rank kernels); this
+module only marshals arrays, builds the same-id pair lists through the library's host code and
+does the final averaging over queries exactly as the reference does.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict, defaultdict
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+
+DEFAULT_PRECISION = "bf16x3"
+
+
+# ------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------
+def _torch():
+    return _lib.require_cuda()
+
+
+def _as_cuda_f32(a, name):
+    torch = _torch()
+    if isinstance(a, np.ndarray):
+        if a.ndim != 2:
+            raise RuntimeError("%s: expected a 2-D array, got ndim=%d" % (name, a.ndim))
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda(), True
+    if isinstance(a, torch.Tensor):
+        if a.dim() != 2:
+            raise RuntimeError("%s: expected a 2-D tensor, got ndim=%d" % (name, a.dim()))
+        t = a if a.is_cuda else a.cuda()
+        if t.dtype not in (torch.float32, torch.float16):
+            t = t.float()
+        return t.contiguous(), False
+    raise RuntimeError("%s: expected numpy.ndarray or torch.Tensor, got %s" % (name, type(a)))
+
+
+def _ids64(a, name):
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    a = np.ascontiguousarray(np.asarray(a), dtype=np.int64)
+    if a.ndim != 1:
+        raise RuntimeError("%s: expected a 1-D array" % name)
+    return a
+
+
+class PairLists:
+    """Same-id (query, gallery) pairs in CSR form (C ABI part 2c); host arrays + device copies."""
+
+    def __init__(self, query_ids, query_cams, gallery_ids, gallery_cams, device=None):
+        lib = _lib.load()
+        qi, qc = _ids64(query_ids, "query_ids"), _ids64(query_cams, "query_cams")
+        gi, gc = _ids64(gallery_ids, "gallery_ids"), _ids64(gallery_cams, "gallery_cams")
+        if qi.shape != qc.shape or gi.shape != gc.shape:
+            raise RuntimeError("ids and cams must have the same length")
+        self.nq, self.ng = int(qi.shape[0]), int(gi.shape[0])
+        n = int(lib.pps_pairs_count(_lib.ptr(qi), self.nq, _lib.ptr(gi), self.ng))
+        if n < 0:
+            _lib.check(n, "pps_pairs_count")
+        self.n_pairs = n
+        self.off = np.zeros(self.nq + 1, dtype=np.int32)
+        self.q = np.zeros(max(n, 1), dtype=np.int32)
+        self.g = np.zeros(max(n, 1), dtype=np.int32)
+        self.pos = np.zeros(max(n, 1), dtype=np.uint8)
+        _lib.check(lib.pps_pairs_fill(_lib.ptr(qi), _lib.ptr(qc), self.nq, _lib.ptr(gi), _lib.ptr(gc), self.ng,
+                                      _lib.ptr(self.off), _lib.ptr(self.q), _lib.ptr(self.g), _lib.ptr(self.pos)),
+                   "pps_pairs_fill")
+        per_q = np.diff(self.off)
+        self.max_pairs = int(per_q.max()) if self.nq else 0
+        # junk (same id, same camera) as its own CSR: the exclusion list of the valid-filtered top-k
+        junk = self.pos[:n] == 0
+        self.junk_g = np.ascontiguousarray(self.g[:n][junk])
+        jcount = np.bincount(self.q[:n][junk], minlength=self.nq) if n else np.zeros(self.nq, dtype=np.int64)
+        self.junk_off = np.zeros(self.nq + 1, dtype=np.int32)
+        self.junk_off[1:] = np.cumsum(jcount)
+        self.n_pos_per_q = (np.bincount(self.q[:n][~junk], minlength=self.nq) if n
+                            else np.zeros(self.nq, dtype=np.int64))
+        self._dev = None
+        if device is not None:
+            self.to(device)
+
+    def to(self, device):
+        torch = _torch()
+        f = lambda a: torch.from_numpy(a).to(device)
+        self._dev = dict(off=f(self.off), q=f(self.q), g=f(self.g), pos=f(self.pos), junk_off=f(self.junk_off),
+                         junk_g=f(self.junk_g if self.junk_g.size else np.zeros(1, dtype=np.int32)))
+        self.device = device
+        return self
+
+    def dev(self, name):
+        return self._dev[name]
+
+
+class RankResult:
+    """Per-query outputs of the rank kernels (host numpy) + the reference's averages."""
+
+    def __init__(self, ap, is_valid, first_rank, neg_before=None, pairs: Optional[PairLists] = None,
+                 topk_index=None, topk_dist=None):
+        self.ap, self.is_valid, self.first_rank = ap, is_valid, first_rank
+        self.neg_before, self.pairs = neg_before, pairs
+        self.topk_index, self.topk_dist = topk_index, topk_dist
+
+    def mean_ap(self):
+        if len(self.ap) == 0:
+            raise RuntimeError("No valid query")
+        return float(np.sum(self.ap)) / np.sum(self.is_valid)   # :437-438 (nan if no query is valid)
+
+    def cmc_matrix(self, topk, first_match_break):
+        m = len(self.ap)
+        ret = np.zeros([m, topk])
+        if first_match_break:
+            ok = (self.is_valid > 0) & (self.first_rank >= 0) & (self.first_rank < topk)
+            ret[np.nonzero(ok)[0], self.first_rank[ok]] += 1
+        else:
+            p = self.pairs
+            n = p.n_pairs
+            sel = (p.pos[:n] == 1) & (self.neg_before[:n] < topk)
+            delta = 1.0 / np.maximum(p.n_pos_per_q, 1)
+            np.add.at(ret, (p.q[:n][sel], self.neg_before[:n][sel]), delta[p.q[:n][sel]])
+        return ret.cumsum(axis=1)
+
+    def cmc(self, topk=10, first_match_break=True, average=True):
+        num_valid = int(np.sum(self.is_valid))
+        if num_valid == 0:
+            raise RuntimeError("No valid query")                 # :358-359
+        ret = self.cmc_matrix(topk, first_match_break)
+        if average:
+            return np.sum(ret, axis=0) / num_valid
+        return ret, self.is_valid.astype(np.float64)
+
+
+def _rank_block(lib, dist, ldd, nq, ncols, col0, pairs: PairLists, pair_d, cnt_le, cnt_first, do_gather, do_count,
+                topk_key=None, topk=0, topk_filtered=True):
+    s = _lib.stream_ptr()
+    if do_gather and pairs.n_pairs:
+        _lib.check(lib.pps_rank_gather(_lib.ptr(dist), ldd, nq, ncols, col0, _lib.ptr(pairs.dev("q")),
+                                       _lib.ptr(pairs.dev("g")), pairs.n_pairs, _lib.ptr(pair_d), s),
+                   "pps_rank_gather")
+    if do_count:
+        if pairs.n_pairs:
+            _lib.check(lib.pps_rank_count(_lib.ptr(dist), ldd, nq, ncols, col0, _lib.ptr(pairs.dev("off")),
+                                          _lib.ptr(pairs.dev("g")), _lib.ptr(pairs.dev("pos")), _lib.ptr(pair_d),
+                                          pairs.max_pairs, _lib.ptr(cnt_le), _lib.ptr(cnt_first), s),
+                       "pps_rank_count")
+        if topk_key is not None:
+            eo = pairs.dev("junk_off") if topk_filtered else None
+            eg = pairs.dev("junk_g") if topk_filtered else None
+            _lib.check(lib.pps_topk_update(_lib.ptr(dist), ldd, nq, ncols, col0, _lib.ptr(eo), _lib.ptr(eg),
+                                           _lib.ptr(topk_key), topk, s), "pps_topk_update")
+
+
+def _finalize(lib, nq, pairs: PairLists, pair_d, cnt_le, cnt_first, want_neg_before):
+    torch = _torch()
+    dev = pair_d.device
+    ap = torch.empty(nq, dtype=torch.float64, device=dev)
+    valid = torch.empty(nq, dtype=torch.uint8, device=dev)
+    first = torch.empty(nq, dtype=torch.int32, device=dev)
+    negb = torch.zeros(max(pairs.n_pairs, 1), dtype=torch.int32, device=dev) if want_neg_before else None
+    _lib.check(lib.pps_rank_finalize(nq, _lib.ptr(pairs.dev("off")), _lib.ptr(pairs.dev("g")),
+                                     _lib.ptr(pairs.dev("pos")), _lib.ptr(pair_d), _lib.ptr(cnt_le),
+                                     _lib.ptr(cnt_first), _lib.ptr(ap), _lib.ptr(valid), _lib.ptr(first),
+                                     _lib.ptr(negb), _lib.stream_ptr()), "pps_rank_finalize")
+    return ap, valid, first, negb
+
+
+def rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams, want_neg_before=False, topk=0,
+                 topk_filtered=True) -> RankResult:
+    """Ranking outputs for a materialised [m, n] distance matrix (numpy or CUDA tensor)."""
+    torch = _torch()
+    lib = _lib.load()
+    dist, _ = _as_cuda_f32(distmat, "distmat")
+    if dist.dtype != torch.float32:
+        dist = dist.float()
+    m, n = int(dist.shape[0]), int(dist.shape[1])
+    with torch.cuda.device(dist.device):
+        pairs = PairLists(query_ids, query_cams, gallery_ids, gallery_cams, device=dist.device)
+        if pairs.nq != m or pairs.ng != n:
+            raise RuntimeError("distmat shape %s does not match %d query / %d gallery ids" % ((m, n), pairs.nq, pairs.ng))
+        E = max(pairs.n_pairs, 1)
+        pair_d = torch.zeros(E, dtype=torch.float32, device=dist.device)
+        cnt_le = torch.zeros(E, dtype=torch.int32, device=dist.device)
+        cnt_first = torch.zeros(max(m, 1), dtype=torch.int32, device=dist.device)
+        key = None
+        if topk:
+            key = torch.empty((m, topk), dtype=torch.int64, device=dist.device)
+            _lib.check(lib.pps_topk_init(_lib.ptr(key), m, topk, _lib.stream_ptr()), "pps_topk_init")
+        _rank_block(lib, dist, int(dist.stride(0)), m, n, 0, pairs, pair_d, cnt_le, cnt_first, True, True, key, topk,
+                    topk_filtered)
+        ap, valid, first, negb = _finalize(lib, m, pairs, pair_d, cnt_le, cnt_first, want_neg_before)
+        ti = td = None
+        if topk:
+            td = torch.empty((m, topk), dtype=torch.float32, device=dist.device)
+            ti = torch.empty((m, topk), dtype=torch.int32, device=dist.device)
+            _lib.check(lib.pps_topk_unpack(_lib.ptr(key), m, topk, _lib.ptr(td), _lib.ptr(ti), _lib.stream_ptr()),
+                       "pps_topk_unpack")
+            ti, td = ti.cpu().numpy(), td.cpu().numpy()
+        return RankResult(ap.cpu().numpy(), valid.cpu().numpy(), first.cpu().numpy(),
+                          negb.cpu().numpy() if negb is not None else None, pairs, ti, td)
+
+
+# ------------------------------------------------------------------------------------
+# distance
+# ------------------------------------------------------------------------------------
+class SplitOperand:
+    """Rows prepared for the tensor-core distance: bf16 residual planes (or fp16 rows) + |x|^2."""
+
+    def __init__(self, feats, planes: int):
+        torch = _torch()
+        lib = _lib.load()
+        if feats.dtype == torch.float16:
+            dtype, planes = _lib.DTYPE_F16, 1
+        elif feats.dtype == torch.float32:
+            dtype = _lib.DTYPE_F32
+        else:
+            raise RuntimeError("features must be float32 or float16")
+        if feats.stride(1) != 1:
+            feats = feats.contiguous()
+        self.rows, self.dim = int(feats.shape[0]), int(feats.shape[1])
+        self.planes_n, self.is_f16 = planes, dtype == _lib.DTYPE_F16
+        nbytes = int(lib.pps_split_bytes(self.rows, self.dim, planes)) if self.rows else 0
+        self.planes = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=feats.device)
+        self.sqnorm = torch.empty(max(self.rows, 1), dtype=torch.float32, device=feats.device)
+        if self.rows:
+            _lib.check(lib.pps_split_rows(_lib.ptr(feats), dtype, self.rows, self.dim, int(feats.stride(0)), planes,
+                                          _lib.ptr(self.planes), _lib.ptr(self.sqnorm), _lib.stream_ptr()),
+                       "pps_split_rows")
+
+    def rows_slice_ptr(self, r0):
+        raise NotImplementedError
+
+
+def _prec_code(precision):
+    if precision not in _lib.PRECISIONS:
+        raise RuntimeError("unknown precision %r (expected one of %s)" % (precision, sorted(_lib.PRECISIONS)))
+    return _lib.PRECISIONS[precision]
+
+
+def dist_block(a: SplitOperand, b: SplitOperand, prec: int, out, flags=0, b_row0=0, b_rows=None):
+    """out[:, :b_rows] = distance(a rows, b rows [b_row0, b_row0+b_rows)) on the tensor cores."""
+    lib = _lib.load()
+    b_rows = b.rows - b_row0 if b_rows is None else b_rows
+    if a.is_f16 != b.is_f16:
+        raise RuntimeError("query and gallery features must have the same dtype")
+    if a.is_f16:
+        prec = _lib.PREC_F16X1
+    if b_row0 != 0 or b_rows != b.rows:
+        # a row window of every plane: planes are [planes][rows][kpad], the TMA map needs the full
+        # plane stride, so windows are expressed by a shifted base and the full row count upstream.
+        raise RuntimeError("dist_block: gallery windows are handled by GalleryChunks")
+    _lib.check(lib.pps_dist_tc(_lib.ptr(a.planes), _lib.ptr(a.sqnorm), a.rows, a.planes_n, _lib.ptr(b.planes),
+                               _lib.ptr(b.sqnorm), b.rows, b.planes_n, a.dim, prec, flags, _lib.ptr(out),
+                               int(out.stride(0)), _lib.stream_ptr()), "pps_dist_tc")
+
+
+def compute_dist(array1, array2, type="euclidean", precision: str = DEFAULT_PRECISION):
+    """Pairwise distance, reid_dataset_evaluator.py:244-272.
+
+    'euclidean' -> sqrt(max(0, |a|^2 + |b|^2 - 2ab)).  'cosine' -> the reference calls an undefined
+    ``normalize`` (NameError, :259-260); what it intends — rows L2-normalised as
+    detectron/core/test_engine.py:52-55 does, then a.b^T (a similarity) — is what this returns.
+    numpy in -> numpy out; CUDA tensor in -> CUDA tensor out.
+    """
+    assert type in ["cosine", "euclidean"]
+    torch = _torch()
+    lib = _lib.load()
+    a, a_np = _as_cuda_f32(array1, "array1")
+    b, b_np = _as_cuda_f32(array2, "array2")
+    if a.shape[1] != b.shape[1]:
+        raise RuntimeError("shapes %s and %s not aligned" % (tuple(a.shape), tuple(b.shape)))
+    prec = _prec_code(precision)
+    m1, m2, dim = int(a.shape[0]), int(b.shape[0]), int(a.shape[1])
+    with torch.cuda.device(a.device):
+        if type == "cosine":
+            a = a.float() / torch.linalg.norm(a.float(), dim=1, keepdim=True).clamp_min(1e-12)
+            b = b.float() / torch.linalg.norm(b.float(), dim=1, keepdim=True).clamp_min(1e-12)
+        flags = _lib.DIST_DOT if type == "cosine" else 0
+        out = torch.empty((m1, m2), dtype=torch.float32, device=a.device)
+        if m1 and m2:
+            if prec == _lib.PREC_FP32:
+                a32, b32 = a.float().contiguous(), b.float().contiguous()
+                an = torch.empty(m1, dtype=torch.float32, device=a.device)
+                bn = torch.empty(m2, dtype=torch.float32, device=a.device)
+                _lib.check(lib.pps_row_sqnorm(_lib.ptr(a32), _lib.DTYPE_F32, m1, dim, dim, _lib.ptr(an),
+                                              _lib.stream_ptr()), "pps_row_sqnorm")
+                _lib.check(lib.pps_row_sqnorm(_lib.ptr(b32), _lib.DTYPE_F32, m2, dim, dim, _lib.ptr(bn),
+                                              _lib.stream_ptr()), "pps_row_sqnorm")
+                _lib.check(lib.pps_dist_fp32(_lib.ptr(a32), dim, _lib.ptr(an), m1, _lib.ptr(b32), dim, _lib.ptr(bn),
+                                             m2, dim, flags, _lib.ptr(out), m2, _lib.stream_ptr()), "pps_dist_fp32")
+            else:
+                planes = _lib.PLANES_FOR[prec]
+                sa, sb = SplitOperand(a, planes), SplitOperand(b, planes)
+                dist_block(sa, sb, prec, out, flags)
+    if a_np and b_np:
+        return out.cpu().numpy()
+    return out
+
+
+# ------------------------------------------------------------------------------------
+# reference-shaped metric entry points on a materialised distance matrix
+# ------------------------------------------------------------------------------------
+def _ensure_arrays(distmat, query_ids, gallery_ids, query_cams, gallery_cams):
+    torch = _torch()
+    ok = lambda a: isinstance(a, np.ndarray) or isinstance(a, torch.Tensor)
+    assert ok(distmat)
+    assert ok(query_ids)
+    assert ok(gallery_ids)
+    assert ok(query_cams)
+    assert ok(gallery_cams)
+
+
+def cmc(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_cams=None, topk=100,
+        separate_camera_set=False, single_gallery_shot=False, first_match_break=False, average=True):
+    """reid_dataset_evaluator.py:283-363.
+
+    ``separate_camera_set`` / ``single_gallery_shot`` are the two branches the reference never
+    reaches (its single_gallery_shot branch calls ``np.bool`` and random sampling, :274-279,334-347);
+    they raise here instead of silently computing something else.
+    """
+    _ensure_arrays(distmat, query_ids, gallery_ids, query_cams, gallery_cams)
+    if separate_camera_set or single_gallery_shot:
+        raise NotImplementedError("cmc: separate_camera_set / single_gallery_shot are not on the PPS eval path "
+                                  "(reid_dataset_evaluator.py:35-37 fixes both to False)")
+    res = rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams,
+                       want_neg_before=not first_match_break)
+    return res.cmc(topk=topk, first_match_break=first_match_break, average=average)
+
+
+def mean_ap(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_cams=None, average=True):
+    """reid_dataset_evaluator.py:366-439 with the installed scikit-learn's (>= 0.19) AP definition."""
+    _ensure_arrays(distmat, query_ids, gallery_ids, query_cams, gallery_cams)
+    res = rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams)
+    if average:
+        return res.mean_ap()
+    return res.ap, res.is_valid.astype(np.float64)
+
+
+# ------------------------------------------------------------------------------------
+# fused path: features -> metrics
+# ------------------------------------------------------------------------------------
+def rank_eval(q_feats, g_feats, query_ids, gallery_ids, query_cams, gallery_cams, topk: int = 0,
+              precision: str = DEFAULT_PRECISION, want_neg_before: bool = False, max_block_bytes: int = 8 << 30,
+              gallery_offset: int = 0, group=None, topk_filtered: bool = True) -> RankResult:
+    """distance + junk filter + exact positive ranks (+ top-k) without keeping the full matrix.
+
+    q_feats [nq, D], g_feats [ng_local, D]: CUDA float32 / float16 tensors.  ``query_ids`` ... are
+    the GLOBAL id / camera arrays.  With ``group`` (a torch.distributed group) every rank passes
+    its contiguous gallery shard ``g_feats`` starting at global row ``gallery_offset``; the three
+    exchanges are one sum-allreduce of the positives' distances, one of the integer counters and
+    an all-gather of the top-k keys, so the merged result equals the unsharded one bit for bit.
+    """
+    torch = _torch()
+    lib = _lib.load()
+    dist_mod = None
+    if group is not None:
+        import torch.distributed as dist_mod
+    q, _ = _as_cuda_f32(q_feats, "q_feats")
+    g, _ = _as_cuda_f32(g_feats, "g_feats")
+    if q.shape[1] != g.shape[1]:
+        raise RuntimeError("feature dims differ: %d vs %d" % (q.shape[1], g.shape[1]))
+    prec = _prec_code(precision)
+    if prec == _lib.PREC_FP32:
+        raise RuntimeError("rank_eval runs the distance on the tensor cores; use bf16x1/bf16x3/bf16x6 (or fp16 inputs)")
+    planes = _lib.PLANES_FOR[prec]
+    nq, ngl, dim = int(q.shape[0]), int(g.shape[0]), int(q.shape[1])
+    dev = q.device
+    with torch.cuda.device(dev):
+        pairs = PairLists(query_ids, query_cams, gallery_ids, gallery_cams, device=dev)
+        if pairs.nq != nq:
+            raise RuntimeError("q_feats has %d rows but %d query ids" % (nq, pairs.nq))
+        if group is None and pairs.ng != ngl:
+            raise RuntimeError("g_feats has %d rows but %d gallery ids" % (ngl, pairs.ng))
+        E = max(pairs.n_pairs, 1)
+        pair_d = torch.zeros(E, dtype=torch.float32, device=dev)
+        cnt_le = torch.zeros(E, dtype=torch.int32, device=dev)
+        cnt_first = torch.zeros(max(nq, 1), dtype=torch.int32, device=dev)
+        key = None
+        if topk:
+            key = torch.empty((nq, topk), dtype=torch.int64, device=dev)
+            _lib.check(lib.pps_topk_init(_lib.ptr(key), nq, topk, _lib.stream_ptr()), "pps_topk_init")
+        sq = SplitOperand(q, planes)
+        # gallery chunks: bounded distance scratch
+        chunk = ngl if nq == 0 else max(256, min(ngl, max_block_bytes // (4 * max(nq, 1))))
+        chunk = max(256, (chunk // 256) * 256) if chunk < ngl else ngl
+        n_chunks = (ngl + chunk - 1) // chunk if ngl else 0
+        ldd = (min(chunk, max(ngl, 1)) + 3) // 4 * 4
+        block = torch.empty((max(nq, 1), ldd), dtype=torch.float32, device=dev)
+        splits = []
+        for c in range(n_chunks):
+            r0 = c * chunk
+            splits.append((r0, SplitOperand(g[r0:r0 + chunk], planes)))
+
+        def distance(sg):
+            p = _lib.PREC_F16X1 if sq.is_f16 else prec
+            _lib.check(lib.pps_dist_tc(_lib.ptr(sq.planes), _lib.ptr(sq.sqnorm), nq, sq.planes_n, _lib.ptr(sg.planes),
+                                       _lib.ptr(sg.sqnorm), sg.rows, sg.planes_n, dim, p, 0, _lib.ptr(block), ldd,
+                                       _lib.stream_ptr()), "pps_dist_tc")
+
+        # sweep 1: the positives' / junk distances (thresholds of the counting sweep)
+        for r0, sg in splits:
+            distance(sg)
+            _rank_block(lib, block, ldd, nq, sg.rows, gallery_offset + r0, pairs, pair_d, cnt_le, cnt_first,
+                        True, False)
+        if group is not None:
+            dist_mod.all_reduce(pair_d, op=dist_mod.ReduceOp.SUM, group=group)
+        # sweep 2: counts (+ top-k); a single chunk is still resident in `block`
+        for r0, sg in splits:
+            if n_chunks > 1:
+                distance(sg)
+            _rank_block(lib, block, ldd, nq, sg.rows, gallery_offset + r0, pairs, pair_d, cnt_le, cnt_first,
+                        False, True, key, topk, topk_filtered)
+        if group is not None:
+            dist_mod.all_reduce(cnt_le, op=dist_mod.ReduceOp.SUM, group=group)
+            dist_mod.all_reduce(cnt_first, op=dist_mod.ReduceOp.SUM, group=group)
+            if topk:
+                key = merge_topk_keys(key, topk, group)
+        ap, valid, first, negb = _finalize(lib, nq, pairs, pair_d, cnt_le, cnt_first, want_neg_before)
+        ti = td = None
+        if topk:
+            td = torch.empty((nq, topk), dtype=torch.float32, device=dev)
+            ti = torch.empty((nq, topk), dtype=torch.int32, device=dev)
+            _lib.check(lib.pps_topk_unpack(_lib.ptr(key), nq, topk, _lib.ptr(td), _lib.ptr(ti), _lib.stream_ptr()),
+                       "pps_topk_unpack")
+            ti, td = ti.cpu().numpy(), td.cpu().numpy()
+        return RankResult(ap.cpu().numpy(), valid.cpu().numpy(), first.cpu().numpy(),
+                          negb.cpu().numpy() if negb is not None else None, pairs, ti, td)
+
+
+def merge_topk_keys(key, topk, group):
+    """All-gather every shard's [nq, k] candidate keys and keep the k smallest per query.
+
+    Keys are (float bits << 32 | gallery index) of non-negative distances, so they are positive
+    int64 values except the all-ones "empty" marker, which is mapped to INT64_MAX for the sort.
+    """
+    import torch
+    import torch.distributed as dist_mod
+    world = dist_mod.get_world_size(group)
+    gathered = [torch.empty_like(key) for _ in range(world)]
+    dist_mod.all_gather(gathered, key, group=group)
+    allk = torch.cat(gathered, dim=1)
+    big = torch.iinfo(torch.int64).max
+    allk = torch.where(allk == -1, torch.full_like(allk, big), allk)
+    merged = torch.sort(allk, dim=1).values[:, :topk]
+    return torch.where(merged == big, torch.full_like(merged, -1), merged).contiguous()
+
+
+# ------------------------------------------------------------------------------------
+# evaluate(): the reference's driver (single-query and multi-query branches)
+# ------------------------------------------------------------------------------------
+def parse_im_name(im_name, parse_type="id"):
+    """reid_dataset_evaluator.py:224-231: '{pid:08d}_{cam:04d}_{k:08d}.jpg'."""
+    assert parse_type in ("id", "cam")
+    return int(im_name[:8]) if parse_type == "id" else int(im_name[9:13])
+
+
+def get_info(entry):
+    im_name = os.path.basename(entry["image"])
+    return parse_im_name(im_name, "id"), parse_im_name(im_name, "cam"), im_name, entry["mark"], entry["image"]
+
+
+def evaluate_arrays(all_feats, ids, cams, marks, precision: str = DEFAULT_PRECISION, verbose: bool = False):
+    """The body of ``evaluate`` after the roidb has been flattened to arrays (:57-159, :209).
+
+    marks: 0 = query, 1 = gallery, 2 = multi-query (json_dataset.py:149,188-189).
+    Returns (mAP, cmc_scores[10], mq_mAP, mq_cmc_scores) like the reference.
+    """
+    torch = _torch()
+    ids, cams, marks = _ids64(ids, "ids"), _ids64(cams, "cams"), _ids64(marks, "marks")
+    feat = all_feats
+    if isinstance(feat, np.ndarray):
+        feat = torch.from_numpy(np.ascontiguousarray(feat, dtype=np.float32))
+    q_inds, g_inds, mq_inds = marks == 0, marks == 1, marks == 2
+    qsel, gsel = torch.from_numpy(np.nonzero(q_inds)[0]), torch.from_numpy(np.nonzero(g_inds)[0])
+    feat_dev = feat.cuda() if not feat.is_cuda else feat
+    gf = feat_dev[gsel.to(feat_dev.device)]
+
+    def compute_score(qf, query_ids, query_cams):
+        res = rank_eval(qf, gf, query_ids, ids[g_inds], query_cams, cams[g_inds], precision=precision)
+        return res.mean_ap(), res.cmc(topk=10, first_match_break=True)     # :70-93
+
+    def print_scores(mAP, cmc_scores):
+        print("[mAP: {:5.2%}], [cmc1: {:5.2%}], [cmc5: {:5.2%}], [cmc10: {:5.2%}]".format(mAP, *cmc_scores[[0, 4, 9]]))
+
+    mAP, cmc_scores = compute_score(feat_dev[qsel.to(feat_dev.device)], ids[q_inds], cams[q_inds])
+    if verbose:
+        print("{:<30}".format("Single Query:"), end="")
+        print_scores(mAP, cmc_scores)
+
+    mq_mAP, mq_cmc_scores = None, None
+    if np.any(mq_inds):
+        # multi-query: average the mark==2 features of each (id, cam) group (:131-143)
+        mq_ids, mq_cams = ids[mq_inds], cams[mq_inds]
+        mq_feat = feat_dev[torch.from_numpy(np.nonzero(mq_inds)[0]).to(feat_dev.device)].float()
+        groups = OrderedDict()
+        for ind, (i, c) in enumerate(zip(mq_ids.tolist(), mq_cams.tolist())):
+            groups.setdefault((i, c), []).append(ind)
+        keys = list(groups.keys())
+        seg = torch.empty(len(mq_ids), dtype=torch.int64)
+        for k, key in enumerate(keys):
+            seg[groups[key]] = k
+        seg = seg.to(feat_dev.device)
+        pooled = torch.zeros((len(keys), mq_feat.shape[1]), dtype=torch.float32, device=feat_dev.device)
+        pooled.index_add_(0, seg, mq_feat)
+        counts = torch.bincount(seg, minlength=len(keys)).clamp_min(1).unsqueeze(1)
+        pooled = pooled / counts
+        mq_mAP, mq_cmc_scores = compute_score(pooled, np.array([k[0] for k in keys]), np.array([k[1] for k in keys]))
+        if verbose:
+            print("{:<30}".format("Multi Query:"), end="")
+            print_scores(mq_mAP, mq_cmc_scores)
+    return mAP, cmc_scores, mq_mAP, mq_cmc_scores
+
+
+def evaluate(json_dataset, all_feats, output_dir=None, precision: str = DEFAULT_PRECISION, verbose: bool = True):
+    """reid_dataset_evaluator.py:29-209 (re-ranking, :161-207, is not part of this build).
+
+    ``json_dataset`` only needs ``get_roidb(gt=True)`` returning entries with 'image' and 'mark'.
+    """
+    roidb = json_dataset.get_roidb(gt=True)
+    ids, cams, marks = [], [], []
+    for entry in roidb:
+        pid, cam, _, mark, _ = get_info(entry)
+        ids.append(pid)
+        cams.append(cam)
+        marks.append(mark)
+    return evaluate_arrays(all_feats, np.asarray(ids), np.asarray(cams), np.asarray(marks), precision, verbose)
+
+
+def reid_results(coco_eval, name="reid"):
+    """detectron/datasets/task_evaluation.py:54-60,345-360: result tuple -> {'ReID': {...}} dict."""
+    res = OrderedDict({"ReID": OrderedDict([("mAP", -1), ("CMC1", -1), ("CMC5", -1), ("CMC10", -1),
+                                             ("mq_mAP", -1), ("mq_CMC1", -1), ("mq_CMC5", -1), ("mq_CMC10", -1)])})
+    if coco_eval is not None:
+        s = coco_eval
+        res["ReID"]["mAP"], res["ReID"]["CMC1"], res["ReID"]["CMC5"], res["ReID"]["CMC10"] = s[0], s[1][0], s[1][4], s[1][9]
+        if s[2] is not None:
+            res["ReID"]["mq_mAP"] = s[2]
+        if s[3] is not None:
+            res["ReID"]["mq_CMC1"], res["ReID"]["mq_CMC5"], res["ReID"]["mq_CMC10"] = s[3][0], s[3][4], s[3][9]
+    return OrderedDict([(name, res)])
+
+
+# ------------------------------------------------------------------------------------
+# host-buffer entry point (what bench.py times as e2e)
+# ------------------------------------------------------------------------------------
+def evaluate_host(q_feats, g_feats, query_ids, gallery_ids, query_cams, gallery_cams, cmc_topk: int = 10,
+                  topk: int = 0, precision: str = DEFAULT_PRECISION, device: int = 0):
+    """pps_evaluate_host: HOST float32 arrays (numpy, or pinned torch CPU tensors) in, metrics out.
+
+    Every host<->device copy happens inside the call.  Returns a dict with mAP, cmc, ap, valid,
+    first_rank and (if topk) topk_index / topk_dist.
+    """
+    lib = _lib.load()
+    _lib.require_cuda()
+
+    def host_f32(a, name):
+        if hasattr(a, "is_cuda"):
+            if a.is_cuda:
+                raise RuntimeError("%s: evaluate_host takes host buffers" % name)
+            import torch
+            if a.dtype != torch.float32 or not a.is_contiguous() or a.dim() != 2:
+                raise RuntimeError("%s: expected a contiguous 2-D float32 tensor" % name)
+            return a, int(a.shape[0]), int(a.shape[1])
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        if a.ndim != 2:
+            raise RuntimeError("%s: expected a 2-D array" % name)
+        return a, int(a.shape[0]), int(a.shape[1])
+
+    q, nq, dq = host_f32(q_feats, "q_feats")
+    g, ng, dg = host_f32(g_feats, "g_feats")
+    if dq != dg:
+        raise RuntimeError("feature dims differ: %d vs %d" % (dq, dg))
+    qi, qc = _ids64(query_ids, "query_ids"), _ids64(query_cams, "query_cams")
+    gi, gc = _ids64(gallery_ids, "gallery_ids"), _ids64(gallery_cams, "gallery_cams")
+    if len(qi) != nq or len(gi) != ng or len(qc) != nq or len(gc) != ng:
+        raise RuntimeError("ids / cams lengths do not match the feature rows")
+    out_map = C.c_double(0.0)
+    out_cmc = np.zeros(max(cmc_topk, 1), dtype=np.float64)
+    ap = np.zeros(nq, dtype=np.float64)
+    valid = np.zeros(nq, dtype=np.uint8)
+    first = np.zeros(nq, dtype=np.int32)
+    ti = np.zeros((nq, topk), dtype=np.int32) if topk else None
+    td = np.zeros((nq, topk), dtype=np.float32) if topk else None
+    rc = lib.pps_evaluate_host(_lib.ptr(q), nq, _lib.ptr(g), ng, dq, _lib.ptr(qi), _lib.ptr(qc), _lib.ptr(gi),
+                               _lib.ptr(gc), _prec_code(precision), cmc_topk, topk, device,
+                               C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc), _lib.ptr(ap), _lib.ptr(valid),
+                               _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
+    _lib.check(rc, "pps_evaluate_host")
+    return dict(mAP=float(out_map.value), cmc=out_cmc[:cmc_topk], ap=ap, valid=valid, first_rank=first,
+                topk_index=ti, topk_dist=td)

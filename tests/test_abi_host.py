@@ -1,0 +1,128 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/pps_b200.h declares,
+its host-only entry points work without a GPU, the host layer mirrors the reference interface, and
+the product refuses to run without CUDA (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import pps_oracle as O
+from pps_b200 import _lib, evaluator, pooling, synthetic
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pps_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pps_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+        assert n in _lib.SIGNATURES, "no ctypes signature for " + n
+    assert lib.pps_abi_version() == 1
+    assert lib.pps_strerror(_lib.PPS_ERR_NO_VALID_QUERY) == b"No valid query"
+    assert lib.pps_kpad(2048) == 2048 and lib.pps_kpad(100) == 128 and lib.pps_kpad(8064) == 8064
+    assert lib.pps_split_bytes(10, 100, 2) == 10 * 128 * 2 * 2
+
+
+def test_pair_lists_host_code_matches_numpy():
+    d = synthetic.make_reid_set(nq=70, ng=600, dim=8, n_ids=20, n_cams=3, n_distractors=50, seed=5)
+    p = evaluator.PairLists(d["qid"], d["qcam"], d["gid"], d["gcam"])
+    assert p.nq == 70 and p.ng == 600
+    for i in range(p.nq):
+        same = np.nonzero(d["gid"] == d["qid"][i])[0]
+        e0, e1 = p.off[i], p.off[i + 1]
+        np.testing.assert_array_equal(p.g[e0:e1], same)                       # ascending gallery index
+        np.testing.assert_array_equal(p.q[e0:e1], np.full(len(same), i))
+        np.testing.assert_array_equal(p.pos[e0:e1], (d["gcam"][same] != d["qcam"][i]).astype(np.uint8))
+        j0, j1 = p.junk_off[i], p.junk_off[i + 1]
+        np.testing.assert_array_equal(p.junk_g[j0:j1], same[d["gcam"][same] == d["qcam"][i]])
+    assert p.max_pairs == int(np.diff(p.off).max())
+    # junk == exactly the complement of the reference's valid mask
+    i = 3
+    valid = O.valid_mask(d["qid"][i], d["qcam"][i], d["gid"], d["gcam"])
+    np.testing.assert_array_equal(np.nonzero(~valid)[0], p.junk_g[p.junk_off[i]:p.junk_off[i + 1]])
+
+
+def test_pair_lists_empty_and_no_match():
+    p = evaluator.PairLists(np.array([5, 6]), np.array([0, 1]), np.array([1, 2, 3]), np.array([0, 0, 0]))
+    assert p.n_pairs == 0 and p.max_pairs == 0 and list(p.off) == [0, 0, 0]
+    p = evaluator.PairLists(np.zeros(0, np.int64), np.zeros(0, np.int64), np.array([1]), np.array([0]))
+    assert p.n_pairs == 0 and list(p.off) == [0]
+
+
+def test_split_helper_mirrors_reference_tables():
+    for n in (5, 6, 7, 9, 10):
+        for scale in (1.0 / 16, 1.0 / 8):
+            assert pooling.uniform_partition_split(n, 384, scale) == O.uniform_partition_split(n, 384, scale)
+    assert pooling.uniform_partition_split(6, 256, 1.0 / 16) == [2] * 6
+
+
+def test_blob_names_and_masks():
+    names = pooling.blob_names(6)
+    assert len(names) == 63 and names[0] == "pps0_pool2" and names[2] == "pps01_pool2" and names[-1] == "pps012345_pool2"
+    masks = [pooling.comb_to_mask(c) for c in pooling.pyramid_combs]
+    assert len(masks) == 21 and masks[0] == 1 and masks[-1] == 63
+    assert pooling.mask_to_comb(0b101001, 6) == [0, 3, 5]
+
+
+def test_rank_result_aggregation_matches_oracle(golden):
+    """RankResult turns per-query kernel outputs into the reference's averages; feed it the oracle's
+    count-based outputs and compare with the oracle's sort-based cmc / mean_ap."""
+    d = golden("small_mid")
+    dist = d["dist"]
+    ap, valid, first, neg_before = O.rank_counts(dist, d["qid"], d["gid"], d["qcam"], d["gcam"])
+    p = evaluator.PairLists(d["qid"], d["qcam"], d["gid"], d["gcam"])
+    nb = np.zeros(max(p.n_pairs, 1), dtype=np.int32)
+    for i in range(p.nq):
+        e = np.arange(p.off[i], p.off[i + 1])
+        nb[e[p.pos[e] == 1]] = neg_before[i]
+    res = evaluator.RankResult(ap, valid, first, nb, p)
+    ids = dict(query_ids=d["qid"], gallery_ids=d["gid"], query_cams=d["qcam"], gallery_cams=d["gcam"])
+    assert abs(res.mean_ap() - float(d["mAP"])) < 1e-12
+    np.testing.assert_allclose(res.cmc(10, True), d["cmc_fmb"], atol=1e-12)
+    np.testing.assert_allclose(res.cmc(20, False), d["cmc_all"], atol=1e-12)
+    rows, v = res.cmc(10, True, average=False)
+    np.testing.assert_array_equal(rows, d["cmc_rows"])
+
+
+def test_no_valid_query_error():
+    res = evaluator.RankResult(np.zeros(3), np.zeros(3, np.uint8), np.full(3, -1, np.int32))
+    with pytest.raises(RuntimeError, match="No valid query"):
+        res.cmc(10, True)
+
+
+def test_reid_results_dict_shape():
+    r = evaluator.reid_results((0.5, np.arange(10) / 10.0, None, None), "market")
+    assert list(r.keys()) == ["market"]
+    assert r["market"]["ReID"]["mAP"] == 0.5 and r["market"]["ReID"]["CMC5"] == 0.4 and r["market"]["ReID"]["mq_mAP"] == -1
+
+
+def test_parse_im_name():
+    assert evaluator.parse_im_name("00000012_0003_00000007.jpg", "id") == 12
+    assert evaluator.parse_im_name("00000012_0003_00000007.jpg", "cam") == 3
+
+
+def test_product_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pooling.pps_pool(torch.zeros(1, 32, 24, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        evaluator.compute_dist(np.zeros((2, 8), np.float32), np.zeros((3, 8), np.float32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pps_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f

@@ -1,0 +1,104 @@
+"""The oracle (oracle/pps_oracle.py) against the fixtures produced by the UNMODIFIED reference
+functions (oracle/make_golden.py), and against the live reference when /root/reference exists."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import pps_oracle as O
+from oracle import ref_loader
+from conftest import GOLDEN_CASES
+
+
+def _ids(d):
+    return dict(query_ids=d["qid"], gallery_ids=d["gid"], query_cams=d["qcam"], gallery_cams=d["gcam"])
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_compute_dist_matches_reference_fixture(golden, name):
+    d = golden(name)
+    dist = O.compute_dist(d["q"], d["g"])
+    assert dist.dtype == np.float32 and dist.shape == d["dist"].shape
+    # same formula, but BLAS / SIMD sgemm order may differ between hosts
+    np.testing.assert_allclose(dist, d["dist"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_mean_ap_and_cmc_match_reference_fixture(golden, name):
+    d = golden(name)
+    dist = d["dist"]          # rank on the reference's own matrix: outputs must agree to the last bit
+    assert abs(O.mean_ap(dist, **_ids(d)) - float(d["mAP"])) < 1e-12
+    aps, valid = O.mean_ap(dist, average=False, **_ids(d))
+    np.testing.assert_allclose(aps, d["aps"], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(valid, d["valid"])
+    if name != "dup_ties":    # CMC under exact ties depends on the (unstable) sort
+        np.testing.assert_allclose(O.cmc(dist, topk=10, first_match_break=True, **_ids(d)), d["cmc_fmb"], atol=1e-12)
+        np.testing.assert_allclose(O.cmc(dist, topk=20, first_match_break=False, **_ids(d)), d["cmc_all"], atol=1e-12)
+        rows, v = O.cmc(dist, topk=10, first_match_break=True, average=False, **_ids(d))
+        np.testing.assert_array_equal(rows, d["cmc_rows"])
+        np.testing.assert_array_equal(v, d["cmc_valid"])
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_restated_ap_definitions(golden, name):
+    d = golden(name)
+    dist = d["dist"]
+    step = O.mean_ap(dist, ap_fn=O.average_precision_step, **_ids(d))
+    assert abs(step - float(d["mAP"])) < 1e-12          # == installed scikit-learn (>= 0.19)
+    trap = O.mean_ap(dist, ap_fn=O.average_precision_trapezoid, **_ids(d))
+    assert 0.0 < trap <= 1.0 and trap != step            # the 0.18.1 definition is a different number
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_count_based_restatement_equals_sort_based(golden, name):
+    """What the GPU kernels compute (<=-counts) equals the reference's sort + sklearn AP."""
+    d = golden(name)
+    dist = d["dist"]
+    ap, valid, first, neg_before = O.rank_counts(dist, d["qid"], d["gid"], d["qcam"], d["gcam"])
+    np.testing.assert_allclose(ap, d["aps"], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(valid, d["valid"].astype(np.uint8))
+    rows, v = O.cmc(dist, topk=10, first_match_break=True, average=False, stable=True, **_ids(d))
+    first_from_rows = np.where(rows[:, -1] > 0, (rows == 0).sum(axis=1), -1)
+    ok = (first >= 0) & (first < 10)
+    np.testing.assert_array_equal(first[ok], first_from_rows[ok])
+    assert np.all(first_from_rows[(valid > 0) & ~ok] == -1)
+
+
+def test_uniform_partition_split_tables():
+    assert O.uniform_partition_split(6) == [4] * 6
+    assert O.uniform_partition_split(5) == [5, 5, 4, 5, 5]
+    assert O.uniform_partition_split(7) == [3, 3, 4, 4, 4, 3, 3]
+    assert O.uniform_partition_split(6, 384, 1.0 / 8) == [8] * 6
+    assert O.uniform_partition_split(5, 384, 1.0 / 8) == [10, 10, 8, 10, 10]
+    assert sum(O.uniform_partition_split(10)) == 24 and sum(O.uniform_partition_split(9)) == 24
+
+
+def test_pooling_restatement_float64_crosscheck():
+    rs = np.random.RandomState(3)
+    x = np.maximum(rs.randn(3, 40, 24, 8), 0).astype(np.float32)
+    for mode in ("max_ave", "avg_max"):
+        y32 = O.pps_pool(x, 6, mode=mode)
+        y64 = O.pps_pool(x.astype(np.float64), 6, mode=mode, dtype=np.float64)
+        assert y32.shape == (3, 63, 40)
+        np.testing.assert_allclose(y32, y64, rtol=2e-6, atol=1e-7)
+    # equal strips: mean of strip averages == region average
+    avg, _ = O.strip_pools(x.astype(np.float64), [4] * 6, np.float64)
+    y = O.pps_pool(x.astype(np.float64), 6, mode="avg_max", dtype=np.float64)
+    np.testing.assert_allclose(y[:, 0, :], avg[0])
+    np.testing.assert_allclose(y[:, 2, :], np.maximum(avg[0], avg[1]))   # mask 3 = parts {0,1}
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_against_live_reference():
+    from pps_b200 import synthetic
+    ref = ref_loader.load()
+    d = synthetic.make_reid_set(nq=60, ng=500, dim=80, n_ids=15, n_cams=3, n_distractors=30, sigma=2.5, seed=21)
+    ids = _ids(d)
+    with contextlib.redirect_stdout(io.StringIO()):
+        dist_ref = ref.compute_dist(d["q"], d["g"], type="euclidean")
+        map_ref = ref.mean_ap(distmat=dist_ref, **ids)
+        cmc_ref = ref.cmc(distmat=dist_ref, topk=10, first_match_break=True, **ids)
+    np.testing.assert_array_equal(O.compute_dist(d["q"], d["g"]), dist_ref)
+    assert O.mean_ap(dist_ref, **ids) == map_ref
+    np.testing.assert_array_equal(O.cmc(dist_ref, topk=10, first_match_break=True, **ids), cmc_ref)
