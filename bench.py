@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — q x g pairs/sec (distance + rank) of the PPS retrieval hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the ranking hot path over the workload: operand split -> tcgen05 distance
+-> junk mask / positive thresholds -> counting sweep -> AP / first-match ranks (reference:
+reid_dataset_evaluator.py:104-122, compute_dist -> mean_ap + cmc).  At N = 1 the workload is BASELINE.json
+configs[1] (Market-1501-shaped, 3 368 x 19 732 x 2048 fp32).  At N > 1 every rank holds a gallery shard of
+that size (weak scaling; global gallery = N x 19 732) and only the positives' distances and the integer
+counters cross NVLink (NCCL all-reduce).
+
+`value`  : whole-job pairs/s with the features resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same metric through the host-buffer entry point (N = 1: the C ABI's pps_evaluate_host;
+           N > 1: pinned host -> device copies + the sharded path), H2D and D2H inside the timed region.
+`roofline`: the distance GEMM (dominant kernel), timed with CUDA events inside the timed steps.
+`cpu_baseline`: the oracle port of the reference's CPU path on this box's host cores (rank 0, N = 1).
+`--impl reference`: only that CPU path, on a bounded query sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "qxg_pairs_per_sec_distance_plus_rank"
+UNIT = "pairs/s"
+WORKLOAD = "market1501"          # BASELINE.json configs[1]
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML, in-process thread)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.01):
+        self.index, self.period = index, period
+        self.samples, self.mask, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except (ValueError, IndexError):
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:                                 # noqa: BLE001 — no NVML: report nulls
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:                             # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        reasons = [name for bit, name in self.REASONS.items() if self.mask & bit]
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_workload(rank, world, gallery_per_gpu=None, dim=None):
+    """Market-1501-shaped set; rank r gets gallery rows [r*ngl, (r+1)*ngl) of a world*ngl-row gallery.
+    ids / cams are global (every rank builds the same arrays), features only for the local shard."""
+    from pps_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS[WORKLOAD])
+    if dim:
+        cfg["dim"] = dim
+    ngl = gallery_per_gpu or cfg["ng"]
+    if world == 1 and ngl == cfg["ng"]:
+        d = synthetic.make_reid_set(seed=0, **cfg)
+        d["g_local"], d["row0"] = d["g"], 0
+        return d, cfg
+    nq, D, n_ids, n_cams = cfg["nq"], cfg["dim"], cfg["n_ids"], cfg["n_cams"]
+    ng = ngl * world
+    rs = np.random.RandomState(0)
+    centers = rs.randn(n_ids, D)
+    qid = rs.randint(1, n_ids + 1, size=nq).astype(np.int64)
+    qcam = rs.randint(0, n_cams, size=nq).astype(np.int64)
+    n_real = min(ng, cfg["ng"] - cfg["n_distractors"])            # Market's real ids + id-0 distractors
+    gid = np.zeros(ng, dtype=np.int64)
+    gid[rs.permutation(ng)[:n_real]] = rs.randint(1, n_ids + 1, size=n_real)
+    gcam = rs.randint(0, n_cams, size=ng).astype(np.int64)
+
+    def feats(ids, seed):
+        r = np.random.RandomState(seed)
+        out = np.empty((len(ids), D), dtype=np.float32)
+        for r0 in range(0, len(ids), 8192):
+            sl = ids[r0:r0 + 8192]
+            x = np.where(sl[:, None] > 0, centers[np.maximum(sl, 1) - 1], 0.0) + 4.0 * r.standard_normal((len(sl), D))
+            x /= np.linalg.norm(x, axis=1, keepdims=True)
+            out[r0:r0 + 8192] = x
+        return out
+
+    row0 = rank * ngl
+    d = dict(q=feats(qid, 1), g_local=feats(gid[row0:row0 + ngl], 100 + rank), qid=qid, gid=gid, qcam=qcam, gcam=gcam,
+             row0=row0)
+    cfg = dict(cfg, ng=ng)
+    return d, cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference) — cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_eval(d, nq_sample):
+    """compute_dist -> mean_ap + cmc(topk=10, first_match_break) on the first nq_sample queries x full gallery."""
+    from oracle import pps_oracle as O
+    q = d["q"][:nq_sample]
+    ids = dict(query_ids=d["qid"][:nq_sample], gallery_ids=d["gid"], query_cams=d["qcam"][:nq_sample],
+               gallery_cams=d["gcam"])
+    t0 = time.perf_counter()
+    dist = O.compute_dist(q, d["g"])
+    t1 = time.perf_counter()
+    m = O.mean_ap(dist, **ids)
+    t2 = time.perf_counter()
+    c = O.cmc(dist, topk=10, first_match_break=True, **ids)
+    t3 = time.perf_counter()
+    return dict(total=t3 - t0, dist=t1 - t0, mean_ap=t2 - t1, cmc=t3 - t2, mAP=m, cmc1=float(c[0]))
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    from pps_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS[WORKLOAD])
+    d = synthetic.make_reid_set(seed=0, **cfg)
+    cores = os.cpu_count() or 1
+    probe = cpu_eval(d, 32)
+    per_q = probe["total"] / 32.0
+    budget = 150.0 / max(args.steps + args.warmup, 1)                 # whole run within a few minutes
+    nq_s = int(max(16, min(cfg["nq"], budget / max(per_q, 1e-6))))
+    for _ in range(args.warmup):
+        cpu_eval(d, nq_s)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_eval(d, nq_s)
+    dt = time.perf_counter() - t0
+    pairs = float(nq_s) * cfg["ng"]
+    value = pairs * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "market1501-shaped 3368x19732x2048 fp32 (BASELINE configs[1])", "nq": cfg["nq"],
+                   "ng": cfg["ng"], "dim": cfg["dim"], "sample": "first %d queries x full gallery per step" % nq_s},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "first %d of %d queries x full %d-row gallery per step; oracle/pps_oracle.py "
+                                   "(numpy sgemm + argsort + sklearn AP, as reid_dataset_evaluator.py:244-439)" %
+                                   (nq_s, cfg["nq"], cfg["ng"]),
+                         "split_s": {k: last[k] for k in ("dist", "mean_ap", "cmc")}},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import pps_b200
+    from pps_b200 import _lib, evaluator
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    peaks = load_peaks()
+
+    d, cfg = make_workload(rank, world, args.gallery_per_gpu, args.dim)
+    nq, ng, dim = cfg["nq"], cfg["ng"], cfg["dim"]
+    ngl = d["g_local"].shape[0]
+    pairs_step = float(nq) * float(ng)                            # all ranks together
+
+    q_host = torch.from_numpy(d["q"]).pin_memory()
+    g_host = torch.from_numpy(d["g_local"]).pin_memory()
+    q_dev, g_dev = q_host.to(dev), g_host.to(dev)
+
+    engine = evaluator.RankEngine(d["qid"], d["gid"], d["qcam"], d["gcam"], nq=nq, ng_local=ngl, dim=dim,
+                                  gallery_offset=d["row0"], precision=args.precision, topk=args.topk, group=group,
+                                  device=dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return engine.run(q_dev, g_dev)
+
+    def step_e2e():
+        if world == 1 and args.topk == 0:
+            return pps_b200.evaluate_host(q_host, g_host, d["qid"], d["gid"], d["qcam"], d["gcam"], cmc_topk=10,
+                                          precision=args.precision, device=local_rank)
+        return engine.run_host(q_host, g_host)
+
+    # ---- correctness gate on the first warm-up result (rank 0 prints mAP with the line) ----
+    res = step_device()
+    mAP = res.mean_ap()
+    cmc = res.cmc(10, True)
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(max(args.warmup - 1, 0)):
+        step_device()
+    barrier()
+    sampler.start()
+    n0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    engine.kernel_events = []
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms_total = ev0.elapsed_time(ev1)
+    gemm_ms = [a.elapsed_time(b) for a, b in engine.kernel_events]
+    engine.kernel_events = None
+
+    # ---- e2e: host buffers -> metrics, copies inside ----
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop()
+
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = pairs_step / (ms_step * 1e-3)
+        gemm_avg_ms = float(np.mean(gemm_ms)) if gemm_ms else None
+        flops_alg = 2.0 * dim * float(nq) * float(ngl)               # per launch (this rank's block)
+        terms = {"bf16x1": 1, "bf16x3": 3, "bf16x6": 6}[args.precision]
+        roofline = None
+        if gemm_avg_ms:
+            achieved = flops_alg / (gemm_avg_ms * 1e-3) / 1e12
+            roofline = {"kernel": "dist_tc_kernel", "bound": "tensor", "achieved": achieved,
+                        "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
+                        "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+                        "ms_per_launch": gemm_avg_ms, "share_of_step": gemm_avg_ms / ms_step,
+                        "tensor_pipe_issued_tflops": achieved * terms,
+                        "tensor_pipe_frac": achieved * terms / peaks["tf_sustained"],
+                        "note": "achieved counts ALGORITHMIC flops (2*D per pair); the fp32-accurate %s split issues "
+                                "%dx that on the tensor pipe" % (args.precision, terms)}
+        h2d = (q_host.numel() + g_host.numel()) * 4 + (len(d["qid"]) + 0) * 0
+        d2h = nq * (8 + 1 + 4)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16x3-split fp32 (fp32 accumulate)" if args.precision == "bf16x3" else args.precision,
+            "data": "synthetic",
+            "config": {"workload": "market1501-shaped %dx%dx%d fp32 (BASELINE configs[1]%s)" %
+                                   (nq, ng, dim, "" if world == 1 else ", gallery sharded %d rows/GPU" % ngl),
+                       "nq": nq, "ng": ng, "dim": dim, "gallery_rows_per_gpu": ngl, "precision": args.precision,
+                       "topk": args.topk, "l2": "inputs larger than L2 (features %.0f MB + planes + %.0f MB distance block per step)" %
+                                                ((nq + ngl) * dim * 4 / 1e6, nq * ngl * 4 / 1e6)},
+            "e2e": {"value": pairs_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "api": "pps_evaluate_host (C ABI, pinned host buffers)" if world == 1 and args.topk == 0
+                           else "RankEngine.run_host (pinned host -> device + sharded path)"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+            "result": {"mAP": mAP, "cmc1": float(cmc[0]), "cmc5": float(cmc[4]), "cmc10": float(cmc[9])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            dd = dict(d, g=d["g_local"])
+            nq_s = min(nq, args.cpu_sample)
+            r = cpu_eval(dd, nq_s)
+            line["cpu_baseline"] = {"value": nq_s * float(ng) / r["total"], "unit": UNIT, "cores": os.cpu_count() or 1,
+                                    "kind": "port",
+                                    "sample": "first %d of %d queries x full %d-row gallery, one pass; oracle/pps_oracle.py" %
+                                              (nq_s, nq, ng),
+                                    "split_s": {k: r[k] for k in ("dist", "mean_ap", "cmc")}, "mAP_on_sample": r["mAP"]}
+            if nq_s == nq:
+                line["result"]["mAP_cpu"] = r["mAP"]
+                line["result"]["mAP_abs_diff"] = abs(r["mAP"] - mAP)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x1", "bf16x3", "bf16x6"])
+    ap.add_argument("--topk", type=int, default=0)
+    ap.add_argument("--gallery-per-gpu", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-sample", type=int, default=3368)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(kCntThreads) rank_count_kernel(const float* __
   __shared__ float win[64];
   __shared__ uint32_t wsum[64];
   __shared__ int s_np;
-  __shared__ unsigned long long s_first_key;   // (d*, g*) of the nearest positive
   __shared__ uint32_t s_first_cnt;
 
   const int q = blockIdx.x;
@@ -64,7 +63,7 @@ __global__ void __launch_bounds__(kCntThreads) rank_count_kernel(const float* __
   const int e0 = pair_off[q], e1 = pair_off[q + 1];
 
   // --- positives of this query, rank-sorted by (distance, gallery index) into thr[] ---
-  if (tid == 0) { s_np = 0; s_first_cnt = 0; s_first_key = ~0ull; }
+  if (tid == 0) { s_np = 0; s_first_cnt = 0; }
   __syncthreads();
   for (int e = e0 + tid; e < e1; e += kCntThreads) {
     if (!pair_pos[e]) continue;
@@ -277,7 +276,9 @@ __global__ void __launch_bounds__(kTopkThreads) topk_update_kernel(const float* 
       }
     }
     __syncthreads();
-    if (s_n > kCand - (int)tile) {
+    const int n_now = s_n;
+    __syncthreads();           // every thread has sampled s_n before anyone appends again
+    if (n_now > kCand - (int)tile) {
       bitonic_sort_smem(cand, kCand, tid, kTopkThreads);
       for (int i = k + tid; i < kCand; i += kTopkThreads) cand[i] = ~0ull;
       if (tid == 0) { s_n = k; s_bound = cand[k - 1]; }

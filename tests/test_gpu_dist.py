@@ -1,0 +1,133 @@
+"""Parity of the CUDA distance (tcgen05 split-precision GEMM + fused norm/clamp/sqrt epilogue, and the
+fp32 CUDA-core variant) with the reference's compute_dist (reid_dataset_evaluator.py:244-272).
+Golden matrices were produced by the unmodified reference (oracle/make_golden.py).
+Tolerance: 1e-4 relative on the distance (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES
+from oracle import pps_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _f64_dist(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * a @ b.T
+    return np.sqrt(np.maximum(d2, 0.0))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x6", "fp32"])
+def test_compute_dist_matches_reference_fixture(golden, name, precision):
+    import pps_b200
+    d = golden(name)
+    dist = pps_b200.compute_dist(d["q"], d["g"], precision=precision)
+    assert isinstance(dist, np.ndarray) and dist.dtype == np.float32 and dist.shape == d["dist"].shape
+    ref = d["dist"]
+    # duplicates (dup_ties) give d ~ 0 where sqrt amplifies the last-bit noise of the fp32 cancellation
+    # |a|^2+|b|^2-2ab (the reference itself is off there): relative test away from 0, absolute near it.
+    np.testing.assert_allclose(dist, ref, rtol=1e-4, atol=2e-3 if name == "dup_ties" else 1e-6)
+    big = ref > 1e-2
+    assert np.max(np.abs(dist[big] - ref[big]) / ref[big]) < 1e-4
+
+
+def test_precision_ladder_against_float64():
+    """bf16x1 is visibly coarse; bf16x3 is fp32-grade; bf16x6 and fp32 are tighter still."""
+    import pps_b200
+    rs = np.random.RandomState(0)
+    a = rs.randn(300, 520).astype(np.float32)
+    b = rs.randn(700, 520).astype(np.float32)
+    exact = _f64_dist(a, b)
+    err = {}
+    for p in ("bf16x1", "bf16x3", "bf16x6", "fp32"):
+        got = pps_b200.compute_dist(a, b, precision=p).astype(np.float64)
+        err[p] = float(np.max(np.abs(got - exact) / exact))
+    ref_err = float(np.max(np.abs(O.compute_dist(a, b).astype(np.float64) - exact) / exact))
+    assert err["bf16x3"] < 1e-5 and err["bf16x6"] < 2e-6 and err["fp32"] < 2e-6
+    assert err["bf16x1"] > err["bf16x3"]
+    assert err["bf16x3"] < 20 * max(ref_err, 1e-7)
+
+
+@pytest.mark.parametrize("m1,m2,dim", [
+    (1, 1, 1), (1, 300, 64), (129, 257, 65), (128, 256, 64), (127, 255, 63), (260, 1000, 2048),
+    (5, 513, 8064 // 8), (300, 10, 200),
+])
+def test_tile_edges_and_ragged_shapes(m1, m2, dim):
+    import pps_b200
+    rs = np.random.RandomState(m1 * 7 + m2)
+    a = rs.randn(m1, dim).astype(np.float32)
+    b = rs.randn(m2, dim).astype(np.float32)
+    got = pps_b200.compute_dist(a, b)
+    np.testing.assert_allclose(got, _f64_dist(a, b), rtol=1e-4, atol=1e-5)
+
+
+def test_empty_inputs():
+    import pps_b200
+    a = np.zeros((0, 16), np.float32)
+    b = np.zeros((5, 16), np.float32)
+    assert pps_b200.compute_dist(a, b).shape == (0, 5)
+    assert pps_b200.compute_dist(b, a).shape == (5, 0)
+
+
+def test_tensor_in_tensor_out_and_fp16_inputs():
+    import torch
+    import pps_b200
+    rs = np.random.RandomState(3)
+    a = rs.randn(200, 256).astype(np.float16)
+    b = rs.randn(333, 256).astype(np.float16)
+    out = pps_b200.compute_dist(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    assert out.is_cuda and out.dtype == torch.float32
+    np.testing.assert_allclose(out.cpu().numpy(), _f64_dist(a.astype(np.float32), b.astype(np.float32)), rtol=1e-4, atol=1e-4)
+
+
+def test_cosine_branch_returns_similarity():
+    import pps_b200
+    rs = np.random.RandomState(4)
+    a = rs.randn(50, 96).astype(np.float32)
+    b = rs.randn(70, 96).astype(np.float32)
+    got = pps_b200.compute_dist(a, b, type="cosine")
+    np.testing.assert_allclose(got, O.compute_dist(a, b, type="cosine"), rtol=1e-4, atol=1e-5)
+
+
+def test_self_distance_clamps_at_zero():
+    import pps_b200
+    rs = np.random.RandomState(5)
+    a = rs.randn(64, 128).astype(np.float32)
+    # d(a, a) is sqrt of pure cancellation noise: ~|a| * sqrt(eps).  bf16x3 drops the p1.p1 term, which
+    # for identical operands is a positive bias of ~1.3e-6 |a|^2; bf16x6 / fp32 are at the reference's level.
+    na = float(np.sqrt((a.astype(np.float64) ** 2).sum(1)).max())
+    for p, bound in (("bf16x3", 3e-3), ("bf16x6", 1e-3), ("fp32", 1e-3)):
+        d = pps_b200.compute_dist(a, a, precision=p)
+        assert np.all(d >= 0) and np.all(np.isfinite(d))
+        assert np.max(np.diag(d)) < bound * na, p
+    assert np.max(np.diag(O.compute_dist(a, a))) < 1e-3 * na
+
+
+def test_error_contract():
+    import pps_b200
+    with pytest.raises(RuntimeError, match="not aligned"):
+        pps_b200.compute_dist(np.zeros((2, 8), np.float32), np.zeros((3, 9), np.float32))
+    with pytest.raises(RuntimeError, match="2-D"):
+        pps_b200.compute_dist(np.zeros(8, np.float32), np.zeros((3, 8), np.float32))
+    with pytest.raises(AssertionError):
+        pps_b200.compute_dist(np.zeros((2, 8), np.float32), np.zeros((3, 8), np.float32), type="manhattan")
+    with pytest.raises(RuntimeError, match="precision"):
+        pps_b200.compute_dist(np.zeros((2, 8), np.float32), np.zeros((3, 8), np.float32), precision="int8")
+
+
+def test_market_shape_distance_rows_vs_oracle():
+    """Full Market-1501 shape (3 368 x 19 732 x 2048) on the GPU; a 64-query slice against the oracle."""
+    import torch
+    import pps_b200
+    from pps_b200 import synthetic
+    d = synthetic.make_config("market1501")
+    dist = pps_b200.compute_dist(torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda())
+    assert tuple(dist.shape) == (3368, 19732)
+    sel = np.arange(0, 3368, 53)[:64]
+    ref = O.compute_dist(d["q"][sel], d["g"])
+    np.testing.assert_allclose(dist[torch.from_numpy(sel).cuda()].cpu().numpy(), ref, rtol=1e-4, atol=1e-6)
+    # symmetry property at full size: d(q, g) == d(g, q)^T up to the fp32 summation-order noise of the
+    # norm add (bit-identical dot products: the split planes and the K loop order are the same)
+    dt = pps_b200.compute_dist(torch.from_numpy(d["g"][:2048]).cuda(), torch.from_numpy(d["q"]).cuda())
+    assert torch.allclose(dist[:, :2048], dt.t(), rtol=1e-6, atol=1e-7)

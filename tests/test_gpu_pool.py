@@ -1,0 +1,173 @@
+"""Parity of the fused CUDA pooling (pps_pool_fwd through the C ABI) with the oracle's restatement of
+bpm_heads.py:18-55 + pps_heads.py:38-142.  Tolerance: 1e-5 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from oracle import pps_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+def _x(shape, seed=0, relu=True):
+    rs = np.random.RandomState(seed)
+    x = rs.randn(*shape)
+    if relu:
+        x = np.maximum(x, 0.0)
+    return x.astype(np.float32)
+
+
+def _run(torch, x, **kw):
+    import pps_b200
+    y = pps_b200.pps_pool(torch.from_numpy(x).cuda(), **kw)
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", ["max_ave", "avg_max"])
+def test_conv5_n6_all_63_combos(torch, mode):
+    x = _x((5, 2048, 24, 8), seed=1)
+    y = _run(torch, x, n_parts=6, mode=mode)
+    ref = O.pps_pool(x, 6, mode=mode)
+    assert y.shape == (5, 63, 2048)
+    np.testing.assert_allclose(y, ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("mode", ["max_ave", "avg_max"])
+def test_shipped_config_n5_uneven_split(torch, mode):
+    # configs/market1501/pps_R-50_1x.yaml: BPM_STRIP_NUM 5 -> [5,5,4,5,5] (bpm_heads.py:29-32)
+    x = _x((3, 256, 24, 8), seed=2)
+    split = O.uniform_partition_split(5)
+    y = _run(torch, x, n_parts=5, split=split, mode=mode)
+    np.testing.assert_allclose(y, O.pps_pool(x, 5, split=split, mode=mode), rtol=RTOL, atol=ATOL)
+    assert y.shape == (3, 31, 256)
+
+
+def test_negative_inputs_and_max_semantics(torch):
+    # not post-ReLU: max / mean must not assume non-negative values
+    x = _x((2, 64, 24, 8), seed=3, relu=False) - 3.0
+    for mode in ("max_ave", "avg_max"):
+        np.testing.assert_allclose(_run(torch, x, n_parts=6, mode=mode), O.pps_pool(x, 6, mode=mode), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("shape,n_parts,split", [
+    ((2, 256, 48, 16), 6, [8] * 6),          # pyramid level res3 (FPN_reid.py:411-416), scale 1/8
+    ((2, 40, 24, 8), 6, None),               # C not a multiple of the 32-channel unit
+    ((3, 33, 24, 8), 6, None),
+    ((2, 16, 12, 4), 3, [4, 4, 4]),
+    ((1, 8, 10, 8), 10, [1] * 10),           # PPS_POOL_MAX_PARTS strips -> 1023 combos
+    ((2, 32, 24, 7), 6, None),               # W % 4 != 0 -> generic kernel
+    ((2, 32, 7, 3), 2, [3, 4]),
+    ((1, 4, 96, 96), 6, [16] * 6),           # plane larger than a ring slot -> generic kernel
+    ((1, 32, 1, 4), 1, [1]),
+])
+def test_shapes_and_edge_cases(torch, shape, n_parts, split):
+    x = _x(shape, seed=sum(shape))
+    for mode in ("max_ave", "avg_max"):
+        y = _run(torch, x, n_parts=n_parts, split=split, mode=mode)
+        np.testing.assert_allclose(y, O.pps_pool(x, n_parts, split=split, mode=mode), rtol=RTOL, atol=ATOL)
+
+
+def test_many_units_per_cta_persistent_loop(torch):
+    # more units than SMs x ring depth: exercises ring wrap-around, phase flips and the double buffer
+    x = _x((40, 512, 24, 8), seed=4)
+    y = _run(torch, x, n_parts=6, mode="max_ave")
+    np.testing.assert_allclose(y, O.pps_pool(x, 6, mode="max_ave"), rtol=RTOL, atol=ATOL)
+
+
+def test_empty_batch(torch):
+    import pps_b200
+    y = pps_b200.pps_pool(torch.zeros((0, 64, 24, 8), device="cuda"), n_parts=6)
+    assert tuple(y.shape) == (0, 63, 64)
+
+
+def test_explicit_combos_pyramid_list_and_knc_layout(torch):
+    import pps_b200
+    x = _x((3, 64, 24, 8), seed=5)
+    masks = [pps_b200.comb_to_mask(c) for c in pps_b200.pyramid_combs]
+    y = _run(torch, x, n_parts=6, mode="max_ave", combos=masks, layout="knc")
+    ref = O.pps_pool(x, 6, mode="max_ave", combos=masks)
+    assert y.shape == (21, 3, 64)
+    np.testing.assert_allclose(y.transpose(1, 0, 2), ref, rtol=RTOL, atol=ATOL)
+
+
+def test_head_function_contract(torch):
+    """add_pps_part_head_(blob_in, dim_in, spatial_scale) -> (blobs_out, dims_out): pps_heads.py:38-80."""
+    import pps_b200
+    x = _x((4, 128, 24, 8), seed=6)
+    cfg = pps_b200.ReIDPoolCfg(BPM_STRIP_NUM=6, MAX_AVE_FEATURE=True)
+    blobs, dims = pps_b200.add_pps_part_head(torch.from_numpy(x).cuda(), 128, 1.0 / 16, cfg)
+    assert len(blobs) == 63 and dims == [128] * 63
+    ref = O.pps_pool(x, 6, mode="max_ave")
+    for k in (0, 1, 2, 30, 62):
+        assert tuple(blobs[k].shape) == (4, 128, 1, 1)
+        np.testing.assert_allclose(blobs[k].cpu().numpy()[:, :, 0, 0], ref[:, k, :], rtol=RTOL, atol=ATOL)
+
+
+def test_multi_scale_heads(torch):
+    """pps_heads.py:83-142: test -> level 0 only; train -> every level; FPN_SHARED -> batch concat."""
+    import pps_b200
+    levels = [_x((2, 256, 24, 8), 7), _x((2, 256, 24, 8), 8), _x((2, 256, 48, 16), 9)]
+    scales = [1.0 / 16, 1.0 / 16, 1.0 / 8]
+    blobs_in = [torch.from_numpy(v).cuda() for v in levels]
+    refs = [O.pps_pool(v, 6, split=O.uniform_partition_split(6, 384, s), mode="max_ave") for v, s in zip(levels, scales)]
+
+    cfg = pps_b200.ReIDPoolCfg(MAX_AVE_FEATURE=True, FPN_ON=True, train=False)
+    blobs, dims = pps_b200.add_pps_part_head(blobs_in, [256] * 3, scales, cfg)
+    assert len(blobs) == 63
+    np.testing.assert_allclose(blobs[62].cpu().numpy()[:, :, 0, 0], refs[0][:, 62], rtol=RTOL, atol=ATOL)
+
+    cfg = pps_b200.ReIDPoolCfg(MAX_AVE_FEATURE=True, FPN_ON=True, train=True)
+    blobs, dims = pps_b200.add_pps_part_head(blobs_in, [256] * 3, scales, cfg)
+    assert len(blobs) == 3 * 63 and len(dims) == 3 * 63
+    for lvl in range(3):
+        for k in (0, 17, 62):
+            np.testing.assert_allclose(blobs[lvl * 63 + k].cpu().numpy()[:, :, 0, 0], refs[lvl][:, k], rtol=RTOL, atol=ATOL)
+
+    cfg = pps_b200.ReIDPoolCfg(MAX_AVE_FEATURE=True, FPN_ON=True, train=True, FPN_SHARED=True)
+    blobs, dims = pps_b200.add_pps_part_head(blobs_in, [256] * 3, scales, cfg)
+    assert len(blobs) == 63 and tuple(blobs[0].shape) == (6, 256, 1, 1)
+    for k in (0, 31, 62):
+        want = np.concatenate([r[:, k] for r in refs], axis=0)
+        np.testing.assert_allclose(blobs[k].cpu().numpy()[:, :, 0, 0], want, rtol=RTOL, atol=ATOL)
+
+
+def test_error_contract(torch):
+    """Bad shapes raise RuntimeError, as CAFFE_ENFORCE does (detectron/tests/test_zero_even_op.py:50-53)."""
+    import pps_b200
+    x = torch.zeros((1, 32, 24, 8), device="cuda")
+    with pytest.raises(RuntimeError, match="shape"):
+        pps_b200.pps_pool(x, n_parts=6, split=[4, 4, 4, 4, 4, 5])        # sum(split) != H
+    with pytest.raises(RuntimeError):
+        pps_b200.pps_pool(x, n_parts=6, split=[4] * 5)
+    with pytest.raises(RuntimeError, match="ndim"):
+        pps_b200.pps_pool(x[0], n_parts=6)
+    with pytest.raises(RuntimeError, match="float32"):
+        pps_b200.pps_pool(x.half(), n_parts=6)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pps_b200.pps_pool(x.cpu(), n_parts=6)
+    with pytest.raises(RuntimeError, match="shape"):
+        pps_b200.pps_pool(x, n_parts=11, split=[2] * 10 + [4])
+    with pytest.raises(RuntimeError, match="shape"):
+        pps_b200.pps_pool(x, n_parts=6, combos=[0, 1])                   # mask 0 is not a combination
+
+
+def test_full_size_property_linearity_in_batch(torch):
+    """Market-shaped batch (1 024 maps = 1.6 GB): each image's result is independent of its batch
+    neighbours (pool(batch)[i] == pool(batch[i:i+1])), and the first images match the oracle."""
+    import pps_b200
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn((1024, 2048, 24, 8), device="cuda", generator=g).clamp_min_(0)
+    y = pps_b200.pps_pool(x, n_parts=6, mode="max_ave")
+    for i in (0, 511, 1023):
+        yi = pps_b200.pps_pool(x[i:i + 1].contiguous(), n_parts=6, mode="max_ave")
+        assert torch.equal(y[i:i + 1], yi)
+    ref = O.pps_pool(x[:2].cpu().numpy(), 6, mode="max_ave")
+    np.testing.assert_allclose(y[:2].cpu().numpy(), ref, rtol=RTOL, atol=ATOL)

@@ -1,0 +1,230 @@
+"""Parity of the CUDA ranking path (junk filter, exact positive ranks by counting, AP, CMC, top-k)
+with the reference's mean_ap / cmc (reid_dataset_evaluator.py:283-439) through the golden fixtures
+written by the unmodified reference, and with the oracle on seeded inputs.
+
+On the reference's OWN distance matrix the integer outputs (valid flags, first-match ranks, CMC rows,
+<=-counts) must be bit-exact and AP equal to the last float64 bit (tolerance 1e-12); from features the
+distances differ in the last fp32 bits, so mAP is compared at 1e-6 absolute (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES
+from oracle import pps_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ids(d):
+    return dict(query_ids=d["qid"], gallery_ids=d["gid"], query_cams=d["qcam"], gallery_cams=d["gcam"])
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_mean_ap_on_reference_matrix(golden, name):
+    import pps_b200
+    d = golden(name)
+    assert abs(pps_b200.mean_ap(d["dist"], **_ids(d)) - float(d["mAP"])) < 1e-12
+    aps, valid = pps_b200.mean_ap(d["dist"], average=False, **_ids(d))
+    np.testing.assert_array_equal(valid, d["valid"])
+    np.testing.assert_allclose(aps, d["aps"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cmc_on_reference_matrix(golden, name):
+    import pps_b200
+    d = golden(name)
+    if name == "dup_ties":
+        # exact ties: the reference's np.argsort is unstable; compare with the oracle's stable order
+        want = O.cmc(d["dist"], topk=10, first_match_break=True, stable=True, **_ids(d))
+        got = pps_b200.cmc(d["dist"], topk=10, first_match_break=True, **_ids(d))
+        np.testing.assert_allclose(got, want, atol=1e-12)
+        return
+    np.testing.assert_allclose(pps_b200.cmc(d["dist"], topk=10, first_match_break=True, **_ids(d)), d["cmc_fmb"], atol=1e-12)
+    np.testing.assert_allclose(pps_b200.cmc(d["dist"], topk=20, first_match_break=False, **_ids(d)), d["cmc_all"], atol=1e-12)
+    rows, v = pps_b200.cmc(d["dist"], topk=10, first_match_break=True, average=False, **_ids(d))
+    np.testing.assert_array_equal(rows, d["cmc_rows"])
+    np.testing.assert_array_equal(v, d["cmc_valid"])
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_integer_outputs_equal_count_oracle(golden, name):
+    import pps_b200
+    d = golden(name)
+    res = pps_b200.rank_distmat(d["dist"], d["qid"], d["gid"], d["qcam"], d["gcam"], want_neg_before=True, topk=16)
+    ap, valid, first, neg_before = O.rank_counts(d["dist"], d["qid"], d["gid"], d["qcam"], d["gcam"])
+    np.testing.assert_array_equal(res.is_valid, valid)
+    np.testing.assert_array_equal(res.first_rank, first)
+    p = res.pairs
+    for i in range(p.nq):
+        e = np.arange(p.off[i], p.off[i + 1])
+        np.testing.assert_array_equal(res.neg_before[e[p.pos[e] == 1]], neg_before[i])
+    ti, td = O.topk_filtered(d["dist"], d["qid"], d["gid"], d["qcam"], d["gcam"], 16)
+    np.testing.assert_array_equal(res.topk_index, ti)
+    np.testing.assert_array_equal(res.topk_dist, td)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x6"])
+def test_rank_eval_from_features(golden, name, precision):
+    import torch
+    import pps_b200
+    d = golden(name)
+    res = pps_b200.rank_eval(torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda(),
+                             d["qid"], d["gid"], d["qcam"], d["gcam"], precision=precision)
+    np.testing.assert_array_equal(res.is_valid, d["valid"].astype(np.uint8))
+    assert abs(res.mean_ap() - float(d["mAP"])) < 1e-6 or name == "dup_ties"
+    if name == "dup_ties":
+        # duplicated gallery rows: the reference's own fp32 distances differ between duplicates by
+        # rounding noise, ours are bit-identical -> AP may legitimately differ inside the tie tolerance
+        assert abs(res.mean_ap() - float(d["mAP"])) < 5e-3
+    else:
+        np.testing.assert_allclose(res.cmc(10, True), d["cmc_fmb"], atol=1e-12)
+
+
+def test_chunked_gallery_equals_single_block(golden):
+    """Counters are integers: sweeping the gallery in chunks gives the same bits as one block."""
+    import torch
+    import pps_b200
+    d = golden("small_mid")
+    q, g = torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda()
+    one = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"], topk=20, want_neg_before=True)
+    many = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"], topk=20, want_neg_before=True,
+                              max_block_bytes=96 * 256 * 4)
+    np.testing.assert_array_equal(one.ap, many.ap)
+    np.testing.assert_array_equal(one.first_rank, many.first_rank)
+    np.testing.assert_array_equal(one.neg_before, many.neg_before)
+    np.testing.assert_array_equal(one.topk_index, many.topk_index)
+    np.testing.assert_array_equal(one.topk_dist, many.topk_dist)
+
+
+def test_more_positives_than_one_window():
+    """> 63 positives per query: the count kernel walks several threshold windows."""
+    import pps_b200
+    rs = np.random.RandomState(7)
+    nq, ng = 9, 5000
+    dist = rs.rand(nq, ng).astype(np.float32)
+    dist[:, ::7] = dist[:, 1::7][:, :dist[:, ::7].shape[1]]       # plenty of exact ties
+    qid = np.arange(1, nq + 1)
+    gid = rs.randint(1, 4, size=ng)                               # ~1 666 same-id items for ids 1..3
+    gid[:50] = np.arange(50) % 9 + 1
+    qcam = rs.randint(0, 3, size=nq)
+    gcam = rs.randint(0, 3, size=ng)
+    res = pps_b200.rank_distmat(dist, qid, gid, qcam, gcam, want_neg_before=True)
+    ap, valid, first, neg_before = O.rank_counts(dist, qid, gid, qcam, gcam)
+    np.testing.assert_array_equal(res.is_valid, valid)
+    np.testing.assert_array_equal(res.first_rank, first)
+    np.testing.assert_allclose(res.ap, ap, rtol=0, atol=1e-12)
+    assert abs(pps_b200.mean_ap(dist, qid, gid, qcam, gcam) - O.mean_ap(dist, qid, gid, qcam, gcam)) < 1e-12
+
+
+def test_no_valid_query_raises():
+    import pps_b200
+    dist = np.random.RandomState(0).rand(4, 10).astype(np.float32)
+    qid, gid = np.arange(4) + 100, np.arange(10)
+    cams_q, cams_g = np.zeros(4, np.int64), np.ones(10, np.int64)
+    with pytest.raises(RuntimeError, match="No valid query"):
+        pps_b200.cmc(dist, qid, gid, cams_q, cams_g, topk=5, first_match_break=True)
+    # junk-only matches (same id, same camera) do not make a query valid either (:327-332)
+    gid2 = gid.copy(); gid2[:4] = qid
+    with pytest.raises(RuntimeError, match="No valid query"):
+        pps_b200.cmc(dist, qid, gid2, cams_q, np.zeros(10, np.int64), topk=5, first_match_break=True)
+    with pytest.raises(AssertionError):
+        pps_b200.mean_ap(dist.tolist(), qid, gid, cams_q, cams_g)   # :411-415 isinstance asserts
+
+
+@pytest.mark.parametrize("name", ["small_mid", "some_invalid"])
+def test_evaluate_host_entry_point(golden, name):
+    """pps_evaluate_host: host buffers in, metrics out (what bench.py times as e2e)."""
+    import pps_b200
+    d = golden(name)
+    out = pps_b200.evaluate_host(d["q"], d["g"], d["qid"], d["gid"], d["qcam"], d["gcam"], cmc_topk=10, topk=8)
+    assert abs(out["mAP"] - float(d["mAP"])) < 1e-6
+    np.testing.assert_allclose(out["cmc"], d["cmc_fmb"], atol=1e-12)
+    np.testing.assert_array_equal(out["valid"], d["valid"].astype(np.uint8))
+    ti, td = O.topk_filtered(d["dist"], d["qid"], d["gid"], d["qcam"], d["gcam"], 8)
+    assert np.mean(out["topk_index"] == ti) > 0.99           # modulo last-bit distance differences
+    np.testing.assert_allclose(out["topk_dist"], td, rtol=1e-4)
+
+
+def test_evaluate_arrays_single_and_multi_query(golden):
+    """evaluate(): marks 0/1/2 split, single-query + multi-query branches (:57-159)."""
+    import pps_b200
+    d = golden("small_mid")
+    rs = np.random.RandomState(1)
+    n_mq = 60
+    mq_src = rs.randint(0, len(d["qid"]), size=n_mq)
+    mq_feat = d["q"][mq_src] + 0.01 * rs.randn(n_mq, d["q"].shape[1]).astype(np.float32)
+    feats = np.concatenate([d["q"], d["g"], mq_feat]).astype(np.float32)
+    ids = np.concatenate([d["qid"], d["gid"], d["qid"][mq_src]])
+    cams = np.concatenate([d["qcam"], d["gcam"], d["qcam"][mq_src]])
+    marks = np.concatenate([np.zeros(len(d["qid"])), np.ones(len(d["gid"])), np.full(n_mq, 2)]).astype(np.int64)
+    mAP, cmc_scores, mq_mAP, mq_cmc = pps_b200.evaluate_arrays(feats, ids, cams, marks)
+    assert abs(mAP - float(d["mAP"])) < 1e-6
+    np.testing.assert_allclose(cmc_scores, d["cmc_fmb"], atol=1e-12)
+    # multi-query oracle: mean of the mark==2 features per (id, cam), then the same scoring (:131-159)
+    keys, pooled = [], []
+    seen = {}
+    for k, (i, c) in enumerate(zip(ids[marks == 2], cams[marks == 2])):
+        seen.setdefault((i, c), []).append(k)
+    for key, idx in seen.items():
+        keys.append(key)
+        pooled.append(mq_feat[idx].mean(axis=0))
+    pooled = np.stack(pooled).astype(np.float32)
+    dist = O.compute_dist(pooled, d["g"])
+    kid, kcam = np.array([k[0] for k in keys]), np.array([k[1] for k in keys])
+    assert abs(mq_mAP - O.mean_ap(dist, kid, d["gid"], kcam, d["gcam"])) < 1e-6
+    np.testing.assert_allclose(mq_cmc, O.cmc(dist, kid, d["gid"], kcam, d["gcam"], topk=10, first_match_break=True), atol=1e-12)
+
+    class FakeDataset:                      # evaluate(json_dataset, all_feats, output_dir)
+        def get_roidb(self, gt=True):
+            return [dict(image="/x/%08d_%04d_%08d.jpg" % (i, c, k), mark=int(m))
+                    for k, (i, c, m) in enumerate(zip(ids, cams, marks))]
+    r = pps_b200.evaluate(FakeDataset(), feats, None, verbose=False)
+    assert r[0] == mAP and r[2] == mq_mAP
+    res = pps_b200.reid_results(r, "market1501_test")
+    assert res["market1501_test"]["ReID"]["CMC1"] == cmc_scores[0]
+
+
+def test_cuhk03_shape_full_parity_with_oracle():
+    """BASELINE configs[0]: 1 400 x 5 332 x 2048 — whole evaluation against the oracle run in full."""
+    import torch
+    import pps_b200
+    from pps_b200 import synthetic
+    d = synthetic.make_config("cuhk03")
+    res = pps_b200.rank_eval(torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda(),
+                             d["qid"], d["gid"], d["qcam"], d["gcam"], topk=10)
+    dist = O.compute_dist(d["q"], d["g"])
+    ids = _ids(d)
+    want_map = O.mean_ap(dist, ap_fn=O.average_precision_step, **ids)
+    want_cmc = O.cmc(dist, topk=10, first_match_break=True, **ids)
+    assert abs(res.mean_ap() - want_map) < 1e-6
+    # CMC is a count of integer ranks; a rank can move only where two distances agree to 1e-4 relative
+    ap, valid, first, _ = O.rank_counts(dist, d["qid"], d["gid"], d["qcam"], d["gcam"])
+    np.testing.assert_array_equal(res.is_valid, valid)
+    moved = np.nonzero(res.first_rank != first)[0]
+    assert len(moved) <= 2, "first-match ranks differ for %d queries" % len(moved)
+    assert np.max(np.abs(res.cmc(10, True) - want_cmc)) <= 2.0 / max(valid.sum(), 1)
+
+
+def test_market_shape_properties_and_subset_parity():
+    """BASELINE configs[1] at full size: (i) gallery-chunked == single block, bit for bit;
+    (ii) the first 64 queries agree with the oracle run on that subset."""
+    import torch
+    import pps_b200
+    from pps_b200 import synthetic
+    d = synthetic.make_config("market1501")
+    q, g = torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda()
+    one = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"], topk=100)
+    many = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"], topk=100, max_block_bytes=64 << 20)
+    np.testing.assert_array_equal(one.ap, many.ap)
+    np.testing.assert_array_equal(one.first_rank, many.first_rank)
+    np.testing.assert_array_equal(one.topk_index, many.topk_index)
+    sub = slice(0, 64)
+    dist = O.compute_dist(d["q"][sub], d["g"])
+    ap, valid, first, _ = O.rank_counts(dist, d["qid"][sub], d["gid"], d["qcam"][sub], d["gcam"])
+    np.testing.assert_array_equal(one.is_valid[sub], valid)
+    np.testing.assert_allclose(one.ap[sub], ap, rtol=0, atol=2e-3)       # a near-tie may swap two ranks
+    assert abs(float(one.ap[sub].sum()) - float(ap.sum())) / max(valid.sum(), 1) < 1e-5
+    assert np.mean(one.first_rank[sub] == first) > 0.95
+    ti, td = O.topk_filtered(dist, d["qid"][sub], d["gid"], d["qcam"][sub], d["gcam"], 100)
+    np.testing.assert_allclose(one.topk_dist[sub], td, rtol=1e-4)
+    assert np.mean(one.topk_index[sub] == ti) > 0.98
