@@ -5,13 +5,13 @@ the C ABI of ``include/pps_b200.h``); PyTorch only hands tensors and streams acr
 """
 from .pooling import (ReIDPoolCfg, add_pps_part_head, add_pps_part_head_, blob_names, comb_to_mask, mask_to_comb,
                       pps_pool, pyramid_combs, uniform_partition_split)
-from .evaluator import (PairLists, RankResult, cmc, compute_dist, evaluate, evaluate_arrays, evaluate_host, mean_ap,
+from .evaluator import (PairLists, RankEngine, RankResult, cmc, compute_dist, evaluate, evaluate_arrays, evaluate_host, mean_ap,
                         rank_distmat, rank_eval, reid_results)
 
 __all__ = [
     "ReIDPoolCfg", "add_pps_part_head", "add_pps_part_head_", "blob_names", "comb_to_mask", "mask_to_comb",
     "pps_pool", "pyramid_combs", "uniform_partition_split",
-    "PairLists", "RankResult", "cmc", "compute_dist", "evaluate", "evaluate_arrays", "evaluate_host", "mean_ap",
+    "PairLists", "RankEngine", "RankResult", "cmc", "compute_dist", "evaluate", "evaluate_arrays", "evaluate_host", "mean_ap",
     "rank_distmat", "rank_eval", "reid_results",
 ]
 __version__ = "0.1.0"

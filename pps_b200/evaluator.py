@@ -352,6 +352,154 @@ def mean_ap(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_
 # ------------------------------------------------------------------------------------
 # fused path: features -> metrics
 # ------------------------------------------------------------------------------------
+class RankEngine:
+    """Preallocated state for repeated distance + rank passes over one (query set, gallery shard) shape.
+
+    ``run(q, g)`` takes CUDA feature tensors ([nq, D] and this rank's [ng_local, D] gallery shard starting at
+    global row ``gallery_offset``) and returns a RankResult.  Every pass rebuilds the same-id pair lists from
+    the id / camera arrays (the junk mask and the matches are part of the timed path), splits the operands,
+    runs the tcgen05 distance per gallery chunk and the two rank sweeps:
+      sweep 1  gather the positives' / junk distances (the thresholds)        [all-reduce SUM over shards]
+      sweep 2  count <= thresholds, first-match counter, top-k                [all-reduce SUM, all-gather]
+    With one chunk the distance block of sweep 1 is reused by sweep 2.
+    """
+
+    def __init__(self, query_ids, gallery_ids, query_cams, gallery_cams, nq, ng_local, dim, gallery_offset=0,
+                 precision=DEFAULT_PRECISION, topk=0, topk_filtered=True, want_neg_before=False, group=None,
+                 device=None, max_block_bytes=8 << 30, in_dtype=None):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.torch = torch
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.qi, self.qc = _ids64(query_ids, "query_ids"), _ids64(query_cams, "query_cams")
+        self.gi, self.gc = _ids64(gallery_ids, "gallery_ids"), _ids64(gallery_cams, "gallery_cams")
+        self.nq, self.ngl, self.dim = int(nq), int(ng_local), int(dim)
+        if len(self.qi) != self.nq:
+            raise RuntimeError("q_feats has %d rows but %d query ids" % (self.nq, len(self.qi)))
+        if group is None and len(self.gi) != self.ngl:
+            raise RuntimeError("g_feats has %d rows but %d gallery ids" % (self.ngl, len(self.gi)))
+        self.offset, self.group = int(gallery_offset), group
+        self.topk, self.topk_filtered, self.want_neg_before = int(topk), topk_filtered, want_neg_before
+        self.is_f16 = in_dtype == torch.float16
+        self.prec = _lib.PREC_F16X1 if self.is_f16 else _prec_code(precision)
+        if self.prec == _lib.PREC_FP32:
+            raise RuntimeError("rank_eval runs the distance on the tensor cores; use bf16x1/bf16x3/bf16x6 (or fp16 inputs)")
+        self.planes = _lib.PLANES_FOR[self.prec]
+        self.in_code = _lib.DTYPE_F16 if self.is_f16 else _lib.DTYPE_F32
+        nq_, ngl_ = max(self.nq, 1), self.ngl
+        chunk = ngl_ if self.nq == 0 else max(256, min(ngl_, max_block_bytes // (4 * nq_)))
+        chunk = max(256, (chunk // 256) * 256) if chunk < ngl_ else ngl_
+        self.chunk = chunk
+        self.n_chunks = (ngl_ + chunk - 1) // chunk if ngl_ else 0
+        self.ldd = (max(min(chunk, max(ngl_, 1)), 1) + 3) // 4 * 4
+        lib, dev = self.lib, self.dev
+        with torch.cuda.device(dev):
+            e8 = lambda n: torch.empty(max(int(n), 16), dtype=torch.uint8, device=dev)
+            self.q_planes = e8(lib.pps_split_bytes(nq_, self.dim, self.planes))
+            self.g_planes = e8(lib.pps_split_bytes(max(chunk, 1), self.dim, self.planes))
+            self.q_sq = torch.empty(nq_, dtype=torch.float32, device=dev)
+            self.g_sq = torch.empty(max(chunk, 1), dtype=torch.float32, device=dev)
+            self.block = torch.empty((nq_, self.ldd), dtype=torch.float32, device=dev)
+            self.cnt_first = torch.zeros(nq_, dtype=torch.int32, device=dev)
+            self.key = torch.empty((nq_, self.topk), dtype=torch.int64, device=dev) if self.topk else None
+        self._pair_cap = 0
+        self.kernel_events = None        # bench.py: list collecting (start, stop) events around the distance GEMM
+        self.h2d_bytes = 0
+
+    # -- helpers --
+    def _pair_buffers(self, n_pairs):
+        torch = self.torch
+        if n_pairs > self._pair_cap or self._pair_cap == 0:
+            cap = max(int(n_pairs * 1.25), 1024)
+            self.pair_d = torch.empty(cap, dtype=torch.float32, device=self.dev)
+            self.cnt_le = torch.empty(cap, dtype=torch.int32, device=self.dev)
+            self._pair_cap = cap
+        self.pair_d.zero_()
+        self.cnt_le.zero_()
+        self.cnt_first.zero_()
+
+    def _split(self, feats, rows, planes_buf, sq_buf):
+        if rows:
+            if feats.stride(1) != 1:
+                feats = feats.contiguous()
+            _lib.check(self.lib.pps_split_rows(_lib.ptr(feats), self.in_code, rows, self.dim, int(feats.stride(0)),
+                                               self.planes, _lib.ptr(planes_buf), _lib.ptr(sq_buf), _lib.stream_ptr()),
+                       "pps_split_rows")
+
+    def _distance(self, rows):
+        torch = self.torch
+        ev = None
+        if self.kernel_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        _lib.check(self.lib.pps_dist_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), self.nq, self.planes,
+                                        _lib.ptr(self.g_planes), _lib.ptr(self.g_sq), rows, self.planes, self.dim,
+                                        self.prec, 0, _lib.ptr(self.block), self.ldd, _lib.stream_ptr()), "pps_dist_tc")
+        if ev is not None:
+            ev[1].record()
+            self.kernel_events.append(ev)
+
+    def run(self, q, g) -> RankResult:
+        torch, lib = self.torch, self.lib
+        want = torch.float16 if self.is_f16 else torch.float32
+        if q.dtype != want or g.dtype != want or not q.is_cuda or not g.is_cuda:
+            raise RuntimeError("RankEngine.run: expected CUDA %s features" % want)
+        if tuple(q.shape) != (self.nq, self.dim) or tuple(g.shape) != (self.ngl, self.dim):
+            raise RuntimeError("RankEngine.run: expected q %s and g %s, got %s and %s" % (
+                (self.nq, self.dim), (self.ngl, self.dim), tuple(q.shape), tuple(g.shape)))
+        dist_mod = None
+        if self.group is not None:
+            import torch.distributed as dist_mod
+        nq = self.nq
+        with torch.cuda.device(self.dev):
+            pairs = PairLists(self.qi, self.qc, self.gi, self.gc, device=self.dev)
+            self._pair_buffers(pairs.n_pairs)
+            pair_d, cnt_le, cnt_first, key = self.pair_d, self.cnt_le, self.cnt_first, self.key
+            if self.topk:
+                _lib.check(lib.pps_topk_init(_lib.ptr(key), nq, self.topk, _lib.stream_ptr()), "pps_topk_init")
+            self._split(q, nq, self.q_planes, self.q_sq)
+            chunks = [(c * self.chunk, min(self.chunk, self.ngl - c * self.chunk)) for c in range(self.n_chunks)]
+            # sweep 1: thresholds
+            for r0, rows in chunks:
+                self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)
+                self._distance(rows)
+                _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
+                            True, False)
+            if self.group is not None:
+                dist_mod.all_reduce(pair_d, op=dist_mod.ReduceOp.SUM, group=self.group)
+            # sweep 2: counts (+ top-k); a single chunk is still resident in the block
+            for r0, rows in chunks:
+                if self.n_chunks > 1:
+                    self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)
+                    self._distance(rows)
+                _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
+                            False, True, key, self.topk, self.topk_filtered)
+            if self.group is not None:
+                dist_mod.all_reduce(cnt_le, op=dist_mod.ReduceOp.SUM, group=self.group)
+                dist_mod.all_reduce(cnt_first, op=dist_mod.ReduceOp.SUM, group=self.group)
+                if self.topk:
+                    key = merge_topk_keys(key, self.topk, self.group)
+            ap, valid, first, negb = _finalize(lib, nq, pairs, pair_d, cnt_le, cnt_first, self.want_neg_before)
+            ti = td = None
+            if self.topk:
+                td = torch.empty((nq, self.topk), dtype=torch.float32, device=self.dev)
+                ti = torch.empty((nq, self.topk), dtype=torch.int32, device=self.dev)
+                _lib.check(lib.pps_topk_unpack(_lib.ptr(key), nq, self.topk, _lib.ptr(td), _lib.ptr(ti),
+                                               _lib.stream_ptr()), "pps_topk_unpack")
+                ti, td = ti.cpu().numpy(), td.cpu().numpy()
+            return RankResult(ap.cpu().numpy(), valid.cpu().numpy(), first.cpu().numpy(),
+                              negb.cpu().numpy() if negb is not None else None, pairs, ti, td)
+
+    def run_host(self, q_host, g_host) -> RankResult:
+        """Host (ideally pinned) feature tensors in: the H2D copies are part of the call."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            q = q_host.to(self.dev, non_blocking=True)
+            g = g_host.to(self.dev, non_blocking=True)
+            self.h2d_bytes = q_host.numel() * q_host.element_size() + g_host.numel() * g_host.element_size()
+            return self.run(q, g)
+
+
 def rank_eval(q_feats, g_feats, query_ids, gallery_ids, query_cams, gallery_cams, topk: int = 0,
               precision: str = DEFAULT_PRECISION, want_neg_before: bool = False, max_block_bytes: int = 8 << 30,
               gallery_offset: int = 0, group=None, topk_filtered: bool = True) -> RankResult:
@@ -364,80 +512,28 @@ def rank_eval(q_feats, g_feats, query_ids, gallery_ids, query_cams, gallery_cams
     an all-gather of the top-k keys, so the merged result equals the unsharded one bit for bit.
     """
     torch = _torch()
-    lib = _lib.load()
-    dist_mod = None
-    if group is not None:
-        import torch.distributed as dist_mod
     q, _ = _as_cuda_f32(q_feats, "q_feats")
     g, _ = _as_cuda_f32(g_feats, "g_feats")
     if q.shape[1] != g.shape[1]:
         raise RuntimeError("feature dims differ: %d vs %d" % (q.shape[1], g.shape[1]))
-    prec = _prec_code(precision)
-    if prec == _lib.PREC_FP32:
-        raise RuntimeError("rank_eval runs the distance on the tensor cores; use bf16x1/bf16x3/bf16x6 (or fp16 inputs)")
-    planes = _lib.PLANES_FOR[prec]
-    nq, ngl, dim = int(q.shape[0]), int(g.shape[0]), int(q.shape[1])
-    dev = q.device
-    with torch.cuda.device(dev):
-        pairs = PairLists(query_ids, query_cams, gallery_ids, gallery_cams, device=dev)
-        if pairs.nq != nq:
-            raise RuntimeError("q_feats has %d rows but %d query ids" % (nq, pairs.nq))
-        if group is None and pairs.ng != ngl:
-            raise RuntimeError("g_feats has %d rows but %d gallery ids" % (ngl, pairs.ng))
-        E = max(pairs.n_pairs, 1)
-        pair_d = torch.zeros(E, dtype=torch.float32, device=dev)
-        cnt_le = torch.zeros(E, dtype=torch.int32, device=dev)
-        cnt_first = torch.zeros(max(nq, 1), dtype=torch.int32, device=dev)
-        key = None
-        if topk:
-            key = torch.empty((nq, topk), dtype=torch.int64, device=dev)
-            _lib.check(lib.pps_topk_init(_lib.ptr(key), nq, topk, _lib.stream_ptr()), "pps_topk_init")
-        sq = SplitOperand(q, planes)
-        # gallery chunks: bounded distance scratch
-        chunk = ngl if nq == 0 else max(256, min(ngl, max_block_bytes // (4 * max(nq, 1))))
-        chunk = max(256, (chunk // 256) * 256) if chunk < ngl else ngl
-        n_chunks = (ngl + chunk - 1) // chunk if ngl else 0
-        ldd = (min(chunk, max(ngl, 1)) + 3) // 4 * 4
-        block = torch.empty((max(nq, 1), ldd), dtype=torch.float32, device=dev)
-        splits = []
-        for c in range(n_chunks):
-            r0 = c * chunk
-            splits.append((r0, SplitOperand(g[r0:r0 + chunk], planes)))
+    if q.dtype != g.dtype:
+        raise RuntimeError("query and gallery features must have the same dtype")
+    with torch.cuda.device(q.device):
+        eng = RankEngine(query_ids, gallery_ids, query_cams, gallery_cams, nq=int(q.shape[0]), ng_local=int(g.shape[0]),
+                         dim=int(q.shape[1]), gallery_offset=gallery_offset, precision=precision, topk=topk,
+                         topk_filtered=topk_filtered, want_neg_before=want_neg_before, group=group, device=q.device,
+                         max_block_bytes=max_block_bytes, in_dtype=q.dtype)
+        return eng.run(q, g)
 
-        def distance(sg):
-            p = _lib.PREC_F16X1 if sq.is_f16 else prec
-            _lib.check(lib.pps_dist_tc(_lib.ptr(sq.planes), _lib.ptr(sq.sqnorm), nq, sq.planes_n, _lib.ptr(sg.planes),
-                                       _lib.ptr(sg.sqnorm), sg.rows, sg.planes_n, dim, p, 0, _lib.ptr(block), ldd,
-                                       _lib.stream_ptr()), "pps_dist_tc")
 
-        # sweep 1: the positives' / junk distances (thresholds of the counting sweep)
-        for r0, sg in splits:
-            distance(sg)
-            _rank_block(lib, block, ldd, nq, sg.rows, gallery_offset + r0, pairs, pair_d, cnt_le, cnt_first,
-                        True, False)
-        if group is not None:
-            dist_mod.all_reduce(pair_d, op=dist_mod.ReduceOp.SUM, group=group)
-        # sweep 2: counts (+ top-k); a single chunk is still resident in `block`
-        for r0, sg in splits:
-            if n_chunks > 1:
-                distance(sg)
-            _rank_block(lib, block, ldd, nq, sg.rows, gallery_offset + r0, pairs, pair_d, cnt_le, cnt_first,
-                        False, True, key, topk, topk_filtered)
-        if group is not None:
-            dist_mod.all_reduce(cnt_le, op=dist_mod.ReduceOp.SUM, group=group)
-            dist_mod.all_reduce(cnt_first, op=dist_mod.ReduceOp.SUM, group=group)
-            if topk:
-                key = merge_topk_keys(key, topk, group)
-        ap, valid, first, negb = _finalize(lib, nq, pairs, pair_d, cnt_le, cnt_first, want_neg_before)
-        ti = td = None
-        if topk:
-            td = torch.empty((nq, topk), dtype=torch.float32, device=dev)
-            ti = torch.empty((nq, topk), dtype=torch.int32, device=dev)
-            _lib.check(lib.pps_topk_unpack(_lib.ptr(key), nq, topk, _lib.ptr(td), _lib.ptr(ti), _lib.stream_ptr()),
-                       "pps_topk_unpack")
-            ti, td = ti.cpu().numpy(), td.cpu().numpy()
-        return RankResult(ap.cpu().numpy(), valid.cpu().numpy(), first.cpu().numpy(),
-                          negb.cpu().numpy() if negb is not None else None, pairs, ti, td)
+def gallery_shard(ng, rank, world):
+    """Contiguous row block of rank ``rank`` when ``ng`` gallery rows are split over ``world`` GPUs
+    (the same np.array_split rule the reference uses to shard test images over GPUs:
+    detectron/utils/subprocess.py:39-103).  Returns (row0, rows)."""
+    base, extra = divmod(int(ng), int(world))
+    rows = base + (1 if rank < extra else 0)
+    row0 = rank * base + min(rank, extra)
+    return row0, rows
 
 
 def merge_topk_keys(key, topk, group):
