@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PPS_ABI_VERSION 1
+#define PPS_ABI_VERSION 2
 
 /* ---- error codes (the Python mirror turns every non-zero code into RuntimeError,
  * like CAFFE_ENFORCE does: detectron/tests/test_zero_even_op.py:50-53) ---- */
@@ -107,6 +107,9 @@ int pps_split_rows_slab(const void* feats, int dtype, long long row0, long long 
  *   PPS_PREC_F16X1   operands are fp16 planes (dtype F16), one pass, exact products
  *   PPS_PREC_FP32    CUDA-core fp32 FMA kernel on the original fp32 rows (a_f32/b_f32)
  * a_planes/b_planes come from pps_split_rows (need >= the planes the precision uses).
+ * a_plane_rows / b_plane_rows: rows between consecutive planes of the buffer (0 = m1 / m2); a row
+ * window [r0, r0+m) of a larger [planes][total_rows][kpad] buffer is passed as base + r0*kpad
+ * elements, its sqnorm + r0, m rows and plane_rows = total_rows.
  * flags: PPS_DIST_SQUARED returns the clamped squared distance (no sqrt);
  *        PPS_DIST_DOT returns a.b only (the reference's 'cosine' branch at :259-263
  *        once rows are L2-normalised).
@@ -120,8 +123,8 @@ int pps_split_rows_slab(const void* feats, int dtype, long long row0, long long 
 #define PPS_DIST_SQUARED 1
 #define PPS_DIST_DOT     2
 
-int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
-                const void* b_planes, const float* b_sqnorm, long long m2, int b_planes_n,
+int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n, long long a_plane_rows,
+                const void* b_planes, const float* b_sqnorm, long long m2, int b_planes_n, long long b_plane_rows,
                 int dim, int precision, int flags,
                 float* dist, long long ldd, void* stream);
 
@@ -148,6 +151,21 @@ long long pps_pairs_count(const int64_t* query_ids, long long nq,
 int pps_pairs_fill(const int64_t* query_ids, const int64_t* query_cams, long long nq,
                    const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
                    int32_t* pair_off, int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos);
+
+/* The same lists built on the device (no sort: a deterministic brute-force sweep, pairs.cu).
+ * query_ids ... gallery_cams, pair_* and totals are DEVICE pointers; workspace needs
+ * pps_pairs_workspace_bytes(nq, ng) bytes.  pps_pairs_count_device writes pair_off[nq+1] and
+ * totals[2] = {n_pairs, max pairs of one query}; the caller reads totals back (the only host
+ * round trip of the path, overlappable with the distance GEMM), sizes pair_q/pair_g/pair_pos and
+ * calls pps_pairs_fill_device with the SAME workspace (entries beyond `capacity` are dropped).
+ * The result is identical to pps_pairs_fill on every rank of a sharded run. */
+long long pps_pairs_workspace_bytes(long long nq, long long ng);
+int pps_pairs_count_device(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
+                           void* workspace, int32_t* pair_off, int32_t* totals, void* stream);
+int pps_pairs_fill_device(const int64_t* query_ids, const int64_t* query_cams, long long nq,
+                          const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
+                          const void* workspace, int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos,
+                          long long capacity, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Part 2d — ranking on a materialised block of the distance matrix.
@@ -189,14 +207,16 @@ int pps_rank_finalize(long long nq,
  *
  * Streams a block of the distance matrix once and merges it into the running state
  * topk_key[nq*k] (uint64 = float bits << 32 | global gallery index; initialise to all
- * ones with pps_topk_init).  exclude_* (optional, CSR per query, global gallery indices)
- * lists items to skip — pass the junk pairs to rank the valid-filtered gallery.
+ * ones with pps_topk_init).  excl_off / excl_g (optional, CSR per query, global gallery indices)
+ * list items to skip; entries whose excl_keep[x] != 0 are NOT skipped (excl_keep may be NULL).
+ * Passing the pair lists (pair_off, pair_g, pair_pos) skips exactly the junk and so ranks the
+ * valid-filtered gallery.
  * pps_topk_unpack splits the state into distances / indices (-1 = fewer than k items).
  * ---------------------------------------------------------------------------------- */
 #define PPS_TOPK_MAX 128
 int pps_topk_init(uint64_t* topk_key, long long nq, int k, void* stream);
 int pps_topk_update(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
-                    const int32_t* excl_off, const int32_t* excl_g,
+                    const int32_t* excl_off, const int32_t* excl_g, const uint8_t* excl_keep,
                     uint64_t* topk_key, int k, void* stream);
 int pps_topk_unpack(const uint64_t* topk_key, long long nq, int k,
                     float* out_dist, int32_t* out_index, void* stream);
@@ -206,15 +226,29 @@ int pps_topk_unpack(const uint64_t* topk_key, long long nq, int k,
  *           (reid_dataset_evaluator.py:104-122: compute_dist -> mean_ap + cmc(topk,
  *           first_match_break=True); the call bench.py times as `e2e`).
  *
- * Copies features to the device (gallery in chunks, overlapped with compute), runs
- * split -> tcgen05 distance -> gather -> count -> finalize [-> top-k], copies the small
- * results back and synchronises.  Uses `device` and allocates/free its own scratch
- * (this is the one entry point that owns memory, because its buffers are host buffers).
+ * Copies features to the device (gallery in row slabs; the split + tcgen05 distance of one
+ * slab overlap the copy of the next), builds the pair lists on the device, runs gather ->
+ * count -> finalize [-> top-k], copies the small results back and synchronises.
+ * A pps_ctx owns the streams and grow-only device / pinned scratch, so repeated evaluations
+ * allocate nothing; pps_evaluate_host is the one-shot form (create ctx, evaluate, destroy).
+ * Host feature buffers should be pinned (cudaHostAlloc / torch pin_memory) for full PCIe
+ * bandwidth; pageable memory works but the driver stages it.
  *   out_ap[nq] float64, out_valid[nq], out_first_rank[nq]; out_cmc[cmc_topk] float64 and
  *   *out_map follow the reference's averaging (:360-362, :437-438).
  *   out_topk_index / out_topk_dist [nq, topk] may be NULL (topk = 0).
  * Returns PPS_ERR_NO_VALID_QUERY if no query has a valid match.
  * ---------------------------------------------------------------------------------- */
+typedef struct pps_ctx pps_ctx;
+int pps_ctx_create(int device, pps_ctx** out);
+int pps_ctx_destroy(pps_ctx* ctx);
+int pps_evaluate_host_ctx(pps_ctx* ctx, const float* q_feats, long long nq,
+                          const float* g_feats, long long ng, int dim,
+                          const int64_t* query_ids, const int64_t* query_cams,
+                          const int64_t* gallery_ids, const int64_t* gallery_cams,
+                          int precision, int cmc_topk, int topk,
+                          double* out_map, double* out_cmc,
+                          double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,
+                          int32_t* out_topk_index, float* out_topk_dist);
 int pps_evaluate_host(const float* q_feats, long long nq,
                       const float* g_feats, long long ng, int dim,
                       const int64_t* query_ids, const int64_t* query_cams,

@@ -13,6 +13,7 @@ import threading
 from . import build as _build
 
 # ---- constants (keep in sync with include/pps_b200.h) ----
+ABI_VERSION = 2
 PPS_OK = 0
 PPS_ERR_INVALID_ARG = -1
 PPS_ERR_SHAPE = -2
@@ -56,17 +57,24 @@ SIGNATURES = {
     "pps_split_bytes": (_ll, [_ll, _i, _i]),
     "pps_split_rows": (_i, [_vp, _i, _ll, _i, _ll, _i, _vp, _vp, _vp]),
     "pps_split_rows_slab": (_i, [_vp, _i, _ll, _ll, _ll, _i, _ll, _i, _vp, _vp, _vp]),
-    "pps_dist_tc": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _ll, _vp]),
+    "pps_dist_tc": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp, _ll, _i, _ll, _i, _i, _i, _vp, _ll, _vp]),
     "pps_dist_fp32": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _vp, _ll, _vp]),
     "pps_row_sqnorm": (_i, [_vp, _i, _ll, _i, _ll, _vp, _vp]),
     "pps_pairs_count": (_ll, [_vp, _ll, _vp, _ll]),
     "pps_pairs_fill": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp]),
+    "pps_pairs_workspace_bytes": (_ll, [_ll, _ll]),
+    "pps_pairs_count_device": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp]),
+    "pps_pairs_fill_device": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp]),
     "pps_rank_gather": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _ll, _vp, _vp]),
     "pps_rank_count": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "pps_rank_finalize": (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_topk_init": (_i, [_vp, _ll, _i, _vp]),
-    "pps_topk_update": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _i, _vp]),
+    "pps_topk_update": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp]),
     "pps_topk_unpack": (_i, [_vp, _ll, _i, _vp, _vp, _vp]),
+    "pps_ctx_create": (_i, [_i, C.POINTER(_vp)]),
+    "pps_ctx_destroy": (_i, [_vp]),
+    "pps_evaluate_host_ctx": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_evaluate_host": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_kernel_launch_count": (C.c_ulonglong, []),
@@ -98,7 +106,7 @@ def load(build_if_missing: bool = True):
             fn = getattr(lib, name)   # AttributeError here == ABI mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args
-        if lib.pps_abi_version() != 1:
+        if lib.pps_abi_version() != ABI_VERSION:
             raise RuntimeError("libpps_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -116,41 +117,103 @@ extern "C" int pps_pairs_fill(const int64_t* query_ids, const int64_t* query_cam
 }
 
 // ------------------------------------------------------------------------------------
-// pps_evaluate_host
+// evaluation context + pps_evaluate_host[_ctx]
 // ------------------------------------------------------------------------------------
 namespace {
 
-struct DevBuf {
+struct GrowBuf {                       // device buffer that only ever grows
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t bytes) {
-    if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMalloc(&p, bytes);
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return PPS_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc"); }
+    cap = want;
     return PPS_OK;
   }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
-struct StreamGuard {
-  cudaStream_t s = nullptr;
-  ~StreamGuard() { if (s) cudaStreamDestroy(s); }
+struct PinBuf {                        // pinned host staging, grow-only
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return PPS_OK;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMallocHost(&p, bytes + 256);
+    if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMallocHost"); }
+    cap = bytes + 256;
+    return PPS_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
 };
-struct EventGuard {
-  cudaEvent_t e = nullptr;
-  ~EventGuard() { if (e) cudaEventDestroy(e); }
-};
+
+constexpr int kMaxSlabs = 64;
 
 #define PPS_TRY(expr) do { int _rc = (expr); if (_rc != PPS_OK) return _rc; } while (0)
 
 }  // namespace
 
-extern "C" int pps_evaluate_host(const float* q_feats, long long nq, const float* g_feats, long long ng, int dim,
-                                 const int64_t* query_ids, const int64_t* query_cams, const int64_t* gallery_ids,
-                                 const int64_t* gallery_cams, int precision, int cmc_topk, int topk, int device,
-                                 double* out_map, double* out_cmc, double* out_ap, uint8_t* out_valid,
-                                 int32_t* out_first_rank, int32_t* out_topk_index, float* out_topk_dist) {
+struct pps_ctx {
+  int device = 0;
+  cudaStream_t copy_s = nullptr, comp_s = nullptr;
+  cudaEvent_t ev_slab[kMaxSlabs] = {};
+  cudaEvent_t ev_totals = nullptr;
+  GrowBuf qf, gf, qs, gs, qn, gn, dist, ids, pair_ws, pair_off, totals, pair_q, pair_g, pair_pos, pair_d, cnt_le,
+      cnt_first, ap, valid, first, topk, tki, tkd;
+  PinBuf h_small;      // totals + per-query results
+};
+
+extern "C" int pps_ctx_create(int device, pps_ctx** out) {
+  if (!out) return PPS_ERR_INVALID_ARG;
+  *out = nullptr;
+  PPS_CUDA_TRY(cudaSetDevice(device));
+  pps_ctx* c = new (std::nothrow) pps_ctx();
+  if (!c) return PPS_ERR_INVALID_ARG;
+  c->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->copy_s, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->comp_s, cudaStreamNonBlocking);
+  for (int i = 0; i < kMaxSlabs && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_slab[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_totals, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    pps_ctx_destroy(c);
+    return cuda_fail(e, "pps_ctx_create");
+  }
+  *out = c;
+  return PPS_OK;
+}
+
+extern "C" int pps_ctx_destroy(pps_ctx* c) {
+  if (!c) return PPS_OK;
+  cudaSetDevice(c->device);
+  if (c->comp_s) cudaStreamSynchronize(c->comp_s);
+  if (c->copy_s) cudaStreamSynchronize(c->copy_s);
+  GrowBuf* bufs[] = {&c->qf, &c->gf, &c->qs, &c->gs, &c->qn, &c->gn, &c->dist, &c->ids, &c->pair_ws, &c->pair_off,
+                     &c->totals, &c->pair_q, &c->pair_g, &c->pair_pos, &c->pair_d, &c->cnt_le, &c->cnt_first, &c->ap,
+                     &c->valid, &c->first, &c->topk, &c->tki, &c->tkd};
+  for (GrowBuf* b : bufs) b->release();
+  c->h_small.release();
+  for (int i = 0; i < kMaxSlabs; ++i) if (c->ev_slab[i]) cudaEventDestroy(c->ev_slab[i]);
+  if (c->ev_totals) cudaEventDestroy(c->ev_totals);
+  if (c->copy_s) cudaStreamDestroy(c->copy_s);
+  if (c->comp_s) cudaStreamDestroy(c->comp_s);
+  delete c;
+  return PPS_OK;
+}
+
+extern "C" int pps_evaluate_host_ctx(pps_ctx* c, const float* q_feats, long long nq, const float* g_feats, long long ng,
+                                     int dim, const int64_t* query_ids, const int64_t* query_cams,
+                                     const int64_t* gallery_ids, const int64_t* gallery_cams, int precision,
+                                     int cmc_topk, int topk, double* out_map, double* out_cmc, double* out_ap,
+                                     uint8_t* out_valid, int32_t* out_first_rank, int32_t* out_topk_index,
+                                     float* out_topk_dist) {
+  if (!c) return PPS_ERR_INVALID_ARG;
   if (nq <= 0 || ng <= 0 || dim <= 0 || cmc_topk < 0 || topk < 0 || topk > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
+  if (nq > 0x7fffffffLL || ng > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
   if (!q_feats || !g_feats || !query_ids || !query_cams || !gallery_ids || !gallery_cams) return PPS_ERR_INVALID_ARG;
   if (!out_map || (cmc_topk > 0 && !out_cmc)) return PPS_ERR_INVALID_ARG;
   int planes;
@@ -160,124 +223,119 @@ extern "C" int pps_evaluate_host(const float* q_feats, long long nq, const float
     case PPS_PREC_BF16X6: planes = 3; break;
     default: return PPS_ERR_INVALID_ARG;
   }
-  PPS_CUDA_TRY(cudaSetDevice(device));
+  PPS_CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t cs = c->comp_s, ps = c->copy_s;
 
-  // ---- host: same-id pair lists (tiny next to the feature upload) ----
-  const long long n_pairs = pps_pairs_count(query_ids, nq, gallery_ids, ng);
-  if (n_pairs < 0) return (int)n_pairs;
-  std::vector<int32_t> pair_off((size_t)nq + 1), pair_q((size_t)n_pairs), pair_g((size_t)n_pairs);
-  std::vector<uint8_t> pair_pos((size_t)n_pairs);
-  PPS_TRY(pps_pairs_fill(query_ids, query_cams, nq, gallery_ids, gallery_cams, ng, pair_off.data(), pair_q.data(),
-                         pair_g.data(), pair_pos.data()));
-  int max_pairs = 0;
-  std::vector<int32_t> junk_off((size_t)nq + 1, 0), junk_g;
-  for (long long i = 0; i < nq; ++i) {
-    max_pairs = std::max(max_pairs, pair_off[i + 1] - pair_off[i]);
-    for (int e = pair_off[i]; e < pair_off[i + 1]; ++e)
-      if (!pair_pos[e]) junk_g.push_back(pair_g[e]);
-    junk_off[i + 1] = (int32_t)junk_g.size();
-  }
-
-  // the distance block is materialised once: bound it (larger galleries go through the chunked
-  // two-sweep path of the Python layer, evaluator.rank_eval)
+  // the distance matrix is materialised once: bound it (larger galleries go through the chunked
+  // two-sweep path of the Python layer, evaluator.RankEngine)
   const long long ldd = (ng + 3) & ~3LL;
   if ((double)nq * (double)ldd * 4.0 > 64.0 * (double)(1LL << 30)) return PPS_ERR_UNSUPPORTED;
+  const int kpad = pps_kpad(dim);
 
-  StreamGuard copy_s, comp_s;
-  PPS_CUDA_TRY(cudaStreamCreateWithFlags(&copy_s.s, cudaStreamNonBlocking));
-  PPS_CUDA_TRY(cudaStreamCreateWithFlags(&comp_s.s, cudaStreamNonBlocking));
+  PPS_TRY(c->qf.ensure((size_t)nq * dim * 4));
+  PPS_TRY(c->gf.ensure((size_t)ng * dim * 4));
+  PPS_TRY(c->qs.ensure((size_t)pps_split_bytes(nq, dim, planes)));
+  PPS_TRY(c->gs.ensure((size_t)pps_split_bytes(ng, dim, planes)));
+  PPS_TRY(c->qn.ensure((size_t)nq * 4));
+  PPS_TRY(c->gn.ensure((size_t)ng * 4));
+  PPS_TRY(c->dist.ensure((size_t)nq * ldd * 4));
+  PPS_TRY(c->ids.ensure((size_t)(2 * nq + 2 * ng) * 8));
+  PPS_TRY(c->pair_ws.ensure((size_t)pps_pairs_workspace_bytes(nq, ng)));
+  PPS_TRY(c->pair_off.ensure(((size_t)nq + 1) * 4));
+  PPS_TRY(c->totals.ensure(16));
+  PPS_TRY(c->cnt_first.ensure((size_t)nq * 4));
+  PPS_TRY(c->ap.ensure((size_t)nq * 8));
+  PPS_TRY(c->valid.ensure((size_t)nq));
+  PPS_TRY(c->first.ensure((size_t)nq * 4));
+  // pinned staging: [0,16) totals | ap[nq] f64 | first[nq] i32 | valid[nq] u8
+  const size_t off_ap = 16, off_first = off_ap + (size_t)nq * 8, off_valid = off_first + (size_t)nq * 4;
+  PPS_TRY(c->h_small.ensure(off_valid + (size_t)nq));
+  int32_t* h_totals = c->h_small.as<int32_t>();
+  unsigned char* h_base = c->h_small.as<unsigned char>();
 
-  DevBuf d_qf, d_gf, d_qs, d_gs, d_qn, d_gn, d_dist, d_poff, d_pq, d_pg, d_ppos, d_pd, d_cle, d_cfirst, d_ap, d_valid,
-      d_first, d_joff, d_jg, d_topk, d_tki, d_tkd;
-  PPS_TRY(d_qf.alloc((size_t)nq * dim * 4));
-  PPS_TRY(d_gf.alloc((size_t)ng * dim * 4));
-  PPS_TRY(d_qs.alloc((size_t)pps_split_bytes(nq, dim, planes)));
-  PPS_TRY(d_gs.alloc((size_t)pps_split_bytes(ng, dim, planes)));
-  PPS_TRY(d_qn.alloc((size_t)nq * 4));
-  PPS_TRY(d_gn.alloc((size_t)ng * 4));
-  PPS_TRY(d_dist.alloc((size_t)nq * ldd * 4));
-  PPS_TRY(d_poff.alloc(((size_t)nq + 1) * 4));
-  PPS_TRY(d_pq.alloc((size_t)n_pairs * 4));
-  PPS_TRY(d_pg.alloc((size_t)n_pairs * 4));
-  PPS_TRY(d_ppos.alloc((size_t)n_pairs));
-  PPS_TRY(d_pd.alloc((size_t)n_pairs * 4));
-  PPS_TRY(d_cle.alloc((size_t)n_pairs * 4));
-  PPS_TRY(d_cfirst.alloc((size_t)nq * 4));
-  PPS_TRY(d_ap.alloc((size_t)nq * 8));
-  PPS_TRY(d_valid.alloc((size_t)nq));
-  PPS_TRY(d_first.alloc((size_t)nq * 4));
-  if (topk > 0) {
-    PPS_TRY(d_joff.alloc(((size_t)nq + 1) * 4));
-    PPS_TRY(d_jg.alloc(junk_g.size() * 4));
-    PPS_TRY(d_topk.alloc((size_t)nq * topk * 8));
-    PPS_TRY(d_tki.alloc((size_t)nq * topk * 4));
-    PPS_TRY(d_tkd.alloc((size_t)nq * topk * 4));
-  }
+  int64_t* d_qid = c->ids.as<int64_t>();
+  int64_t* d_qcam = d_qid + nq;
+  int64_t* d_gid = d_qcam + nq;
+  int64_t* d_gcam = d_gid + ng;
 
-  // ---- uploads: queries + pair lists on the compute stream, gallery in row chunks on the copy stream ----
-  PPS_CUDA_TRY(cudaMemcpyAsync(d_qf.p, q_feats, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, comp_s.s));
-  PPS_CUDA_TRY(cudaMemcpyAsync(d_poff.p, pair_off.data(), ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, comp_s.s));
-  if (n_pairs > 0) {
-    PPS_CUDA_TRY(cudaMemcpyAsync(d_pq.p, pair_q.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice, comp_s.s));
-    PPS_CUDA_TRY(cudaMemcpyAsync(d_pg.p, pair_g.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice, comp_s.s));
-    PPS_CUDA_TRY(cudaMemcpyAsync(d_ppos.p, pair_pos.data(), (size_t)n_pairs, cudaMemcpyHostToDevice, comp_s.s));
-  }
-  PPS_CUDA_TRY(cudaMemsetAsync(d_pd.p, 0, std::max<size_t>(16, (size_t)n_pairs * 4), comp_s.s));
-  PPS_CUDA_TRY(cudaMemsetAsync(d_cle.p, 0, std::max<size_t>(16, (size_t)n_pairs * 4), comp_s.s));
-  PPS_CUDA_TRY(cudaMemsetAsync(d_cfirst.p, 0, (size_t)nq * 4, comp_s.s));
-  if (topk > 0) {
-    PPS_CUDA_TRY(cudaMemcpyAsync(d_joff.p, junk_off.data(), ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, comp_s.s));
-    if (!junk_g.empty())
-      PPS_CUDA_TRY(cudaMemcpyAsync(d_jg.p, junk_g.data(), junk_g.size() * 4, cudaMemcpyHostToDevice, comp_s.s));
-    PPS_TRY(pps_topk_init(d_topk.as<uint64_t>(), nq, topk, comp_s.s));
-  }
-  PPS_TRY(pps_split_rows(d_qf.p, PPS_DTYPE_F32, nq, dim, dim, planes, d_qs.p, d_qn.as<float>(), comp_s.s));
+  // ---- ids up, pair counts + offsets, totals back (tiny; the host reads them while the GEMM runs) ----
+  PPS_CUDA_TRY(cudaMemcpyAsync(d_qid, query_ids, (size_t)nq * 8, cudaMemcpyHostToDevice, cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(d_qcam, query_cams, (size_t)nq * 8, cudaMemcpyHostToDevice, cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(d_gid, gallery_ids, (size_t)ng * 8, cudaMemcpyHostToDevice, cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(d_gcam, gallery_cams, (size_t)ng * 8, cudaMemcpyHostToDevice, cs));
+  PPS_TRY(pps_pairs_count_device(d_qid, nq, d_gid, ng, c->pair_ws.p, c->pair_off.as<int32_t>(),
+                                 c->totals.as<int32_t>(), cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(h_totals, c->totals.p, 8, cudaMemcpyDeviceToHost, cs));
+  PPS_CUDA_TRY(cudaEventRecord(c->ev_totals, cs));
 
-  // gallery upload + split in row slabs so the H2D copy overlaps the split kernels
-  const long long slab = std::max<long long>(1024, (64LL << 20) / ((long long)dim * 4));
-  std::vector<EventGuard> evs((size_t)((ng + slab - 1) / slab));
-  size_t ei = 0;
-  for (long long r0 = 0; r0 < ng; r0 += slab, ++ei) {
+  // ---- queries up + split ----
+  PPS_CUDA_TRY(cudaMemcpyAsync(c->qf.p, q_feats, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, cs));
+  PPS_TRY(pps_split_rows(c->qf.p, PPS_DTYPE_F32, nq, dim, dim, planes, c->qs.p, c->qn.as<float>(), cs));
+  PPS_CUDA_TRY(cudaMemsetAsync(c->cnt_first.p, 0, (size_t)nq * 4, cs));
+
+  // ---- gallery in row slabs: H2D on the copy stream; split + distance of slab s overlap the copy of s+1 ----
+  long long slab = ((ng + 7) / 8 + 255) & ~255LL;              // ~8 slabs, whole 256-column tiles
+  if (slab < 1024) slab = 1024;
+  while ((ng + slab - 1) / slab > kMaxSlabs) slab *= 2;
+  int si = 0;
+  const size_t esz = 2;   // bf16 planes
+  for (long long r0 = 0; r0 < ng; r0 += slab, ++si) {
     const long long nr = std::min(slab, ng - r0);
-    PPS_CUDA_TRY(cudaMemcpyAsync(d_gf.as<float>() + r0 * dim, g_feats + r0 * dim, (size_t)nr * dim * 4,
-                                 cudaMemcpyHostToDevice, copy_s.s));
-    PPS_CUDA_TRY(cudaEventCreateWithFlags(&evs[ei].e, cudaEventDisableTiming));
-    PPS_CUDA_TRY(cudaEventRecord(evs[ei].e, copy_s.s));
-    PPS_CUDA_TRY(cudaStreamWaitEvent(comp_s.s, evs[ei].e, 0));
-    // all slabs write into the one [planes][ng][kpad] buffer
-    PPS_TRY(pps_split_rows_slab(d_gf.p, PPS_DTYPE_F32, r0, nr, ng, dim, dim, planes, d_gs.p, d_gn.as<float>(),
-                                comp_s.s));
+    PPS_CUDA_TRY(cudaMemcpyAsync(c->gf.as<float>() + r0 * dim, g_feats + r0 * dim, (size_t)nr * dim * 4,
+                                 cudaMemcpyHostToDevice, ps));
+    PPS_CUDA_TRY(cudaEventRecord(c->ev_slab[si], ps));
+    PPS_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_slab[si], 0));
+    PPS_TRY(pps_split_rows_slab(c->gf.p, PPS_DTYPE_F32, r0, nr, ng, dim, dim, planes, c->gs.p, c->gn.as<float>(), cs));
+    PPS_TRY(pps_dist_tc(c->qs.p, c->qn.as<float>(), nq, planes, 0,
+                        c->gs.as<unsigned char>() + (size_t)r0 * kpad * esz, c->gn.as<float>() + r0, nr, planes, ng, dim,
+                        precision, 0, c->dist.as<float>() + r0, ldd, cs));
   }
 
-  PPS_TRY(pps_dist_tc(d_qs.p, d_qn.as<float>(), nq, planes, d_gs.p, d_gn.as<float>(), ng, planes, dim, precision, 0,
-                      d_dist.as<float>(), ldd, comp_s.s));
-  PPS_TRY(pps_rank_gather(d_dist.as<float>(), ldd, nq, ng, 0, d_pq.as<int32_t>(), d_pg.as<int32_t>(), n_pairs,
-                          d_pd.as<float>(), comp_s.s));
-  PPS_TRY(pps_rank_count(d_dist.as<float>(), ldd, nq, ng, 0, d_poff.as<int32_t>(), d_pg.as<int32_t>(),
-                         d_ppos.as<uint8_t>(), d_pd.as<float>(), max_pairs, d_cle.as<uint32_t>(),
-                         d_cfirst.as<uint32_t>(), comp_s.s));
-  PPS_TRY(pps_rank_finalize(nq, d_poff.as<int32_t>(), d_pg.as<int32_t>(), d_ppos.as<uint8_t>(), d_pd.as<float>(),
-                            d_cle.as<uint32_t>(), d_cfirst.as<uint32_t>(), d_ap.as<double>(), d_valid.as<uint8_t>(),
-                            d_first.as<int32_t>(), nullptr, comp_s.s));
+  // ---- pair lists (now that their size is known), thresholds, counts, finalize ----
+  PPS_CUDA_TRY(cudaEventSynchronize(c->ev_totals));
+  const long long n_pairs = h_totals[0];
+  const int max_pairs = h_totals[1];
+  const size_t np1 = (size_t)std::max<long long>(n_pairs, 1);
+  PPS_TRY(c->pair_q.ensure(np1 * 4));
+  PPS_TRY(c->pair_g.ensure(np1 * 4));
+  PPS_TRY(c->pair_pos.ensure(np1));
+  PPS_TRY(c->pair_d.ensure(np1 * 4));
+  PPS_TRY(c->cnt_le.ensure(np1 * 4));
+  PPS_TRY(pps_pairs_fill_device(d_qid, d_qcam, nq, d_gid, d_gcam, ng, c->pair_ws.p, c->pair_q.as<int32_t>(),
+                                c->pair_g.as<int32_t>(), c->pair_pos.as<uint8_t>(), n_pairs, cs));
+  PPS_CUDA_TRY(cudaMemsetAsync(c->pair_d.p, 0, np1 * 4, cs));
+  PPS_CUDA_TRY(cudaMemsetAsync(c->cnt_le.p, 0, np1 * 4, cs));
+  PPS_TRY(pps_rank_gather(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_q.as<int32_t>(), c->pair_g.as<int32_t>(), n_pairs,
+                          c->pair_d.as<float>(), cs));
+  PPS_TRY(pps_rank_count(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(),
+                         c->pair_pos.as<uint8_t>(), c->pair_d.as<float>(), max_pairs, c->cnt_le.as<uint32_t>(),
+                         c->cnt_first.as<uint32_t>(), cs));
+  PPS_TRY(pps_rank_finalize(nq, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(), c->pair_pos.as<uint8_t>(),
+                            c->pair_d.as<float>(), c->cnt_le.as<uint32_t>(), c->cnt_first.as<uint32_t>(),
+                            c->ap.as<double>(), c->valid.as<uint8_t>(), c->first.as<int32_t>(), nullptr, cs));
   if (topk > 0) {
-    PPS_TRY(pps_topk_update(d_dist.as<float>(), ldd, nq, ng, 0, d_joff.as<int32_t>(), d_jg.as<int32_t>(),
-                            d_topk.as<uint64_t>(), topk, comp_s.s));
-    PPS_TRY(pps_topk_unpack(d_topk.as<uint64_t>(), nq, topk, d_tkd.as<float>(), d_tki.as<int32_t>(), comp_s.s));
+    PPS_TRY(c->topk.ensure((size_t)nq * topk * 8));
+    PPS_TRY(c->tki.ensure((size_t)nq * topk * 4));
+    PPS_TRY(c->tkd.ensure((size_t)nq * topk * 4));
+    PPS_TRY(pps_topk_init(c->topk.as<uint64_t>(), nq, topk, cs));
+    PPS_TRY(pps_topk_update(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(),
+                            c->pair_pos.as<uint8_t>(), c->topk.as<uint64_t>(), topk, cs));
+    PPS_TRY(pps_topk_unpack(c->topk.as<uint64_t>(), nq, topk, c->tkd.as<float>(), c->tki.as<int32_t>(), cs));
   }
 
   // ---- results back ----
-  std::vector<double> ap((size_t)nq);
-  std::vector<uint8_t> valid((size_t)nq);
-  std::vector<int32_t> first((size_t)nq);
-  PPS_CUDA_TRY(cudaMemcpyAsync(ap.data(), d_ap.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, comp_s.s));
-  PPS_CUDA_TRY(cudaMemcpyAsync(valid.data(), d_valid.p, (size_t)nq, cudaMemcpyDeviceToHost, comp_s.s));
-  PPS_CUDA_TRY(cudaMemcpyAsync(first.data(), d_first.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, comp_s.s));
+  double* ap = reinterpret_cast<double*>(h_base + off_ap);
+  int32_t* first = reinterpret_cast<int32_t*>(h_base + off_first);
+  uint8_t* valid = h_base + off_valid;
+  PPS_CUDA_TRY(cudaMemcpyAsync(ap, c->ap.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(first, c->first.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(valid, c->valid.p, (size_t)nq, cudaMemcpyDeviceToHost, cs));
   if (topk > 0 && out_topk_index)
-    PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_index, d_tki.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, comp_s.s));
+    PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_index, c->tki.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
   if (topk > 0 && out_topk_dist)
-    PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_dist, d_tkd.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, comp_s.s));
-  PPS_CUDA_TRY(cudaStreamSynchronize(comp_s.s));
-  PPS_CUDA_TRY(cudaStreamSynchronize(copy_s.s));
+    PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_dist, c->tkd.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
+  PPS_CUDA_TRY(cudaStreamSynchronize(cs));
+  PPS_CUDA_TRY(cudaStreamSynchronize(ps));
 
   // ---- host averaging, as the reference does it (:360-362, :437-438) ----
   double ap_sum = 0.0;
@@ -289,9 +347,9 @@ extern "C" int pps_evaluate_host(const float* q_feats, long long nq, const float
     ap_sum += ap[i];
     if (first[i] >= 0 && first[i] < cmc_topk) hist[(size_t)first[i]] += 1.0;
   }
-  if (out_ap) std::memcpy(out_ap, ap.data(), (size_t)nq * 8);
-  if (out_valid) std::memcpy(out_valid, valid.data(), (size_t)nq);
-  if (out_first_rank) std::memcpy(out_first_rank, first.data(), (size_t)nq * 4);
+  if (out_ap) std::memcpy(out_ap, ap, (size_t)nq * 8);
+  if (out_valid) std::memcpy(out_valid, valid, (size_t)nq);
+  if (out_first_rank) std::memcpy(out_first_rank, first, (size_t)nq * 4);
   if (n_valid == 0) return PPS_ERR_NO_VALID_QUERY;
   *out_map = ap_sum / (double)n_valid;
   double run = 0.0;
@@ -300,4 +358,19 @@ extern "C" int pps_evaluate_host(const float* q_feats, long long nq, const float
     out_cmc[k] = run / (double)n_valid;
   }
   return PPS_OK;
+}
+
+extern "C" int pps_evaluate_host(const float* q_feats, long long nq, const float* g_feats, long long ng, int dim,
+                                 const int64_t* query_ids, const int64_t* query_cams, const int64_t* gallery_ids,
+                                 const int64_t* gallery_cams, int precision, int cmc_topk, int topk, int device,
+                                 double* out_map, double* out_cmc, double* out_ap, uint8_t* out_valid,
+                                 int32_t* out_first_rank, int32_t* out_topk_index, float* out_topk_dist) {
+  pps_ctx* c = nullptr;
+  int rc = pps_ctx_create(device, &c);
+  if (rc != PPS_OK) return rc;
+  rc = pps_evaluate_host_ctx(c, q_feats, nq, g_feats, ng, dim, query_ids, query_cams, gallery_ids, gallery_cams,
+                             precision, cmc_topk, topk, out_map, out_cmc, out_ap, out_valid, out_first_rank,
+                             out_topk_index, out_topk_dist);
+  pps_ctx_destroy(c);
+  return rc;
 }

@@ -270,12 +270,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 // planes: [n_planes][rows][kpad] 16-bit elements, K-major
-static int make_operand_map(CUtensorMap* tm, const void* planes, long long rows, int kpad, int n_planes, int box_rows,
-                            bool f16) {
+static int make_operand_map(CUtensorMap* tm, const void* planes, long long rows, long long plane_rows, int kpad,
+                            int n_planes, int box_rows, bool f16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return cuda_fail(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[3] = {(cuuint64_t)kpad, (cuuint64_t)rows, (cuuint64_t)n_planes};
-  cuuint64_t strides[2] = {(cuuint64_t)kpad * 2, (cuuint64_t)rows * (cuuint64_t)kpad * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)kpad * 2, (cuuint64_t)plane_rows * (cuuint64_t)kpad * 2};
   cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
@@ -290,9 +290,13 @@ static int make_operand_map(CUtensorMap* tm, const void* planes, long long rows,
 using namespace pps;
 
 extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
-                           const void* b_planes, const float* b_sqnorm, long long m2, int b_planes_n, int dim,
-                           int precision, int flags, float* dist, long long ldd, void* stream) {
+                           long long a_plane_rows, const void* b_planes, const float* b_sqnorm, long long m2,
+                           int b_planes_n, long long b_plane_rows, int dim, int precision, int flags, float* dist,
+                           long long ldd, void* stream) {
   if (m1 < 0 || m2 < 0 || dim <= 0 || ldd < m2) return PPS_ERR_INVALID_ARG;
+  if (a_plane_rows == 0) a_plane_rows = m1;
+  if (b_plane_rows == 0) b_plane_rows = m2;
+  if (a_plane_rows < m1 || b_plane_rows < m2) return PPS_ERR_INVALID_ARG;
   if (m1 == 0 || m2 == 0) return PPS_OK;
   if (!a_planes || !b_planes || !dist) return PPS_ERR_INVALID_ARG;
   if (!(flags & PPS_DIST_DOT) && (!a_sqnorm || !b_sqnorm)) return PPS_ERR_INVALID_ARG;
@@ -333,9 +337,9 @@ extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long lon
   g.n_tiles = (int)((m2 + kBN - 1) / kBN);
 
   CUtensorMap tmA, tmB;
-  int rc = make_operand_map(&tmA, a_planes, m1, kpad, a_planes_n, kBM, f16);
+  int rc = make_operand_map(&tmA, a_planes, m1, a_plane_rows, kpad, a_planes_n, kBM, f16);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, b_planes, m2, kpad, b_planes_n, kBN, f16);
+  rc = make_operand_map(&tmB, b_planes, m2, b_plane_rows, kpad, b_planes_n, kBN, f16);
   if (rc) return rc;
 
   static thread_local int configured_dev = -1;

@@ -1,0 +1,209 @@
+// Same-id pair lists built on the device (the junk mask and the matches of
+// reid_dataset_evaluator.py:320,327-328,421,427-428 without the [m1, m2] boolean matrices).
+//
+// For query i the gallery items g with gallery_ids[g] == query_ids[i] are its pairs: positives
+// (camera differs) and junk (same camera).  Output is the same CSR the host builder
+// (pps_pairs_fill, c_api.cu) produces — pair_off[nq+1], pair_q[E], pair_g[E] ascending inside a
+// query, pair_pos[E] — so every rank of a sharded run builds identical lists and the later
+// all-reduces line up element by element.
+//
+// Brute force on purpose: nq x ng 64-bit compares are ~2000x cheaper than the nq x ng x D
+// contraction they accompany, need no sort and no hash table, and the order is deterministic:
+//   count : CTA (query block of 32, gallery segment) -> 8 warps x 4 queries; a warp streams the
+//           segment's ids once (coalesced), 4 ballots per 32 ids, popc-accumulates per query.
+//   scan  : one CTA turns the [nq][segments] counts into exclusive offsets (query-major), writes
+//           pair_off and {n_pairs, max pairs per query}.
+//   fill  : same sweep as count; the ballot prefix gives each hit its slot -> ascending g.
+#include "common.cuh"
+
+namespace pps {
+
+constexpr int kPairQPerWarp = 4;
+constexpr int kPairWarps = 8;
+constexpr int kPairQPerCta = kPairQPerWarp * kPairWarps;   // 32
+
+template <bool FILL>
+__global__ void __launch_bounds__(32 * kPairWarps)
+pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ qcam, int nq,
+                   const int64_t* __restrict__ gid, const int64_t* __restrict__ gcam, long long ng, long long seg,
+                   int nseg, int32_t* __restrict__ seg_cnt /*[nq][nseg]: counts (count) / exclusive offsets (fill)*/,
+                   int32_t* __restrict__ pair_q, int32_t* __restrict__ pair_g, uint8_t* __restrict__ pair_pos,
+                   long long capacity) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * kPairQPerCta + warp * kPairQPerWarp;
+  const int s = blockIdx.y;
+  if (q0 >= nq) return;
+  int64_t ids[kPairQPerWarp], cams[kPairQPerWarp];
+  int acc[kPairQPerWarp];
+  bool live[kPairQPerWarp];
+#pragma unroll
+  for (int u = 0; u < kPairQPerWarp; ++u) {
+    live[u] = q0 + u < nq;
+    ids[u] = live[u] ? qid[q0 + u] : 0;
+    cams[u] = (FILL && live[u]) ? qcam[q0 + u] : 0;
+    acc[u] = (FILL && live[u]) ? seg_cnt[(long long)(q0 + u) * nseg + s] : 0;
+  }
+  const long long g_begin = (long long)s * seg;
+  const long long g_end = min(ng, g_begin + seg);
+  const unsigned lt = (1u << lane) - 1u;
+  for (long long g0 = g_begin; g0 < g_end; g0 += 128) {
+    int64_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long g = g0 + k * 32 + lane;
+      v[k] = g < g_end ? gid[g] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long g = g0 + k * 32 + lane;
+      const bool in = g < g_end;
+#pragma unroll
+      for (int u = 0; u < kPairQPerWarp; ++u) {
+        const bool hit = in && live[u] && v[k] == ids[u];
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (FILL) {
+          if (hit) {
+            const long long slot = (long long)acc[u] + __popc(b & lt);
+            if (slot < capacity) {
+              pair_q[slot] = q0 + u;
+              pair_g[slot] = (int32_t)g;
+              pair_pos[slot] = gcam[g] != cams[u] ? 1 : 0;
+            }
+          }
+        }
+        acc[u] += __popc(b);
+      }
+    }
+  }
+  if (!FILL && lane == 0) {
+#pragma unroll
+    for (int u = 0; u < kPairQPerWarp; ++u)
+      if (live[u]) seg_cnt[(long long)(q0 + u) * nseg + s] = acc[u];
+  }
+}
+
+// exclusive scan of n = nq*nseg counts in place (query-major), one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) pairs_scan_kernel(int32_t* __restrict__ seg_cnt, int nq, int nseg,
+                                                          int32_t* __restrict__ pair_off, int32_t* __restrict__ totals) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  __shared__ int max_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n = (long long)nq * nseg;
+  if (tid == 0) { carry_s = 0; max_s = 0; }
+  __syncthreads();
+  for (long long base = 0; base < n; base += 4096) {
+    int v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = base + 4LL * tid + k;
+      v[k] = i < n ? seg_cnt[i] : 0;
+      sum += v[k];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_sum[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int run = carry + (warp ? warp_sum[warp - 1] : 0) + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = base + 4LL * tid + k;
+      if (i < n) seg_cnt[i] = run;
+      run += v[k];
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sum[31];
+    __syncthreads();
+  }
+  const int total = carry_s;
+  // pair_off[q] = offset of (q, segment 0); per-query maximum
+  int mx = 0;
+  for (int q = tid; q < nq; q += 1024) {
+    const int o = seg_cnt[(long long)q * nseg];
+    pair_off[q] = o;
+    const int nxt = q + 1 < nq ? seg_cnt[(long long)(q + 1) * nseg] : total;
+    mx = max(mx, nxt - o);
+  }
+  if (tid == 0) pair_off[nq] = total;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) atomicMax(&max_s, mx);
+  __syncthreads();
+  if (tid == 0) { totals[0] = total; totals[1] = max_s; }
+}
+
+static void pair_segments(long long ng, long long* seg, int* nseg) {
+  long long s = 2048;
+  while ((ng + s - 1) / s > 512) s *= 2;
+  *seg = s;
+  *nseg = (int)((ng + s - 1) / s);
+  if (*nseg < 1) *nseg = 1;
+}
+
+}  // namespace pps
+
+using namespace pps;
+
+extern "C" long long pps_pairs_workspace_bytes(long long nq, long long ng) {
+  if (nq < 0 || ng < 0) return PPS_ERR_INVALID_ARG;
+  long long seg; int nseg;
+  pair_segments(ng, &seg, &nseg);
+  return (nq > 0 ? nq : 1) * (long long)nseg * 4;
+}
+
+extern "C" int pps_pairs_count_device(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
+                                      void* workspace, int32_t* pair_off, int32_t* totals, void* stream) {
+  if (nq < 0 || ng < 0 || nq > 0x7fffffffLL || ng > 0x7fffffffLL) return PPS_ERR_INVALID_ARG;
+  if (!pair_off || !totals || !workspace) return PPS_ERR_INVALID_ARG;
+  if (nq > 0 && ng > 0 && (!query_ids || !gallery_ids)) return PPS_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long seg; int nseg;
+  pair_segments(ng, &seg, &nseg);
+  int32_t* seg_cnt = static_cast<int32_t*>(workspace);
+  if ((long long)nq * nseg > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  if (nq > 0) {
+    if (ng == 0) PPS_CUDA_TRY(cudaMemsetAsync(seg_cnt, 0, (size_t)nq * nseg * 4, st));
+    else {
+      const dim3 grid((unsigned)((nq + kPairQPerCta - 1) / kPairQPerCta), (unsigned)nseg);
+      pairs_sweep_kernel<false><<<grid, 32 * kPairWarps, 0, st>>>(query_ids, nullptr, (int)nq, gallery_ids, nullptr, ng,
+                                                                  seg, nseg, seg_cnt, nullptr, nullptr, nullptr, 0);
+      PPS_LAUNCH_CHECK("pairs_sweep_kernel<count>");
+    }
+  }
+  pairs_scan_kernel<<<1, 1024, 0, st>>>(seg_cnt, (int)nq, nseg, pair_off, totals);
+  PPS_LAUNCH_CHECK("pairs_scan_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_pairs_fill_device(const int64_t* query_ids, const int64_t* query_cams, long long nq,
+                                     const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
+                                     const void* workspace, int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos,
+                                     long long capacity, void* stream) {
+  if (nq < 0 || ng < 0 || nq > 0x7fffffffLL || ng > 0x7fffffffLL || capacity < 0) return PPS_ERR_INVALID_ARG;
+  if (nq == 0 || ng == 0 || capacity == 0) return PPS_OK;
+  if (!query_ids || !query_cams || !gallery_ids || !gallery_cams || !workspace || !pair_q || !pair_g || !pair_pos)
+    return PPS_ERR_INVALID_ARG;
+  long long seg; int nseg;
+  pair_segments(ng, &seg, &nseg);
+  const dim3 grid((unsigned)((nq + kPairQPerCta - 1) / kPairQPerCta), (unsigned)nseg);
+  pairs_sweep_kernel<true><<<grid, 32 * kPairWarps, 0, static_cast<cudaStream_t>(stream)>>>(
+      query_ids, query_cams, (int)nq, gallery_ids, gallery_cams, ng, seg, nseg,
+      const_cast<int32_t*>(static_cast<const int32_t*>(workspace)), pair_q, pair_g, pair_pos, capacity);
+  PPS_LAUNCH_CHECK("pairs_sweep_kernel<fill>");
+  return PPS_OK;
+}

@@ -22,7 +22,7 @@
 namespace pps {
 
 constexpr int kCB = 32;                  // channels per unit
-constexpr int kPoolStages = 4;           // shared-memory ring depth
+constexpr int kPoolStages = 3;           // shared-memory ring depth (2 CTAs per SM -> 6 slots in flight per SM)
 constexpr int kStageBytes = 32 * 1024;   // bytes per ring slot
 constexpr int kConsumerWarps = 8;
 constexpr int kPoolThreads = 32 * (1 + kConsumerWarps);
@@ -42,35 +42,47 @@ struct PoolArgs {
   int combos[kMaxComboList];
 };
 
-// one output row (combination `idx`) for the 32 channels of a unit; lane = channel
-__device__ __forceinline__ void combine_store(const PoolArgs& a, const float* pavg, const float* pmax, int idx,
-                                              int lane, int nch, float* ybase) {
-  int m = a.use_list ? a.combos[idx] : idx + 1;
-  float s = 0.f, mxa = -FLT_MAX, mxm = -FLT_MAX;
-  int cnt = 0;
-  while (m) {
-    const int j = __ffs(m) - 1;
-    m &= m - 1;
-    const float av = pavg[j * kCB + lane];
-    s = cnt ? s + av : av;   // ascending-j sequential sum, like Caffe2 Mean
-    mxa = fmaxf(mxa, av);
-    mxm = fmaxf(mxm, pmax[j * kCB + lane]);
-    ++cnt;
+// All output rows of one unit.  lane = channel: the thread keeps its channel's NP strip averages / maxes in
+// registers and walks this warp's share of the subset masks with a fully unrolled, predicated bit loop
+// (no per-bit shared-memory reads, no data-dependent branches).  Sums run over ascending part index, like
+// Caffe2 Mean (sum in input order, then one multiply by 1.0f / count).
+template <int NP, int MODE>
+__device__ __forceinline__ void combine_unit(const PoolArgs& a, const float* pavg, const float* pmax, int cw,
+                                             int nwarps, int lane, int nch, float* ybase) {
+  float av[NP], mv[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    av[j] = pavg[j * kCB + lane];
+    mv[j] = MODE == PPS_POOL_MAX_AVE ? pmax[j * kCB + lane] : 0.f;
   }
-  float val;
-  if (a.mode == PPS_POOL_MAX_AVE) {
-    const float mean = cnt > 1 ? s * a.inv_cnt[cnt] : s;
-    val = mean + mxm;
-  } else {
-    val = mxa;
+  for (int idx = cw; idx < a.n_out; idx += nwarps) {
+    const int m = a.use_list ? a.combos[idx] : idx + 1;
+    float val;
+    if (MODE == PPS_POOL_MAX_AVE) {
+      float s = 0.f, mx = -FLT_MAX;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const bool on = (m >> j) & 1;
+        s = on ? s + av[j] : s;
+        mx = on ? fmaxf(mx, mv[j]) : mx;
+      }
+      const int cnt = __popc(m);
+      val = (cnt > 1 ? s * a.inv_cnt[cnt] : s) + mx;
+    } else {
+      float mx = -FLT_MAX;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) mx = ((m >> j) & 1) ? fmaxf(mx, av[j]) : mx;
+      val = mx;
+    }
+    if (lane < nch) st_stream_f32(ybase + (long long)idx * a.ysk + lane, val);
   }
-  if (lane < nch) st_stream_f32(ybase + (long long)idx * a.ysk + lane, val);
 }
 
 // ------------------------------------------------------------------------------------
 // fast path: W % 4 == 0, 16-byte aligned x, one plane fits a ring slot
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPoolThreads, 1) pool_tma_kernel(const __grid_constant__ PoolArgs a) {
+template <int NP, int MODE>
+__global__ void __launch_bounds__(kPoolThreads, 2) pool_tma_kernel(const __grid_constant__ PoolArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage = reinterpret_cast<float*>(smem_raw);                               // [stages][kStageBytes/4]
   float* pavg = reinterpret_cast<float*>(smem_raw + kPoolStages * kStageBytes);    // [2][MAXP][kCB]
@@ -130,9 +142,9 @@ __global__ void __launch_bounds__(kPoolThreads, 1) pool_tma_kernel(const __grid_
         const uint32_t s = it % kPoolStages, ph = (it / kPoolStages) & 1u;
         mbar_wait(&full[s], ph);
         const float* sbase = stage + (size_t)s * (kStageBytes / 4);
-        const int tasks = npl * a.n_parts;
+        const int tasks = npl * NP;
         for (int t = ctid; t < tasks; t += 32 * kConsumerWarps) {
-          const int pl = t / a.n_parts, j = t - pl * a.n_parts;
+          const int pl = t / NP, j = t - pl * NP;
           const int r0 = a.row0[j], r1 = a.row0[j + 1];
           const int L4 = ((r1 - r0) * a.W) >> 2;
           const float4* b4 = reinterpret_cast<const float4*>(sbase + pl * HW + r0 * a.W);
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) pool_tma_kernel(const __grid_
           }
           const float sum = (acc.x + acc.y) + (acc.z + acc.w);
           ua[j * kCB + p0 + pl] = __fdiv_rn(sum, (float)((r1 - r0) * a.W));
-          um[j * kCB + p0 + pl] = fmaxf(fmaxf(mx.x, mx.y), fmaxf(mx.z, mx.w));
+          if (MODE == PPS_POOL_MAX_AVE) um[j * kCB + p0 + pl] = fmaxf(fmaxf(mx.x, mx.y), fmaxf(mx.z, mx.w));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);   // slot may be refilled
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) pool_tma_kernel(const __grid_
       // all strip results of this unit are in ua/um
       asm volatile("bar.sync 1, %0;" ::"r"(32 * kConsumerWarps) : "memory");
       float* ybase = a.y + n * a.ysn + c0;
-      for (int idx = cw; idx < a.n_out; idx += kConsumerWarps) combine_store(a, ua, um, idx, lane, nch, ybase);
+      combine_unit<NP, MODE>(a, ua, um, cw, kConsumerWarps, lane, nch, ybase);
       ubuf ^= 1;
     }
   }
@@ -165,6 +177,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) pool_tma_kernel(const __grid_
 // ------------------------------------------------------------------------------------
 // generic path: any W / alignment / plane size. One CTA per unit, plain global loads.
 // ------------------------------------------------------------------------------------
+template <int NP, int MODE>
 __global__ void __launch_bounds__(256) pool_generic_kernel(const __grid_constant__ PoolArgs a) {
   __shared__ float pavg[PPS_POOL_MAX_PARTS * kCB];
   __shared__ float pmax[PPS_POOL_MAX_PARTS * kCB];
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(256) pool_generic_kernel(const __grid_constant
   const int nch = min(kCB, a.C - c0);
   for (int pl = warp; pl < nch; pl += 8) {
     const float* plane = a.x + (n * a.C + c0 + pl) * (long long)HW;
-    for (int j = 0; j < a.n_parts; ++j) {
+    for (int j = 0; j < NP; ++j) {
       const int e0 = a.row0[j] * a.W, e1 = a.row0[j + 1] * a.W;
       float s = 0.f, mx = -FLT_MAX;
       for (int e = e0 + lane; e < e1; e += 32) {
@@ -198,7 +211,45 @@ __global__ void __launch_bounds__(256) pool_generic_kernel(const __grid_constant
   }
   __syncthreads();
   float* ybase = a.y + n * a.ysn + c0;
-  for (int idx = warp; idx < a.n_out; idx += 8) combine_store(a, pavg, pmax, idx, lane, nch, ybase);
+  combine_unit<NP, MODE>(a, pavg, pmax, warp, 8, lane, nch, ybase);
+}
+
+template <int NP, int MODE>
+static int launch_pool(const PoolArgs& a, bool fast, long long units, size_t smem, cudaStream_t st) {
+  if (fast) {
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    PPS_CUDA_TRY(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+      PPS_CUDA_TRY(cudaFuncSetAttribute(pool_tma_kernel<NP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_dev = dev;
+    }
+    const long long slots = 2LL * sm_count();   // two resident CTAs per SM
+    const int grid = (int)(units < slots ? units : slots);
+    pool_tma_kernel<NP, MODE><<<grid, kPoolThreads, smem, st>>>(a);
+    PPS_LAUNCH_CHECK("pool_tma_kernel");
+  } else {
+    pool_generic_kernel<NP, MODE><<<(int)units, 256, 0, st>>>(a);
+    PPS_LAUNCH_CHECK("pool_generic_kernel");
+  }
+  return PPS_OK;
+}
+
+template <int MODE>
+static int dispatch_parts(const PoolArgs& a, bool fast, long long units, size_t smem, cudaStream_t st) {
+  switch (a.n_parts) {
+    case 1: return launch_pool<1, MODE>(a, fast, units, smem, st);
+    case 2: return launch_pool<2, MODE>(a, fast, units, smem, st);
+    case 3: return launch_pool<3, MODE>(a, fast, units, smem, st);
+    case 4: return launch_pool<4, MODE>(a, fast, units, smem, st);
+    case 5: return launch_pool<5, MODE>(a, fast, units, smem, st);
+    case 6: return launch_pool<6, MODE>(a, fast, units, smem, st);
+    case 7: return launch_pool<7, MODE>(a, fast, units, smem, st);
+    case 8: return launch_pool<8, MODE>(a, fast, units, smem, st);
+    case 9: return launch_pool<9, MODE>(a, fast, units, smem, st);
+    case 10: return launch_pool<10, MODE>(a, fast, units, smem, st);
+    default: return PPS_ERR_SHAPE;
+  }
 }
 
 }  // namespace pps
@@ -245,26 +296,10 @@ extern "C" int pps_pool_fwd(const float* x, int N, int C, int H, int W, int n_pa
   const int cblocks = (C + kCB - 1) / kCB;
   const long long units = (long long)N * cblocks;
   const bool fast = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && plane_bytes <= kStageBytes;
-  if (fast) {
-    a.planes_per_stage = (int)((kStageBytes / plane_bytes) < kCB ? (kStageBytes / plane_bytes) : kCB);
-    const size_t smem = (size_t)kPoolStages * kStageBytes + 4 * PPS_POOL_MAX_PARTS * kCB * sizeof(float) +
-                        2 * kPoolStages * sizeof(uint64_t);
-    static thread_local int configured_dev = -1;
-    int dev = 0;
-    PPS_CUDA_TRY(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
-      PPS_CUDA_TRY(cudaFuncSetAttribute(pool_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured_dev = dev;
-    }
-    const int sms = sm_count();
-    const int grid = (int)(units < sms ? units : sms);
-    pool_tma_kernel<<<grid, kPoolThreads, smem, st>>>(a);
-    PPS_LAUNCH_CHECK("pool_tma_kernel");
-  } else {
-    if (units > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
-    a.planes_per_stage = 0;
-    pool_generic_kernel<<<(int)units, 256, 0, st>>>(a);
-    PPS_LAUNCH_CHECK("pool_generic_kernel");
-  }
-  return PPS_OK;
+  if (units > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  a.planes_per_stage = fast ? (int)((kStageBytes / plane_bytes) < kCB ? (kStageBytes / plane_bytes) : kCB) : 0;
+  const size_t smem = (size_t)kPoolStages * kStageBytes + 4 * PPS_POOL_MAX_PARTS * kCB * sizeof(float) +
+                      2 * kPoolStages * sizeof(uint64_t);
+  return mode == PPS_POOL_MAX_AVE ? dispatch_parts<PPS_POOL_MAX_AVE>(a, fast, units, smem, st)
+                                  : dispatch_parts<PPS_POOL_AVG_MAX>(a, fast, units, smem, st);
 }

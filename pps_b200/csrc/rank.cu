@@ -29,11 +29,12 @@ constexpr int kWin = 63;            // thresholds per pass (slot 63 is a +inf se
 __global__ void rank_gather_kernel(const float* __restrict__ dist, long long ldd, long long ncols, long long col0,
                                    const int32_t* __restrict__ pair_q, const int32_t* __restrict__ pair_g,
                                    long long n_pairs, float* __restrict__ pair_d) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_pairs) return;
-  const long long c = (long long)pair_g[e] - col0;
-  if (c < 0 || c >= ncols) return;
-  pair_d[e] = dist[(long long)pair_q[e] * ldd + c];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_pairs;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long c = (long long)pair_g[e] - col0;
+    if (c < 0 || c >= ncols) continue;
+    pair_d[e] = dist[(long long)pair_q[e] * ldd + c];
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(kTopkThreads) topk_update_kernel(const float* 
                                                                     long long ncols, long long col0,
                                                                     const int32_t* __restrict__ excl_off,
                                                                     const int32_t* __restrict__ excl_g,
+                                                                    const uint8_t* __restrict__ excl_keep,
                                                                     unsigned long long* __restrict__ topk_key, int k) {
   __shared__ unsigned long long cand[kCand];
   __shared__ int s_n;
@@ -267,7 +269,8 @@ __global__ void __launch_bounds__(kTopkThreads) topk_update_kernel(const float* 
         const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(uint32_t)(col0 + c);
         if (key < bound) {
           bool skip = false;
-          for (int x = x0; x < x1; ++x) skip |= ((long long)excl_g[x] == col0 + c);
+          for (int x = x0; x < x1; ++x)
+            skip |= ((long long)excl_g[x] == col0 + c) && !(excl_keep && excl_keep[x]);
           if (!skip) {
             const int slot = atomicAdd(&s_n, 1);
             cand[slot] = key;        // s_n <= kCand - tile at tile start, so slot < kCand
@@ -382,15 +385,15 @@ extern "C" int pps_topk_init(uint64_t* topk_key, long long nq, int k, void* stre
 }
 
 extern "C" int pps_topk_update(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
-                               const int32_t* excl_off, const int32_t* excl_g, uint64_t* topk_key, int k,
-                               void* stream) {
+                               const int32_t* excl_off, const int32_t* excl_g, const uint8_t* excl_keep,
+                               uint64_t* topk_key, int k, void* stream) {
   if (nq < 0 || ncols < 0 || ldd < ncols || k < 1 || k > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
   if (nq == 0 || ncols == 0) return PPS_OK;
   if (!dist || !topk_key) return PPS_ERR_INVALID_ARG;
   if (excl_off && !excl_g) return PPS_ERR_INVALID_ARG;
   if (nq > 0x7fffffffLL || col0 + ncols > 0xffffffffLL) return PPS_ERR_UNSUPPORTED;
   topk_update_kernel<<<(unsigned)nq, kTopkThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      dist, ldd, ncols, col0, excl_off, excl_g, reinterpret_cast<unsigned long long*>(topk_key), k);
+      dist, ldd, ncols, col0, excl_off, excl_g, excl_keep, reinterpret_cast<unsigned long long*>(topk_key), k);
   PPS_LAUNCH_CHECK("topk_update_kernel");
   return PPS_OK;
 }

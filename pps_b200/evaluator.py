@@ -106,6 +106,87 @@ class PairLists:
         return self._dev[name]
 
 
+class DevicePairs:
+    """Same-id pair lists built ON THE DEVICE (C ABI part 2c, pairs.cu) from resident id / camera arrays.
+
+    ``begin()`` launches count + scan and an 8-byte read-back of {n_pairs, max_pairs}; ``finish()`` waits
+    for that read-back (the caller enqueues the distance GEMM in between, so the device never idles),
+    sizes the lists and launches the fill.  Host copies (``off``, ``q``, ``g``, ``pos`` ...) are
+    downloaded lazily, only for the outputs that need them (cmc with first_match_break=False)."""
+
+    def __init__(self, query_ids, query_cams, gallery_ids, gallery_cams, device):
+        torch = _torch()
+        self.lib = _lib.load()
+        qi, qc = _ids64(query_ids, "query_ids"), _ids64(query_cams, "query_cams")
+        gi, gc = _ids64(gallery_ids, "gallery_ids"), _ids64(gallery_cams, "gallery_cams")
+        if qi.shape != qc.shape or gi.shape != gc.shape:
+            raise RuntimeError("ids and cams must have the same length")
+        self.nq, self.ng = int(qi.shape[0]), int(gi.shape[0])
+        if self.ng > 0x7fffffff or self.nq > 0x7fffffff:
+            raise RuntimeError("pair lists index the gallery with int32")
+        self.device = torch.device(device)
+        up = lambda a: torch.from_numpy(a if a.size else np.zeros(1, np.int64)).to(self.device)
+        self.qid, self.qcam, self.gid, self.gcam = up(qi), up(qc), up(gi), up(gc)
+        ws = int(self.lib.pps_pairs_workspace_bytes(self.nq, self.ng))
+        self.ws = torch.empty(max(ws, 16), dtype=torch.uint8, device=self.device)
+        self.off_d = torch.empty(self.nq + 1, dtype=torch.int32, device=self.device)
+        self.totals_d = torch.empty(2, dtype=torch.int32, device=self.device)
+        self.totals_h = torch.empty(2, dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.cap = 0
+        self.q_d = self.g_d = self.pos_d = None
+        self.n_pairs = self.max_pairs = 0
+        self._host = None
+
+    def begin(self):
+        lib = self.lib
+        _lib.check(lib.pps_pairs_count_device(_lib.ptr(self.qid), self.nq, _lib.ptr(self.gid), self.ng, _lib.ptr(self.ws),
+                                              _lib.ptr(self.off_d), _lib.ptr(self.totals_d), _lib.stream_ptr()),
+                   "pps_pairs_count_device")
+        self.totals_h.copy_(self.totals_d, non_blocking=True)
+        self.event.record()
+        self._host = None
+        return self
+
+    def finish(self):
+        torch = _torch()
+        self.event.synchronize()
+        self.n_pairs, self.max_pairs = int(self.totals_h[0]), int(self.totals_h[1])
+        if self.n_pairs > self.cap or self.q_d is None:
+            self.cap = max(int(self.n_pairs * 1.25), 1024)
+            self.q_d = torch.empty(self.cap, dtype=torch.int32, device=self.device)
+            self.g_d = torch.empty(self.cap, dtype=torch.int32, device=self.device)
+            self.pos_d = torch.empty(self.cap, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.pps_pairs_fill_device(_lib.ptr(self.qid), _lib.ptr(self.qcam), self.nq, _lib.ptr(self.gid),
+                                                  _lib.ptr(self.gcam), self.ng, _lib.ptr(self.ws), _lib.ptr(self.q_d),
+                                                  _lib.ptr(self.g_d), _lib.ptr(self.pos_d), self.n_pairs,
+                                                  _lib.stream_ptr()), "pps_pairs_fill_device")
+        return self
+
+    def dev(self, name):
+        return {"off": self.off_d, "q": self.q_d, "g": self.g_d, "pos": self.pos_d}[name]
+
+    # ---- lazy host mirrors (same fields as PairLists) ----
+    def _download(self):
+        if self._host is None:
+            n = self.n_pairs
+            self._host = dict(off=self.off_d.cpu().numpy(), q=self.q_d[:max(n, 1)].cpu().numpy(),
+                              g=self.g_d[:max(n, 1)].cpu().numpy(), pos=self.pos_d[:max(n, 1)].cpu().numpy())
+        return self._host
+
+    off = property(lambda self: self._download()["off"])
+    q = property(lambda self: self._download()["q"])
+    g = property(lambda self: self._download()["g"])
+    pos = property(lambda self: self._download()["pos"])
+
+    @property
+    def n_pos_per_q(self):
+        n = self.n_pairs
+        if not n:
+            return np.zeros(self.nq, dtype=np.int64)
+        return np.bincount(self.q[:n][self.pos[:n] == 1], minlength=self.nq)
+
+
 class RankResult:
     """Per-query outputs of the rank kernels (host numpy) + the reference's averages."""
 
@@ -158,10 +239,12 @@ def _rank_block(lib, dist, ldd, nq, ncols, col0, pairs: PairLists, pair_d, cnt_l
                                           pairs.max_pairs, _lib.ptr(cnt_le), _lib.ptr(cnt_first), s),
                        "pps_rank_count")
         if topk_key is not None:
-            eo = pairs.dev("junk_off") if topk_filtered else None
-            eg = pairs.dev("junk_g") if topk_filtered else None
+            use = topk_filtered and pairs.n_pairs > 0
+            eo = pairs.dev("off") if use else None
+            eg = pairs.dev("g") if use else None
+            ek = pairs.dev("pos") if use else None
             _lib.check(lib.pps_topk_update(_lib.ptr(dist), ldd, nq, ncols, col0, _lib.ptr(eo), _lib.ptr(eg),
-                                           _lib.ptr(topk_key), topk, s), "pps_topk_update")
+                                           _lib.ptr(ek), _lib.ptr(topk_key), topk, s), "pps_topk_update")
 
 
 def _finalize(lib, nq, pairs: PairLists, pair_d, cnt_le, cnt_first, want_neg_before):
@@ -188,7 +271,7 @@ def rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams, want
         dist = dist.float()
     m, n = int(dist.shape[0]), int(dist.shape[1])
     with torch.cuda.device(dist.device):
-        pairs = PairLists(query_ids, query_cams, gallery_ids, gallery_cams, device=dist.device)
+        pairs = DevicePairs(query_ids, query_cams, gallery_ids, gallery_cams, dist.device).begin().finish()
         if pairs.nq != m or pairs.ng != n:
             raise RuntimeError("distmat shape %s does not match %d query / %d gallery ids" % ((m, n), pairs.nq, pairs.ng))
         E = max(pairs.n_pairs, 1)
@@ -262,8 +345,8 @@ def dist_block(a: SplitOperand, b: SplitOperand, prec: int, out, flags=0, b_row0
         # a row window of every plane: planes are [planes][rows][kpad], the TMA map needs the full
         # plane stride, so windows are expressed by a shifted base and the full row count upstream.
         raise RuntimeError("dist_block: gallery windows are handled by GalleryChunks")
-    _lib.check(lib.pps_dist_tc(_lib.ptr(a.planes), _lib.ptr(a.sqnorm), a.rows, a.planes_n, _lib.ptr(b.planes),
-                               _lib.ptr(b.sqnorm), b.rows, b.planes_n, a.dim, prec, flags, _lib.ptr(out),
+    _lib.check(lib.pps_dist_tc(_lib.ptr(a.planes), _lib.ptr(a.sqnorm), a.rows, a.planes_n, 0, _lib.ptr(b.planes),
+                               _lib.ptr(b.sqnorm), b.rows, b.planes_n, 0, a.dim, prec, flags, _lib.ptr(out),
                                int(out.stride(0)), _lib.stream_ptr()), "pps_dist_tc")
 
 
@@ -402,6 +485,7 @@ class RankEngine:
             self.block = torch.empty((nq_, self.ldd), dtype=torch.float32, device=dev)
             self.cnt_first = torch.zeros(nq_, dtype=torch.int32, device=dev)
             self.key = torch.empty((nq_, self.topk), dtype=torch.int64, device=dev) if self.topk else None
+            self.pairs = DevicePairs(self.qi, self.qc, self.gi, self.gc, dev)
         self._pair_cap = 0
         self.kernel_events = None        # bench.py: list collecting (start, stop) events around the distance GEMM
         self.h2d_bytes = 0
@@ -432,8 +516,8 @@ class RankEngine:
         if self.kernel_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        _lib.check(self.lib.pps_dist_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), self.nq, self.planes,
-                                        _lib.ptr(self.g_planes), _lib.ptr(self.g_sq), rows, self.planes, self.dim,
+        _lib.check(self.lib.pps_dist_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), self.nq, self.planes, 0,
+                                        _lib.ptr(self.g_planes), _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
                                         self.prec, 0, _lib.ptr(self.block), self.ldd, _lib.stream_ptr()), "pps_dist_tc")
         if ev is not None:
             ev[1].record()
@@ -452,19 +536,30 @@ class RankEngine:
             import torch.distributed as dist_mod
         nq = self.nq
         with torch.cuda.device(self.dev):
-            pairs = PairLists(self.qi, self.qc, self.gi, self.gc, device=self.dev)
-            self._pair_buffers(pairs.n_pairs)
-            pair_d, cnt_le, cnt_first, key = self.pair_d, self.cnt_le, self.cnt_first, self.key
+            pairs = self.pairs.begin()          # junk mask / matches from the resident ids, on the device
+            key = self.key
             if self.topk:
                 _lib.check(lib.pps_topk_init(_lib.ptr(key), nq, self.topk, _lib.stream_ptr()), "pps_topk_init")
             self._split(q, nq, self.q_planes, self.q_sq)
             chunks = [(c * self.chunk, min(self.chunk, self.ngl - c * self.chunk)) for c in range(self.n_chunks)]
             # sweep 1: thresholds
+            first_chunk = True
+            pair_d = cnt_le = None
+            cnt_first = self.cnt_first
             for r0, rows in chunks:
                 self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)
                 self._distance(rows)
+                if first_chunk:                 # the pair count came back while the GEMM was queued / running
+                    pairs.finish()
+                    self._pair_buffers(pairs.n_pairs)
+                    pair_d, cnt_le = self.pair_d, self.cnt_le
+                    first_chunk = False
                 _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
                             True, False)
+            if first_chunk:                     # empty gallery shard
+                pairs.finish()
+                self._pair_buffers(pairs.n_pairs)
+                pair_d, cnt_le = self.pair_d, self.cnt_le
             if self.group is not None:
                 dist_mod.all_reduce(pair_d, op=dist_mod.ReduceOp.SUM, group=self.group)
             # sweep 2: counts (+ top-k); a single chunk is still resident in the block
@@ -652,9 +747,30 @@ def reid_results(coco_eval, name="reid"):
 # ------------------------------------------------------------------------------------
 # host-buffer entry point (what bench.py times as e2e)
 # ------------------------------------------------------------------------------------
+_HOST_CTX = {}
+
+
+def _host_ctx(device: int):
+    """One pps_ctx (streams + grow-only device / pinned scratch) per device, created on first use."""
+    ctx = _HOST_CTX.get(device)
+    if ctx is None:
+        lib = _lib.load()
+        handle = C.c_void_p(0)
+        _lib.check(lib.pps_ctx_create(int(device), C.byref(handle)), "pps_ctx_create")
+        ctx = _HOST_CTX[device] = handle
+    return ctx
+
+
+def release_host_contexts():
+    lib = _lib.load()
+    for dev, handle in list(_HOST_CTX.items()):
+        lib.pps_ctx_destroy(handle)
+        del _HOST_CTX[dev]
+
+
 def evaluate_host(q_feats, g_feats, query_ids, gallery_ids, query_cams, gallery_cams, cmc_topk: int = 10,
                   topk: int = 0, precision: str = DEFAULT_PRECISION, device: int = 0):
-    """pps_evaluate_host: HOST float32 arrays (numpy, or pinned torch CPU tensors) in, metrics out.
+    """pps_evaluate_host_ctx: HOST float32 arrays (numpy, or pinned torch CPU tensors) in, metrics out.
 
     Every host<->device copy happens inside the call.  Returns a dict with mAP, cmc, ap, valid,
     first_rank and (if topk) topk_index / topk_dist.
@@ -690,10 +806,10 @@ def evaluate_host(q_feats, g_feats, query_ids, gallery_ids, query_cams, gallery_
     first = np.zeros(nq, dtype=np.int32)
     ti = np.zeros((nq, topk), dtype=np.int32) if topk else None
     td = np.zeros((nq, topk), dtype=np.float32) if topk else None
-    rc = lib.pps_evaluate_host(_lib.ptr(q), nq, _lib.ptr(g), ng, dq, _lib.ptr(qi), _lib.ptr(qc), _lib.ptr(gi),
-                               _lib.ptr(gc), _prec_code(precision), cmc_topk, topk, device,
-                               C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc), _lib.ptr(ap), _lib.ptr(valid),
-                               _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
-    _lib.check(rc, "pps_evaluate_host")
+    rc = lib.pps_evaluate_host_ctx(_host_ctx(device), _lib.ptr(q), nq, _lib.ptr(g), ng, dq, _lib.ptr(qi), _lib.ptr(qc),
+                                   _lib.ptr(gi), _lib.ptr(gc), _prec_code(precision), cmc_topk, topk,
+                                   C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc), _lib.ptr(ap),
+                                   _lib.ptr(valid), _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
+    _lib.check(rc, "pps_evaluate_host_ctx")
     return dict(mAP=float(out_map.value), cmc=out_cmc[:cmc_topk], ap=ap, valid=valid, first_rank=first,
                 topk_index=ti, topk_dist=td)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export: " + n
         assert n in _lib.SIGNATURES, "no ctypes signature for " + n
-    assert lib.pps_abi_version() == 1
+    assert lib.pps_abi_version() == _lib.ABI_VERSION
     assert lib.pps_strerror(_lib.PPS_ERR_NO_VALID_QUERY) == b"No valid query"
     assert lib.pps_kpad(2048) == 2048 and lib.pps_kpad(100) == 128 and lib.pps_kpad(8064) == 8064
     assert lib.pps_split_bytes(10, 100, 2) == 10 * 128 * 2 * 2

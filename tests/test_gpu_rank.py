@@ -228,3 +228,43 @@ def test_market_shape_properties_and_subset_parity():
     ti, td = O.topk_filtered(dist, d["qid"][sub], d["gid"], d["qcam"][sub], d["gcam"], 100)
     np.testing.assert_allclose(one.topk_dist[sub], td, rtol=1e-4)
     assert np.mean(one.topk_index[sub] == ti) > 0.98
+
+
+@pytest.mark.parametrize("nq,ng,n_ids", [(70, 600, 20), (33, 5000, 7), (1, 1, 1), (257, 2049, 300), (5, 70000, 3)])
+def test_device_pair_lists_equal_host_builder(nq, ng, n_ids):
+    """pairs.cu (count / scan / fill on the device) reproduces pps_pairs_fill element for element."""
+    from pps_b200 import evaluator
+    rs = np.random.RandomState(nq + ng)
+    qid, gid = rs.randint(1, n_ids + 1, size=nq), rs.randint(0, n_ids + 1, size=ng)
+    qcam, gcam = rs.randint(0, 3, size=nq), rs.randint(0, 3, size=ng)
+    host = evaluator.PairLists(qid, qcam, gid, gcam)
+    dev = evaluator.DevicePairs(qid, qcam, gid, gcam, "cuda").begin().finish()
+    assert dev.n_pairs == host.n_pairs and dev.max_pairs == host.max_pairs
+    np.testing.assert_array_equal(dev.off, host.off)
+    n = host.n_pairs
+    np.testing.assert_array_equal(dev.q[:n], host.q[:n])
+    np.testing.assert_array_equal(dev.g[:n], host.g[:n])
+    np.testing.assert_array_equal(dev.pos[:n], host.pos[:n])
+    np.testing.assert_array_equal(dev.n_pos_per_q, host.n_pos_per_q)
+    # a second build on the same object (what RankEngine does every step) gives the same lists
+    dev.begin().finish()
+    np.testing.assert_array_equal(dev.g[:n], host.g[:n])
+
+
+def test_device_pair_lists_no_matches():
+    from pps_b200 import evaluator
+    dev = evaluator.DevicePairs(np.array([5, 6]), np.array([0, 1]), np.array([1, 2, 3]), np.array([0, 0, 0]), "cuda")
+    dev.begin().finish()
+    assert dev.n_pairs == 0 and dev.max_pairs == 0 and list(dev.off) == [0, 0, 0]
+
+
+def test_host_context_reuse_gives_identical_results(golden):
+    import pps_b200
+    d = golden("small_mid")
+    a = pps_b200.evaluate_host(d["q"], d["g"], d["qid"], d["gid"], d["qcam"], d["gcam"], cmc_topk=10, topk=5)
+    d2 = golden("many_pos")
+    pps_b200.evaluate_host(d2["q"], d2["g"], d2["qid"], d2["gid"], d2["qcam"], d2["gcam"], cmc_topk=10)
+    b = pps_b200.evaluate_host(d["q"], d["g"], d["qid"], d["gid"], d["qcam"], d["gcam"], cmc_topk=10, topk=5)
+    assert a["mAP"] == b["mAP"]
+    np.testing.assert_array_equal(a["ap"], b["ap"])
+    np.testing.assert_array_equal(a["topk_index"], b["topk_index"])
