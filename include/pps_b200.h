@@ -110,6 +110,8 @@ int pps_split_rows_slab(const void* feats, int dtype, long long row0, long long 
  * a_plane_rows / b_plane_rows: rows between consecutive planes of the buffer (0 = m1 / m2); a row
  * window [r0, r0+m) of a larger [planes][total_rows][kpad] buffer is passed as base + r0*kpad
  * elements, its sqnorm + r0, m rows and plane_rows = total_rows.
+ * Default kernel: cluster of 2 CTAs, tcgen05.mma.cta_group::2, 256 x 256 tiles, every plane tile
+ * loaded once per k-block and reused by all terms.
  * flags: PPS_DIST_SQUARED returns the clamped squared distance (no sqrt);
  *        PPS_DIST_DOT returns a.b only (the reference's 'cosine' branch at :259-263
  *        once rows are L2-normalised).
@@ -122,6 +124,7 @@ int pps_split_rows_slab(const void* feats, int dtype, long long row0, long long 
 
 #define PPS_DIST_SQUARED 1
 #define PPS_DIST_DOT     2
+#define PPS_DIST_KERNEL_1CTA 0x100   /* use the single-CTA 128x256 kernel instead of the 2-CTA 256x256 one */
 
 int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n, long long a_plane_rows,
                 const void* b_planes, const float* b_sqnorm, long long m2, int b_planes_n, long long b_plane_rows,
@@ -175,9 +178,10 @@ int pps_pairs_fill_device(const int64_t* query_ids, const int64_t* query_cams, l
  *         gallery item lies in the block (others untouched; zero pair_d first, then a
  *         sum-allreduce over gallery shards completes it).
  * Step 2  pps_rank_count  : for every positive pair e, cnt_le[e] += #{columns j of the
- *         block : dist[q,j] <= pair_d[e]}; cnt_first[q] += #{j : (dist[q,j], j) <
- *         (d*, g*)} with (d*, g*) the query's nearest positive (ties by gallery index,
- *         i.e. the order a stable argsort gives).  No id/camera arrays are read: junk
+ *         block : dist[q,j] <= pair_d[e]}; cnt_first[q] += #{j : d == d*, j < g*} - #{j : d == d*}
+ *         (a signed correction stored mod 2^32) with (d*, g*) the query's nearest positive, ties
+ *         by gallery index, i.e. the order a stable argsort gives; step 3 adds cnt_le of that
+ *         positive to get #{j : (dist[q,j], j) < (d*, g*)}.  No id/camera arrays are read: junk
  *         and positives are subtracted in step 3 from their own pair distances.
  *         Counters are exact integers, so summing them over gallery shards / chunks
  *         gives the unsharded result bit for bit.

@@ -38,6 +38,7 @@ PREC_FP32 = 32
 
 DIST_SQUARED = 1
 DIST_DOT = 2
+DIST_KERNEL_1CTA = 0x100
 
 TOPK_MAX = 128
 

@@ -197,6 +197,202 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------
+// 2-CTA kernel (default): a cluster of two CTAs (one SM pair) owns a 256 x 256 output tile and
+// issues tcgen05.mma.cta_group::2 (M = 256: 128 rows per CTA, N = 256).  Per 64-wide k-block each
+// CTA loads ONLY its 128 rows of every A plane and its 128-row half of every B plane, and all
+// plane-pair terms of the split product reuse those tiles: for bf16x3 that is 4 x 16 KB per CTA
+// for 12 MMAs (5.3 KB of L2->SM traffic per 128-cycle MMA slot and SM, against 12 KB for the
+// 1-CTA kernel above, which sits at the chip's TMA/L2 delivery limit rather than at the tensor
+// pipe).  Barriers: full[] lives in the leader (rank 0) and collects both CTAs' TMA bytes;
+// empty[] / tfull[] exist in both CTAs and are signalled by multicast tcgen05.commit; tempty[]
+// lives in the leader and takes the arrivals of both CTAs' epilogue warps.
+// ------------------------------------------------------------------------------------
+constexpr int kT2Rows = 128;
+constexpr int kTile2Bytes = kT2Rows * kBK * 2;      // 16 KB: one plane of one operand for one k-block
+constexpr int kRing2Bytes = 192 * 1024;
+constexpr int kMaxStages2 = 6;
+constexpr int kOutChunkBytes = 32 * 32 * 4;                 // one warp's 32 x 32 fp32 staging tile
+constexpr int kOutStageBytes = 4 * 2 * kOutChunkBytes;      // 4 epilogue warps, double-buffered
+constexpr size_t kGemm2Smem = (size_t)kRing2Bytes + kOutStageBytes + 2 * kBN * 4 /*|b|^2*/ + 256 /*barriers*/;
+
+struct Gemm2Args {
+  GemmArgs g;
+  int planes;       // planes of each operand loaded per k-block (1..3)
+  int stages;       // ring depth = kRing2Bytes / (2 * planes * 16 KB)
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Gemm2Args ga) {
+  extern __shared__ __align__(1024) unsigned char smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  unsigned char* stage_out = smem + kRing2Bytes;                                   // [4 warps][2][4 KB]
+  float* bn_s = reinterpret_cast<float*>(stage_out + kOutStageBytes);             // [2][256]
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(bn_s) + 2 * kBN * 4);
+  uint64_t* empty = full + kMaxStages2;
+  uint64_t* tfull = empty + kMaxStages2;      // [2]
+  uint64_t* tempty = tfull + 2;               // [2] (used in the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const GemmArgs& g = ga.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const long long tiles = (long long)g.m_tiles * g.n_tiles;      // 256 x 256 tiles
+  const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int planes = ga.planes, stages = ga.stages;
+  const uint32_t stage_bytes = 2u * (uint32_t)planes * kTile2Bytes;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < kMaxStages2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 8);   // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, 2 * kBN);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long t = pair; t < tiles; t += npairs) {
+        const int m0 = (int)(t % g.m_tiles) * 256 + (int)rank * kT2Rows;
+        const int n0 = (int)(t / g.m_tiles) * 256 + (int)rank * kT2Rows;
+        for (int kb = 0; kb < g.kblocks; ++kb, ++it) {
+          const uint32_t s = it % stages, ph = (it / stages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          if (rank == 0) mbar_expect_tx(&full[s], 2u * stage_bytes);
+          const uint32_t full0 = map_to_cta(smem_u32(&full[s]), 0);
+          unsigned char* slot = smem + (size_t)s * stage_bytes;
+          for (int p = 0; p < planes; ++p) tma_load_3d_2cta(slot + p * kTile2Bytes, &tmA, full0, kb * kBK, m0, p);
+          for (int p = 0; p < planes; ++p)
+            tma_load_3d_2cta(slot + (planes + p) * kTile2Bytes, &tmB, full0, kb * kBK, n0, p);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (rank == 0 && lane == 0) {
+      uint32_t it = 0, acc_it = 0;
+      for (long long t = pair; t < tiles; t += npairs, ++acc_it) {
+        const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        mbar_wait(&tempty[as], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kBN;
+        for (int kb = 0; kb < g.kblocks; ++kb, ++it) {
+          const uint32_t s = it % stages, ph = (it / stages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t slot = smem_u32(smem + (size_t)s * stage_bytes);
+          for (int term = 0; term < g.nterms; ++term) {
+            const uint64_t adesc = umma_desc_k_sw128(slot + g.term_a[term] * kTile2Bytes);
+            const uint64_t bdesc = umma_desc_k_sw128(slot + (planes + g.term_b[term]) * kTile2Bytes);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              tc_mma_f16_2cta(d_tmem, adesc + 2u * k, bdesc + 2u * k, g.idesc, (kb | term | k) ? 1u : 0u);
+          }
+          tc_commit_2cta(&empty[s], 3);          // both CTAs' slots reusable once these MMAs retire
+        }
+        tc_commit_2cta(&tfull[as], 3);           // accumulator complete in both CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs) =====================
+    // TMEM -> registers (thread = row) -> |a|^2 + |b|^2 - 2ab, clamp, sqrt -> 128B-swizzled staging tile in
+    // shared memory -> one TMA store per 32 x 32 chunk (coalesced, clipped at the matrix edges by the tensor map).
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;
+    const int etid = (int)threadIdx.x - 64;     // 0..127 among the epilogue threads
+    uint32_t acc_it = 0, chunk_it = 0;
+    const bool want_sq = (g.flags & PPS_DIST_SQUARED) != 0;
+    const bool want_dot = (g.flags & PPS_DIST_DOT) != 0;
+    unsigned char* my_stage = stage_out + (size_t)lane_grp * (2 * kOutChunkBytes);
+    const uint32_t swz = (uint32_t)(lane & 7);
+    for (long long t = pair; t < tiles; t += npairs, ++acc_it) {
+      const int m0 = (int)(t % g.m_tiles) * 256 + (int)rank * kT2Rows;
+      const int n0 = (int)(t / g.m_tiles) * 256;
+      const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+      // |b|^2 of the tile's 256 gallery rows -> shared (double-buffered by accumulator stage)
+      float* bn = bn_s + as * kBN;
+      if (!want_dot) {
+        const long long gj = (long long)n0 + etid;
+        bn[etid] = gj < g.m2 ? __ldg(g.b_sqnorm + gj) : 0.f;
+        bn[etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_sqnorm + gj + 128) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const long long gi = (long long)m0 + row;
+      const float an = (gi < g.m1 && !want_dot) ? __ldg(g.a_sqnorm + gi) : 0.f;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + as * kBN + ((uint32_t)(lane_grp * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < kBN; c += 32, ++chunk_it) {
+        uint32_t r[32];
+        tmem_ld_32x32(tbase + c, r);
+        unsigned char* buf = my_stage + (chunk_it & 1u) * kOutChunkBytes;
+        bulk_wait_group_read<1>();               // the store that last read this buffer has drained it
+        __syncwarp();
+        tmem_ld_wait();
+        const float4* bn4 = reinterpret_cast<const float4*>(bn + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[4];
+          const float4 b4 = bn4[j];
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float dot = __uint_as_float(r[4 * j + e]);
+            if (want_dot) {
+              v[e] = dot;
+            } else {
+              // same association as the reference: (-2*ab + |a|^2) + |b|^2   (-2*ab is exact, so the FMA rounds once)
+              float d2 = __fadd_rn(__fmaf_rn(-2.f, dot, an), bb[e]);
+              d2 = fmaxf(d2, 0.f);
+              v[e] = want_sq ? d2 : sqrt_approx(d2);
+            }
+          }
+          *reinterpret_cast<float4*>(buf + lane * 128 + (((uint32_t)j ^ swz) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (m0 + lane_grp * 32 < g.m1 && n0 + c < g.m2) tma_store_2d(&tmO, buf, n0 + c, m0 + lane_grp * 32);
+          bulk_commit_group();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty[as]);
+        else mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[as]), 0));
+      }
+    }
+    bulk_wait_group_read<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();      // no CTA of the pair leaves (or frees TMEM) while its peer still signals it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 2 * kBN);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // CUDA-core fp32 distance (PPS_PREC_FP32): exact-product FMA path on the original rows.
 // 64x64 tile per CTA, 16x16 threads, 4x4 outputs per thread, K tile 16.
 // ------------------------------------------------------------------------------------
@@ -336,23 +532,64 @@ extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long lon
   g.m_tiles = (int)((m1 + kBM - 1) / kBM);
   g.n_tiles = (int)((m2 + kBN - 1) / kBN);
 
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0;
+  PPS_CUDA_TRY(cudaGetDevice(&dev));
+  const int sms = sm_count();
   CUtensorMap tmA, tmB;
+
+  const bool out_tma_ok = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dist) & 15u) == 0);
+  if (!(flags & PPS_DIST_KERNEL_1CTA) && sms >= 2 && out_tma_ok) {
+    // ---- 2-CTA kernel: 256 x 256 tiles, 128-row boxes for both operands ----
+    Gemm2Args ga;
+    ga.g = g;
+    ga.g.m_tiles = (int)((m1 + 255) / 256);
+    ga.g.n_tiles = (int)((m2 + 255) / 256);
+    ga.g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    ga.planes = need;
+    ga.stages = kRing2Bytes / (2 * need * kTile2Bytes);
+    if (ga.stages > kMaxStages2) ga.stages = kMaxStages2;
+    int rc = make_operand_map(&tmA, a_planes, m1, a_plane_rows, kpad, a_planes_n, kT2Rows, f16);
+    if (rc) return rc;
+    rc = make_operand_map(&tmB, b_planes, m2, b_plane_rows, kpad, b_planes_n, kT2Rows, f16);
+    if (rc) return rc;
+    CUtensorMap tmO;
+    {
+      EncodeTiledFn fn = encode_fn();
+      if (!fn) return cuda_fail(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point not found");
+      cuuint64_t dims[2] = {(cuuint64_t)m2, (cuuint64_t)m1};
+      cuuint64_t strides[1] = {(cuuint64_t)ldd * 4};
+      cuuint32_t box[2] = {32, 32};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = fn(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dist, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(output) failed");
+    }
+    static thread_local int configured2_dev = -1;
+    if (configured2_dev != dev) {
+      PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemm2Smem));
+      configured2_dev = dev;
+    }
+    const long long tiles2 = (long long)ga.g.m_tiles * ga.g.n_tiles;
+    const long long pairs = tiles2 < sms / 2 ? tiles2 : sms / 2;
+    dist_tc2_kernel<<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga);
+    PPS_LAUNCH_CHECK("dist_tc2_kernel");
+    return PPS_OK;
+  }
+
   int rc = make_operand_map(&tmA, a_planes, m1, a_plane_rows, kpad, a_planes_n, kBM, f16);
   if (rc) return rc;
   rc = make_operand_map(&tmB, b_planes, m2, b_plane_rows, kpad, b_planes_n, kBN, f16);
   if (rc) return rc;
-
   static thread_local int configured_dev = -1;
-  int dev = 0;
-  PPS_CUDA_TRY(cudaGetDevice(&dev));
   if (configured_dev != dev) {
     PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     configured_dev = dev;
   }
   const long long tiles = (long long)g.m_tiles * g.n_tiles;
-  const int sms = sm_count();
   const int grid = (int)(tiles < sms ? tiles : sms);
-  dist_tc_kernel<<<grid, kGemmThreads, kGemmSmem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, g);
+  dist_tc_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, g);
   PPS_LAUNCH_CHECK("dist_tc_kernel");
   return PPS_OK;
 }

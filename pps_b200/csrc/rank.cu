@@ -21,7 +21,8 @@ namespace pps {
 
 constexpr int kCntThreads = 128;
 constexpr int kCntWarps = kCntThreads / 32;
-constexpr int kWin = 63;            // thresholds per pass (slot 63 is a +inf sentinel)
+constexpr int kWin = 31;            // thresholds per pass (slot 31 is a +inf sentinel -> 5-step search)
+constexpr int kBuckets = 32;
 
 // ------------------------------------------------------------------------------------
 // step 1: gather the pair distances out of the block
@@ -39,10 +40,16 @@ __global__ void rank_gather_kernel(const float* __restrict__ dist, long long ldd
 
 // ------------------------------------------------------------------------------------
 // step 2: counts.  grid = (nq, splits); CTA (q, s) sweeps columns [s*seg, (s+1)*seg).
-// dynamic smem: thr[maxp] (sorted positive distances), tpair[maxp] (pair index of each),
-//               hist[kCntWarps][64][32]
+// dynamic smem: thr[maxp] (sorted positive distances), tpair[maxp] (pair index of each)
+// static smem : win_rep[32][32]  the window's thresholds replicated once per bank, so the
+//                                data-dependent reads of the binary search never conflict;
+//               hist[warps][32][32] lane-private bucket counters (bank = lane).
+// Per element: range check, 5-step search (the two top levels from registers), one counter
+// increment.  The first-match counter is not touched per element: with (d*, g*) the nearest
+// positive, first = cnt_le(d*) - #{d == d*} + #{d == d*, col < g*}; only exact ties with d*
+// (rare) do extra work, and cnt_first accumulates the signed correction (mod 2^32).
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCntThreads) rank_count_kernel(const float* __restrict__ dist, long long ldd,
+__global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float* __restrict__ dist, long long ldd,
                                                                   long long ncols, long long col0, long long seg,
                                                                   const int32_t* __restrict__ pair_off,
                                                                   const int32_t* __restrict__ pair_g,
@@ -53,9 +60,9 @@ __global__ void __launch_bounds__(kCntThreads) rank_count_kernel(const float* __
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* thr = reinterpret_cast<float*>(smem_raw);                          // [maxp]
   int32_t* tpair = reinterpret_cast<int32_t*>(thr + maxp);                  // [maxp]
-  uint32_t* hist = reinterpret_cast<uint32_t*>(tpair + maxp);               // [warps][64][32]
-  __shared__ float win[64];
-  __shared__ uint32_t wsum[64];
+  __shared__ float win_rep[kBuckets * 32];
+  __shared__ uint32_t hist[kCntWarps * kBuckets * 32];
+  __shared__ uint32_t wsum[kBuckets];
   __shared__ int s_np;
   __shared__ uint32_t s_first_cnt;
 
@@ -84,34 +91,42 @@ __global__ void __launch_bounds__(kCntThreads) rank_count_kernel(const float* __
   const int np = s_np;
   if (np == 0) return;                                     // query without a valid match: nothing to count
   const float dstar = thr[0];
-  const int gstar = pair_g[tpair[0]];
+  const long long gstar = pair_g[tpair[0]];
 
   const long long c_begin = (long long)blockIdx.y * seg;
   const long long c_end = min(ncols, c_begin + seg);
   if (c_begin >= c_end) return;
   const float* drow = dist + (long long)q * ldd;
   const bool vec = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dist) & 15u) == 0) && ((c_begin & 3) == 0);
-  uint32_t* myhist = hist + warp * (64 * 32) + lane;       // column `lane` of this warp's table
-  uint32_t first_local = 0;
-  uint32_t carry = 0;                                      // elements counted in earlier windows
+  uint32_t* myhist = hist + warp * (kBuckets * 32) + lane;  // column `lane` of this warp's table
+  const float* wr = win_rep + lane;                         // this lane's private copy of the window
+  uint32_t tie_corr = 0;                                    // signed: -#{d == d*} + #{d == d*, col < g*}
+  uint32_t carry = 0;                                       // elements counted in earlier windows
 
   for (int w0 = 0; w0 < np; w0 += kWin) {
     const int wn = min(kWin, np - w0);
     __syncthreads();                                       // previous window fully consumed
-    if (tid < 64) win[tid] = tid < wn ? thr[w0 + tid] : FLT_MAX;
-    for (int i = tid; i < kCntWarps * 64 * 32; i += kCntThreads) hist[i] = 0;
+    for (int i = tid; i < kBuckets * 32; i += kCntThreads) {
+      const int slot = i >> 5;
+      win_rep[i] = slot < wn ? thr[w0 + slot] : FLT_MAX;
+    }
+    for (int i = tid; i < kCntWarps * kBuckets * 32; i += kCntThreads) hist[i] = 0;
     __syncthreads();
     const float lo = w0 ? thr[w0 - 1] : -FLT_MAX;          // elements <= lo belong to earlier windows
-    const float hi = win[wn - 1];
+    const float hi = wr[(wn - 1) * 32];
+    const float t15 = wr[15 * 32], t7 = wr[7 * 32], t23 = wr[23 * 32];
     const bool do_first = (w0 == 0);
 
     auto visit = [&](float d, long long col) {
-      if (do_first) first_local += (d < dstar) || (d == dstar && (col0 + col) < (long long)gstar);
-      if (d <= hi && (w0 == 0 || d > lo)) {
-        int b = 0;                                          // b = #{window thresholds < d}
-#pragma unroll
-        for (int s = 32; s > 0; s >>= 1) b += (win[b + s - 1] < d) ? s : 0;
+      if (d <= hi && d > lo) {
+        const bool g1 = t15 < d;
+        int b = g1 ? 16 : 0;
+        b += ((g1 ? t23 : t7) < d) ? 8 : 0;
+        b += (wr[(b + 3) * 32] < d) ? 4 : 0;
+        b += (wr[(b + 1) * 32] < d) ? 2 : 0;
+        b += (wr[b * 32] < d) ? 1 : 0;
         myhist[b * 32] += 1;
+        if (do_first && d == dstar) tie_corr += ((col0 + col) < gstar ? 1u : 0u) - 1u;
       }
     };
 
@@ -126,15 +141,15 @@ __global__ void __launch_bounds__(kCntThreads) rank_count_kernel(const float* __
       for (long long c = c_begin + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
     }
     __syncthreads();
-    // reduce the lane-private columns: thread t < 64 owns bucket t
-    if (tid < 64) {
-      uint32_t s = 0;
+    // reduce the lane-private columns: thread t < 32 owns bucket t
+    if (tid < kBuckets) {
+      uint32_t sum = 0;
       for (int w = 0; w < kCntWarps; ++w) {
-        const uint32_t* hb = hist + w * (64 * 32) + tid * 32;
+        const uint32_t* hb = hist + w * (kBuckets * 32) + tid * 32;
 #pragma unroll
-        for (int l = 0; l < 32; ++l) s += hb[(l + tid) & 31];
+        for (int l = 0; l < 32; ++l) sum += hb[(l + tid) & 31];
       }
-      wsum[tid] = s;
+      wsum[tid] = sum;
     }
     __syncthreads();
     if (tid == 0) {
@@ -148,10 +163,10 @@ __global__ void __launch_bounds__(kCntThreads) rank_count_kernel(const float* __
     __syncthreads();
     carry = wsum[0];
   }
-  // first-match counter
+  // first-match correction
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) first_local += __shfl_xor_sync(0xffffffffu, first_local, o);
-  if (lane == 0 && first_local) atomicAdd(&s_first_cnt, first_local);
+  for (int o = 16; o > 0; o >>= 1) tie_corr += __shfl_xor_sync(0xffffffffu, tie_corr, o);
+  if (lane == 0 && tie_corr) atomicAdd(&s_first_cnt, tie_corr);
   __syncthreads();
   if (tid == 0 && s_first_cnt) atomicAdd(&cnt_first[q], s_first_cnt);
 }
@@ -176,6 +191,7 @@ __global__ void __launch_bounds__(128) rank_finalize_kernel(long long nq, const 
   int np = 0;
   float dstar = FLT_MAX;
   int gstar = 0x7fffffff;
+  uint32_t le_star = 0;        // cnt_le of the nearest positive (ties by gallery index)
   for (int e = e0 + lane; e < e1; e += 32) {
     if (!pair_pos[e]) continue;
     const float d = pair_d[e];
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(128) rank_finalize_kernel(long long nq, const 
     acc += (double)c_pos / (double)n_valid;
     if (neg_before) neg_before[e] = n_valid - c_pos;
     ++np;
-    if (d < dstar || (d == dstar && g < gstar)) { dstar = d; gstar = g; }
+    if (d < dstar || (d == dstar && g < gstar)) { dstar = d; gstar = g; le_star = cnt_le[e]; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -197,7 +213,8 @@ __global__ void __launch_bounds__(128) rank_finalize_kernel(long long nq, const 
     np += __shfl_xor_sync(0xffffffffu, np, o);
     const float od = __shfl_xor_sync(0xffffffffu, dstar, o);
     const int og = __shfl_xor_sync(0xffffffffu, gstar, o);
-    if (od < dstar || (od == dstar && og < gstar)) { dstar = od; gstar = og; }
+    const uint32_t ol = __shfl_xor_sync(0xffffffffu, le_star, o);
+    if (od < dstar || (od == dstar && og < gstar)) { dstar = od; gstar = og; le_star = ol; }
   }
   // junk items ranked before the nearest positive
   int jb = 0;
@@ -213,7 +230,8 @@ __global__ void __launch_bounds__(128) rank_finalize_kernel(long long nq, const 
   if (lane == 0) {
     ap[q] = np > 0 ? acc / (double)np : 0.0;
     is_valid[q] = np > 0 ? 1 : 0;
-    first_rank[q] = np > 0 ? (int32_t)cnt_first[q] - jb : -1;
+    // #{(d, g) < (d*, g*)} = #{d <= d*} - #{d == d*} + #{d == d*, g < g*}; cnt_first holds the last two (mod 2^32)
+    first_rank[q] = np > 0 ? (int32_t)(le_star + cnt_first[q]) - jb : -1;
   }
 }
 
@@ -336,8 +354,8 @@ extern "C" int pps_rank_count(const float* dist, long long ldd, long long nq, lo
   if (!pair_g || !pair_pos || !pair_d || !cnt_le) return PPS_ERR_INVALID_ARG;
   if (nq > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
   const int maxp = (max_pairs_per_query + 3) & ~3;
-  const size_t smem = (size_t)maxp * 8 + (size_t)kCntWarps * 64 * 32 * 4;
-  if (smem > 200 * 1024) return PPS_ERR_UNSUPPORTED;          // > ~21k same-id items for one query
+  const size_t smem = (size_t)maxp * 8;
+  if (smem > 160 * 1024) return PPS_ERR_UNSUPPORTED;          // > ~20k same-id items for one query
   // column splits: enough CTAs to fill the GPU when there are few queries
   const int sms = sm_count();
   long long splits = 1;
@@ -350,7 +368,7 @@ extern "C" int pps_rank_count(const float* dist, long long ldd, long long nq, lo
   int dev = 0;
   PPS_CUDA_TRY(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    PPS_CUDA_TRY(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PPS_CUDA_TRY(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured_dev = dev;
   }
   rank_count_kernel<<<dim3((unsigned)nq, (unsigned)splits), kCntThreads, smem, static_cast<cudaStream_t>(stream)>>>(

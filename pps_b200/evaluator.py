@@ -25,6 +25,9 @@ import numpy as np
 from . import _lib
 
 DEFAULT_PRECISION = "bf16x3"
+# extra PPS_DIST_* flags OR-ed into every tensor-core distance call (tests / profiling use
+# _lib.DIST_KERNEL_1CTA to select the single-CTA kernel; 0 = the 2-CTA default)
+DIST_KERNEL_FLAGS = _lib.DIST_KERNEL_1CTA if os.environ.get("PPS_DIST_KERNEL", "") == "1cta" else 0
 
 
 # ------------------------------------------------------------------------------------
@@ -346,7 +349,8 @@ def dist_block(a: SplitOperand, b: SplitOperand, prec: int, out, flags=0, b_row0
         # plane stride, so windows are expressed by a shifted base and the full row count upstream.
         raise RuntimeError("dist_block: gallery windows are handled by GalleryChunks")
     _lib.check(lib.pps_dist_tc(_lib.ptr(a.planes), _lib.ptr(a.sqnorm), a.rows, a.planes_n, 0, _lib.ptr(b.planes),
-                               _lib.ptr(b.sqnorm), b.rows, b.planes_n, 0, a.dim, prec, flags, _lib.ptr(out),
+                               _lib.ptr(b.sqnorm), b.rows, b.planes_n, 0, a.dim, prec, flags | DIST_KERNEL_FLAGS,
+                               _lib.ptr(out),
                                int(out.stride(0)), _lib.stream_ptr()), "pps_dist_tc")
 
 
@@ -518,7 +522,8 @@ class RankEngine:
             ev[0].record()
         _lib.check(self.lib.pps_dist_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), self.nq, self.planes, 0,
                                         _lib.ptr(self.g_planes), _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
-                                        self.prec, 0, _lib.ptr(self.block), self.ldd, _lib.stream_ptr()), "pps_dist_tc")
+                                        self.prec, DIST_KERNEL_FLAGS, _lib.ptr(self.block), self.ldd,
+                                        _lib.stream_ptr()), "pps_dist_tc")
         if ev is not None:
             ev[1].record()
             self.kernel_events.append(ev)
