@@ -164,10 +164,13 @@ int pps_pairs_fill(const int64_t* query_ids, const int64_t* query_cams, long lon
  * The result is identical to pps_pairs_fill on every rank of a sharded run. */
 long long pps_pairs_workspace_bytes(long long nq, long long ng);
 int pps_pairs_count_device(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
-                           void* workspace, int32_t* pair_off, int32_t* totals, void* stream);
+                           void* workspace, int32_t* pair_off, int32_t* totals,
+                           uint32_t* zero_per_query /* optional [nq]: set to 0 (cnt_first) */, void* stream);
 int pps_pairs_fill_device(const int64_t* query_ids, const int64_t* query_cams, long long nq,
                           const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
-                          const void* workspace, int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos,
+                          const void* workspace, const int32_t* pair_off,
+                          int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos,
+                          float* zero_f32 /* optional [capacity]: pair_d */, uint32_t* zero_u32 /* optional: cnt_le */,
                           long long capacity, void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -253,6 +256,25 @@ int pps_evaluate_host_ctx(pps_ctx* ctx, const float* q_feats, long long nq,
                           double* out_map, double* out_cmc,
                           double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,
                           int32_t* out_topk_index, float* out_topk_dist);
+/* the same evaluation with features (fp32, contiguous [rows, dim]) and int64 ids / cameras already
+ * RESIDENT on the device; everything is enqueued on `stream`, the call returns once the small
+ * results are on the host (what bench.py times as `value`). */
+int pps_evaluate_device_ctx(pps_ctx* ctx, const float* d_q, long long nq,
+                            const float* d_g, long long ng, int dim,
+                            const int64_t* d_query_ids, const int64_t* d_query_cams,
+                            const int64_t* d_gallery_ids, const int64_t* d_gallery_cams,
+                            int precision, int cmc_topk, int topk, void* stream,
+                            double* out_map, double* out_cmc,
+                            double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,
+                            int32_t* out_topk_index, float* out_topk_dist);
+/* Phase timing of pps_evaluate_device_ctx: when enabled, CUDA events are recorded on the caller's
+ * stream between the phases and pps_ctx_phase_ms returns the device time of each phase of the
+ * LAST call: 0 hand-off of the pair-list kernels to the side stream (they overlap the GEMM),
+ * 1 operand split, 2 distance GEMM, 3 wait for the pair lists + threshold gather,
+ * 4 counting sweep, 5 finalize (+top-k), 6 result copies. */
+#define PPS_N_PHASES 7
+int pps_ctx_set_timing(pps_ctx* ctx, int enabled);
+int pps_ctx_phase_ms(const pps_ctx* ctx, float* out_ms /* [PPS_N_PHASES] */);
 int pps_evaluate_host(const float* q_feats, long long nq,
                       const float* g_feats, long long ng, int dim,
                       const int64_t* query_ids, const int64_t* query_cams,

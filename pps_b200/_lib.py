@@ -41,6 +41,8 @@ DIST_DOT = 2
 DIST_KERNEL_1CTA = 0x100
 
 TOPK_MAX = 128
+N_PHASES = 7
+PHASE_NAMES = ["pairs_enqueue", "split", "dist_gemm", "pairs_wait_gather", "rank_count", "finalize", "d2h"]
 
 PRECISIONS = {"bf16x1": PREC_BF16X1, "bf16x3": PREC_BF16X3, "bf16x6": PREC_BF16X6,
               "fp16": PREC_F16X1, "fp32": PREC_FP32}
@@ -64,8 +66,8 @@ SIGNATURES = {
     "pps_pairs_count": (_ll, [_vp, _ll, _vp, _ll]),
     "pps_pairs_fill": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp]),
     "pps_pairs_workspace_bytes": (_ll, [_ll, _ll]),
-    "pps_pairs_count_device": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp]),
-    "pps_pairs_fill_device": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "pps_pairs_count_device": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _vp]),
+    "pps_pairs_fill_device": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "pps_rank_gather": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _ll, _vp, _vp]),
     "pps_rank_count": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "pps_rank_finalize": (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -76,6 +78,10 @@ SIGNATURES = {
     "pps_ctx_destroy": (_i, [_vp]),
     "pps_evaluate_host_ctx": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _i, _i,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_evaluate_device_ctx": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp,
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_ctx_set_timing": (_i, [_vp, _i]),
+    "pps_ctx_phase_ms": (_i, [_vp, _vp]),
     "pps_evaluate_host": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_kernel_launch_count": (C.c_ulonglong, []),

@@ -160,13 +160,23 @@ constexpr int kMaxSlabs = 64;
 
 struct pps_ctx {
   int device = 0;
-  cudaStream_t copy_s = nullptr, comp_s = nullptr;
+  cudaStream_t copy_s = nullptr, comp_s = nullptr, side_s = nullptr;
   cudaEvent_t ev_slab[kMaxSlabs] = {};
-  cudaEvent_t ev_totals = nullptr;
+  cudaEvent_t ev_totals = nullptr, ev_in = nullptr, ev_pairs = nullptr;
   GrowBuf qf, gf, qs, gs, qn, gn, dist, ids, pair_ws, pair_off, totals, pair_q, pair_g, pair_pos, pair_d, cnt_le,
       cnt_first, ap, valid, first, topk, tki, tkd;
   PinBuf h_small;      // totals + per-query results
+  // optional phase timing of pps_evaluate_device_ctx (events on the caller's stream)
+  bool timing = false;
+  cudaEvent_t ev_phase[PPS_N_PHASES + 1] = {};
+  float phase_ms[PPS_N_PHASES] = {};
 };
+
+namespace {
+inline void mark(pps_ctx* c, int i, cudaStream_t s) {
+  if (c->timing && c->ev_phase[i]) cudaEventRecord(c->ev_phase[i], s);
+}
+}  // namespace
 
 extern "C" int pps_ctx_create(int device, pps_ctx** out) {
   if (!out) return PPS_ERR_INVALID_ARG;
@@ -177,8 +187,12 @@ extern "C" int pps_ctx_create(int device, pps_ctx** out) {
   c->device = device;
   cudaError_t e = cudaStreamCreateWithFlags(&c->copy_s, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->comp_s, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side_s, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pairs, cudaEventDisableTiming);
   for (int i = 0; i < kMaxSlabs && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_slab[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_totals, cudaEventDisableTiming);
+  for (int i = 0; i <= PPS_N_PHASES && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev_phase[i]);
   if (e != cudaSuccess) {
     pps_ctx_destroy(c);
     return cuda_fail(e, "pps_ctx_create");
@@ -192,6 +206,7 @@ extern "C" int pps_ctx_destroy(pps_ctx* c) {
   cudaSetDevice(c->device);
   if (c->comp_s) cudaStreamSynchronize(c->comp_s);
   if (c->copy_s) cudaStreamSynchronize(c->copy_s);
+  if (c->side_s) cudaStreamSynchronize(c->side_s);
   GrowBuf* bufs[] = {&c->qf, &c->gf, &c->qs, &c->gs, &c->qn, &c->gn, &c->dist, &c->ids, &c->pair_ws, &c->pair_off,
                      &c->totals, &c->pair_q, &c->pair_g, &c->pair_pos, &c->pair_d, &c->cnt_le, &c->cnt_first, &c->ap,
                      &c->valid, &c->first, &c->topk, &c->tki, &c->tkd};
@@ -199,11 +214,162 @@ extern "C" int pps_ctx_destroy(pps_ctx* c) {
   c->h_small.release();
   for (int i = 0; i < kMaxSlabs; ++i) if (c->ev_slab[i]) cudaEventDestroy(c->ev_slab[i]);
   if (c->ev_totals) cudaEventDestroy(c->ev_totals);
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  if (c->ev_pairs) cudaEventDestroy(c->ev_pairs);
+  if (c->side_s) cudaStreamDestroy(c->side_s);
+  for (int i = 0; i <= PPS_N_PHASES; ++i) if (c->ev_phase[i]) cudaEventDestroy(c->ev_phase[i]);
   if (c->copy_s) cudaStreamDestroy(c->copy_s);
   if (c->comp_s) cudaStreamDestroy(c->comp_s);
   delete c;
   return PPS_OK;
 }
+
+namespace {
+
+struct EvalShape {
+  long long nq, ng, ldd;
+  int dim, kpad, planes, precision, cmc_topk, topk;
+};
+
+int eval_shape(long long nq, long long ng, int dim, int precision, int cmc_topk, int topk, EvalShape* e) {
+  if (nq <= 0 || ng <= 0 || dim <= 0 || cmc_topk < 0 || topk < 0 || topk > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
+  if (nq > 0x7fffffffLL || ng > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  switch (precision) {
+    case PPS_PREC_BF16X1: e->planes = 1; break;
+    case PPS_PREC_BF16X3: e->planes = 2; break;
+    case PPS_PREC_BF16X6: e->planes = 3; break;
+    default: return PPS_ERR_INVALID_ARG;
+  }
+  e->nq = nq; e->ng = ng; e->dim = dim; e->precision = precision; e->cmc_topk = cmc_topk; e->topk = topk;
+  e->ldd = (ng + 3) & ~3LL;
+  e->kpad = pps_kpad(dim);
+  // the distance matrix is materialised once: bound it (larger galleries go through the chunked
+  // two-sweep path of the Python layer, evaluator.RankEngine)
+  if ((double)nq * (double)e->ldd * 4.0 > 64.0 * (double)(1LL << 30)) return PPS_ERR_UNSUPPORTED;
+  return PPS_OK;
+}
+
+// pinned staging layout: [0,16) totals | ap[nq] f64 | first[nq] i32 | valid[nq] u8
+struct Staging {
+  int32_t* totals; double* ap; int32_t* first; uint8_t* valid;
+};
+
+int ensure_common(pps_ctx* c, const EvalShape& e, Staging* st) {
+  PPS_TRY(c->qs.ensure((size_t)pps_split_bytes(e.nq, e.dim, e.planes)));
+  PPS_TRY(c->gs.ensure((size_t)pps_split_bytes(e.ng, e.dim, e.planes)));
+  PPS_TRY(c->qn.ensure((size_t)e.nq * 4));
+  PPS_TRY(c->gn.ensure((size_t)e.ng * 4));
+  PPS_TRY(c->dist.ensure((size_t)e.nq * e.ldd * 4));
+  PPS_TRY(c->pair_ws.ensure((size_t)pps_pairs_workspace_bytes(e.nq, e.ng)));
+  PPS_TRY(c->pair_off.ensure(((size_t)e.nq + 1) * 4));
+  PPS_TRY(c->totals.ensure(16));
+  PPS_TRY(c->cnt_first.ensure((size_t)e.nq * 4));
+  PPS_TRY(c->ap.ensure((size_t)e.nq * 8));
+  PPS_TRY(c->valid.ensure((size_t)e.nq));
+  PPS_TRY(c->first.ensure((size_t)e.nq * 4));
+  const size_t off_ap = 16, off_first = off_ap + (size_t)e.nq * 8, off_valid = off_first + (size_t)e.nq * 4;
+  PPS_TRY(c->h_small.ensure(off_valid + (size_t)e.nq));
+  unsigned char* base = c->h_small.as<unsigned char>();
+  st->totals = reinterpret_cast<int32_t*>(base);
+  st->ap = reinterpret_cast<double*>(base + off_ap);
+  st->first = reinterpret_cast<int32_t*>(base + off_first);
+  st->valid = base + off_valid;
+  return PPS_OK;
+}
+
+// ids (device) -> pair counts + offsets, {n_pairs, max_pairs} on their way back to the host.  Runs on the ctx's
+// SIDE stream (ordered after `ready_on`, the stream the ids become valid on): the pair kernels are independent of
+// the distance GEMM and hide under it.
+int begin_pairs(pps_ctx* c, const EvalShape& e, const int64_t* d_qid, const int64_t* d_gid, const Staging& st,
+                cudaStream_t ready_on) {
+  cudaStream_t ss = c->side_s;
+  if (ready_on != ss) {
+    PPS_CUDA_TRY(cudaEventRecord(c->ev_in, ready_on));
+    PPS_CUDA_TRY(cudaStreamWaitEvent(ss, c->ev_in, 0));
+  }
+  PPS_TRY(pps_pairs_count_device(d_qid, e.nq, d_gid, e.ng, c->pair_ws.p, c->pair_off.as<int32_t>(),
+                                 c->totals.as<int32_t>(), c->cnt_first.as<uint32_t>(), ss));
+  PPS_CUDA_TRY(cudaMemcpyAsync(st.totals, c->totals.p, 8, cudaMemcpyDeviceToHost, ss));
+  PPS_CUDA_TRY(cudaEventRecord(c->ev_totals, ss));
+  return PPS_OK;
+}
+
+// everything after the distance matrix is complete: pair lists, thresholds, counts, finalize, results back
+int rank_tail(pps_ctx* c, const EvalShape& e, const int64_t* d_qid, const int64_t* d_qcam, const int64_t* d_gid,
+              const int64_t* d_gcam, const Staging& st, cudaStream_t cs, double* out_map, double* out_cmc,
+              double* out_ap, uint8_t* out_valid, int32_t* out_first_rank, int32_t* out_topk_index,
+              float* out_topk_dist) {
+  const long long nq = e.nq, ng = e.ng, ldd = e.ldd;
+  const int topk = e.topk, cmc_topk = e.cmc_topk;
+  PPS_CUDA_TRY(cudaEventSynchronize(c->ev_totals));     // side stream: back while the GEMM is still running
+  const long long n_pairs = st.totals[0];
+  const int max_pairs = st.totals[1];
+  const size_t np1 = (size_t)std::max<long long>(n_pairs, 1);
+  PPS_TRY(c->pair_q.ensure(np1 * 4));
+  PPS_TRY(c->pair_g.ensure(np1 * 4));
+  PPS_TRY(c->pair_pos.ensure(np1));
+  PPS_TRY(c->pair_d.ensure(np1 * 4));
+  PPS_TRY(c->cnt_le.ensure(np1 * 4));
+  PPS_TRY(pps_pairs_fill_device(d_qid, d_qcam, nq, d_gid, d_gcam, ng, c->pair_ws.p, c->pair_off.as<int32_t>(),
+                                c->pair_q.as<int32_t>(), c->pair_g.as<int32_t>(), c->pair_pos.as<uint8_t>(),
+                                c->pair_d.as<float>(), c->cnt_le.as<uint32_t>(), n_pairs, c->side_s));
+  PPS_CUDA_TRY(cudaEventRecord(c->ev_pairs, c->side_s));
+  PPS_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_pairs, 0));     // the rank sweeps need the lists; the GEMM did not
+  PPS_TRY(pps_rank_gather(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_q.as<int32_t>(), c->pair_g.as<int32_t>(), n_pairs,
+                          c->pair_d.as<float>(), cs));
+  mark(c, 4, cs);
+  PPS_TRY(pps_rank_count(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(),
+                         c->pair_pos.as<uint8_t>(), c->pair_d.as<float>(), max_pairs, c->cnt_le.as<uint32_t>(),
+                         c->cnt_first.as<uint32_t>(), cs));
+  mark(c, 5, cs);
+  PPS_TRY(pps_rank_finalize(nq, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(), c->pair_pos.as<uint8_t>(),
+                            c->pair_d.as<float>(), c->cnt_le.as<uint32_t>(), c->cnt_first.as<uint32_t>(),
+                            c->ap.as<double>(), c->valid.as<uint8_t>(), c->first.as<int32_t>(), nullptr, cs));
+  if (topk > 0) {
+    PPS_TRY(c->topk.ensure((size_t)nq * topk * 8));
+    PPS_TRY(c->tki.ensure((size_t)nq * topk * 4));
+    PPS_TRY(c->tkd.ensure((size_t)nq * topk * 4));
+    PPS_TRY(pps_topk_init(c->topk.as<uint64_t>(), nq, topk, cs));
+    PPS_TRY(pps_topk_update(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(),
+                            c->pair_pos.as<uint8_t>(), c->topk.as<uint64_t>(), topk, cs));
+    PPS_TRY(pps_topk_unpack(c->topk.as<uint64_t>(), nq, topk, c->tkd.as<float>(), c->tki.as<int32_t>(), cs));
+  }
+  mark(c, 6, cs);
+  // ---- results back ----
+  PPS_CUDA_TRY(cudaMemcpyAsync(st.ap, c->ap.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(st.first, c->first.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(st.valid, c->valid.p, (size_t)nq, cudaMemcpyDeviceToHost, cs));
+  if (topk > 0 && out_topk_index)
+    PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_index, c->tki.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
+  if (topk > 0 && out_topk_dist)
+    PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_dist, c->tkd.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
+  mark(c, 7, cs);
+  PPS_CUDA_TRY(cudaStreamSynchronize(cs));
+
+  // ---- host averaging, as the reference does it (:360-362, :437-438) ----
+  double ap_sum = 0.0;
+  long long n_valid = 0;
+  std::vector<double> hist((size_t)std::max(cmc_topk, 1), 0.0);
+  for (long long i = 0; i < nq; ++i) {
+    if (!st.valid[i]) continue;
+    ++n_valid;
+    ap_sum += st.ap[i];
+    if (st.first[i] >= 0 && st.first[i] < cmc_topk) hist[(size_t)st.first[i]] += 1.0;
+  }
+  if (out_ap) std::memcpy(out_ap, st.ap, (size_t)nq * 8);
+  if (out_valid) std::memcpy(out_valid, st.valid, (size_t)nq);
+  if (out_first_rank) std::memcpy(out_first_rank, st.first, (size_t)nq * 4);
+  if (n_valid == 0) return PPS_ERR_NO_VALID_QUERY;
+  *out_map = ap_sum / (double)n_valid;
+  double run = 0.0;
+  for (int k = 0; k < cmc_topk; ++k) {
+    run += hist[(size_t)k];
+    out_cmc[k] = run / (double)n_valid;
+  }
+  return PPS_OK;
+}
+
+}  // namespace
 
 extern "C" int pps_evaluate_host_ctx(pps_ctx* c, const float* q_feats, long long nq, const float* g_feats, long long ng,
                                      int dim, const int64_t* query_ids, const int64_t* query_cams,
@@ -212,66 +378,36 @@ extern "C" int pps_evaluate_host_ctx(pps_ctx* c, const float* q_feats, long long
                                      uint8_t* out_valid, int32_t* out_first_rank, int32_t* out_topk_index,
                                      float* out_topk_dist) {
   if (!c) return PPS_ERR_INVALID_ARG;
-  if (nq <= 0 || ng <= 0 || dim <= 0 || cmc_topk < 0 || topk < 0 || topk > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
-  if (nq > 0x7fffffffLL || ng > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  EvalShape e;
+  PPS_TRY(eval_shape(nq, ng, dim, precision, cmc_topk, topk, &e));
   if (!q_feats || !g_feats || !query_ids || !query_cams || !gallery_ids || !gallery_cams) return PPS_ERR_INVALID_ARG;
   if (!out_map || (cmc_topk > 0 && !out_cmc)) return PPS_ERR_INVALID_ARG;
-  int planes;
-  switch (precision) {
-    case PPS_PREC_BF16X1: planes = 1; break;
-    case PPS_PREC_BF16X3: planes = 2; break;
-    case PPS_PREC_BF16X6: planes = 3; break;
-    default: return PPS_ERR_INVALID_ARG;
-  }
   PPS_CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t cs = c->comp_s, ps = c->copy_s;
+  const int planes = e.planes, kpad = e.kpad;
+  const long long ldd = e.ldd;
 
-  // the distance matrix is materialised once: bound it (larger galleries go through the chunked
-  // two-sweep path of the Python layer, evaluator.RankEngine)
-  const long long ldd = (ng + 3) & ~3LL;
-  if ((double)nq * (double)ldd * 4.0 > 64.0 * (double)(1LL << 30)) return PPS_ERR_UNSUPPORTED;
-  const int kpad = pps_kpad(dim);
-
+  Staging st;
+  PPS_TRY(ensure_common(c, e, &st));
   PPS_TRY(c->qf.ensure((size_t)nq * dim * 4));
   PPS_TRY(c->gf.ensure((size_t)ng * dim * 4));
-  PPS_TRY(c->qs.ensure((size_t)pps_split_bytes(nq, dim, planes)));
-  PPS_TRY(c->gs.ensure((size_t)pps_split_bytes(ng, dim, planes)));
-  PPS_TRY(c->qn.ensure((size_t)nq * 4));
-  PPS_TRY(c->gn.ensure((size_t)ng * 4));
-  PPS_TRY(c->dist.ensure((size_t)nq * ldd * 4));
   PPS_TRY(c->ids.ensure((size_t)(2 * nq + 2 * ng) * 8));
-  PPS_TRY(c->pair_ws.ensure((size_t)pps_pairs_workspace_bytes(nq, ng)));
-  PPS_TRY(c->pair_off.ensure(((size_t)nq + 1) * 4));
-  PPS_TRY(c->totals.ensure(16));
-  PPS_TRY(c->cnt_first.ensure((size_t)nq * 4));
-  PPS_TRY(c->ap.ensure((size_t)nq * 8));
-  PPS_TRY(c->valid.ensure((size_t)nq));
-  PPS_TRY(c->first.ensure((size_t)nq * 4));
-  // pinned staging: [0,16) totals | ap[nq] f64 | first[nq] i32 | valid[nq] u8
-  const size_t off_ap = 16, off_first = off_ap + (size_t)nq * 8, off_valid = off_first + (size_t)nq * 4;
-  PPS_TRY(c->h_small.ensure(off_valid + (size_t)nq));
-  int32_t* h_totals = c->h_small.as<int32_t>();
-  unsigned char* h_base = c->h_small.as<unsigned char>();
-
   int64_t* d_qid = c->ids.as<int64_t>();
   int64_t* d_qcam = d_qid + nq;
   int64_t* d_gid = d_qcam + nq;
   int64_t* d_gcam = d_gid + ng;
 
   // ---- ids up, pair counts + offsets, totals back (tiny; the host reads them while the GEMM runs) ----
-  PPS_CUDA_TRY(cudaMemcpyAsync(d_qid, query_ids, (size_t)nq * 8, cudaMemcpyHostToDevice, cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(d_qcam, query_cams, (size_t)nq * 8, cudaMemcpyHostToDevice, cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(d_gid, gallery_ids, (size_t)ng * 8, cudaMemcpyHostToDevice, cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(d_gcam, gallery_cams, (size_t)ng * 8, cudaMemcpyHostToDevice, cs));
-  PPS_TRY(pps_pairs_count_device(d_qid, nq, d_gid, ng, c->pair_ws.p, c->pair_off.as<int32_t>(),
-                                 c->totals.as<int32_t>(), cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(h_totals, c->totals.p, 8, cudaMemcpyDeviceToHost, cs));
-  PPS_CUDA_TRY(cudaEventRecord(c->ev_totals, cs));
+  cudaStream_t ss = c->side_s;
+  PPS_CUDA_TRY(cudaMemcpyAsync(d_qid, query_ids, (size_t)nq * 8, cudaMemcpyHostToDevice, ss));
+  PPS_CUDA_TRY(cudaMemcpyAsync(d_qcam, query_cams, (size_t)nq * 8, cudaMemcpyHostToDevice, ss));
+  PPS_CUDA_TRY(cudaMemcpyAsync(d_gid, gallery_ids, (size_t)ng * 8, cudaMemcpyHostToDevice, ss));
+  PPS_CUDA_TRY(cudaMemcpyAsync(d_gcam, gallery_cams, (size_t)ng * 8, cudaMemcpyHostToDevice, ss));
+  PPS_TRY(begin_pairs(c, e, d_qid, d_gid, st, ss));
 
   // ---- queries up + split ----
   PPS_CUDA_TRY(cudaMemcpyAsync(c->qf.p, q_feats, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, cs));
   PPS_TRY(pps_split_rows(c->qf.p, PPS_DTYPE_F32, nq, dim, dim, planes, c->qs.p, c->qn.as<float>(), cs));
-  PPS_CUDA_TRY(cudaMemsetAsync(c->cnt_first.p, 0, (size_t)nq * 4, cs));
 
   // ---- gallery in row slabs: H2D on the copy stream; split + distance of slab s overlap the copy of s+1 ----
   long long slab = ((ng + 7) / 8 + 255) & ~255LL;              // ~8 slabs, whole 256-column tiles
@@ -290,73 +426,59 @@ extern "C" int pps_evaluate_host_ctx(pps_ctx* c, const float* q_feats, long long
                         c->gs.as<unsigned char>() + (size_t)r0 * kpad * esz, c->gn.as<float>() + r0, nr, planes, ng, dim,
                         precision, 0, c->dist.as<float>() + r0, ldd, cs));
   }
+  const int rc = rank_tail(c, e, d_qid, d_qcam, d_gid, d_gcam, st, cs, out_map, out_cmc, out_ap, out_valid,
+                           out_first_rank, out_topk_index, out_topk_dist);
+  cudaStreamSynchronize(ps);
+  return rc;
+}
 
-  // ---- pair lists (now that their size is known), thresholds, counts, finalize ----
-  PPS_CUDA_TRY(cudaEventSynchronize(c->ev_totals));
-  const long long n_pairs = h_totals[0];
-  const int max_pairs = h_totals[1];
-  const size_t np1 = (size_t)std::max<long long>(n_pairs, 1);
-  PPS_TRY(c->pair_q.ensure(np1 * 4));
-  PPS_TRY(c->pair_g.ensure(np1 * 4));
-  PPS_TRY(c->pair_pos.ensure(np1));
-  PPS_TRY(c->pair_d.ensure(np1 * 4));
-  PPS_TRY(c->cnt_le.ensure(np1 * 4));
-  PPS_TRY(pps_pairs_fill_device(d_qid, d_qcam, nq, d_gid, d_gcam, ng, c->pair_ws.p, c->pair_q.as<int32_t>(),
-                                c->pair_g.as<int32_t>(), c->pair_pos.as<uint8_t>(), n_pairs, cs));
-  PPS_CUDA_TRY(cudaMemsetAsync(c->pair_d.p, 0, np1 * 4, cs));
-  PPS_CUDA_TRY(cudaMemsetAsync(c->cnt_le.p, 0, np1 * 4, cs));
-  PPS_TRY(pps_rank_gather(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_q.as<int32_t>(), c->pair_g.as<int32_t>(), n_pairs,
-                          c->pair_d.as<float>(), cs));
-  PPS_TRY(pps_rank_count(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(),
-                         c->pair_pos.as<uint8_t>(), c->pair_d.as<float>(), max_pairs, c->cnt_le.as<uint32_t>(),
-                         c->cnt_first.as<uint32_t>(), cs));
-  PPS_TRY(pps_rank_finalize(nq, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(), c->pair_pos.as<uint8_t>(),
-                            c->pair_d.as<float>(), c->cnt_le.as<uint32_t>(), c->cnt_first.as<uint32_t>(),
-                            c->ap.as<double>(), c->valid.as<uint8_t>(), c->first.as<int32_t>(), nullptr, cs));
-  if (topk > 0) {
-    PPS_TRY(c->topk.ensure((size_t)nq * topk * 8));
-    PPS_TRY(c->tki.ensure((size_t)nq * topk * 4));
-    PPS_TRY(c->tkd.ensure((size_t)nq * topk * 4));
-    PPS_TRY(pps_topk_init(c->topk.as<uint64_t>(), nq, topk, cs));
-    PPS_TRY(pps_topk_update(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(),
-                            c->pair_pos.as<uint8_t>(), c->topk.as<uint64_t>(), topk, cs));
-    PPS_TRY(pps_topk_unpack(c->topk.as<uint64_t>(), nq, topk, c->tkd.as<float>(), c->tki.as<int32_t>(), cs));
+// Same evaluation with everything already RESIDENT on the device (features fp32 [rows, dim] contiguous, ids /
+// cameras int64): what bench.py times as `value`.  All work is enqueued on `stream` (the caller's stream, so it
+// is ordered after whatever produced the inputs); the call returns after the small results are on the host.
+extern "C" int pps_evaluate_device_ctx(pps_ctx* c, const float* d_q, long long nq, const float* d_g, long long ng,
+                                       int dim, const int64_t* d_qid, const int64_t* d_qcam, const int64_t* d_gid,
+                                       const int64_t* d_gcam, int precision, int cmc_topk, int topk, void* stream,
+                                       double* out_map, double* out_cmc, double* out_ap, uint8_t* out_valid,
+                                       int32_t* out_first_rank, int32_t* out_topk_index, float* out_topk_dist) {
+  if (!c) return PPS_ERR_INVALID_ARG;
+  EvalShape e;
+  PPS_TRY(eval_shape(nq, ng, dim, precision, cmc_topk, topk, &e));
+  if (!d_q || !d_g || !d_qid || !d_qcam || !d_gid || !d_gcam) return PPS_ERR_INVALID_ARG;
+  if (!out_map || (cmc_topk > 0 && !out_cmc)) return PPS_ERR_INVALID_ARG;
+  PPS_CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  Staging st;
+  PPS_TRY(ensure_common(c, e, &st));
+  mark(c, 0, cs);
+  PPS_TRY(begin_pairs(c, e, d_qid, d_gid, st, cs));
+  mark(c, 1, cs);
+  PPS_TRY(pps_split_rows(d_q, PPS_DTYPE_F32, nq, dim, dim, e.planes, c->qs.p, c->qn.as<float>(), cs));
+  PPS_TRY(pps_split_rows(d_g, PPS_DTYPE_F32, ng, dim, dim, e.planes, c->gs.p, c->gn.as<float>(), cs));
+  mark(c, 2, cs);
+  PPS_TRY(pps_dist_tc(c->qs.p, c->qn.as<float>(), nq, e.planes, 0, c->gs.p, c->gn.as<float>(), ng, e.planes, 0, dim,
+                      precision, 0, c->dist.as<float>(), e.ldd, cs));
+  mark(c, 3, cs);
+  const int rc = rank_tail(c, e, d_qid, d_qcam, d_gid, d_gcam, st, cs, out_map, out_cmc, out_ap, out_valid,
+                           out_first_rank, out_topk_index, out_topk_dist);
+  if (c->timing && (rc == PPS_OK || rc == PPS_ERR_NO_VALID_QUERY)) {
+    for (int i = 0; i < PPS_N_PHASES; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->ev_phase[i], c->ev_phase[i + 1]) != cudaSuccess) ms = -1.f;
+      c->phase_ms[i] = ms;
+    }
   }
+  return rc;
+}
 
-  // ---- results back ----
-  double* ap = reinterpret_cast<double*>(h_base + off_ap);
-  int32_t* first = reinterpret_cast<int32_t*>(h_base + off_first);
-  uint8_t* valid = h_base + off_valid;
-  PPS_CUDA_TRY(cudaMemcpyAsync(ap, c->ap.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(first, c->first.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(valid, c->valid.p, (size_t)nq, cudaMemcpyDeviceToHost, cs));
-  if (topk > 0 && out_topk_index)
-    PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_index, c->tki.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
-  if (topk > 0 && out_topk_dist)
-    PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_dist, c->tkd.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
-  PPS_CUDA_TRY(cudaStreamSynchronize(cs));
-  PPS_CUDA_TRY(cudaStreamSynchronize(ps));
+extern "C" int pps_ctx_set_timing(pps_ctx* c, int enabled) {
+  if (!c) return PPS_ERR_INVALID_ARG;
+  c->timing = enabled != 0;
+  return PPS_OK;
+}
 
-  // ---- host averaging, as the reference does it (:360-362, :437-438) ----
-  double ap_sum = 0.0;
-  long long n_valid = 0;
-  std::vector<double> hist((size_t)std::max(cmc_topk, 1), 0.0);
-  for (long long i = 0; i < nq; ++i) {
-    if (!valid[i]) continue;
-    ++n_valid;
-    ap_sum += ap[i];
-    if (first[i] >= 0 && first[i] < cmc_topk) hist[(size_t)first[i]] += 1.0;
-  }
-  if (out_ap) std::memcpy(out_ap, ap, (size_t)nq * 8);
-  if (out_valid) std::memcpy(out_valid, valid, (size_t)nq);
-  if (out_first_rank) std::memcpy(out_first_rank, first, (size_t)nq * 4);
-  if (n_valid == 0) return PPS_ERR_NO_VALID_QUERY;
-  *out_map = ap_sum / (double)n_valid;
-  double run = 0.0;
-  for (int k = 0; k < cmc_topk; ++k) {
-    run += hist[(size_t)k];
-    out_cmc[k] = run / (double)n_valid;
-  }
+extern "C" int pps_ctx_phase_ms(const pps_ctx* c, float* out_ms) {
+  if (!c || !out_ms) return PPS_ERR_INVALID_ARG;
+  for (int i = 0; i < PPS_N_PHASES; ++i) out_ms[i] = c->phase_ms[i];
   return PPS_OK;
 }
 

@@ -11,9 +11,10 @@
 // contraction they accompany, need no sort and no hash table, and the order is deterministic:
 //   count : CTA (query block of 32, gallery segment) -> 8 warps x 4 queries; a warp streams the
 //           segment's ids once (coalesced), 4 ballots per 32 ids, popc-accumulates per query.
-//   scan  : one CTA turns the [nq][segments] counts into exclusive offsets (query-major), writes
-//           pair_off and {n_pairs, max pairs per query}.
-//   fill  : same sweep as count; the ballot prefix gives each hit its slot -> ascending g.
+//   scan  : one CTA sums each query's segment counts and scans over queries -> pair_off and
+//           {n_pairs, max pairs per query}.
+//   fill  : same sweep as count; slot = pair_off[q] + hits in earlier segments + ballot prefix
+//           -> ascending g.  It also zero-fills the per-pair accumulators of the rank sweeps.
 #include "common.cuh"
 
 namespace pps {
@@ -26,8 +27,9 @@ template <bool FILL>
 __global__ void __launch_bounds__(32 * kPairWarps)
 pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ qcam, int nq,
                    const int64_t* __restrict__ gid, const int64_t* __restrict__ gcam, long long ng, long long seg,
-                   int nseg, int32_t* __restrict__ seg_cnt /*[nq][nseg]: counts (count) / exclusive offsets (fill)*/,
-                   int32_t* __restrict__ pair_q, int32_t* __restrict__ pair_g, uint8_t* __restrict__ pair_pos,
+                   int nseg, int32_t* __restrict__ seg_cnt /*[nq][nseg] hits of query q in segment s*/,
+                   const int32_t* __restrict__ pair_off, int32_t* __restrict__ pair_q, int32_t* __restrict__ pair_g,
+                   uint8_t* __restrict__ pair_pos, float* __restrict__ zero_f32, uint32_t* __restrict__ zero_u32,
                    long long capacity) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * kPairQPerCta + warp * kPairQPerWarp;
@@ -41,20 +43,29 @@ pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ 
     live[u] = q0 + u < nq;
     ids[u] = live[u] ? qid[q0 + u] : 0;
     cams[u] = (FILL && live[u]) ? qcam[q0 + u] : 0;
-    acc[u] = (FILL && live[u]) ? seg_cnt[(long long)(q0 + u) * nseg + s] : 0;
+    acc[u] = 0;
+    if (FILL && live[u]) {
+      // first slot of (query, segment) = pair_off[q] + hits of q in the earlier segments
+      int part = 0;
+      for (int sp = lane; sp < s; sp += 32) part += seg_cnt[(long long)(q0 + u) * nseg + sp];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      acc[u] = pair_off[q0 + u] + part;
+    }
   }
   const long long g_begin = (long long)s * seg;
   const long long g_end = min(ng, g_begin + seg);
   const unsigned lt = (1u << lane) - 1u;
-  for (long long g0 = g_begin; g0 < g_end; g0 += 128) {
-    int64_t v[4];
+  constexpr int kB = 8;                                     // batches of 32 ids in flight per warp
+  for (long long g0 = g_begin; g0 < g_end; g0 += 32 * kB) {
+    int64_t v[kB];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kB; ++k) {
       const long long g = g0 + k * 32 + lane;
       v[k] = g < g_end ? gid[g] : 0;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kB; ++k) {
       const long long g = g0 + k * 32 + lane;
       const bool in = g < g_end;
 #pragma unroll
@@ -68,6 +79,8 @@ pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ 
               pair_q[slot] = q0 + u;
               pair_g[slot] = (int32_t)g;
               pair_pos[slot] = gcam[g] != cams[u] ? 1 : 0;
+              if (zero_f32) zero_f32[slot] = 0.f;
+              if (zero_u32) zero_u32[slot] = 0u;
             }
           }
         }
@@ -82,24 +95,27 @@ pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ 
   }
 }
 
-// exclusive scan of n = nq*nseg counts in place (query-major), one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) pairs_scan_kernel(int32_t* __restrict__ seg_cnt, int nq, int nseg,
-                                                          int32_t* __restrict__ pair_off, int32_t* __restrict__ totals) {
+// pair_off[q] = exclusive scan over queries of their total hits (sum over segments); totals = {n_pairs, max per
+// query}; optionally zeroes a per-query counter array.  One CTA of 1024 threads, 1024 queries per iteration.
+__global__ void __launch_bounds__(1024) pairs_scan_kernel(const int32_t* __restrict__ seg_cnt, int nq, int nseg,
+                                                          int32_t* __restrict__ pair_off, int32_t* __restrict__ totals,
+                                                          uint32_t* __restrict__ zero_per_query) {
   __shared__ int warp_sum[32];
   __shared__ int carry_s;
   __shared__ int max_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long n = (long long)nq * nseg;
   if (tid == 0) { carry_s = 0; max_s = 0; }
   __syncthreads();
-  for (long long base = 0; base < n; base += 4096) {
-    int v[4], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long i = base + 4LL * tid + k;
-      v[k] = i < n ? seg_cnt[i] : 0;
-      sum += v[k];
+  int mx = 0;
+  for (int base = 0; base < nq; base += 1024) {
+    const int q = base + tid;
+    int sum = 0;
+    if (q < nq) {
+      const int32_t* row = seg_cnt + (long long)q * nseg;
+      for (int sgi = 0; sgi < nseg; ++sgi) sum += row[sgi];
+      if (zero_per_query) zero_per_query[q] = 0u;
     }
+    mx = max(mx, sum);
     int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -119,36 +135,20 @@ __global__ void __launch_bounds__(1024) pairs_scan_kernel(int32_t* __restrict__ 
     }
     __syncthreads();
     const int carry = carry_s;
-    int run = carry + (warp ? warp_sum[warp - 1] : 0) + incl - sum;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long i = base + 4LL * tid + k;
-      if (i < n) seg_cnt[i] = run;
-      run += v[k];
-    }
+    if (q < nq) pair_off[q] = carry + (warp ? warp_sum[warp - 1] : 0) + incl - sum;
     __syncthreads();
     if (tid == 1023) carry_s = carry + warp_sum[31];
     __syncthreads();
   }
-  const int total = carry_s;
-  // pair_off[q] = offset of (q, segment 0); per-query maximum
-  int mx = 0;
-  for (int q = tid; q < nq; q += 1024) {
-    const int o = seg_cnt[(long long)q * nseg];
-    pair_off[q] = o;
-    const int nxt = q + 1 < nq ? seg_cnt[(long long)(q + 1) * nseg] : total;
-    mx = max(mx, nxt - o);
-  }
-  if (tid == 0) pair_off[nq] = total;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) atomicMax(&max_s, mx);
   __syncthreads();
-  if (tid == 0) { totals[0] = total; totals[1] = max_s; }
+  if (tid == 0) { pair_off[nq] = carry_s; totals[0] = carry_s; totals[1] = max_s; }
 }
 
 static void pair_segments(long long ng, long long* seg, int* nseg) {
-  long long s = 2048;
+  long long s = 1024;
   while ((ng + s - 1) / s > 512) s *= 2;
   *seg = s;
   *nseg = (int)((ng + s - 1) / s);
@@ -167,7 +167,8 @@ extern "C" long long pps_pairs_workspace_bytes(long long nq, long long ng) {
 }
 
 extern "C" int pps_pairs_count_device(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
-                                      void* workspace, int32_t* pair_off, int32_t* totals, void* stream) {
+                                      void* workspace, int32_t* pair_off, int32_t* totals, uint32_t* zero_per_query,
+                                      void* stream) {
   if (nq < 0 || ng < 0 || nq > 0x7fffffffLL || ng > 0x7fffffffLL) return PPS_ERR_INVALID_ARG;
   if (!pair_off || !totals || !workspace) return PPS_ERR_INVALID_ARG;
   if (nq > 0 && ng > 0 && (!query_ids || !gallery_ids)) return PPS_ERR_INVALID_ARG;
@@ -181,29 +182,33 @@ extern "C" int pps_pairs_count_device(const int64_t* query_ids, long long nq, co
     else {
       const dim3 grid((unsigned)((nq + kPairQPerCta - 1) / kPairQPerCta), (unsigned)nseg);
       pairs_sweep_kernel<false><<<grid, 32 * kPairWarps, 0, st>>>(query_ids, nullptr, (int)nq, gallery_ids, nullptr, ng,
-                                                                  seg, nseg, seg_cnt, nullptr, nullptr, nullptr, 0);
+                                                                  seg, nseg, seg_cnt, nullptr, nullptr, nullptr, nullptr,
+                                                                  nullptr, nullptr, 0);
       PPS_LAUNCH_CHECK("pairs_sweep_kernel<count>");
     }
   }
-  pairs_scan_kernel<<<1, 1024, 0, st>>>(seg_cnt, (int)nq, nseg, pair_off, totals);
+  pairs_scan_kernel<<<1, 1024, 0, st>>>(seg_cnt, (int)nq, nseg, pair_off, totals, zero_per_query);
   PPS_LAUNCH_CHECK("pairs_scan_kernel");
   return PPS_OK;
 }
 
 extern "C" int pps_pairs_fill_device(const int64_t* query_ids, const int64_t* query_cams, long long nq,
                                      const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
-                                     const void* workspace, int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos,
-                                     long long capacity, void* stream) {
+                                     const void* workspace, const int32_t* pair_off, int32_t* pair_q, int32_t* pair_g,
+                                     uint8_t* pair_pos, float* zero_f32, uint32_t* zero_u32, long long capacity,
+                                     void* stream) {
   if (nq < 0 || ng < 0 || nq > 0x7fffffffLL || ng > 0x7fffffffLL || capacity < 0) return PPS_ERR_INVALID_ARG;
   if (nq == 0 || ng == 0 || capacity == 0) return PPS_OK;
-  if (!query_ids || !query_cams || !gallery_ids || !gallery_cams || !workspace || !pair_q || !pair_g || !pair_pos)
+  if (!query_ids || !query_cams || !gallery_ids || !gallery_cams || !workspace || !pair_off || !pair_q || !pair_g ||
+      !pair_pos)
     return PPS_ERR_INVALID_ARG;
   long long seg; int nseg;
   pair_segments(ng, &seg, &nseg);
   const dim3 grid((unsigned)((nq + kPairQPerCta - 1) / kPairQPerCta), (unsigned)nseg);
   pairs_sweep_kernel<true><<<grid, 32 * kPairWarps, 0, static_cast<cudaStream_t>(stream)>>>(
       query_ids, query_cams, (int)nq, gallery_ids, gallery_cams, ng, seg, nseg,
-      const_cast<int32_t*>(static_cast<const int32_t*>(workspace)), pair_q, pair_g, pair_pos, capacity);
+      const_cast<int32_t*>(static_cast<const int32_t*>(workspace)), pair_off, pair_q, pair_g, pair_pos, zero_f32,
+      zero_u32, capacity);
   PPS_LAUNCH_CHECK("pairs_sweep_kernel<fill>");
   return PPS_OK;
 }

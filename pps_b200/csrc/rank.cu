@@ -40,7 +40,8 @@ __global__ void rank_gather_kernel(const float* __restrict__ dist, long long ldd
 
 // ------------------------------------------------------------------------------------
 // step 2: counts.  grid = (nq, splits); CTA (q, s) sweeps columns [s*seg, (s+1)*seg).
-// dynamic smem: thr[maxp] (sorted positive distances), tpair[maxp] (pair index of each)
+// dynamic smem: thr[maxp] (sorted positive distances), tpair[maxp] (pair index of each),
+//               sd[maxp] / sg[maxp] (the query's staged pair list)
 // static smem : win_rep[32][32]  the window's thresholds replicated once per bank, so the
 //                                data-dependent reads of the binary search never conflict;
 //               hist[warps][32][32] lane-private bucket counters (bank = lane).
@@ -71,20 +72,29 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
   const int e0 = pair_off[q], e1 = pair_off[q + 1];
 
   // --- positives of this query, rank-sorted by (distance, gallery index) into thr[] ---
+  // stage the query's pair list in shared memory first (coalesced), then rank from there: the
+  // O(P^2) ranking loop must not chase global-memory latency
+  float* sd = reinterpret_cast<float*>(tpair + maxp);                       // [maxp] pair distances
+  int32_t* sg = reinterpret_cast<int32_t*>(sd + maxp);                      // [maxp] gallery index, -1 = junk
   if (tid == 0) { s_np = 0; s_first_cnt = 0; }
+  const int npair = e1 - e0;
+  for (int i = tid; i < npair; i += kCntThreads) {
+    sd[i] = pair_d[e0 + i];
+    sg[i] = pair_pos[e0 + i] ? pair_g[e0 + i] : -1;
+  }
   __syncthreads();
-  for (int e = e0 + tid; e < e1; e += kCntThreads) {
-    if (!pair_pos[e]) continue;
-    const float d = pair_d[e];
-    const int g = pair_g[e];
+  for (int i = tid; i < npair; i += kCntThreads) {
+    const int g = sg[i];
+    if (g < 0) continue;
+    const float d = sd[i];
     int pos = 0;
-    for (int f = e0; f < e1; ++f) {
-      if (!pair_pos[f]) continue;
-      const float df = pair_d[f];
-      pos += (df < d) || (df == d && pair_g[f] < g);
+    for (int f = 0; f < npair; ++f) {
+      const int gf = sg[f];
+      const float df = sd[f];
+      pos += (gf >= 0) && ((df < d) || (df == d && gf < g));
     }
     thr[pos] = d;
-    tpair[pos] = e;
+    tpair[pos] = e0 + i;
     atomicAdd(&s_np, 1);
   }
   __syncthreads();
@@ -132,11 +142,24 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
 
     if (vec) {
       const long long c4_end = c_begin + ((c_end - c_begin) & ~3LL);
-      for (long long c = c_begin + 4LL * tid; c < c4_end; c += 4LL * kCntThreads) {
+      constexpr long long kStep = 4LL * kCntThreads;       // columns per pass of the CTA
+      long long c = c_begin + 4LL * tid;
+      // four independent 128-bit loads in flight per thread before any of them is consumed
+      for (; c + 3 * kStep < c4_end; c += 4 * kStep) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(reinterpret_cast<const float4*>(drow + c + u * kStep));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long cu = c + u * kStep;
+          visit(v[u].x, cu); visit(v[u].y, cu + 1); visit(v[u].z, cu + 2); visit(v[u].w, cu + 3);
+        }
+      }
+      for (; c < c4_end; c += kStep) {
         const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(drow + c));
         visit(v.x, c); visit(v.y, c + 1); visit(v.z, c + 2); visit(v.w, c + 3);
       }
-      for (long long c = c4_end + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
+      for (c = c4_end + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
     } else {
       for (long long c = c_begin + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
     }
@@ -354,8 +377,8 @@ extern "C" int pps_rank_count(const float* dist, long long ldd, long long nq, lo
   if (!pair_g || !pair_pos || !pair_d || !cnt_le) return PPS_ERR_INVALID_ARG;
   if (nq > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
   const int maxp = (max_pairs_per_query + 3) & ~3;
-  const size_t smem = (size_t)maxp * 8;
-  if (smem > 160 * 1024) return PPS_ERR_UNSUPPORTED;          // > ~20k same-id items for one query
+  const size_t smem = (size_t)maxp * 16;                      // thr, tpair, staged distances, staged indices
+  if (smem > 160 * 1024) return PPS_ERR_UNSUPPORTED;          // > ~10k same-id items for one query
   // column splits: enough CTAs to fill the GPU when there are few queries
   const int sms = sm_count();
   long long splits = 1;

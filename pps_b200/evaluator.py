@@ -141,17 +141,20 @@ class DevicePairs:
         self.n_pairs = self.max_pairs = 0
         self._host = None
 
-    def begin(self):
+    def begin(self, zero_per_query=None):
+        """``zero_per_query``: optional uint32/int32 [nq] device tensor the scan kernel zero-fills (cnt_first)."""
         lib = self.lib
         _lib.check(lib.pps_pairs_count_device(_lib.ptr(self.qid), self.nq, _lib.ptr(self.gid), self.ng, _lib.ptr(self.ws),
-                                              _lib.ptr(self.off_d), _lib.ptr(self.totals_d), _lib.stream_ptr()),
-                   "pps_pairs_count_device")
+                                              _lib.ptr(self.off_d), _lib.ptr(self.totals_d), _lib.ptr(zero_per_query),
+                                              _lib.stream_ptr()), "pps_pairs_count_device")
         self.totals_h.copy_(self.totals_d, non_blocking=True)
         self.event.record()
         self._host = None
         return self
 
-    def finish(self):
+    def finish(self, zero_f32=None, zero_u32=None):
+        """``zero_f32`` / ``zero_u32``: optional per-pair device arrays (capacity >= n_pairs) the fill kernel
+        zero-fills (pair_d / cnt_le); pass callables to allocate them once n_pairs is known."""
         torch = _torch()
         self.event.synchronize()
         self.n_pairs, self.max_pairs = int(self.totals_h[0]), int(self.totals_h[1])
@@ -160,9 +163,14 @@ class DevicePairs:
             self.q_d = torch.empty(self.cap, dtype=torch.int32, device=self.device)
             self.g_d = torch.empty(self.cap, dtype=torch.int32, device=self.device)
             self.pos_d = torch.empty(self.cap, dtype=torch.uint8, device=self.device)
+        if callable(zero_f32):
+            zero_f32 = zero_f32(self.n_pairs)
+        if callable(zero_u32):
+            zero_u32 = zero_u32(self.n_pairs)
         _lib.check(self.lib.pps_pairs_fill_device(_lib.ptr(self.qid), _lib.ptr(self.qcam), self.nq, _lib.ptr(self.gid),
-                                                  _lib.ptr(self.gcam), self.ng, _lib.ptr(self.ws), _lib.ptr(self.q_d),
-                                                  _lib.ptr(self.g_d), _lib.ptr(self.pos_d), self.n_pairs,
+                                                  _lib.ptr(self.gcam), self.ng, _lib.ptr(self.ws), _lib.ptr(self.off_d),
+                                                  _lib.ptr(self.q_d), _lib.ptr(self.g_d), _lib.ptr(self.pos_d),
+                                                  _lib.ptr(zero_f32), _lib.ptr(zero_u32), self.n_pairs,
                                                   _lib.stream_ptr()), "pps_pairs_fill_device")
         return self
 
@@ -274,13 +282,14 @@ def rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams, want
         dist = dist.float()
     m, n = int(dist.shape[0]), int(dist.shape[1])
     with torch.cuda.device(dist.device):
-        pairs = DevicePairs(query_ids, query_cams, gallery_ids, gallery_cams, dist.device).begin().finish()
+        pairs = DevicePairs(query_ids, query_cams, gallery_ids, gallery_cams, dist.device)
         if pairs.nq != m or pairs.ng != n:
             raise RuntimeError("distmat shape %s does not match %d query / %d gallery ids" % ((m, n), pairs.nq, pairs.ng))
+        cnt_first = torch.empty(max(m, 1), dtype=torch.int32, device=dist.device)
+        pairs.begin(zero_per_query=cnt_first).finish()
         E = max(pairs.n_pairs, 1)
         pair_d = torch.zeros(E, dtype=torch.float32, device=dist.device)
         cnt_le = torch.zeros(E, dtype=torch.int32, device=dist.device)
-        cnt_first = torch.zeros(max(m, 1), dtype=torch.int32, device=dist.device)
         key = None
         if topk:
             key = torch.empty((m, topk), dtype=torch.int64, device=dist.device)
@@ -492,19 +501,52 @@ class RankEngine:
             self.pairs = DevicePairs(self.qi, self.qc, self.gi, self.gc, dev)
         self._pair_cap = 0
         self.kernel_events = None        # bench.py: list collecting (start, stop) events around the distance GEMM
+        self.use_c_path = True           # single GPU + one block: run the pass as one C call
         self.h2d_bytes = 0
 
     # -- helpers --
     def _pair_buffers(self, n_pairs):
+        """(pair_d, cnt_le) with capacity >= n_pairs; the pair fill kernel zero-fills the used part."""
         torch = self.torch
         if n_pairs > self._pair_cap or self._pair_cap == 0:
             cap = max(int(n_pairs * 1.25), 1024)
-            self.pair_d = torch.empty(cap, dtype=torch.float32, device=self.dev)
-            self.cnt_le = torch.empty(cap, dtype=torch.int32, device=self.dev)
+            self.pair_d = torch.zeros(cap, dtype=torch.float32, device=self.dev)
+            self.cnt_le = torch.zeros(cap, dtype=torch.int32, device=self.dev)
             self._pair_cap = cap
-        self.pair_d.zero_()
-        self.cnt_le.zero_()
-        self.cnt_first.zero_()
+        return self.pair_d, self.cnt_le
+
+    def _finish_pairs(self, pairs):
+        pairs.finish(zero_f32=lambda n: self._pair_buffers(n)[0], zero_u32=lambda n: self._pair_buffers(n)[1])
+        return self.pair_d, self.cnt_le
+
+    def set_phase_timing(self, enabled: bool):
+        """Device-time the phases of the C fast path (pps_ctx_set_timing); read them with last_phase_ms()."""
+        _lib.check(self.lib.pps_ctx_set_timing(_host_ctx(self.dev.index or 0), 1 if enabled else 0), "pps_ctx_set_timing")
+
+    def last_phase_ms(self):
+        out = np.zeros(_lib.N_PHASES, dtype=np.float32)
+        _lib.check(self.lib.pps_ctx_phase_ms(_host_ctx(self.dev.index or 0), _lib.ptr(out)), "pps_ctx_phase_ms")
+        return dict(zip(_lib.PHASE_NAMES, out.tolist()))
+
+    def _run_resident_c(self, q, g):
+        """Single GPU, one distance block: the whole pass is one C call (pps_evaluate_device_ctx)."""
+        nq, topk = self.nq, self.topk
+        p = self.pairs
+        out_map = C.c_double(0.0)
+        out_cmc = np.zeros(10, dtype=np.float64)
+        ap = np.zeros(nq, dtype=np.float64)
+        valid = np.zeros(nq, dtype=np.uint8)
+        first = np.zeros(nq, dtype=np.int32)
+        ti = np.zeros((nq, topk), dtype=np.int32) if topk else None
+        td = np.zeros((nq, topk), dtype=np.float32) if topk else None
+        rc = self.lib.pps_evaluate_device_ctx(_host_ctx(self.dev.index or 0), _lib.ptr(q), nq, _lib.ptr(g), self.ngl,
+                                              self.dim, _lib.ptr(p.qid), _lib.ptr(p.qcam), _lib.ptr(p.gid), _lib.ptr(p.gcam),
+                                              self.prec, 10, topk, _lib.stream_ptr(),
+                                              C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc), _lib.ptr(ap),
+                                              _lib.ptr(valid), _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
+        if rc != _lib.PPS_ERR_NO_VALID_QUERY:
+            _lib.check(rc, "pps_evaluate_device_ctx")
+        return RankResult(ap, valid, first, None, None, ti, td)
 
     def _split(self, feats, rows, planes_buf, sq_buf):
         if rows:
@@ -540,8 +582,13 @@ class RankEngine:
         if self.group is not None:
             import torch.distributed as dist_mod
         nq = self.nq
+        if (self.use_c_path and self.group is None and self.n_chunks == 1 and not self.want_neg_before
+                and not self.is_f16 and self.topk_filtered and nq > 0 and self.kernel_events is None
+                and q.is_contiguous() and g.is_contiguous() and DIST_KERNEL_FLAGS == 0):
+            with torch.cuda.device(self.dev):
+                return self._run_resident_c(q, g)
         with torch.cuda.device(self.dev):
-            pairs = self.pairs.begin()          # junk mask / matches from the resident ids, on the device
+            pairs = self.pairs.begin(zero_per_query=self.cnt_first)   # junk mask / matches, on the device
             key = self.key
             if self.topk:
                 _lib.check(lib.pps_topk_init(_lib.ptr(key), nq, self.topk, _lib.stream_ptr()), "pps_topk_init")
@@ -555,16 +602,12 @@ class RankEngine:
                 self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)
                 self._distance(rows)
                 if first_chunk:                 # the pair count came back while the GEMM was queued / running
-                    pairs.finish()
-                    self._pair_buffers(pairs.n_pairs)
-                    pair_d, cnt_le = self.pair_d, self.cnt_le
+                    pair_d, cnt_le = self._finish_pairs(pairs)
                     first_chunk = False
                 _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
                             True, False)
             if first_chunk:                     # empty gallery shard
-                pairs.finish()
-                self._pair_buffers(pairs.n_pairs)
-                pair_d, cnt_le = self.pair_d, self.cnt_le
+                pair_d, cnt_le = self._finish_pairs(pairs)
             if self.group is not None:
                 dist_mod.all_reduce(pair_d, op=dist_mod.ReduceOp.SUM, group=self.group)
             # sweep 2: counts (+ top-k); a single chunk is still resident in the block
