@@ -30,6 +30,10 @@ import time
 
 import numpy as np
 
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"              # NCCL prints its version to stdout at these levels: keep stdout
+                                                   # to the one JSON line (set NCCL_DEBUG=INFO to debug)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -274,7 +278,7 @@ def run_ours(args):
     sampler.start()
     n0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c_path = world == 1 and engine.n_chunks == 1
+    c_path = engine.n_chunks == 1 and args.topk == 0
     phase_sum = {}
     if c_path:
         engine.set_phase_timing(True)      # events between the phases of the one C call, on the same stream
@@ -338,7 +342,7 @@ def run_ours(args):
                         "tensor_pipe_frac": achieved * terms / peaks["tf_sustained"],
                         "note": "achieved counts ALGORITHMIC flops (2*D per pair); the fp32-accurate %s split issues "
                                 "%dx that on the tensor pipe" % (args.precision, terms)}
-        h2d = (q_host.numel() + g_host.numel()) * 4 + (len(d["qid"]) + 0) * 0
+        h2d = (q_host.numel() + g_host.numel()) * 4
         d2h = nq * (8 + 1 + 4)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PPS_ABI_VERSION 2
+#define PPS_ABI_VERSION 3
 
 /* ---- error codes (the Python mirror turns every non-zero code into RuntimeError,
  * like CAFFE_ENFORCE does: detectron/tests/test_zero_even_op.py:50-53) ---- */
@@ -125,6 +125,9 @@ int pps_split_rows_slab(const void* feats, int dtype, long long row0, long long 
 #define PPS_DIST_SQUARED 1
 #define PPS_DIST_DOT     2
 #define PPS_DIST_KERNEL_1CTA 0x100   /* use the single-CTA 128x256 kernel instead of the 2-CTA 256x256 one */
+#define PPS_DIST_RESERVE_SM_PAIR 0x200 /* persistent grid leaves one SM pair idle: the kernel fills the shared memory
+                                          of every SM it runs on, so a concurrent NCCL / pair-list kernel on another
+                                          stream could otherwise only start when it ends */
 
 int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n, long long a_plane_rows,
                 const void* b_planes, const float* b_sqnorm, long long m2, int b_planes_n, long long b_plane_rows,
@@ -156,22 +159,38 @@ int pps_pairs_fill(const int64_t* query_ids, const int64_t* query_cams, long lon
                    int32_t* pair_off, int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos);
 
 /* The same lists built on the device (no sort: a deterministic brute-force sweep, pairs.cu).
- * query_ids ... gallery_cams, pair_* and totals are DEVICE pointers; workspace needs
- * pps_pairs_workspace_bytes(nq, ng) bytes.  pps_pairs_count_device writes pair_off[nq+1] and
- * totals[2] = {n_pairs, max pairs of one query}; the caller reads totals back (the only host
- * round trip of the path, overlappable with the distance GEMM), sizes pair_q/pair_g/pair_pos and
- * calls pps_pairs_fill_device with the SAME workspace (entries beyond `capacity` are dropped).
- * The result is identical to pps_pairs_fill on every rank of a sharded run. */
+ * All pointers are DEVICE pointers; workspace needs pps_pairs_workspace_bytes(nq, ng) bytes.
+ * Single block:  pps_pairs_count_device writes pair_off[nq+1] and totals[2] = {n_pairs, max pairs of
+ * one query}; the caller reads totals back (the only host round trip of the path, overlappable with
+ * the distance GEMM), sizes pair_q/pair_g/pair_pos and calls pps_pairs_fill_device with the SAME
+ * workspace (entries beyond `capacity` are dropped; the optional zero_* arrays are zero-filled for
+ * the slots written).  The result is identical to pps_pairs_fill.
+ * Sharded gallery (each rank sweeps only ITS block of ng rows starting at global row
+ * gallery_offset): pps_pairs_local_count -> *local_cnt[nq] (inside the workspace) -> all-gather over
+ * ranks into cnt_all[world][nq] -> pps_pairs_offsets (global pair_off, totals; this rank's first
+ * slot per query stays in the workspace) -> pps_pairs_fill_local writes the block's pairs into their
+ * GLOBAL slots with global gallery indices (pair_pos as bytes and/or as int32 for a SUM exchange). */
 long long pps_pairs_workspace_bytes(long long nq, long long ng);
 int pps_pairs_count_device(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
-                           void* workspace, int32_t* pair_off, int32_t* totals,
-                           uint32_t* zero_per_query /* optional [nq]: set to 0 (cnt_first) */, void* stream);
+                           void* workspace, int32_t* pair_off, int32_t* totals, void* stream);
 int pps_pairs_fill_device(const int64_t* query_ids, const int64_t* query_cams, long long nq,
                           const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
-                          const void* workspace, const int32_t* pair_off,
+                          const void* workspace,
                           int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos,
                           float* zero_f32 /* optional [capacity]: pair_d */, uint32_t* zero_u32 /* optional: cnt_le */,
+                          uint32_t* zero_per_query /* optional [nq]: cnt_first */,
                           long long capacity, void* stream);
+int pps_pairs_local_count(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
+                          void* workspace, int32_t** local_cnt, void* stream);
+int pps_pairs_offsets(const int32_t* cnt_all, int world, int rank, long long nq, long long ng_local,
+                      void* workspace, int32_t* pair_off, int32_t* totals, void* stream);
+int pps_pairs_fill_local(const int64_t* query_ids, const int64_t* query_cams, long long nq,
+                         const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
+                         long long gallery_offset, const void* workspace,
+                         int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos, int32_t* pair_pos32,
+                         float* zero_f32, uint32_t* zero_u32, uint32_t* zero_per_query,
+                         long long capacity, void* stream);
+int pps_pairs_unpack_pos(const int32_t* pair_pos32, long long n_pairs, uint8_t* pair_pos, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Part 2d — ranking on a materialised block of the distance matrix.
@@ -267,6 +286,32 @@ int pps_evaluate_device_ctx(pps_ctx* ctx, const float* d_q, long long nq,
                             double* out_map, double* out_cmc,
                             double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,
                             int32_t* out_topk_index, float* out_topk_dist);
+/* The resident evaluation in steps, so that a gallery sharded over several GPUs can put its exchanges
+ * in between (query ids / cameras are replicated; d_g, d_gallery_ids, d_gallery_cams are the rank's
+ * block of ng_local rows starting at global row gallery_offset; world = number of blocks):
+ *   pps_rank_begin        (also enqueues the operand split + the distance of the local block)
+ *                         -> all-gather of *d_local_cnt [nq int32 per rank] into cnt_all[world][nq]
+ *   pps_rank_thresholds   -> all-reduce(SUM, int32) of *d_exchange [*n_words = 3*n_pairs: thresholds as
+ *                            float bits | global gallery index | positive flag; one non-zero contributor each]
+ *   pps_rank_count_local  -> all-reduce(SUM) of *d_counters [*n_counters = nq + n_pairs uint32]
+ *   pps_rank_end          finalize, results to the host (top-k here is the LOCAL block's; sharded top-k
+ *                         is merged by the Python layer).
+ * With world == 1 (d_cnt_all = NULL) there is nothing to exchange.  The returned device pointers belong
+ * to the ctx and stay valid until the next pps_rank_begin. */
+int pps_rank_begin(pps_ctx* ctx, const float* d_q, long long nq, const float* d_g, long long ng_local, int dim,
+                   const int64_t* d_query_ids, const int64_t* d_query_cams,
+                   const int64_t* d_gallery_ids, const int64_t* d_gallery_cams,
+                   long long gallery_offset, int world, int precision, int topk, void* stream,
+                   void* pair_stream /* optional: the pair-list kernels run here (and the caller's all-gather
+                                        should too), overlapping the split + GEMM on `stream`; NULL = ctx policy */,
+                   int32_t** d_local_cnt);
+int pps_rank_thresholds(pps_ctx* ctx, const int32_t* d_cnt_all, int rank, void* stream,
+                      long long* n_pairs, int32_t** d_exchange, long long* n_words);
+int pps_rank_count_local(pps_ctx* ctx, void* stream, uint32_t** d_counters, long long* n_counters);
+int pps_rank_end(pps_ctx* ctx, int cmc_topk, void* stream, double* out_map, double* out_cmc,
+                 double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,
+                 int32_t* out_topk_index, float* out_topk_dist);
+
 /* Phase timing of pps_evaluate_device_ctx: when enabled, CUDA events are recorded on the caller's
  * stream between the phases and pps_ctx_phase_ms returns the device time of each phase of the
  * LAST call: 0 hand-off of the pair-list kernels to the side stream (they overlap the GEMM),

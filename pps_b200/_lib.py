@@ -13,7 +13,7 @@ import threading
 from . import build as _build
 
 # ---- constants (keep in sync with include/pps_b200.h) ----
-ABI_VERSION = 2
+ABI_VERSION = 3
 PPS_OK = 0
 PPS_ERR_INVALID_ARG = -1
 PPS_ERR_SHAPE = -2
@@ -66,8 +66,12 @@ SIGNATURES = {
     "pps_pairs_count": (_ll, [_vp, _ll, _vp, _ll]),
     "pps_pairs_fill": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp]),
     "pps_pairs_workspace_bytes": (_ll, [_ll, _ll]),
-    "pps_pairs_count_device": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _vp]),
+    "pps_pairs_count_device": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp]),
     "pps_pairs_fill_device": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "pps_pairs_local_count": (_i, [_vp, _ll, _vp, _ll, _vp, C.POINTER(_vp), _vp]),
+    "pps_pairs_offsets": (_i, [_vp, _i, _i, _ll, _ll, _vp, _vp, _vp, _vp]),
+    "pps_pairs_fill_local": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "pps_pairs_unpack_pos": (_i, [_vp, _ll, _vp, _vp]),
     "pps_rank_gather": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _ll, _vp, _vp]),
     "pps_rank_count": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "pps_rank_finalize": (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -80,6 +84,10 @@ SIGNATURES = {
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_evaluate_device_ctx": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_rank_begin": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp, _vp, C.POINTER(_vp)]),
+    "pps_rank_thresholds": (_i, [_vp, _vp, _i, _vp, C.POINTER(_ll), C.POINTER(_vp), C.POINTER(_ll)]),
+    "pps_rank_count_local": (_i, [_vp, _vp, C.POINTER(_vp), C.POINTER(_ll)]),
+    "pps_rank_end": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_ctx_set_timing": (_i, [_vp, _i]),
     "pps_ctx_phase_ms": (_i, [_vp, _vp]),
     "pps_evaluate_host": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i,

@@ -158,14 +158,39 @@ constexpr int kMaxSlabs = 64;
 
 }  // namespace
 
+namespace {
+struct EvalShape {
+  long long nq, ng /*rows of the local gallery block (and of its id arrays)*/, col0 /*its first global row*/, ldd;
+  int dim, kpad, planes, precision, topk;
+};
+struct Staging {   // pinned: totals, per-query results
+  int32_t* totals; double* ap; int32_t* first; uint8_t* valid;
+};
+}  // namespace
+
 struct pps_ctx {
   int device = 0;
   cudaStream_t copy_s = nullptr, comp_s = nullptr, side_s = nullptr;
   cudaEvent_t ev_slab[kMaxSlabs] = {};
   cudaEvent_t ev_totals = nullptr, ev_in = nullptr, ev_pairs = nullptr;
-  GrowBuf qf, gf, qs, gs, qn, gn, dist, ids, pair_ws, pair_off, totals, pair_q, pair_g, pair_pos, pair_d, cnt_le,
-      cnt_first, ap, valid, first, topk, tki, tkd;
+  GrowBuf qf, gf, qs, gs, qn, gn, dist, ids, pair_ws, pair_off, totals, pair_q, pair_pos, xbuf, counters,
+      ap, valid, first, topk, tki, tkd;
   PinBuf h_small;      // totals + per-query results
+  // state of the evaluation in flight (pps_rank_begin .. pps_rank_end)
+  EvalShape cur = {};
+  Staging st = {};
+  const int64_t *d_qid = nullptr, *d_qcam = nullptr, *d_gid = nullptr, *d_gcam = nullptr;
+  const float *d_q = nullptr, *d_g = nullptr;
+  long long n_pairs = 0;
+  int max_pairs = 0;
+  int world = 1;
+  int32_t* local_cnt = nullptr;                 // inside pair_ws
+  // exchange buffer xbuf = [pair_d bits (E) | pair_g (E) | pair_pos as int32 (E)], E = n_pairs
+  float* pair_d() const { return xbuf.as<float>(); }
+  int32_t* pair_g() const { return xbuf.as<int32_t>() + n_pairs; }
+  int32_t* pair_pos32() const { return xbuf.as<int32_t>() + 2 * n_pairs; }
+  cudaStream_t ext_pair_s = nullptr;            // caller-provided stream for the pair kernels (sharded runs)
+  cudaStream_t pair_stream(cudaStream_t cs) const { return ext_pair_s ? ext_pair_s : (world == 1 ? side_s : cs); }
   // optional phase timing of pps_evaluate_device_ctx (events on the caller's stream)
   bool timing = false;
   cudaEvent_t ev_phase[PPS_N_PHASES + 1] = {};
@@ -208,7 +233,7 @@ extern "C" int pps_ctx_destroy(pps_ctx* c) {
   if (c->copy_s) cudaStreamSynchronize(c->copy_s);
   if (c->side_s) cudaStreamSynchronize(c->side_s);
   GrowBuf* bufs[] = {&c->qf, &c->gf, &c->qs, &c->gs, &c->qn, &c->gn, &c->dist, &c->ids, &c->pair_ws, &c->pair_off,
-                     &c->totals, &c->pair_q, &c->pair_g, &c->pair_pos, &c->pair_d, &c->cnt_le, &c->cnt_first, &c->ap,
+                     &c->totals, &c->pair_q, &c->pair_pos, &c->xbuf, &c->counters, &c->ap,
                      &c->valid, &c->first, &c->topk, &c->tki, &c->tkd};
   for (GrowBuf* b : bufs) b->release();
   c->h_small.release();
@@ -226,35 +251,25 @@ extern "C" int pps_ctx_destroy(pps_ctx* c) {
 
 namespace {
 
-struct EvalShape {
-  long long nq, ng, ldd;
-  int dim, kpad, planes, precision, cmc_topk, topk;
-};
-
-int eval_shape(long long nq, long long ng, int dim, int precision, int cmc_topk, int topk, EvalShape* e) {
-  if (nq <= 0 || ng <= 0 || dim <= 0 || cmc_topk < 0 || topk < 0 || topk > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
-  if (nq > 0x7fffffffLL || ng > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+int eval_shape(long long nq, long long ng, long long col0, int dim, int precision, int topk, EvalShape* e) {
+  if (nq <= 0 || ng <= 0 || dim <= 0 || topk < 0 || topk > PPS_TOPK_MAX || col0 < 0) return PPS_ERR_INVALID_ARG;
+  if (nq > 0x7fffffffLL || col0 + ng > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
   switch (precision) {
     case PPS_PREC_BF16X1: e->planes = 1; break;
     case PPS_PREC_BF16X3: e->planes = 2; break;
     case PPS_PREC_BF16X6: e->planes = 3; break;
     default: return PPS_ERR_INVALID_ARG;
   }
-  e->nq = nq; e->ng = ng; e->dim = dim; e->precision = precision; e->cmc_topk = cmc_topk; e->topk = topk;
+  e->nq = nq; e->ng = ng; e->col0 = col0; e->dim = dim; e->precision = precision; e->topk = topk;
   e->ldd = (ng + 3) & ~3LL;
   e->kpad = pps_kpad(dim);
-  // the distance matrix is materialised once: bound it (larger galleries go through the chunked
+  // the distance block is materialised once: bound it (larger galleries go through the chunked
   // two-sweep path of the Python layer, evaluator.RankEngine)
   if ((double)nq * (double)e->ldd * 4.0 > 64.0 * (double)(1LL << 30)) return PPS_ERR_UNSUPPORTED;
   return PPS_OK;
 }
 
-// pinned staging layout: [0,16) totals | ap[nq] f64 | first[nq] i32 | valid[nq] u8
-struct Staging {
-  int32_t* totals; double* ap; int32_t* first; uint8_t* valid;
-};
-
-int ensure_common(pps_ctx* c, const EvalShape& e, Staging* st) {
+int ensure_common(pps_ctx* c, const EvalShape& e) {
   PPS_TRY(c->qs.ensure((size_t)pps_split_bytes(e.nq, e.dim, e.planes)));
   PPS_TRY(c->gs.ensure((size_t)pps_split_bytes(e.ng, e.dim, e.planes)));
   PPS_TRY(c->qn.ensure((size_t)e.nq * 4));
@@ -263,79 +278,107 @@ int ensure_common(pps_ctx* c, const EvalShape& e, Staging* st) {
   PPS_TRY(c->pair_ws.ensure((size_t)pps_pairs_workspace_bytes(e.nq, e.ng)));
   PPS_TRY(c->pair_off.ensure(((size_t)e.nq + 1) * 4));
   PPS_TRY(c->totals.ensure(16));
-  PPS_TRY(c->cnt_first.ensure((size_t)e.nq * 4));
   PPS_TRY(c->ap.ensure((size_t)e.nq * 8));
   PPS_TRY(c->valid.ensure((size_t)e.nq));
   PPS_TRY(c->first.ensure((size_t)e.nq * 4));
+  // pinned staging: [0,16) totals | ap[nq] f64 | first[nq] i32 | valid[nq] u8
   const size_t off_ap = 16, off_first = off_ap + (size_t)e.nq * 8, off_valid = off_first + (size_t)e.nq * 4;
   PPS_TRY(c->h_small.ensure(off_valid + (size_t)e.nq));
   unsigned char* base = c->h_small.as<unsigned char>();
-  st->totals = reinterpret_cast<int32_t*>(base);
-  st->ap = reinterpret_cast<double*>(base + off_ap);
-  st->first = reinterpret_cast<int32_t*>(base + off_first);
-  st->valid = base + off_valid;
+  c->st.totals = reinterpret_cast<int32_t*>(base);
+  c->st.ap = reinterpret_cast<double*>(base + off_ap);
+  c->st.first = reinterpret_cast<int32_t*>(base + off_first);
+  c->st.valid = base + off_valid;
   return PPS_OK;
 }
 
-// ids (device) -> pair counts + offsets, {n_pairs, max_pairs} on their way back to the host.  Runs on the ctx's
-// SIDE stream (ordered after `ready_on`, the stream the ids become valid on): the pair kernels are independent of
-// the distance GEMM and hide under it.
-int begin_pairs(pps_ctx* c, const EvalShape& e, const int64_t* d_qid, const int64_t* d_gid, const Staging& st,
-                cudaStream_t ready_on) {
-  cudaStream_t ss = c->side_s;
-  if (ready_on != ss) {
+// Pair lists, step 1: hits of every query in the LOCAL gallery block.  Single GPU: on the ctx's side stream (ordered
+// after `ready_on`, the stream the ids become valid on) so that the pair kernels hide under the distance GEMM.
+// Sharded: on the caller's stream, because the caller all-gathers the counts right after.
+int pairs_local_count(pps_ctx* c, cudaStream_t ready_on) {
+  const EvalShape& e = c->cur;
+  cudaStream_t ps = c->pair_stream(ready_on);
+  if (ready_on != ps) {
     PPS_CUDA_TRY(cudaEventRecord(c->ev_in, ready_on));
-    PPS_CUDA_TRY(cudaStreamWaitEvent(ss, c->ev_in, 0));
+    PPS_CUDA_TRY(cudaStreamWaitEvent(ps, c->ev_in, 0));
   }
-  PPS_TRY(pps_pairs_count_device(d_qid, e.nq, d_gid, e.ng, c->pair_ws.p, c->pair_off.as<int32_t>(),
-                                 c->totals.as<int32_t>(), c->cnt_first.as<uint32_t>(), ss));
-  PPS_CUDA_TRY(cudaMemcpyAsync(st.totals, c->totals.p, 8, cudaMemcpyDeviceToHost, ss));
-  PPS_CUDA_TRY(cudaEventRecord(c->ev_totals, ss));
+  return pps_pairs_local_count(c->d_qid, e.nq, c->d_gid, e.ng, c->pair_ws.p, &c->local_cnt, ps);
+}
+
+// step 2: global offsets from the (all-gathered) per-block counts; {n_pairs, max_pairs} on their way to the host
+int pairs_offsets(pps_ctx* c, const int32_t* cnt_all, int rank, cudaStream_t cs) {
+  const EvalShape& e = c->cur;
+  cudaStream_t ps = c->pair_stream(cs);
+  PPS_TRY(pps_pairs_offsets(cnt_all, c->world, rank, e.nq, e.ng, c->pair_ws.p, c->pair_off.as<int32_t>(),
+                            c->totals.as<int32_t>(), ps));
+  PPS_CUDA_TRY(cudaMemcpyAsync(c->st.totals, c->totals.p, 8, cudaMemcpyDeviceToHost, ps));
+  PPS_CUDA_TRY(cudaEventRecord(c->ev_totals, ps));
   return PPS_OK;
 }
 
-// everything after the distance matrix is complete: pair lists, thresholds, counts, finalize, results back
-int rank_tail(pps_ctx* c, const EvalShape& e, const int64_t* d_qid, const int64_t* d_qcam, const int64_t* d_gid,
-              const int64_t* d_gcam, const Staging& st, cudaStream_t cs, double* out_map, double* out_cmc,
-              double* out_ap, uint8_t* out_valid, int32_t* out_first_rank, int32_t* out_topk_index,
-              float* out_topk_dist) {
-  const long long nq = e.nq, ng = e.ng, ldd = e.ldd;
-  const int topk = e.topk, cmc_topk = e.cmc_topk;
-  PPS_CUDA_TRY(cudaEventSynchronize(c->ev_totals));     // side stream: back while the GEMM is still running
-  const long long n_pairs = st.totals[0];
-  const int max_pairs = st.totals[1];
-  const size_t np1 = (size_t)std::max<long long>(n_pairs, 1);
+// step 3, after the distance block is enqueued: size + fill the local pairs into their global slots, gather the
+// thresholds that live in this block.  counters = [cnt_first (nq) | cnt_le (n_pairs)], zero-filled by the fill.
+int pairs_and_thresholds(pps_ctx* c, cudaStream_t cs) {
+  const EvalShape& e = c->cur;
+  cudaStream_t ps = c->pair_stream(cs);
+  PPS_CUDA_TRY(cudaEventSynchronize(c->ev_totals));     // came back while the GEMM is still running
+  c->n_pairs = c->st.totals[0];
+  c->max_pairs = c->st.totals[1];
+  const size_t np1 = (size_t)std::max<long long>(c->n_pairs, 1);
   PPS_TRY(c->pair_q.ensure(np1 * 4));
-  PPS_TRY(c->pair_g.ensure(np1 * 4));
   PPS_TRY(c->pair_pos.ensure(np1));
-  PPS_TRY(c->pair_d.ensure(np1 * 4));
-  PPS_TRY(c->cnt_le.ensure(np1 * 4));
-  PPS_TRY(pps_pairs_fill_device(d_qid, d_qcam, nq, d_gid, d_gcam, ng, c->pair_ws.p, c->pair_off.as<int32_t>(),
-                                c->pair_q.as<int32_t>(), c->pair_g.as<int32_t>(), c->pair_pos.as<uint8_t>(),
-                                c->pair_d.as<float>(), c->cnt_le.as<uint32_t>(), n_pairs, c->side_s));
-  PPS_CUDA_TRY(cudaEventRecord(c->ev_pairs, c->side_s));
-  PPS_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_pairs, 0));     // the rank sweeps need the lists; the GEMM did not
-  PPS_TRY(pps_rank_gather(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_q.as<int32_t>(), c->pair_g.as<int32_t>(), n_pairs,
-                          c->pair_d.as<float>(), cs));
-  mark(c, 4, cs);
-  PPS_TRY(pps_rank_count(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(),
-                         c->pair_pos.as<uint8_t>(), c->pair_d.as<float>(), max_pairs, c->cnt_le.as<uint32_t>(),
-                         c->cnt_first.as<uint32_t>(), cs));
-  mark(c, 5, cs);
-  PPS_TRY(pps_rank_finalize(nq, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(), c->pair_pos.as<uint8_t>(),
-                            c->pair_d.as<float>(), c->cnt_le.as<uint32_t>(), c->cnt_first.as<uint32_t>(),
-                            c->ap.as<double>(), c->valid.as<uint8_t>(), c->first.as<int32_t>(), nullptr, cs));
+  PPS_TRY(c->xbuf.ensure(np1 * 12));
+  PPS_TRY(c->counters.ensure(((size_t)e.nq + np1) * 4));
+  uint32_t* cnt_first = c->counters.as<uint32_t>();
+  uint32_t* cnt_le = cnt_first + e.nq;
+  if (c->world > 1) {
+    // slots of pairs that live on other shards: zero (they are summed in by the exchange) and marked unfilled
+    PPS_CUDA_TRY(cudaMemsetAsync(c->xbuf.p, 0, np1 * 12, ps));
+    PPS_CUDA_TRY(cudaMemsetAsync(c->pair_q.p, 0xFF, np1 * 4, ps));
+    PPS_CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, ((size_t)e.nq + np1) * 4, ps));
+  }
+  PPS_TRY(pps_pairs_fill_local(c->d_qid, c->d_qcam, e.nq, c->d_gid, c->d_gcam, e.ng, e.col0, c->pair_ws.p,
+                               c->pair_q.as<int32_t>(), c->pair_g(), c->pair_pos.as<uint8_t>(),
+                               c->world > 1 ? c->pair_pos32() : nullptr, c->pair_d(), cnt_le, cnt_first, c->n_pairs, ps));
+  if (ps != cs) {
+    PPS_CUDA_TRY(cudaEventRecord(c->ev_pairs, ps));
+    PPS_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_pairs, 0));   // the rank sweeps need the lists; the GEMM did not
+  }
+  PPS_TRY(pps_rank_gather(c->dist.as<float>(), e.ldd, e.nq, e.ng, e.col0, c->pair_q.as<int32_t>(), c->pair_g(),
+                          c->n_pairs, c->pair_d(), cs));
+  return PPS_OK;
+}
+
+int count_local(pps_ctx* c, cudaStream_t cs) {
+  const EvalShape& e = c->cur;
+  uint32_t* cnt_first = c->counters.as<uint32_t>();
+  if (c->world > 1)    // after the exchange every rank holds all pairs; the kernels read the flags as bytes
+    PPS_TRY(pps_pairs_unpack_pos(c->pair_pos32(), c->n_pairs, c->pair_pos.as<uint8_t>(), cs));
+  return pps_rank_count(c->dist.as<float>(), e.ldd, e.nq, e.ng, e.col0, c->pair_off.as<int32_t>(), c->pair_g(),
+                        c->pair_pos.as<uint8_t>(), c->pair_d(), c->max_pairs, cnt_first + e.nq, cnt_first, cs);
+}
+
+// finalize from the (reduced) counters, optional local top-k, results back, the reference's averaging
+int finalize_and_fetch(pps_ctx* c, int cmc_topk, cudaStream_t cs, double* out_map, double* out_cmc, double* out_ap,
+                       uint8_t* out_valid, int32_t* out_first_rank, int32_t* out_topk_index, float* out_topk_dist) {
+  const EvalShape& e = c->cur;
+  const long long nq = e.nq;
+  const int topk = e.topk;
+  const Staging& st = c->st;
+  uint32_t* cnt_first = c->counters.as<uint32_t>();
+  PPS_TRY(pps_rank_finalize(nq, c->pair_off.as<int32_t>(), c->pair_g(), c->pair_pos.as<uint8_t>(),
+                            c->pair_d(), cnt_first + nq, cnt_first, c->ap.as<double>(),
+                            c->valid.as<uint8_t>(), c->first.as<int32_t>(), nullptr, cs));
   if (topk > 0) {
     PPS_TRY(c->topk.ensure((size_t)nq * topk * 8));
     PPS_TRY(c->tki.ensure((size_t)nq * topk * 4));
     PPS_TRY(c->tkd.ensure((size_t)nq * topk * 4));
     PPS_TRY(pps_topk_init(c->topk.as<uint64_t>(), nq, topk, cs));
-    PPS_TRY(pps_topk_update(c->dist.as<float>(), ldd, nq, ng, 0, c->pair_off.as<int32_t>(), c->pair_g.as<int32_t>(),
+    PPS_TRY(pps_topk_update(c->dist.as<float>(), e.ldd, nq, e.ng, e.col0, c->pair_off.as<int32_t>(), c->pair_g(),
                             c->pair_pos.as<uint8_t>(), c->topk.as<uint64_t>(), topk, cs));
     PPS_TRY(pps_topk_unpack(c->topk.as<uint64_t>(), nq, topk, c->tkd.as<float>(), c->tki.as<int32_t>(), cs));
   }
   mark(c, 6, cs);
-  // ---- results back ----
   PPS_CUDA_TRY(cudaMemcpyAsync(st.ap, c->ap.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, cs));
   PPS_CUDA_TRY(cudaMemcpyAsync(st.first, c->first.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, cs));
   PPS_CUDA_TRY(cudaMemcpyAsync(st.valid, c->valid.p, (size_t)nq, cudaMemcpyDeviceToHost, cs));
@@ -360,13 +403,22 @@ int rank_tail(pps_ctx* c, const EvalShape& e, const int64_t* d_qid, const int64_
   if (out_valid) std::memcpy(out_valid, st.valid, (size_t)nq);
   if (out_first_rank) std::memcpy(out_first_rank, st.first, (size_t)nq * 4);
   if (n_valid == 0) return PPS_ERR_NO_VALID_QUERY;
-  *out_map = ap_sum / (double)n_valid;
+  if (out_map) *out_map = ap_sum / (double)n_valid;
   double run = 0.0;
-  for (int k = 0; k < cmc_topk; ++k) {
+  for (int k = 0; k < cmc_topk && out_cmc; ++k) {
     run += hist[(size_t)k];
     out_cmc[k] = run / (double)n_valid;
   }
   return PPS_OK;
+}
+
+void collect_phase_times(pps_ctx* c) {
+  if (!c->timing) return;
+  for (int i = 0; i < PPS_N_PHASES; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_phase[i], c->ev_phase[i + 1]) != cudaSuccess) ms = -1.f;
+    c->phase_ms[i] = ms;
+  }
 }
 
 }  // namespace
@@ -377,18 +429,19 @@ extern "C" int pps_evaluate_host_ctx(pps_ctx* c, const float* q_feats, long long
                                      int cmc_topk, int topk, double* out_map, double* out_cmc, double* out_ap,
                                      uint8_t* out_valid, int32_t* out_first_rank, int32_t* out_topk_index,
                                      float* out_topk_dist) {
-  if (!c) return PPS_ERR_INVALID_ARG;
-  EvalShape e;
-  PPS_TRY(eval_shape(nq, ng, dim, precision, cmc_topk, topk, &e));
+  if (!c || cmc_topk < 0) return PPS_ERR_INVALID_ARG;
+  PPS_TRY(eval_shape(nq, ng, 0, dim, precision, topk, &c->cur));
+  c->world = 1;
+  c->ext_pair_s = nullptr;
+  const EvalShape& e = c->cur;
   if (!q_feats || !g_feats || !query_ids || !query_cams || !gallery_ids || !gallery_cams) return PPS_ERR_INVALID_ARG;
   if (!out_map || (cmc_topk > 0 && !out_cmc)) return PPS_ERR_INVALID_ARG;
   PPS_CUDA_TRY(cudaSetDevice(c->device));
-  cudaStream_t cs = c->comp_s, ps = c->copy_s;
+  cudaStream_t cs = c->comp_s, ps = c->copy_s, ss = c->side_s;
   const int planes = e.planes, kpad = e.kpad;
   const long long ldd = e.ldd;
 
-  Staging st;
-  PPS_TRY(ensure_common(c, e, &st));
+  PPS_TRY(ensure_common(c, e));
   PPS_TRY(c->qf.ensure((size_t)nq * dim * 4));
   PPS_TRY(c->gf.ensure((size_t)ng * dim * 4));
   PPS_TRY(c->ids.ensure((size_t)(2 * nq + 2 * ng) * 8));
@@ -396,14 +449,15 @@ extern "C" int pps_evaluate_host_ctx(pps_ctx* c, const float* q_feats, long long
   int64_t* d_qcam = d_qid + nq;
   int64_t* d_gid = d_qcam + nq;
   int64_t* d_gcam = d_gid + ng;
+  c->d_qid = d_qid; c->d_qcam = d_qcam; c->d_gid = d_gid; c->d_gcam = d_gcam;
 
-  // ---- ids up, pair counts + offsets, totals back (tiny; the host reads them while the GEMM runs) ----
-  cudaStream_t ss = c->side_s;
+  // ---- ids up, pair counts + offsets, totals back: all on the side stream, hidden under the feature upload ----
   PPS_CUDA_TRY(cudaMemcpyAsync(d_qid, query_ids, (size_t)nq * 8, cudaMemcpyHostToDevice, ss));
   PPS_CUDA_TRY(cudaMemcpyAsync(d_qcam, query_cams, (size_t)nq * 8, cudaMemcpyHostToDevice, ss));
   PPS_CUDA_TRY(cudaMemcpyAsync(d_gid, gallery_ids, (size_t)ng * 8, cudaMemcpyHostToDevice, ss));
   PPS_CUDA_TRY(cudaMemcpyAsync(d_gcam, gallery_cams, (size_t)ng * 8, cudaMemcpyHostToDevice, ss));
-  PPS_TRY(begin_pairs(c, e, d_qid, d_gid, st, ss));
+  PPS_TRY(pairs_local_count(c, ss));
+  PPS_TRY(pairs_offsets(c, c->local_cnt, 0, ss));
 
   // ---- queries up + split ----
   PPS_CUDA_TRY(cudaMemcpyAsync(c->qf.p, q_feats, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, cs));
@@ -426,48 +480,100 @@ extern "C" int pps_evaluate_host_ctx(pps_ctx* c, const float* q_feats, long long
                         c->gs.as<unsigned char>() + (size_t)r0 * kpad * esz, c->gn.as<float>() + r0, nr, planes, ng, dim,
                         precision, 0, c->dist.as<float>() + r0, ldd, cs));
   }
-  const int rc = rank_tail(c, e, d_qid, d_qcam, d_gid, d_gcam, st, cs, out_map, out_cmc, out_ap, out_valid,
-                           out_first_rank, out_topk_index, out_topk_dist);
+  int rc = pairs_and_thresholds(c, cs);
+  if (rc == PPS_OK) rc = count_local(c, cs);
+  if (rc == PPS_OK)
+    rc = finalize_and_fetch(c, cmc_topk, cs, out_map, out_cmc, out_ap, out_valid, out_first_rank, out_topk_index,
+                            out_topk_dist);
   cudaStreamSynchronize(ps);
   return rc;
 }
 
-// Same evaluation with everything already RESIDENT on the device (features fp32 [rows, dim] contiguous, ids /
-// cameras int64): what bench.py times as `value`.  All work is enqueued on `stream` (the caller's stream, so it
-// is ordered after whatever produced the inputs); the call returns after the small results are on the host.
+// ------------------------------------------------------------------------------------
+// Resident evaluation in steps, so that a gallery sharded over several GPUs can put its exchanges in between:
+//   pps_rank_begin        hits of each query in the LOCAL block; operand split + distance of the local block enqueued
+//                                                                      -> all-gather *d_local_cnt over ranks [nq int32 each]
+//   pps_rank_thresholds   global pair offsets, local pairs into their global slots, their thresholds
+//                                                                      -> all-reduce(SUM, int32) *d_exchange [*n_words]
+//   pps_rank_count_local  counting sweep over the local block          -> all-reduce(SUM) *d_counters [nq + n_pairs u32]
+//   pps_rank_end          finalize, (local) top-k, results to the host, the reference's averaging
+// With world == 1 the exchanges are skipped and the pair kernels run on a side stream under the GEMM.
+// ------------------------------------------------------------------------------------
+extern "C" int pps_rank_begin(pps_ctx* c, const float* d_q, long long nq, const float* d_g, long long ng_local, int dim,
+                              const int64_t* d_qid, const int64_t* d_qcam, const int64_t* d_gid_local,
+                              const int64_t* d_gcam_local, long long gallery_offset, int world, int precision, int topk,
+                              void* stream, void* pair_stream, int32_t** d_local_cnt) {
+  if (!c || world < 1) return PPS_ERR_INVALID_ARG;
+  PPS_TRY(eval_shape(nq, ng_local, gallery_offset, dim, precision, topk, &c->cur));
+  if (!d_q || !d_g || !d_qid || !d_qcam || !d_gid_local || !d_gcam_local) return PPS_ERR_INVALID_ARG;
+  PPS_CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  c->d_qid = d_qid; c->d_qcam = d_qcam; c->d_gid = d_gid_local; c->d_gcam = d_gcam_local;
+  c->d_q = d_q; c->d_g = d_g;
+  c->world = world;
+  c->ext_pair_s = static_cast<cudaStream_t>(pair_stream);
+  PPS_TRY(ensure_common(c, c->cur));
+  const EvalShape& e = c->cur;
+  mark(c, 0, cs);
+  PPS_TRY(pairs_local_count(c, cs));
+  if (d_local_cnt) *d_local_cnt = c->local_cnt;
+  mark(c, 1, cs);
+  // the distance block is enqueued NOW, so that the caller's all-gather (host latency included) hides under it
+  PPS_TRY(pps_split_rows(d_q, PPS_DTYPE_F32, e.nq, e.dim, e.dim, e.planes, c->qs.p, c->qn.as<float>(), cs));
+  PPS_TRY(pps_split_rows(d_g, PPS_DTYPE_F32, e.ng, e.dim, e.dim, e.planes, c->gs.p, c->gn.as<float>(), cs));
+  mark(c, 2, cs);
+  PPS_TRY(pps_dist_tc(c->qs.p, c->qn.as<float>(), e.nq, e.planes, 0, c->gs.p, c->gn.as<float>(), e.ng, e.planes, 0,
+                      e.dim, e.precision, world > 1 ? PPS_DIST_RESERVE_SM_PAIR : 0, c->dist.as<float>(), e.ldd, cs));
+  mark(c, 3, cs);
+  return PPS_OK;
+}
+
+extern "C" int pps_rank_thresholds(pps_ctx* c, const int32_t* d_cnt_all, int rank, void* stream, long long* n_pairs,
+                                   int32_t** d_exchange, long long* n_words) {
+  if (!c || c->cur.nq <= 0 || rank < 0 || rank >= c->world) return PPS_ERR_INVALID_ARG;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  PPS_TRY(pairs_offsets(c, d_cnt_all ? d_cnt_all : c->local_cnt, rank, cs));
+  PPS_TRY(pairs_and_thresholds(c, cs));
+  mark(c, 4, cs);
+  if (n_pairs) *n_pairs = c->n_pairs;
+  if (d_exchange) *d_exchange = c->xbuf.as<int32_t>();
+  if (n_words) *n_words = 3 * c->n_pairs;
+  return PPS_OK;
+}
+
+extern "C" int pps_rank_count_local(pps_ctx* c, void* stream, uint32_t** d_counters, long long* n_counters) {
+  if (!c || c->cur.nq <= 0) return PPS_ERR_INVALID_ARG;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  PPS_TRY(count_local(c, cs));
+  mark(c, 5, cs);
+  if (d_counters) *d_counters = c->counters.as<uint32_t>();
+  if (n_counters) *n_counters = c->cur.nq + c->n_pairs;
+  return PPS_OK;
+}
+
+extern "C" int pps_rank_end(pps_ctx* c, int cmc_topk, void* stream, double* out_map, double* out_cmc, double* out_ap,
+                            uint8_t* out_valid, int32_t* out_first_rank, int32_t* out_topk_index,
+                            float* out_topk_dist) {
+  if (!c || c->cur.nq <= 0 || cmc_topk < 0) return PPS_ERR_INVALID_ARG;
+  const int rc = finalize_and_fetch(c, cmc_topk, static_cast<cudaStream_t>(stream), out_map, out_cmc, out_ap, out_valid,
+                                    out_first_rank, out_topk_index, out_topk_dist);
+  if (rc == PPS_OK || rc == PPS_ERR_NO_VALID_QUERY) collect_phase_times(c);
+  return rc;
+}
+
+// Same evaluation with everything already RESIDENT on one device: what bench.py times as `value` at N = 1.
 extern "C" int pps_evaluate_device_ctx(pps_ctx* c, const float* d_q, long long nq, const float* d_g, long long ng,
                                        int dim, const int64_t* d_qid, const int64_t* d_qcam, const int64_t* d_gid,
                                        const int64_t* d_gcam, int precision, int cmc_topk, int topk, void* stream,
                                        double* out_map, double* out_cmc, double* out_ap, uint8_t* out_valid,
                                        int32_t* out_first_rank, int32_t* out_topk_index, float* out_topk_dist) {
-  if (!c) return PPS_ERR_INVALID_ARG;
-  EvalShape e;
-  PPS_TRY(eval_shape(nq, ng, dim, precision, cmc_topk, topk, &e));
-  if (!d_q || !d_g || !d_qid || !d_qcam || !d_gid || !d_gcam) return PPS_ERR_INVALID_ARG;
   if (!out_map || (cmc_topk > 0 && !out_cmc)) return PPS_ERR_INVALID_ARG;
-  PPS_CUDA_TRY(cudaSetDevice(c->device));
-  cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  Staging st;
-  PPS_TRY(ensure_common(c, e, &st));
-  mark(c, 0, cs);
-  PPS_TRY(begin_pairs(c, e, d_qid, d_gid, st, cs));
-  mark(c, 1, cs);
-  PPS_TRY(pps_split_rows(d_q, PPS_DTYPE_F32, nq, dim, dim, e.planes, c->qs.p, c->qn.as<float>(), cs));
-  PPS_TRY(pps_split_rows(d_g, PPS_DTYPE_F32, ng, dim, dim, e.planes, c->gs.p, c->gn.as<float>(), cs));
-  mark(c, 2, cs);
-  PPS_TRY(pps_dist_tc(c->qs.p, c->qn.as<float>(), nq, e.planes, 0, c->gs.p, c->gn.as<float>(), ng, e.planes, 0, dim,
-                      precision, 0, c->dist.as<float>(), e.ldd, cs));
-  mark(c, 3, cs);
-  const int rc = rank_tail(c, e, d_qid, d_qcam, d_gid, d_gcam, st, cs, out_map, out_cmc, out_ap, out_valid,
-                           out_first_rank, out_topk_index, out_topk_dist);
-  if (c->timing && (rc == PPS_OK || rc == PPS_ERR_NO_VALID_QUERY)) {
-    for (int i = 0; i < PPS_N_PHASES; ++i) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, c->ev_phase[i], c->ev_phase[i + 1]) != cudaSuccess) ms = -1.f;
-      c->phase_ms[i] = ms;
-    }
-  }
-  return rc;
+  PPS_TRY(pps_rank_begin(c, d_q, nq, d_g, ng, dim, d_qid, d_qcam, d_gid, d_gcam, 0, 1, precision, topk, stream, nullptr,
+                         nullptr));
+  PPS_TRY(pps_rank_thresholds(c, nullptr, 0, stream, nullptr, nullptr, nullptr));
+  PPS_TRY(pps_rank_count_local(c, stream, nullptr, nullptr));
+  return pps_rank_end(c, cmc_topk, stream, out_map, out_cmc, out_ap, out_valid, out_first_rank, out_topk_index,
+                      out_topk_dist);
 }
 
 extern "C" int pps_ctx_set_timing(pps_ctx* c, int enabled) {

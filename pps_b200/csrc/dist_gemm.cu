@@ -572,7 +572,9 @@ extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long lon
       configured2_dev = dev;
     }
     const long long tiles2 = (long long)ga.g.m_tiles * ga.g.n_tiles;
-    const long long pairs = tiles2 < sms / 2 ? tiles2 : sms / 2;
+    long long slots = sms / 2;
+    if ((flags & PPS_DIST_RESERVE_SM_PAIR) && slots > 8) slots -= 1;   // leave one SM pair to concurrent small kernels
+    const long long pairs = tiles2 < slots ? tiles2 : slots;
     dist_tc2_kernel<<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga);
     PPS_LAUNCH_CHECK("dist_tc2_kernel");
     return PPS_OK;

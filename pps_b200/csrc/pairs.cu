@@ -11,10 +11,12 @@
 // contraction they accompany, need no sort and no hash table, and the order is deterministic:
 //   count : CTA (query block of 32, gallery segment) -> 8 warps x 4 queries; a warp streams the
 //           segment's ids once (coalesced), 4 ballots per 32 ids, popc-accumulates per query.
-//   scan  : one CTA sums each query's segment counts and scans over queries -> pair_off and
-//           {n_pairs, max pairs per query}.
-//   fill  : same sweep as count; slot = pair_off[q] + hits in earlier segments + ballot prefix
+//   offsets: per-query totals of this gallery block -> (sharded: all-gather over ranks ->) one CTA
+//           scans over queries -> pair_off, this block's first slot per query, {n_pairs, max/query}.
+//   fill  : same sweep as count; slot = my_base[q] + hits in earlier segments + ballot prefix
 //           -> ascending g.  It also zero-fills the per-pair accumulators of the rank sweeps.
+// A gallery sharded over ranks sweeps only its own block (nq x ng_local compares per rank); the
+// blocks' lists interleave into one global CSR because blocks are contiguous row ranges.
 #include "common.cuh"
 
 namespace pps {
@@ -28,9 +30,11 @@ __global__ void __launch_bounds__(32 * kPairWarps)
 pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ qcam, int nq,
                    const int64_t* __restrict__ gid, const int64_t* __restrict__ gcam, long long ng, long long seg,
                    int nseg, int32_t* __restrict__ seg_cnt /*[nq][nseg] hits of query q in segment s*/,
-                   const int32_t* __restrict__ pair_off, int32_t* __restrict__ pair_q, int32_t* __restrict__ pair_g,
-                   uint8_t* __restrict__ pair_pos, float* __restrict__ zero_f32, uint32_t* __restrict__ zero_u32,
-                   long long capacity) {
+                   const int32_t* __restrict__ my_base /*[nq] first global slot of this block's hits of query q*/,
+                   long long g_offset /*global index of local gallery row 0*/, int32_t* __restrict__ pair_q,
+                   int32_t* __restrict__ pair_g, uint8_t* __restrict__ pair_pos, int32_t* __restrict__ pair_pos32,
+                   float* __restrict__ zero_f32, uint32_t* __restrict__ zero_u32,
+                   uint32_t* __restrict__ zero_per_query, long long capacity) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * kPairQPerCta + warp * kPairQPerWarp;
   const int s = blockIdx.y;
@@ -45,12 +49,13 @@ pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ 
     cams[u] = (FILL && live[u]) ? qcam[q0 + u] : 0;
     acc[u] = 0;
     if (FILL && live[u]) {
-      // first slot of (query, segment) = pair_off[q] + hits of q in the earlier segments
+      // first slot of (query, segment) = my_base[q] + hits of q in the earlier segments of this block
       int part = 0;
       for (int sp = lane; sp < s; sp += 32) part += seg_cnt[(long long)(q0 + u) * nseg + sp];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      acc[u] = pair_off[q0 + u] + part;
+      acc[u] = my_base[q0 + u] + part;
+      if (zero_per_query && s == 0 && lane == 0) zero_per_query[q0 + u] = 0u;
     }
   }
   const long long g_begin = (long long)s * seg;
@@ -77,8 +82,10 @@ pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ 
             const long long slot = (long long)acc[u] + __popc(b & lt);
             if (slot < capacity) {
               pair_q[slot] = q0 + u;
-              pair_g[slot] = (int32_t)g;
-              pair_pos[slot] = gcam[g] != cams[u] ? 1 : 0;
+              pair_g[slot] = (int32_t)(g + g_offset);
+              const int pos = gcam[g] != cams[u] ? 1 : 0;
+              if (pair_pos) pair_pos[slot] = (uint8_t)pos;
+              if (pair_pos32) pair_pos32[slot] = pos;
               if (zero_f32) zero_f32[slot] = 0.f;
               if (zero_u32) zero_u32[slot] = 0u;
             }
@@ -95,11 +102,23 @@ pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ 
   }
 }
 
-// pair_off[q] = exclusive scan over queries of their total hits (sum over segments); totals = {n_pairs, max per
-// query}; optionally zeroes a per-query counter array.  One CTA of 1024 threads, 1024 queries per iteration.
-__global__ void __launch_bounds__(1024) pairs_scan_kernel(const int32_t* __restrict__ seg_cnt, int nq, int nseg,
-                                                          int32_t* __restrict__ pair_off, int32_t* __restrict__ totals,
-                                                          uint32_t* __restrict__ zero_per_query) {
+// local_cnt[q] = hits of query q in this gallery block (sum over its segments)
+__global__ void pairs_rowsum_kernel(const int32_t* __restrict__ seg_cnt, int nq, int nseg, int32_t* __restrict__ local_cnt) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int32_t* row = seg_cnt + (long long)q * nseg;
+  int sum = 0;
+  for (int sgi = 0; sgi < nseg; ++sgi) sum += row[sgi];
+  local_cnt[q] = sum;
+}
+
+// Global CSR offsets from the per-block counts cnt_all[world][nq] (world = 1: the local counts):
+//   pair_off[q] = sum over q' < q and all blocks;  my_base[q] = pair_off[q] + sum over blocks r' < rank of cnt_all[r'][q]
+//   (blocks are contiguous gallery ranges in rank order, so block-major order inside a query is ascending g);
+//   totals = {n_pairs, max pairs of one query}.  One CTA of 1024 threads, 1024 queries per iteration.
+__global__ void __launch_bounds__(1024) pairs_offsets_kernel(const int32_t* __restrict__ cnt_all, int world, int rank,
+                                                             int nq, int32_t* __restrict__ pair_off,
+                                                             int32_t* __restrict__ my_base, int32_t* __restrict__ totals) {
   __shared__ int warp_sum[32];
   __shared__ int carry_s;
   __shared__ int max_s;
@@ -109,11 +128,13 @@ __global__ void __launch_bounds__(1024) pairs_scan_kernel(const int32_t* __restr
   int mx = 0;
   for (int base = 0; base < nq; base += 1024) {
     const int q = base + tid;
-    int sum = 0;
+    int sum = 0, before = 0;
     if (q < nq) {
-      const int32_t* row = seg_cnt + (long long)q * nseg;
-      for (int sgi = 0; sgi < nseg; ++sgi) sum += row[sgi];
-      if (zero_per_query) zero_per_query[q] = 0u;
+      for (int r = 0; r < world; ++r) {
+        const int v = cnt_all[(long long)r * nq + q];
+        sum += v;
+        before += r < rank ? v : 0;
+      }
     }
     mx = max(mx, sum);
     int incl = sum;
@@ -135,7 +156,11 @@ __global__ void __launch_bounds__(1024) pairs_scan_kernel(const int32_t* __restr
     }
     __syncthreads();
     const int carry = carry_s;
-    if (q < nq) pair_off[q] = carry + (warp ? warp_sum[warp - 1] : 0) + incl - sum;
+    if (q < nq) {
+      const int off = carry + (warp ? warp_sum[warp - 1] : 0) + incl - sum;
+      pair_off[q] = off;
+      my_base[q] = off + before;
+    }
     __syncthreads();
     if (tid == 1023) carry_s = carry + warp_sum[31];
     __syncthreads();
@@ -145,6 +170,11 @@ __global__ void __launch_bounds__(1024) pairs_scan_kernel(const int32_t* __restr
   if (lane == 0) atomicMax(&max_s, mx);
   __syncthreads();
   if (tid == 0) { pair_off[nq] = carry_s; totals[0] = carry_s; totals[1] = max_s; }
+}
+
+__global__ void pairs_unpack_pos_kernel(const int32_t* __restrict__ pos32, long long n, uint8_t* __restrict__ pos8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pos8[i] = (uint8_t)(pos32[i] != 0);
 }
 
 static void pair_segments(long long ng, long long* seg, int* nseg) {
@@ -159,56 +189,114 @@ static void pair_segments(long long ng, long long* seg, int* nseg) {
 
 using namespace pps;
 
-extern "C" long long pps_pairs_workspace_bytes(long long nq, long long ng) {
-  if (nq < 0 || ng < 0) return PPS_ERR_INVALID_ARG;
+// workspace: [nq][nseg] segment counts | [nq] local counts | [nq] my_base
+static long long ws_ints(long long nq, long long ng, int* nseg_out) {
   long long seg; int nseg;
   pair_segments(ng, &seg, &nseg);
-  return (nq > 0 ? nq : 1) * (long long)nseg * 4;
+  if (nseg_out) *nseg_out = nseg;
+  return (nq > 0 ? nq : 1) * ((long long)nseg + 2);
 }
 
-extern "C" int pps_pairs_count_device(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
-                                      void* workspace, int32_t* pair_off, int32_t* totals, uint32_t* zero_per_query,
-                                      void* stream) {
+extern "C" long long pps_pairs_workspace_bytes(long long nq, long long ng) {
+  if (nq < 0 || ng < 0) return PPS_ERR_INVALID_ARG;
+  return ws_ints(nq, ng, nullptr) * 4;
+}
+
+extern "C" int pps_pairs_local_count(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
+                                     void* workspace, int32_t** local_cnt, void* stream) {
   if (nq < 0 || ng < 0 || nq > 0x7fffffffLL || ng > 0x7fffffffLL) return PPS_ERR_INVALID_ARG;
-  if (!pair_off || !totals || !workspace) return PPS_ERR_INVALID_ARG;
+  if (!workspace) return PPS_ERR_INVALID_ARG;
   if (nq > 0 && ng > 0 && (!query_ids || !gallery_ids)) return PPS_ERR_INVALID_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long seg; int nseg;
   pair_segments(ng, &seg, &nseg);
   int32_t* seg_cnt = static_cast<int32_t*>(workspace);
+  int32_t* lc = seg_cnt + (nq > 0 ? nq : 1) * (long long)nseg;
+  if (local_cnt) *local_cnt = lc;
   if ((long long)nq * nseg > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
-  if (nq > 0) {
-    if (ng == 0) PPS_CUDA_TRY(cudaMemsetAsync(seg_cnt, 0, (size_t)nq * nseg * 4, st));
-    else {
-      const dim3 grid((unsigned)((nq + kPairQPerCta - 1) / kPairQPerCta), (unsigned)nseg);
-      pairs_sweep_kernel<false><<<grid, 32 * kPairWarps, 0, st>>>(query_ids, nullptr, (int)nq, gallery_ids, nullptr, ng,
-                                                                  seg, nseg, seg_cnt, nullptr, nullptr, nullptr, nullptr,
-                                                                  nullptr, nullptr, 0);
-      PPS_LAUNCH_CHECK("pairs_sweep_kernel<count>");
-    }
+  if (nq == 0) return PPS_OK;
+  if (ng == 0) {
+    PPS_CUDA_TRY(cudaMemsetAsync(seg_cnt, 0, (size_t)nq * (nseg + 1) * 4, st));
+    return PPS_OK;
   }
-  pairs_scan_kernel<<<1, 1024, 0, st>>>(seg_cnt, (int)nq, nseg, pair_off, totals, zero_per_query);
-  PPS_LAUNCH_CHECK("pairs_scan_kernel");
+  const dim3 grid((unsigned)((nq + kPairQPerCta - 1) / kPairQPerCta), (unsigned)nseg);
+  pairs_sweep_kernel<false><<<grid, 32 * kPairWarps, 0, st>>>(query_ids, nullptr, (int)nq, gallery_ids, nullptr, ng, seg,
+                                                              nseg, seg_cnt, nullptr, 0, nullptr, nullptr, nullptr,
+                                                              nullptr, nullptr, nullptr, nullptr, 0);
+  PPS_LAUNCH_CHECK("pairs_sweep_kernel<count>");
+  pairs_rowsum_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(seg_cnt, (int)nq, nseg, lc);
+  PPS_LAUNCH_CHECK("pairs_rowsum_kernel");
   return PPS_OK;
+}
+
+extern "C" int pps_pairs_offsets(const int32_t* cnt_all, int world, int rank, long long nq, long long ng_local,
+                                 void* workspace, int32_t* pair_off, int32_t* totals, void* stream) {
+  if (nq < 0 || world < 1 || rank < 0 || rank >= world || nq > 0x7fffffffLL) return PPS_ERR_INVALID_ARG;
+  if (!cnt_all || !workspace || !pair_off || !totals) return PPS_ERR_INVALID_ARG;
+  int nseg;
+  ws_ints(nq, ng_local, &nseg);
+  int32_t* my_base = static_cast<int32_t*>(workspace) + (nq > 0 ? nq : 1) * ((long long)nseg + 1);
+  pairs_offsets_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(cnt_all, world, rank, (int)nq, pair_off, my_base,
+                                                                          totals);
+  PPS_LAUNCH_CHECK("pairs_offsets_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_pairs_fill_local(const int64_t* query_ids, const int64_t* query_cams, long long nq,
+                                    const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
+                                    long long gallery_offset, const void* workspace, int32_t* pair_q, int32_t* pair_g,
+                                    uint8_t* pair_pos, int32_t* pair_pos32, float* zero_f32, uint32_t* zero_u32,
+                                    uint32_t* zero_per_query, long long capacity, void* stream) {
+  if (nq < 0 || ng < 0 || nq > 0x7fffffffLL || ng > 0x7fffffffLL || capacity < 0 || gallery_offset < 0 ||
+      gallery_offset + ng > 0x7fffffffLL)
+    return PPS_ERR_INVALID_ARG;
+  if (nq == 0) return PPS_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ng == 0 || capacity == 0) {     // no local pairs: only the per-query counters need their zero
+    if (zero_per_query) PPS_CUDA_TRY(cudaMemsetAsync(zero_per_query, 0, (size_t)nq * 4, st));
+    return PPS_OK;
+  }
+  if (!query_ids || !query_cams || !gallery_ids || !gallery_cams || !workspace || !pair_q || !pair_g ||
+      (!pair_pos && !pair_pos32))
+    return PPS_ERR_INVALID_ARG;
+  long long seg; int nseg;
+  pair_segments(ng, &seg, &nseg);
+  int32_t* seg_cnt = const_cast<int32_t*>(static_cast<const int32_t*>(workspace));
+  const int32_t* my_base = seg_cnt + nq * ((long long)nseg + 1);
+  const dim3 grid((unsigned)((nq + kPairQPerCta - 1) / kPairQPerCta), (unsigned)nseg);
+  pairs_sweep_kernel<true><<<grid, 32 * kPairWarps, 0, st>>>(query_ids, query_cams, (int)nq, gallery_ids, gallery_cams, ng,
+                                                             seg, nseg, seg_cnt, my_base, gallery_offset, pair_q, pair_g,
+                                                             pair_pos, pair_pos32, zero_f32, zero_u32, zero_per_query,
+                                                             capacity);
+  PPS_LAUNCH_CHECK("pairs_sweep_kernel<fill>");
+  return PPS_OK;
+}
+
+extern "C" int pps_pairs_unpack_pos(const int32_t* pair_pos32, long long n_pairs, uint8_t* pair_pos, void* stream) {
+  if (n_pairs < 0) return PPS_ERR_INVALID_ARG;
+  if (n_pairs == 0) return PPS_OK;
+  if (!pair_pos32 || !pair_pos) return PPS_ERR_INVALID_ARG;
+  pairs_unpack_pos_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pair_pos32, n_pairs, pair_pos);
+  PPS_LAUNCH_CHECK("pairs_unpack_pos_kernel");
+  return PPS_OK;
+}
+
+// ---- single-block convenience forms (whole gallery on one device) ----
+extern "C" int pps_pairs_count_device(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
+                                      void* workspace, int32_t* pair_off, int32_t* totals, void* stream) {
+  if (!pair_off || !totals) return PPS_ERR_INVALID_ARG;
+  int32_t* lc = nullptr;
+  int rc = pps_pairs_local_count(query_ids, nq, gallery_ids, ng, workspace, &lc, stream);
+  if (rc != PPS_OK) return rc;
+  return pps_pairs_offsets(lc, 1, 0, nq, ng, workspace, pair_off, totals, stream);
 }
 
 extern "C" int pps_pairs_fill_device(const int64_t* query_ids, const int64_t* query_cams, long long nq,
                                      const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
-                                     const void* workspace, const int32_t* pair_off, int32_t* pair_q, int32_t* pair_g,
-                                     uint8_t* pair_pos, float* zero_f32, uint32_t* zero_u32, long long capacity,
+                                     const void* workspace, int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos,
+                                     float* zero_f32, uint32_t* zero_u32, uint32_t* zero_per_query, long long capacity,
                                      void* stream) {
-  if (nq < 0 || ng < 0 || nq > 0x7fffffffLL || ng > 0x7fffffffLL || capacity < 0) return PPS_ERR_INVALID_ARG;
-  if (nq == 0 || ng == 0 || capacity == 0) return PPS_OK;
-  if (!query_ids || !query_cams || !gallery_ids || !gallery_cams || !workspace || !pair_off || !pair_q || !pair_g ||
-      !pair_pos)
-    return PPS_ERR_INVALID_ARG;
-  long long seg; int nseg;
-  pair_segments(ng, &seg, &nseg);
-  const dim3 grid((unsigned)((nq + kPairQPerCta - 1) / kPairQPerCta), (unsigned)nseg);
-  pairs_sweep_kernel<true><<<grid, 32 * kPairWarps, 0, static_cast<cudaStream_t>(stream)>>>(
-      query_ids, query_cams, (int)nq, gallery_ids, gallery_cams, ng, seg, nseg,
-      const_cast<int32_t*>(static_cast<const int32_t*>(workspace)), pair_off, pair_q, pair_g, pair_pos, zero_f32,
-      zero_u32, capacity);
-  PPS_LAUNCH_CHECK("pairs_sweep_kernel<fill>");
-  return PPS_OK;
+  return pps_pairs_fill_local(query_ids, query_cams, nq, gallery_ids, gallery_cams, ng, 0, workspace, pair_q, pair_g,
+                              pair_pos, nullptr, zero_f32, zero_u32, zero_per_query, capacity, stream);
 }

@@ -32,9 +32,11 @@ __global__ void rank_gather_kernel(const float* __restrict__ dist, long long ldd
                                    long long n_pairs, float* __restrict__ pair_d) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_pairs;
        e += (long long)gridDim.x * blockDim.x) {
+    const int q = pair_q[e];
+    if (q < 0) continue;                 // slot of a pair that lives on another gallery shard
     const long long c = (long long)pair_g[e] - col0;
     if (c < 0 || c >= ncols) continue;
-    pair_d[e] = dist[(long long)pair_q[e] * ldd + c];
+    pair_d[e] = dist[(long long)q * ldd + c];
   }
 }
 

@@ -141,20 +141,20 @@ class DevicePairs:
         self.n_pairs = self.max_pairs = 0
         self._host = None
 
-    def begin(self, zero_per_query=None):
-        """``zero_per_query``: optional uint32/int32 [nq] device tensor the scan kernel zero-fills (cnt_first)."""
+    def begin(self):
         lib = self.lib
         _lib.check(lib.pps_pairs_count_device(_lib.ptr(self.qid), self.nq, _lib.ptr(self.gid), self.ng, _lib.ptr(self.ws),
-                                              _lib.ptr(self.off_d), _lib.ptr(self.totals_d), _lib.ptr(zero_per_query),
-                                              _lib.stream_ptr()), "pps_pairs_count_device")
+                                              _lib.ptr(self.off_d), _lib.ptr(self.totals_d), _lib.stream_ptr()),
+                   "pps_pairs_count_device")
         self.totals_h.copy_(self.totals_d, non_blocking=True)
         self.event.record()
         self._host = None
         return self
 
-    def finish(self, zero_f32=None, zero_u32=None):
+    def finish(self, zero_f32=None, zero_u32=None, zero_per_query=None):
         """``zero_f32`` / ``zero_u32``: optional per-pair device arrays (capacity >= n_pairs) the fill kernel
-        zero-fills (pair_d / cnt_le); pass callables to allocate them once n_pairs is known."""
+        zero-fills (pair_d / cnt_le); pass callables to allocate them once n_pairs is known.
+        ``zero_per_query``: optional int32 [nq] device tensor it zero-fills too (cnt_first)."""
         torch = _torch()
         self.event.synchronize()
         self.n_pairs, self.max_pairs = int(self.totals_h[0]), int(self.totals_h[1])
@@ -168,10 +168,10 @@ class DevicePairs:
         if callable(zero_u32):
             zero_u32 = zero_u32(self.n_pairs)
         _lib.check(self.lib.pps_pairs_fill_device(_lib.ptr(self.qid), _lib.ptr(self.qcam), self.nq, _lib.ptr(self.gid),
-                                                  _lib.ptr(self.gcam), self.ng, _lib.ptr(self.ws), _lib.ptr(self.off_d),
+                                                  _lib.ptr(self.gcam), self.ng, _lib.ptr(self.ws),
                                                   _lib.ptr(self.q_d), _lib.ptr(self.g_d), _lib.ptr(self.pos_d),
-                                                  _lib.ptr(zero_f32), _lib.ptr(zero_u32), self.n_pairs,
-                                                  _lib.stream_ptr()), "pps_pairs_fill_device")
+                                                  _lib.ptr(zero_f32), _lib.ptr(zero_u32), _lib.ptr(zero_per_query),
+                                                  self.n_pairs, _lib.stream_ptr()), "pps_pairs_fill_device")
         return self
 
     def dev(self, name):
@@ -286,7 +286,7 @@ def rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams, want
         if pairs.nq != m or pairs.ng != n:
             raise RuntimeError("distmat shape %s does not match %d query / %d gallery ids" % ((m, n), pairs.nq, pairs.ng))
         cnt_first = torch.empty(max(m, 1), dtype=torch.int32, device=dist.device)
-        pairs.begin(zero_per_query=cnt_first).finish()
+        pairs.begin().finish(zero_per_query=cnt_first)
         E = max(pairs.n_pairs, 1)
         pair_d = torch.zeros(E, dtype=torch.float32, device=dist.device)
         cnt_le = torch.zeros(E, dtype=torch.int32, device=dist.device)
@@ -448,6 +448,19 @@ def mean_ap(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_
 # ------------------------------------------------------------------------------------
 # fused path: features -> metrics
 # ------------------------------------------------------------------------------------
+class _DevArray:
+    """A raw device pointer dressed as a __cuda_array_interface__ object (so torch can alias library-owned memory)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _wrap_device(torch, ptr, n, typestr, dtype, device):
+    t = torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
+    assert t.dtype == dtype and t.data_ptr() == ptr
+    return t
+
+
 class RankEngine:
     """Preallocated state for repeated distance + rank passes over one (query set, gallery shard) shape.
 
@@ -501,7 +514,9 @@ class RankEngine:
             self.pairs = DevicePairs(self.qi, self.qc, self.gi, self.gc, dev)
         self._pair_cap = 0
         self.kernel_events = None        # bench.py: list collecting (start, stop) events around the distance GEMM
-        self.use_c_path = True           # single GPU + one block: run the pass as one C call
+        self.use_c_path = True           # one gallery block per rank: run the pass through the C step functions
+        self._cnt_all = None
+        self._side = None
         self.h2d_bytes = 0
 
     # -- helpers --
@@ -516,7 +531,8 @@ class RankEngine:
         return self.pair_d, self.cnt_le
 
     def _finish_pairs(self, pairs):
-        pairs.finish(zero_f32=lambda n: self._pair_buffers(n)[0], zero_u32=lambda n: self._pair_buffers(n)[1])
+        pairs.finish(zero_f32=lambda n: self._pair_buffers(n)[0], zero_u32=lambda n: self._pair_buffers(n)[1],
+                     zero_per_query=self.cnt_first)
         return self.pair_d, self.cnt_le
 
     def set_phase_timing(self, enabled: bool):
@@ -529,9 +545,53 @@ class RankEngine:
         return dict(zip(_lib.PHASE_NAMES, out.tolist()))
 
     def _run_resident_c(self, q, g):
-        """Single GPU, one distance block: the whole pass is one C call (pps_evaluate_device_ctx)."""
+        """One gallery block per rank: the pass is four C calls (pps_rank_begin / _distance / _count_local / _end) with,
+        for a sharded gallery, the three NCCL exchanges in between: all-gather of the per-query local pair counts,
+        all-reduce of the thresholds (+ pair metadata), all-reduce of the integer counters."""
+        torch = self.torch
         nq, topk = self.nq, self.topk
         p = self.pairs
+        ctx = _host_ctx(self.dev.index or 0)
+        s = _lib.stream_ptr()
+        sharded = self.group is not None
+        world = rank = None
+        if sharded:
+            import torch.distributed as dist_mod
+            world, rank = dist_mod.get_world_size(self.group), dist_mod.get_rank(self.group)
+        gid_l = p.gid[self.offset:self.offset + self.ngl] if sharded else p.gid
+        gcam_l = p.gcam[self.offset:self.offset + self.ngl] if sharded else p.gcam
+        d_lc = C.c_void_p(0)
+        side = None
+        if sharded:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            side = self._side
+        _lib.check(self.lib.pps_rank_begin(ctx, _lib.ptr(q), nq, _lib.ptr(g), self.ngl, self.dim, _lib.ptr(p.qid),
+                                           _lib.ptr(p.qcam), _lib.ptr(gid_l), _lib.ptr(gcam_l), self.offset,
+                                           world if sharded else 1, self.prec, topk, s,
+                                           C.c_void_p(side.cuda_stream) if side is not None else None, C.byref(d_lc)),
+                   "pps_rank_begin")
+        cnt_all = None
+        if sharded:
+            # the local pair counts were launched on the side stream; gather them there too, so that the pair-list
+            # work (count -> all-gather -> offsets -> fill) overlaps the split + GEMM on the main stream
+            local_cnt = _wrap_device(torch, d_lc.value, nq, "<i4", torch.int32, self.dev)
+            if self._cnt_all is None:
+                self._cnt_all = torch.empty((world, nq), dtype=torch.int32, device=self.dev)
+            cnt_all = self._cnt_all
+            with torch.cuda.stream(side):
+                dist_mod.all_gather_into_tensor(cnt_all.view(-1), local_cnt, group=self.group)
+        n_pairs, n_words, n_cnt = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        d_x, d_cnt = C.c_void_p(0), C.c_void_p(0)
+        _lib.check(self.lib.pps_rank_thresholds(ctx, _lib.ptr(cnt_all), rank if sharded else 0, s, C.byref(n_pairs),
+                                              C.byref(d_x), C.byref(n_words)), "pps_rank_thresholds")
+        if sharded and n_words.value:
+            xbuf = _wrap_device(torch, d_x.value, n_words.value, "<i4", torch.int32, self.dev)
+            dist_mod.all_reduce(xbuf, op=dist_mod.ReduceOp.SUM, group=self.group)
+        _lib.check(self.lib.pps_rank_count_local(ctx, s, C.byref(d_cnt), C.byref(n_cnt)), "pps_rank_count_local")
+        if sharded:
+            counters = _wrap_device(torch, d_cnt.value, n_cnt.value, "<i4", torch.int32, self.dev)
+            dist_mod.all_reduce(counters, op=dist_mod.ReduceOp.SUM, group=self.group)
         out_map = C.c_double(0.0)
         out_cmc = np.zeros(10, dtype=np.float64)
         ap = np.zeros(nq, dtype=np.float64)
@@ -539,13 +599,10 @@ class RankEngine:
         first = np.zeros(nq, dtype=np.int32)
         ti = np.zeros((nq, topk), dtype=np.int32) if topk else None
         td = np.zeros((nq, topk), dtype=np.float32) if topk else None
-        rc = self.lib.pps_evaluate_device_ctx(_host_ctx(self.dev.index or 0), _lib.ptr(q), nq, _lib.ptr(g), self.ngl,
-                                              self.dim, _lib.ptr(p.qid), _lib.ptr(p.qcam), _lib.ptr(p.gid), _lib.ptr(p.gcam),
-                                              self.prec, 10, topk, _lib.stream_ptr(),
-                                              C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc), _lib.ptr(ap),
-                                              _lib.ptr(valid), _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
+        rc = self.lib.pps_rank_end(ctx, 10, s, C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc), _lib.ptr(ap),
+                                   _lib.ptr(valid), _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
         if rc != _lib.PPS_ERR_NO_VALID_QUERY:
-            _lib.check(rc, "pps_evaluate_device_ctx")
+            _lib.check(rc, "pps_rank_end")
         return RankResult(ap, valid, first, None, None, ti, td)
 
     def _split(self, feats, rows, planes_buf, sq_buf):
@@ -582,13 +639,14 @@ class RankEngine:
         if self.group is not None:
             import torch.distributed as dist_mod
         nq = self.nq
-        if (self.use_c_path and self.group is None and self.n_chunks == 1 and not self.want_neg_before
-                and not self.is_f16 and self.topk_filtered and nq > 0 and self.kernel_events is None
+        if (self.use_c_path and self.n_chunks == 1 and not self.want_neg_before and not self.is_f16
+                and self.topk_filtered and nq > 0 and self.ngl > 0 and self.kernel_events is None
+                and (self.group is None or self.topk == 0)
                 and q.is_contiguous() and g.is_contiguous() and DIST_KERNEL_FLAGS == 0):
             with torch.cuda.device(self.dev):
                 return self._run_resident_c(q, g)
         with torch.cuda.device(self.dev):
-            pairs = self.pairs.begin(zero_per_query=self.cnt_first)   # junk mask / matches, on the device
+            pairs = self.pairs.begin()          # junk mask / matches from the resident ids, on the device
             key = self.key
             if self.topk:
                 _lib.check(lib.pps_topk_init(_lib.ptr(key), nq, self.topk, _lib.stream_ptr()), "pps_topk_init")

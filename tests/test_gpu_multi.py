@@ -35,8 +35,11 @@ def _worker(rank, world, port, golden_path, out_dir):
     g = torch.from_numpy(d["g"][row0:row0 + rows]).cuda()
     res = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"], topk=12, want_neg_before=True,
                              gallery_offset=row0, group=dist.group.WORLD)
+    # the C step path (no top-k, no neg_before): begin -> all-gather -> distance -> all-reduce -> count -> all-reduce -> end
+    fast = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"], gallery_offset=row0, group=dist.group.WORLD)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), ap=res.ap, valid=res.is_valid, first=res.first_rank,
-             neg_before=res.neg_before, ti=res.topk_index, td=res.topk_dist)
+             neg_before=res.neg_before, ti=res.topk_index, td=res.topk_dist, fast_ap=fast.ap, fast_valid=fast.is_valid,
+             fast_first=fast.first_rank)
     dist.destroy_process_group()
 
 
@@ -61,4 +64,7 @@ def test_sharded_gallery_equals_single_gpu(tmp_path, name):
         np.testing.assert_array_equal(o["neg_before"][:one.pairs.n_pairs], one.neg_before[:one.pairs.n_pairs])
         np.testing.assert_array_equal(o["ti"], one.topk_index)
         np.testing.assert_array_equal(o["td"], one.topk_dist)
+        np.testing.assert_array_equal(o["fast_ap"], one.ap)
+        np.testing.assert_array_equal(o["fast_valid"], one.is_valid)
+        np.testing.assert_array_equal(o["fast_first"], one.first_rank)
     assert abs(float(np.sum(one.ap)) / np.sum(one.is_valid) - float(d["mAP"])) < (5e-3 if name == "dup_ties" else 1e-6)
