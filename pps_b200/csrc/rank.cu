@@ -20,9 +20,13 @@
 namespace pps {
 
 constexpr int kCntThreads = 128;
-constexpr int kCntWarps = kCntThreads / 32;
-constexpr int kWin = 31;            // thresholds per pass (slot 31 is a +inf sentinel -> 5-step search)
-constexpr int kBuckets = 32;
+constexpr int kNB = 1024;           // bins of the per-query distance histogram
+
+// monotone integer key of a float: signed-int order == float order (negative values: flip the low 31 bits)
+__device__ __forceinline__ int fkey(float x) {
+  const int k = __float_as_int(x);
+  return k ^ ((k >> 31) & 0x7fffffff);
+}
 
 // ------------------------------------------------------------------------------------
 // step 1: gather the pair distances out of the block
@@ -42,48 +46,58 @@ __global__ void rank_gather_kernel(const float* __restrict__ dist, long long ldd
 
 // ------------------------------------------------------------------------------------
 // step 2: counts.  grid = (nq, splits); CTA (q, s) sweeps columns [s*seg, (s+1)*seg).
-// dynamic smem: thr[maxp] (sorted positive distances), tpair[maxp] (pair index of each),
-//               sd[maxp] / sg[maxp] (the query's staged pair list)
-// static smem : win_rep[32][32]  the window's thresholds replicated once per bank, so the
-//                                data-dependent reads of the binary search never conflict;
-//               hist[warps][32][32] lane-private bucket counters (bank = lane).
-// Per element: range check, 5-step search (the two top levels from registers), one counter
-// increment.  The first-match counter is not touched per element: with (d*, g*) the nearest
-// positive, first = cnt_le(d*) - #{d == d*} + #{d == d*, col < g*}; only exact ties with d*
-// (rare) do extra work, and cnt_first accumulates the signed correction (mod 2^32).
+//
+// n_le(t_p) for all P thresholds of a query in ONE sweep and ~8 instructions per element:
+// float bits (low 31 bits flipped for negatives) are monotone integer keys.  The key range
+// [key(t_min), key(t_max)] is cut into kNB equal-width bins (shift chosen per query).  Per element:
+//   key < key(t_min)  -> a register counter (it lies below every threshold);
+//   bin >= kNB        -> beyond every threshold, ignored;
+//   else              -> one shared-memory atomicAdd on hist[bin].  Bins that contain a threshold
+//                        carry a flag in bit 31 of their counter, which the atomic returns: only
+//                        those elements (a few % of a row) take the exact path - a short search
+//                        among the thresholds of that bin and one atomicAdd on exact[first + j],
+//                        j = #thresholds of the bin below the element.
+// Then n_le(t_p) = below + sum of hist over bins before bin(t_p) + sum of exact[] from the bin's
+// first threshold up to p.  Integer arithmetic throughout, so partial results add up exactly over
+// column splits, gallery chunks and gallery shards.  The first-match counter is not touched per
+// element either: with (d*, g*) the nearest positive, first = n_le(d*) - #{d == d*} + #{d == d*,
+// col < g*}; exact ties with d* (on the exact path by construction) accumulate the signed correction.
+// dynamic smem: thr[maxp] sorted positive distances, tpair[maxp] their pair index, sd/sg[maxp] the
+//               staged pair list, exact[maxp]
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float* __restrict__ dist, long long ldd,
-                                                                  long long ncols, long long col0, long long seg,
-                                                                  const int32_t* __restrict__ pair_off,
-                                                                  const int32_t* __restrict__ pair_g,
-                                                                  const uint8_t* __restrict__ pair_pos,
-                                                                  const float* __restrict__ pair_d, int maxp,
-                                                                  uint32_t* __restrict__ cnt_le,
-                                                                  uint32_t* __restrict__ cnt_first) {
+                                                                     long long ncols, long long col0, long long seg,
+                                                                     const int32_t* __restrict__ pair_off,
+                                                                     const int32_t* __restrict__ pair_g,
+                                                                     const uint8_t* __restrict__ pair_pos,
+                                                                     const float* __restrict__ pair_d, int maxp,
+                                                                     uint32_t* __restrict__ cnt_le,
+                                                                     uint32_t* __restrict__ cnt_first) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* thr = reinterpret_cast<float*>(smem_raw);                          // [maxp]
   int32_t* tpair = reinterpret_cast<int32_t*>(thr + maxp);                  // [maxp]
-  __shared__ float win_rep[kBuckets * 32];
-  __shared__ uint32_t hist[kCntWarps * kBuckets * 32];
-  __shared__ uint32_t wsum[kBuckets];
+  float* sd = reinterpret_cast<float*>(tpair + maxp);                       // [maxp] pair distances
+  int32_t* sg = reinterpret_cast<int32_t*>(sd + maxp);                      // [maxp] gallery index, -1 = junk
+  uint32_t* exact = reinterpret_cast<uint32_t*>(sg + maxp);                 // [maxp]
+  __shared__ uint32_t hist[kNB];          // bit 31: the bin holds a threshold
+  __shared__ uint32_t binfo[kNB];         // (index of the bin's first threshold << 16) | thresholds in the bin
+  __shared__ uint32_t part[kCntThreads];
   __shared__ int s_np;
-  __shared__ uint32_t s_first_cnt;
+  __shared__ uint32_t s_below, s_first_cnt;
 
   const int q = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int e0 = pair_off[q], e1 = pair_off[q + 1];
 
   // --- positives of this query, rank-sorted by (distance, gallery index) into thr[] ---
-  // stage the query's pair list in shared memory first (coalesced), then rank from there: the
-  // O(P^2) ranking loop must not chase global-memory latency
-  float* sd = reinterpret_cast<float*>(tpair + maxp);                       // [maxp] pair distances
-  int32_t* sg = reinterpret_cast<int32_t*>(sd + maxp);                      // [maxp] gallery index, -1 = junk
-  if (tid == 0) { s_np = 0; s_first_cnt = 0; }
+  // stage the pair list in shared memory first (coalesced): the O(P^2) ranking must not chase global latency
+  if (tid == 0) { s_np = 0; s_below = 0; s_first_cnt = 0; }
   const int npair = e1 - e0;
   for (int i = tid; i < npair; i += kCntThreads) {
     sd[i] = pair_d[e0 + i];
     sg[i] = pair_pos[e0 + i] ? pair_g[e0 + i] : -1;
   }
+  for (int i = tid; i < kNB; i += kCntThreads) { hist[i] = 0; binfo[i] = 0; }
   __syncthreads();
   for (int i = tid; i < npair; i += kCntThreads) {
     const int g = sg[i];
@@ -104,95 +118,121 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
   if (np == 0) return;                                     // query without a valid match: nothing to count
   const float dstar = thr[0];
   const long long gstar = pair_g[tpair[0]];
+  const int key_min = fkey(thr[0]);
+  const unsigned key_span = (unsigned)fkey(thr[np - 1]) - (unsigned)key_min;
+  int shift = 0;
+  while ((key_span >> shift) >= (unsigned)kNB) ++shift;
 
   const long long c_begin = (long long)blockIdx.y * seg;
   const long long c_end = min(ncols, c_begin + seg);
   if (c_begin >= c_end) return;
+
+  // --- flag the bins that hold thresholds; thresholds are sorted, so a bin's thresholds are contiguous ---
+  for (int p = tid; p < np; p += kCntThreads) {
+    const unsigned b = ((unsigned)fkey(thr[p]) - (unsigned)key_min) >> shift;
+    const bool is_first = (p == 0) || ((((unsigned)fkey(thr[p - 1]) - (unsigned)key_min) >> shift) != b);
+    atomicAdd(&binfo[b], 1u + (is_first ? ((uint32_t)p << 16) : 0u));
+    if (is_first) hist[b] = 0x80000000u;
+    exact[p] = 0;
+  }
+  __syncthreads();
+
   const float* drow = dist + (long long)q * ldd;
   const bool vec = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(dist) & 15u) == 0) && ((c_begin & 3) == 0);
-  uint32_t* myhist = hist + warp * (kBuckets * 32) + lane;  // column `lane` of this warp's table
-  const float* wr = win_rep + lane;                         // this lane's private copy of the window
-  uint32_t tie_corr = 0;                                    // signed: -#{d == d*} + #{d == d*, col < g*}
-  uint32_t carry = 0;                                       // elements counted in earlier windows
+  uint32_t below = 0;                                      // elements under every threshold
+  uint32_t tie_corr = 0;                                   // signed: -#{d == d*} + #{d == d*, col < g*}
 
-  for (int w0 = 0; w0 < np; w0 += kWin) {
-    const int wn = min(kWin, np - w0);
-    __syncthreads();                                       // previous window fully consumed
-    for (int i = tid; i < kBuckets * 32; i += kCntThreads) {
-      const int slot = i >> 5;
-      win_rep[i] = slot < wn ? thr[w0 + slot] : FLT_MAX;
+  auto visit = [&](float d, long long col) {
+    const int key = fkey(d);
+    const bool lt = key < key_min;
+    below += lt ? 1u : 0u;
+    const unsigned b = ((unsigned)key - (unsigned)key_min) >> shift;
+    if (!lt && b < (unsigned)kNB) {
+      const uint32_t old = atomicAdd(&hist[b], 1u);
+      if (old & 0x80000000u) {                             // the bin holds thresholds: exact comparison
+        const uint32_t info = binfo[b];
+        const int first = (int)(info >> 16), cnt = (int)(info & 0xffffu);
+        int j = 0;
+        while (j < cnt && thr[first + j] < d) ++j;
+        if (j < cnt) atomicAdd(&exact[first + j], 1u);
+        if (d == dstar) tie_corr += ((col0 + col) < gstar ? 1u : 0u) - 1u;
+      }
     }
-    for (int i = tid; i < kCntWarps * kBuckets * 32; i += kCntThreads) hist[i] = 0;
-    __syncthreads();
-    const float lo = w0 ? thr[w0 - 1] : -FLT_MAX;          // elements <= lo belong to earlier windows
-    const float hi = wr[(wn - 1) * 32];
-    const float t15 = wr[15 * 32], t7 = wr[7 * 32], t23 = wr[23 * 32];
-    const bool do_first = (w0 == 0);
+  };
 
-    auto visit = [&](float d, long long col) {
-      if (d <= hi && d > lo) {
-        const bool g1 = t15 < d;
-        int b = g1 ? 16 : 0;
-        b += ((g1 ? t23 : t7) < d) ? 8 : 0;
-        b += (wr[(b + 3) * 32] < d) ? 4 : 0;
-        b += (wr[(b + 1) * 32] < d) ? 2 : 0;
-        b += (wr[b * 32] < d) ? 1 : 0;
-        myhist[b * 32] += 1;
-        if (do_first && d == dstar) tie_corr += ((col0 + col) < gstar ? 1u : 0u) - 1u;
-      }
-    };
-
-    if (vec) {
-      const long long c4_end = c_begin + ((c_end - c_begin) & ~3LL);
-      constexpr long long kStep = 4LL * kCntThreads;       // columns per pass of the CTA
-      long long c = c_begin + 4LL * tid;
-      // four independent 128-bit loads in flight per thread before any of them is consumed
-      for (; c + 3 * kStep < c4_end; c += 4 * kStep) {
-        float4 v[4];
+  if (vec) {
+    const long long c4_end = c_begin + ((c_end - c_begin) & ~3LL);
+    constexpr long long kStep = 4LL * kCntThreads;         // columns per pass of the CTA
+    long long c = c_begin + 4LL * tid;
+    // four independent 128-bit loads in flight per thread before any of them is consumed
+    for (; c + 3 * kStep < c4_end; c += 4 * kStep) {
+      float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(reinterpret_cast<const float4*>(drow + c + u * kStep));
+      for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(reinterpret_cast<const float4*>(drow + c + u * kStep));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const long long cu = c + u * kStep;
-          visit(v[u].x, cu); visit(v[u].y, cu + 1); visit(v[u].z, cu + 2); visit(v[u].w, cu + 3);
-        }
+      for (int u = 0; u < 4; ++u) {
+        const long long cu = c + u * kStep;
+        visit(v[u].x, cu); visit(v[u].y, cu + 1); visit(v[u].z, cu + 2); visit(v[u].w, cu + 3);
       }
-      for (; c < c4_end; c += kStep) {
-        const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(drow + c));
-        visit(v.x, c); visit(v.y, c + 1); visit(v.z, c + 2); visit(v.w, c + 3);
-      }
-      for (c = c4_end + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
-    } else {
-      for (long long c = c_begin + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
     }
-    __syncthreads();
-    // reduce the lane-private columns: thread t < 32 owns bucket t
-    if (tid < kBuckets) {
-      uint32_t sum = 0;
-      for (int w = 0; w < kCntWarps; ++w) {
-        const uint32_t* hb = hist + w * (kBuckets * 32) + tid * 32;
-#pragma unroll
-        for (int l = 0; l < 32; ++l) sum += hb[(l + tid) & 31];
-      }
-      wsum[tid] = sum;
+    for (; c < c4_end; c += kStep) {
+      const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(drow + c));
+      visit(v.x, c); visit(v.y, c + 1); visit(v.z, c + 2); visit(v.w, c + 3);
     }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t run = carry;
-      for (int b = 0; b < wn; ++b) {
-        run += wsum[b];
-        if (run) atomicAdd(&cnt_le[tpair[w0 + b]], run);
-      }
-      wsum[0] = run;
-    }
-    __syncthreads();
-    carry = wsum[0];
+    for (c = c4_end + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
+  } else {
+    for (long long c = c_begin + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
   }
-  // first-match correction
+
+  // --- reductions: below, tie correction, exclusive prefix of the histogram ---
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tie_corr += __shfl_xor_sync(0xffffffffu, tie_corr, o);
-  if (lane == 0 && tie_corr) atomicAdd(&s_first_cnt, tie_corr);
+  for (int o = 16; o > 0; o >>= 1) {
+    below += __shfl_xor_sync(0xffffffffu, below, o);
+    tie_corr += __shfl_xor_sync(0xffffffffu, tie_corr, o);
+  }
+  if (lane == 0) {
+    if (below) atomicAdd(&s_below, below);
+    if (tie_corr) atomicAdd(&s_first_cnt, tie_corr);
+  }
   __syncthreads();
+  constexpr int kPer = kNB / kCntThreads;                  // 8 consecutive bins per thread
+  uint32_t local[kPer], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    local[k] = hist[tid * kPer + k] & 0x7fffffffu;
+    sum += local[k];
+  }
+  part[tid] = sum;
+  __syncthreads();
+  if (tid < 32) {                                          // scan of the 128 per-thread sums by one warp
+    uint32_t v[4], run = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = part[tid * 4 + k]; run += v[k]; }
+    uint32_t incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t excl = incl - run;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { part[tid * 4 + k] = excl; excl += v[k]; }
+  }
+  __syncthreads();
+  {
+    uint32_t run = part[tid];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { hist[tid * kPer + k] = run; run += local[k]; }   // hist := exclusive prefix
+  }
+  __syncthreads();
+  const uint32_t below_all = s_below;
+  for (int p = tid; p < np; p += kCntThreads) {
+    const unsigned b = ((unsigned)fkey(thr[p]) - (unsigned)key_min) >> shift;
+    const int first = (int)(binfo[b] >> 16);
+    uint32_t n = below_all + hist[b];
+    for (int k = first; k <= p; ++k) n += exact[k];
+    if (n) atomicAdd(&cnt_le[tpair[p]], n);
+  }
   if (tid == 0 && s_first_cnt) atomicAdd(&cnt_first[q], s_first_cnt);
 }
 
@@ -379,8 +419,8 @@ extern "C" int pps_rank_count(const float* dist, long long ldd, long long nq, lo
   if (!pair_g || !pair_pos || !pair_d || !cnt_le) return PPS_ERR_INVALID_ARG;
   if (nq > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
   const int maxp = (max_pairs_per_query + 3) & ~3;
-  const size_t smem = (size_t)maxp * 16;                      // thr, tpair, staged distances, staged indices
-  if (smem > 160 * 1024) return PPS_ERR_UNSUPPORTED;          // > ~10k same-id items for one query
+  const size_t smem = (size_t)maxp * 20;                      // thr, tpair, staged distances / indices, exact
+  if (smem > 160 * 1024) return PPS_ERR_UNSUPPORTED;          // > ~8k same-id items for one query
   // column splits: enough CTAs to fill the GPU when there are few queries
   const int sms = sm_count();
   long long splits = 1;

@@ -268,3 +268,28 @@ def test_host_context_reuse_gives_identical_results(golden):
     assert a["mAP"] == b["mAP"]
     np.testing.assert_array_equal(a["ap"], b["ap"])
     np.testing.assert_array_equal(a["topk_index"], b["topk_index"])
+
+
+def test_rank_on_matrix_with_negative_and_tied_values():
+    """mean_ap / cmc accept any real-valued 'distance' (e.g. a negated similarity): the count kernel's integer
+    keys must stay monotone across the sign, over exact ties and over a very wide dynamic range."""
+    import pps_b200
+    rs = np.random.RandomState(21)
+    nq, ng = 24, 3000
+    dist = (rs.randn(nq, ng) * np.exp(rs.uniform(-12, 12, size=(nq, 1)))).astype(np.float32)
+    dist[:, 100:200] = dist[:, 300:400]                       # exact ties
+    dist[3] = np.round(dist[3] / np.abs(dist[3]).max() * 4)   # a row with only 9 distinct values
+    dist[4] = 0.0
+    dist[5, ::2] = -0.0
+    qid = rs.randint(1, 9, size=nq)
+    gid = rs.randint(0, 9, size=ng)
+    qcam, gcam = rs.randint(0, 3, size=nq), rs.randint(0, 3, size=ng)
+    res = pps_b200.rank_distmat(dist, qid, gid, qcam, gcam, want_neg_before=True)
+    ap, valid, first, neg_before = O.rank_counts(dist, qid, gid, qcam, gcam)
+    np.testing.assert_array_equal(res.is_valid, valid)
+    np.testing.assert_array_equal(res.first_rank, first)
+    np.testing.assert_allclose(res.ap, ap, rtol=0, atol=1e-12)
+    p = res.pairs
+    for i in range(p.nq):
+        e = np.arange(p.off[i], p.off[i + 1])
+        np.testing.assert_array_equal(res.neg_before[e[p.pos[e] == 1]], neg_before[i])
