@@ -220,7 +220,6 @@ int pps_rank_gather(const float* dist, long long ldd, long long nq, long long nc
 int pps_rank_count(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
                    const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
                    const float* pair_d, int max_pairs_per_query,
-                   int nonneg /* 1: every value of dist is >= +0 (what pps_dist_* writes): skips the sign handling */,
                    uint32_t* cnt_le, uint32_t* cnt_first, void* stream);
 
 int pps_rank_finalize(long long nq,

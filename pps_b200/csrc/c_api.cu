@@ -355,7 +355,7 @@ int count_local(pps_ctx* c, cudaStream_t cs) {
   if (c->world > 1)    // after the exchange every rank holds all pairs; the kernels read the flags as bytes
     PPS_TRY(pps_pairs_unpack_pos(c->pair_pos32(), c->n_pairs, c->pair_pos.as<uint8_t>(), cs));
   return pps_rank_count(c->dist.as<float>(), e.ldd, e.nq, e.ng, e.col0, c->pair_off.as<int32_t>(), c->pair_g(),
-                        c->pair_pos.as<uint8_t>(), c->pair_d(), c->max_pairs, 1, cnt_first + e.nq, cnt_first, cs);
+                        c->pair_pos.as<uint8_t>(), c->pair_d(), c->max_pairs, cnt_first + e.nq, cnt_first, cs);
 }
 
 // finalize from the (reduced) counters, optional local top-k, results back, the reference's averaging

@@ -237,7 +237,7 @@ class RankResult:
 
 
 def _rank_block(lib, dist, ldd, nq, ncols, col0, pairs: PairLists, pair_d, cnt_le, cnt_first, do_gather, do_count,
-                topk_key=None, topk=0, topk_filtered=True, nonneg=0):
+                topk_key=None, topk=0, topk_filtered=True):
     s = _lib.stream_ptr()
     if do_gather and pairs.n_pairs:
         _lib.check(lib.pps_rank_gather(_lib.ptr(dist), ldd, nq, ncols, col0, _lib.ptr(pairs.dev("q")),
@@ -247,7 +247,7 @@ def _rank_block(lib, dist, ldd, nq, ncols, col0, pairs: PairLists, pair_d, cnt_l
         if pairs.n_pairs:
             _lib.check(lib.pps_rank_count(_lib.ptr(dist), ldd, nq, ncols, col0, _lib.ptr(pairs.dev("off")),
                                           _lib.ptr(pairs.dev("g")), _lib.ptr(pairs.dev("pos")), _lib.ptr(pair_d),
-                                          pairs.max_pairs, nonneg, _lib.ptr(cnt_le), _lib.ptr(cnt_first), s),
+                                          pairs.max_pairs, _lib.ptr(cnt_le), _lib.ptr(cnt_first), s),
                        "pps_rank_count")
         if topk_key is not None:
             use = topk_filtered and pairs.n_pairs > 0
@@ -674,7 +674,7 @@ class RankEngine:
                     self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)
                     self._distance(rows)
                 _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
-                            False, True, key, self.topk, self.topk_filtered, nonneg=1)
+                            False, True, key, self.topk, self.topk_filtered)
             if self.group is not None:
                 dist_mod.all_reduce(cnt_le, op=dist_mod.ReduceOp.SUM, group=self.group)
                 dist_mod.all_reduce(cnt_first, op=dist_mod.ReduceOp.SUM, group=self.group)
