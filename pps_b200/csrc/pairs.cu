@@ -73,6 +73,13 @@ pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ 
     for (int k = 0; k < kB; ++k) {
       const long long g = g0 + k * 32 + lane;
       const bool in = g < g_end;
+      // fast path: matches are rare (a few dozen per query in the whole gallery), so first ask whether ANY lane
+      // matches ANY of the warp's queries on the low 32 bits; only then do the exact 64-bit compares and ballots
+      const uint32_t vlo = (uint32_t)v[k];
+      bool maybe = false;
+#pragma unroll
+      for (int u = 0; u < kPairQPerWarp; ++u) maybe |= (vlo == (uint32_t)ids[u]);
+      if (!__any_sync(0xffffffffu, maybe && in)) continue;
 #pragma unroll
       for (int u = 0; u < kPairQPerWarp; ++u) {
         const bool hit = in && live[u] && v[k] == ids[u];

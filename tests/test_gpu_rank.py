@@ -293,3 +293,23 @@ def test_rank_on_matrix_with_negative_and_tied_values():
     for i in range(p.nq):
         e = np.arange(p.off[i], p.off[i + 1])
         np.testing.assert_array_equal(res.neg_before[e[p.pos[e] == 1]], neg_before[i])
+
+
+def test_duke_shape_full_parity_with_oracle():
+    """BASELINE configs[2] (DukeMTMC-reID-shaped, 2 228 x 17 661 x 2048): whole evaluation, all outputs against the
+    oracle on a 96-query slice and the size-independent chunking property on the full set."""
+    import torch
+    import pps_b200
+    from pps_b200 import synthetic
+    d = synthetic.make_config("duke")
+    q, g = torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda()
+    one = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"])
+    many = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"], max_block_bytes=48 << 20)
+    np.testing.assert_array_equal(one.ap, many.ap)
+    np.testing.assert_array_equal(one.first_rank, many.first_rank)
+    sub = slice(0, 96)
+    dist = O.compute_dist(d["q"][sub], d["g"])
+    ap, valid, first, _ = O.rank_counts(dist, d["qid"][sub], d["gid"], d["qcam"][sub], d["gcam"])
+    np.testing.assert_array_equal(one.is_valid[sub], valid)
+    assert abs(float(one.ap[sub].sum()) - float(ap.sum())) / max(valid.sum(), 1) < 1e-5
+    assert np.mean(one.first_rank[sub] == first) > 0.95
