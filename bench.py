@@ -50,6 +50,16 @@ def env_int(name, default):
         return default
 
 
+def load_traffic(key):
+    """Measured DRAM bytes per launch of a kernel at a given shape (ncu capture summarised under profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(key)
+    except (OSError, ValueError):
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -336,12 +346,30 @@ def run_ours(args):
             achieved = flops_alg / (gemm_avg_ms * 1e-3) / 1e12
             roofline = {"kernel": "dist_tc2_kernel", "bound": "tensor", "achieved": achieved,
                         "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-                        "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+                        "traffic": load_traffic("dist_tc2_kernel@%dx%dx%d/%s" % (nq, ngl, dim, args.precision)),
+                        "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_d_dist_gemm.md); algorithmic = %d" %
+                                        int((nq + ngl) * dim * 2 * (2 if args.precision == "bf16x3" else 1) + nq * ngl * 4),
+                        "peak_source": peaks["source"] + " (sustained bf16)",
                         "ms_per_launch": gemm_avg_ms, "share_of_step": gemm_avg_ms / ms_step,
                         "tensor_pipe_issued_tflops": achieved * terms,
                         "tensor_pipe_frac": achieved * terms / peaks["tf_sustained"],
                         "note": "achieved counts ALGORITHMIC flops (2*D per pair); the fp32-accurate %s split issues "
                                 "%dx that on the tensor pipe" % (args.precision, terms)}
+        # the HBM-bound kernels of the step, from the same phase events (algorithmic bytes / device time)
+        kernels = None
+        if phases:
+            n_planes = {"bf16x1": 1, "bf16x3": 2, "bf16x6": 3}[args.precision]
+            split_b = (nq + ngl) * dim * 4.0 + (nq + ngl) * dim * 2.0 * n_planes
+            count_b = 4.0 * nq * ngl
+            kernels = {
+                "split_rows_kernel": {"bound": "hbm", "ms": phases["split"], "achieved": split_b / phases["split"] / 1e6,
+                                      "peak": peaks["hbm"], "unit": "GB/s", "frac": split_b / phases["split"] / 1e6 / peaks["hbm"],
+                                      "note": "two launches (queries, gallery) + launch gap; overlaps the pair-list sweeps"},
+                "rank_count_kernel": {"bound": "hbm (shared-atomic limited)", "ms": phases["rank_count"],
+                                      "achieved": count_b / phases["rank_count"] / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
+                                      "frac": count_b / phases["rank_count"] / 1e6 / peaks["hbm"],
+                                      "traffic": load_traffic("rank_count_kernel@%dx%d" % (nq, ngl))},
+            }
         h2d = (q_host.numel() + g_host.numel()) * 4
         d2h = nq * (8 + 1 + 4)
         line = {
@@ -362,6 +390,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "roofline": roofline,
             "phases_ms": phases,
+            "kernels": kernels,
             "pooling": pooling,
             "result": {"mAP": mAP, "cmc1": float(cmc[0]), "cmc5": float(cmc[4]), "cmc10": float(cmc[9])},
         }
@@ -408,7 +437,9 @@ def bench_pooling(torch, pps_b200, _lib, peaks, dev, args):
     return {"kernel": "pool_tma_kernel", "images_per_s": n_img / (ms * 1e-3), "ms_per_launch": ms,
             "shape": [n_img, C, H, W], "n_parts": n_parts, "combos": 63, "mode": "max_ave",
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": gbs / peaks["hbm"], "traffic": None, "peak_source": peaks["source"]}}
+                         "frac": gbs / peaks["hbm"],
+                         "traffic": load_traffic("pool_tma_kernel@%dx%dx%dx%d/n%d/max_ave" % (n_img, C, H, W, n_parts)),
+                         "algorithmic_bytes": int(bytes_alg), "peak_source": peaks["source"]}}
 
 
 def main():

@@ -329,6 +329,26 @@ int pps_evaluate_host(const float* q_feats, long long nq,
                       double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,
                       int32_t* out_topk_index, float* out_topk_dist);
 
+/* ------------------------------------------------------------------------------------
+ * Next row — the reference's training-side triplet mining ops.
+ *   PairWiseDistance[Gradient]   detectron/ops/pairwise_distance_op.cu:9-22, :78-91
+ *       z[p,q] = sum_d (x[p,d]-x[q,d])^2  (squared, no sqrt);  dx = 2 sum_q (x_n - x_q)(dz[n,q] + dz[q,n])
+ *   BatchHard[Gradient]          detectron/ops/batch_hard_op.cc:9-59, :62-123
+ *       ap[a] = max_{label==} xdist[a,:] (init 0), an[a] = min_{label!=} xdist[a,:] (init FLT_MAX);
+ *       idx_p / idx_n (optional on forward) = the first index reaching them, -1 if none;
+ *       backward scatters dap / dan to those indices of a zeroed [N, N] (rows with idx -1 get nothing:
+ *       the reference writes out of the row there).
+ *   pps_batch_hard_fused_fwd mines straight from the features, no [N, N] matrix.
+ * ---------------------------------------------------------------------------------- */
+int pps_pairwise_distance_fwd(const float* x, int N, int D, float* z, void* stream);
+int pps_pairwise_distance_bwd(const float* x, const float* dz, int N, int D, float* dx, void* stream);
+int pps_batch_hard_fwd(const float* xdist, const int32_t* labels, int N, float* ap, float* an,
+                       int32_t* idx_p, int32_t* idx_n, void* stream);
+int pps_batch_hard_fused_fwd(const float* x, const int32_t* labels, int N, int D, float* ap, float* an,
+                             int32_t* idx_p, int32_t* idx_n, void* stream);
+int pps_batch_hard_bwd(const int32_t* idx_p, const int32_t* idx_n, const float* dap, const float* dan, int N,
+                       float* dx, void* stream);
+
 /* instrumentation: number of kernels this library has launched in this process
  * (bench.py reports the delta over the timed region as `gpu_launches`). */
 unsigned long long pps_kernel_launch_count(void);

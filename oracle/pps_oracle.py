@@ -267,3 +267,55 @@ def topk_filtered(distmat, query_ids, gallery_ids, query_cams, gallery_cams, k):
         idx_out[i, :len(order)] = order
         d_out[i, :len(order)] = distmat[i][order]
     return idx_out, d_out
+
+
+# ------------------------------------------------------------------------------------
+# training-side triplet mining ops — parity unpinned: the reference has no test for them
+# and PairWiseDistance has no CPU implementation (pairwise_distance_op.cc:5-24 holds schema + gradient only)
+# ------------------------------------------------------------------------------------
+
+
+def pairwise_distance(x):
+    """pairwise_distance_op.cu:9-22: Z[p,q] = sum_d (X[p,d]-X[q,d])^2, float32, sequential over d."""
+    x = np.asarray(x, dtype=np.float32)
+    diff = x[:, None, :] - x[None, :, :]
+    return np.sum(diff * diff, axis=2, dtype=np.float32)
+
+
+def pairwise_distance_grad(x, dz):
+    """pairwise_distance_op.cu:78-91: for every (p,q): dX[p] += 2 (x_p-x_q) dZ[p,q]; dX[q] -= 2 (x_p-x_q) dZ[p,q]."""
+    x = np.asarray(x, dtype=np.float64)
+    dz = np.asarray(dz, dtype=np.float64)
+    diff = x[:, None, :] - x[None, :, :]                       # [p, q, d]
+    g = 2.0 * diff * dz[:, :, None]
+    return (g.sum(axis=1) - g.sum(axis=0)).astype(np.float32)
+
+
+def batch_hard(xdist, labels):
+    """batch_hard_op.cc:9-59 (and the index search of :62-123): strict compares in index order.
+    Returns ap, an, idx_p, idx_n (-1 where no candidate improved on the initial 0 / FLT_MAX)."""
+    xdist = np.asarray(xdist, dtype=np.float32)
+    n = xdist.shape[0]
+    ap = np.zeros(n, np.float32); an = np.full(n, np.finfo(np.float32).max, np.float32)
+    ip = np.full(n, -1, np.int32); inn = np.full(n, -1, np.int32)
+    for a in range(n):
+        for j in range(n):
+            if labels[j] == labels[a]:
+                if ap[a] < xdist[a, j]:
+                    ap[a], ip[a] = xdist[a, j], j
+            else:
+                if an[a] > xdist[a, j]:
+                    an[a], inn[a] = xdist[a, j], j
+    return ap, an, ip, inn
+
+
+def batch_hard_grad(idx_p, idx_n, dap, dan):
+    """batch_hard_op.cc:62-123 with the out-of-row writes for idx == -1 left out."""
+    n = len(idx_p)
+    dx = np.zeros((n, n), np.float32)
+    for a in range(n):
+        if idx_p[a] >= 0:
+            dx[a, idx_p[a]] = dap[a]
+        if idx_n[a] >= 0:
+            dx[a, idx_n[a]] = dan[a]
+    return dx

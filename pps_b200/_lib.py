@@ -92,6 +92,11 @@ SIGNATURES = {
     "pps_ctx_phase_ms": (_i, [_vp, _vp]),
     "pps_evaluate_host": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_pairwise_distance_fwd": (_i, [_vp, _i, _i, _vp, _vp]),
+    "pps_pairwise_distance_bwd": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "pps_batch_hard_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pps_batch_hard_fused_fwd": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pps_batch_hard_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "pps_kernel_launch_count": (C.c_ulonglong, []),
 }
 

@@ -126,3 +126,20 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_json_dataset_reader_orders_by_image_id_and_reads_marks(tmp_path):
+    import json
+    from pps_b200 import dataset_io
+    images = [dict(id=3, file_name="00000007_0001_00000002.jpg"), dict(id=1, file_name="00000005_0000_00000000.jpg"),
+              dict(id=2, file_name="00000005_0002_00000001.jpg")]
+    anns = [dict(id=10, image_id=1, mark=0), dict(id=11, image_id=2, mark=1), dict(id=12, image_id=3, mark=2)]
+    path = tmp_path / "split.json"
+    path.write_text(json.dumps(dict(images=images, annotations=anns)))
+    ds = dataset_io.JsonReidDataset(str(path))
+    roidb = ds.get_roidb(gt=True)
+    assert [e["id"] for e in roidb] == [1, 2, 3] and [e["mark"] for e in roidb] == [0, 1, 2]
+    assert evaluator.get_info(roidb[2])[:2] == (7, 1)
+    path.write_text(json.dumps(dict(images=images, annotations=anns[:2])))
+    with pytest.raises(RuntimeError, match="no annotation"):
+        dataset_io.JsonReidDataset(str(path))

@@ -313,3 +313,23 @@ def test_duke_shape_full_parity_with_oracle():
     np.testing.assert_array_equal(one.is_valid[sub], valid)
     assert abs(float(one.ap[sub].sum()) - float(ap.sum())) / max(valid.sum(), 1) < 1e-5
     assert np.mean(one.first_rank[sub] == first) > 0.95
+
+
+def test_features_npy_cli_roundtrip(tmp_path, golden):
+    """features.npy + COCO-style json on disk -> the CLI -> the reference's result dict (task_evaluation.py:437-452)."""
+    import json
+    from pps_b200 import dataset_io
+    d = golden("small_mid")
+    feats = np.concatenate([d["q"], d["g"]]).astype(np.float32)
+    ids = np.concatenate([d["qid"], d["gid"]]); cams = np.concatenate([d["qcam"], d["gcam"]])
+    marks = np.concatenate([np.zeros(len(d["qid"])), np.ones(len(d["gid"]))]).astype(int)
+    order = np.random.RandomState(0).permutation(len(ids))            # image ids in a shuffled order: the reader sorts them
+    images = [dict(id=int(i), file_name="%08d_%04d_%08d.jpg" % (ids[i], cams[i], i)) for i in order]
+    anns = [dict(id=1000 + int(i), image_id=int(i), mark=int(marks[i])) for i in order]
+    (tmp_path / "split.json").write_text(json.dumps(dict(images=images, annotations=anns)))
+    np.save(tmp_path / "features.npy", feats)
+    res = dataset_io.main(["--features", str(tmp_path / "features.npy"), "--annotations", str(tmp_path / "split.json"),
+                           "--output", str(tmp_path / "out.json")])
+    r = res["split"]["ReID"]
+    assert abs(r["mAP"] - float(d["mAP"])) < 1e-6 and abs(r["CMC1"] - d["cmc_fmb"][0]) < 1e-12 and r["mq_mAP"] == -1
+    assert json.loads((tmp_path / "out.json").read_text())["split"]["ReID"]["CMC10"] == r["CMC10"]
