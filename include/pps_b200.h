@@ -96,6 +96,12 @@ int pps_split_rows_slab(const void* feats, int dtype, long long row0, long long 
                         long long total_rows, int dim, long long ld, int planes,
                         void* out_planes, float* out_sqnorm, void* stream);
 
+/* same, gathering: output row r is source row row_index[r] - index_base of `feats`
+ * (the threshold pass of a multi-block gallery splits only the rows that appear in a same-id pair). */
+int pps_split_rows_gather(const void* feats, int dtype, const int32_t* row_index, long long index_base,
+                          long long rows, int dim, long long ld, int planes,
+                          void* out_planes, float* out_sqnorm, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Part 2b — distance matrix        (reid_dataset_evaluator.py:244-272, 'euclidean')
  *
@@ -191,6 +197,21 @@ int pps_pairs_fill_local(const int64_t* query_ids, const int64_t* query_cams, lo
                          float* zero_f32, uint32_t* zero_u32, uint32_t* zero_per_query,
                          long long capacity, void* stream);
 int pps_pairs_unpack_pos(const int32_t* pair_pos32, long long n_pairs, uint8_t* pair_pos, void* stream);
+
+/* Compacted same-id gallery for the threshold pass of a gallery that does not fit one distance block.
+ * The thresholds of the ranking are the distances of the same-id pairs only; all queries of one id share one
+ * gallery list, so the rows needed are the lists of one representative query per id, restricted to the
+ * gallery rows [row_lo, row_hi) this device holds:
+ *   gp_rows[0 .. *n_rows)  the distinct gallery rows (global indices) that appear in a pair, grouped by id
+ *   pair_col[e]            column of pair e in the product queries x gp_rows, or -1 (row outside the window)
+ * The caller runs pps_split_rows_gather(gp_rows) + pps_dist_tc + pps_rank_gather(pair_g := pair_col), i.e. a
+ * product with a few 10^4 rows instead of a first sweep over the whole gallery.  All pointers are device
+ * pointers; gp_rows / pair_col have n_pairs entries; workspace: pps_pairs_compact_workspace_bytes(nq). */
+long long pps_pairs_compact_workspace_bytes(long long nq);
+int pps_pairs_compact_rows(const int64_t* query_ids, long long nq, const int32_t* pair_off,
+                           const int32_t* pair_q, const int32_t* pair_g, long long n_pairs,
+                           long long row_lo, long long row_hi, void* workspace,
+                           int32_t* gp_rows, int32_t* pair_col, int32_t* n_rows, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Part 2d — ranking on a materialised block of the distance matrix.
@@ -348,6 +369,28 @@ int pps_batch_hard_fused_fwd(const float* x, const int32_t* labels, int N, int D
                              int32_t* idx_p, int32_t* idx_n, void* stream);
 int pps_batch_hard_bwd(const int32_t* idx_p, const int32_t* idx_n, const float* dap, const float* dan, int N,
                        float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Next row — the per-combination embedding between pooling and distance
+ * (detectron/modeling/reid_heads.py:34-76 at test time, one branch per pooled blob):
+ *   Conv1x1(C -> E, bias) -> SpatialBN(is_test: an affine map) -> ReLU, then Concat(axis=1) of the K
+ *   branches (:95-101) and, with REID.NORMALIZE_FEATURE, Normalize(axis=1) (:123-127, triplet_loss.py:18).
+ * pps_embed_tc: out[n, k*E + e] = max(0, alpha[k*E+e] * sum_c x[k, n, c] * w[k, e, c] + beta[k*E+e]);
+ *   the caller folds the conv bias and the BN statistics into alpha / beta:
+ *   alpha = bn_scale / sqrt(bn_var + eps), beta = (conv_bias - bn_mean) * alpha + bn_bias.
+ *   x_planes : pps_split_rows of the pooled features laid out [K*N, C] (the [K, N, C] pooling output);
+ *   w_planes : pps_split_rows of the weights laid out [K*E, C].  One grouped launch of the 2-CTA tcgen05
+ *   kernel (256 x 128 tiles), same split precisions as pps_dist_tc.  E must be 128 (REID.BPM_DIM of
+ *   every shipped PPS config) for now: PPS_ERR_UNSUPPORTED otherwise.
+ * pps_l2_normalize_rows: x[r, :] /= max(|x[r, :]|_2, 1e-12)   (Caffe2 Normalize, kEps = 1e-12), in place
+ *   when out == x.
+ * ---------------------------------------------------------------------------------- */
+int pps_embed_tc(const void* x_planes, int x_planes_n, long long N,
+                 const void* w_planes, int w_planes_n, int E, int K, int C,
+                 const float* alpha, const float* beta, int precision,
+                 float* out, long long ldo, void* stream);
+int pps_l2_normalize_rows(const float* x, long long rows, int dim, long long ld,
+                          float* out, long long ldo, void* stream);
 
 /* instrumentation: number of kernels this library has launched in this process
  * (bench.py reports the delta over the timed region as `gpu_launches`). */

@@ -319,3 +319,33 @@ def batch_hard_grad(idx_p, idx_n, dap, dan):
         if idx_n[a] >= 0:
             dx[a, idx_n[a]] = dan[a]
     return dx
+
+
+# ------------------------------------------------------------------------------------
+# per-combination embedding + concat + normalise — parity unpinned: a Caffe2 graph
+# (Conv, SpatialBN, Relu, Concat, Normalize of pytorch v1.0.1) with no reference test
+# ------------------------------------------------------------------------------------
+
+
+def reid_embed(pooled, weight, conv_bias, bn_scale, bn_bias, bn_mean, bn_var, eps=1e-5, normalize=True,
+               dtype=np.float64):
+    """reid_heads.py:34-127 at test time.
+
+    pooled [K, N, C] (blob k = pooled[k] as [N, C, 1, 1]); weight [K, E, C]; the five per-channel vectors [K, E].
+    Branch k: z = pooled[k] @ weight[k].T + conv_bias[k]            (Conv 1x1, :41-57)
+              y = (z - mean) / sqrt(var + eps) * scale + bias       (SpatialBN is_test, :58-60)
+              y = max(y, 0)                                         (Relu, :76)
+    Concat(axis=1) of the K branches (:95-101), then x / max(|x|_2, 1e-12) per row (Normalize, :123-127).
+    """
+    pooled, weight = np.asarray(pooled, dtype=dtype), np.asarray(weight, dtype=dtype)
+    K, N, _ = pooled.shape
+    outs = []
+    for k in range(K):
+        z = pooled[k] @ weight[k].T + np.asarray(conv_bias[k], dtype=dtype)
+        y = (z - np.asarray(bn_mean[k], dtype)) / np.sqrt(np.asarray(bn_var[k], dtype) + eps)
+        y = y * np.asarray(bn_scale[k], dtype) + np.asarray(bn_bias[k], dtype)
+        outs.append(np.maximum(y, 0))
+    feat = np.concatenate(outs, axis=1)
+    if normalize:
+        feat = feat / np.maximum(np.sqrt((feat * feat).sum(axis=1, keepdims=True)), 1e-12)
+    return feat

@@ -7,11 +7,13 @@ from .pooling import (ReIDPoolCfg, add_pps_part_head, add_pps_part_head_, blob_n
                       pps_pool, pyramid_combs, uniform_partition_split)
 from .evaluator import (PairLists, RankEngine, RankResult, cmc, compute_dist, evaluate, evaluate_arrays, evaluate_host, mean_ap,
                         rank_distmat, rank_eval, reid_results)
+from .embedding import ReidEmbedHead, add_reid_outputs, fold_bn, l2_normalize_rows
 
 __all__ = [
     "ReIDPoolCfg", "add_pps_part_head", "add_pps_part_head_", "blob_names", "comb_to_mask", "mask_to_comb",
     "pps_pool", "pyramid_combs", "uniform_partition_split",
     "PairLists", "RankEngine", "RankResult", "cmc", "compute_dist", "evaluate", "evaluate_arrays", "evaluate_host", "mean_ap",
     "rank_distmat", "rank_eval", "reid_results",
+    "ReidEmbedHead", "add_reid_outputs", "fold_bn", "l2_normalize_rows",
 ]
 __version__ = "0.1.0"

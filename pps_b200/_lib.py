@@ -60,6 +60,7 @@ SIGNATURES = {
     "pps_split_bytes": (_ll, [_ll, _i, _i]),
     "pps_split_rows": (_i, [_vp, _i, _ll, _i, _ll, _i, _vp, _vp, _vp]),
     "pps_split_rows_slab": (_i, [_vp, _i, _ll, _ll, _ll, _i, _ll, _i, _vp, _vp, _vp]),
+    "pps_split_rows_gather": (_i, [_vp, _i, _vp, _ll, _ll, _i, _ll, _i, _vp, _vp, _vp]),
     "pps_dist_tc": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp, _ll, _i, _ll, _i, _i, _i, _vp, _ll, _vp]),
     "pps_dist_fp32": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _vp, _ll, _vp]),
     "pps_row_sqnorm": (_i, [_vp, _i, _ll, _i, _ll, _vp, _vp]),
@@ -72,6 +73,8 @@ SIGNATURES = {
     "pps_pairs_offsets": (_i, [_vp, _i, _i, _ll, _ll, _vp, _vp, _vp, _vp]),
     "pps_pairs_fill_local": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "pps_pairs_unpack_pos": (_i, [_vp, _ll, _vp, _vp]),
+    "pps_pairs_compact_workspace_bytes": (_ll, [_ll]),
+    "pps_pairs_compact_rows": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _vp]),
     "pps_rank_gather": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _ll, _vp, _vp]),
     "pps_rank_count": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "pps_rank_finalize": (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -97,6 +100,8 @@ SIGNATURES = {
     "pps_batch_hard_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "pps_batch_hard_fused_fwd": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "pps_batch_hard_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "pps_embed_tc": (_i, [_vp, _i, _ll, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _vp]),
+    "pps_l2_normalize_rows": (_i, [_vp, _ll, _i, _ll, _vp, _ll, _vp]),
     "pps_kernel_launch_count": (C.c_ulonglong, []),
 }
 

@@ -213,22 +213,31 @@ constexpr int kRing2Bytes = 192 * 1024;
 constexpr int kMaxStages2 = 6;
 constexpr int kOutChunkBytes = 32 * 32 * 4;                 // one warp's 32 x 32 fp32 staging tile
 constexpr int kOutStageBytes = 4 * 2 * kOutChunkBytes;      // 4 epilogue warps, double-buffered
-constexpr size_t kGemm2Smem = (size_t)kRing2Bytes + kOutStageBytes + 2 * kBN * 4 /*|b|^2*/ + 256 /*barriers*/;
+constexpr size_t kGemm2Smem = (size_t)kRing2Bytes + kOutStageBytes + 2 * 256 * 4 /*|b|^2 or alpha/beta*/ + 256 /*barriers*/;
 
 struct Gemm2Args {
   GemmArgs g;
   int planes;       // planes of each operand loaded per k-block (1..3)
-  int stages;       // ring depth = kRing2Bytes / (2 * planes * 16 KB)
+  int stages;       // ring depth = kRing2Bytes / stage bytes
+  // grouped form (embedding head): `groups` independent products; group grp uses A rows [grp*a_group_rows, ...),
+  // B rows [grp*b_group_rows, ...) and writes output columns [grp*out_group_cols, ...).  Distance: groups = 1.
+  int groups;
+  long long a_group_rows, b_group_rows, out_group_cols;
 };
 
+constexpr int EPI_DIST = 0;      // |a|^2 + |b|^2 - 2ab, clamp, sqrt (or squared / raw dot by flags)
+constexpr int EPI_AFFINE_RELU = 1;   // max(0, dot * alpha[col] + beta[col])   (a_sqnorm = alpha, b_sqnorm = beta)
+
+template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Gemm2Args ga) {
   extern __shared__ __align__(1024) unsigned char smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   unsigned char* stage_out = smem + kRing2Bytes;                                   // [4 warps][2][4 KB]
-  float* bn_s = reinterpret_cast<float*>(stage_out + kOutStageBytes);             // [2][256]
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(bn_s) + 2 * kBN * 4);
+  float* bn_s = reinterpret_cast<float*>(stage_out + kOutStageBytes);             // [2][256] (or [2][2][128])
+  constexpr int kBTile = (BN / 2) * kBK * 2;                 // this CTA's half of a B plane tile
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(bn_s) + 2 * 256 * 4);
   uint64_t* empty = full + kMaxStages2;
   uint64_t* tfull = empty + kMaxStages2;      // [2]
   uint64_t* tempty = tfull + 2;               // [2] (used in the leader)
@@ -237,10 +246,11 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const GemmArgs& g = ga.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const long long tiles = (long long)g.m_tiles * g.n_tiles;      // 256 x 256 tiles
+  const long long tiles_per_group = (long long)g.m_tiles * g.n_tiles;   // 256 x BN tiles
+  const long long tiles = tiles_per_group * ga.groups;
   const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int planes = ga.planes, stages = ga.stages;
-  const uint32_t stage_bytes = 2u * (uint32_t)planes * kTile2Bytes;
+  const uint32_t stage_bytes = (uint32_t)planes * (kTile2Bytes + kBTile);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -257,7 +267,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc_2cta(tmem_slot, 2 * kBN);
+    tmem_alloc_2cta(tmem_slot, 512);
     tmem_relinquish_2cta();
   }
   tc_fence_before();
@@ -270,8 +280,9 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       uint32_t it = 0;
       for (long long t = pair; t < tiles; t += npairs) {
-        const int m0 = (int)(t % g.m_tiles) * 256 + (int)rank * kT2Rows;
-        const int n0 = (int)(t / g.m_tiles) * 256 + (int)rank * kT2Rows;
+        const long long grp = t / tiles_per_group, tt = t % tiles_per_group;
+        const int m0 = (int)(grp * ga.a_group_rows) + (int)(tt % g.m_tiles) * 256 + (int)rank * kT2Rows;
+        const int n0 = (int)(grp * ga.b_group_rows) + (int)(tt / g.m_tiles) * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < g.kblocks; ++kb, ++it) {
           const uint32_t s = it % stages, ph = (it / stages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
@@ -280,7 +291,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           unsigned char* slot = smem + (size_t)s * stage_bytes;
           for (int p = 0; p < planes; ++p) tma_load_3d_2cta(slot + p * kTile2Bytes, &tmA, full0, kb * kBK, m0, p);
           for (int p = 0; p < planes; ++p)
-            tma_load_3d_2cta(slot + (planes + p) * kTile2Bytes, &tmB, full0, kb * kBK, n0, p);
+            tma_load_3d_2cta(slot + planes * kTile2Bytes + p * kBTile, &tmB, full0, kb * kBK, n0, p);
         }
       }
     }
@@ -292,7 +303,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
         mbar_wait(&tempty[as], aph ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kBN;
+        const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < g.kblocks; ++kb, ++it) {
           const uint32_t s = it % stages, ph = (it / stages) & 1u;
           mbar_wait(&full[s], ph);
@@ -300,7 +311,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t slot = smem_u32(smem + (size_t)s * stage_bytes);
           for (int term = 0; term < g.nterms; ++term) {
             const uint64_t adesc = umma_desc_k_sw128(slot + g.term_a[term] * kTile2Bytes);
-            const uint64_t bdesc = umma_desc_k_sw128(slot + (planes + g.term_b[term]) * kTile2Bytes);
+            const uint64_t bdesc = umma_desc_k_sw128(slot + planes * kTile2Bytes + g.term_b[term] * kBTile);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
               tc_mma_f16_2cta(d_tmem, adesc + 2u * k, bdesc + 2u * k, g.idesc, (kb | term | k) ? 1u : 0u);
@@ -323,24 +334,31 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     unsigned char* my_stage = stage_out + (size_t)lane_grp * (2 * kOutChunkBytes);
     const uint32_t swz = (uint32_t)(lane & 7);
     for (long long t = pair; t < tiles; t += npairs, ++acc_it) {
-      const int m0 = (int)(t % g.m_tiles) * 256 + (int)rank * kT2Rows;
-      const int n0 = (int)(t / g.m_tiles) * 256;
+      const long long grp = t / tiles_per_group, tt = t % tiles_per_group;
+      const int m0 = (int)(tt % g.m_tiles) * 256 + (int)rank * kT2Rows;             // output row (within the group's rows)
+      const int n0 = (int)(grp * ga.out_group_cols) + (int)(tt / g.m_tiles) * BN;   // output column
+      const int n_end = EPI == EPI_DIST ? (int)g.m2 : (int)((grp + 1) * ga.out_group_cols);   // first column not ours
       const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-      // |b|^2 of the tile's 256 gallery rows -> shared (double-buffered by accumulator stage)
-      float* bn = bn_s + as * kBN;
-      if (!want_dot) {
+      // per-column operands of the tile -> shared (double-buffered by accumulator stage):
+      // |b|^2 of the gallery rows, or alpha / beta of the output channels
+      float* bn = bn_s + as * 256;
+      if (EPI == EPI_AFFINE_RELU) {
+        const long long gj = (long long)n0 + etid;            // BN == 128 == number of epilogue threads
+        bn[etid] = gj < n_end ? __ldg(g.a_sqnorm + gj) : 0.f;
+        bn[etid + 128] = gj < n_end ? __ldg(g.b_sqnorm + gj) : 0.f;
+      } else if (!want_dot) {
         const long long gj = (long long)n0 + etid;
         bn[etid] = gj < g.m2 ? __ldg(g.b_sqnorm + gj) : 0.f;
-        bn[etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_sqnorm + gj + 128) : 0.f;
+        if (BN > 128) bn[etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_sqnorm + gj + 128) : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const long long gi = (long long)m0 + row;
-      const float an = (gi < g.m1 && !want_dot) ? __ldg(g.a_sqnorm + gi) : 0.f;
+      const float an = (EPI == EPI_DIST && gi < g.m1 && !want_dot) ? __ldg(g.a_sqnorm + gi) : 0.f;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + as * kBN + ((uint32_t)(lane_grp * 32) << 16);
+      const uint32_t tbase = tmem_base + as * BN + ((uint32_t)(lane_grp * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < kBN; c += 32, ++chunk_it) {
+      for (int c = 0; c < BN; c += 32, ++chunk_it) {
         uint32_t r[32];
         tmem_ld_32x32(tbase + c, r);
         unsigned char* buf = my_stage + (chunk_it & 1u) * kOutChunkBytes;
@@ -353,10 +371,17 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           float v[4];
           const float4 b4 = bn4[j];
           const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          float cc[4] = {0.f, 0.f, 0.f, 0.f};
+          if (EPI == EPI_AFFINE_RELU) {
+            const float4 c4 = reinterpret_cast<const float4*>(bn + 128 + c)[j];
+            cc[0] = c4.x; cc[1] = c4.y; cc[2] = c4.z; cc[3] = c4.w;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float dot = __uint_as_float(r[4 * j + e]);
-            if (want_dot) {
+            if (EPI == EPI_AFFINE_RELU) {
+              v[e] = fmaxf(fmaf(dot, bb[e], cc[e]), 0.f);
+            } else if (want_dot) {
               v[e] = dot;
             } else {
               // same association as the reference: (-2*ab + |a|^2) + |b|^2   (-2*ab is exact, so the FMA rounds once)
@@ -370,7 +395,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (m0 + lane_grp * 32 < g.m1 && n0 + c < g.m2) tma_store_2d(&tmO, buf, n0 + c, m0 + lane_grp * 32);
+          if (m0 + lane_grp * 32 < g.m1 && n0 + c < n_end) tma_store_2d(&tmO, buf, n0 + c, m0 + lane_grp * 32);
           bulk_commit_group();
         }
       }
@@ -388,7 +413,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();      // no CTA of the pair leaves (or frees TMEM) while its peer still signals it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_2cta(tmem_base, 2 * kBN);
+    tmem_dealloc_2cta(tmem_base, 512);
   }
 }
 
@@ -549,6 +574,7 @@ extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long lon
     ga.planes = need;
     ga.stages = kRing2Bytes / (2 * need * kTile2Bytes);
     if (ga.stages > kMaxStages2) ga.stages = kMaxStages2;
+    ga.groups = 1; ga.a_group_rows = 0; ga.b_group_rows = 0; ga.out_group_cols = 0;
     int rc = make_operand_map(&tmA, a_planes, m1, a_plane_rows, kpad, a_planes_n, kT2Rows, f16);
     if (rc) return rc;
     rc = make_operand_map(&tmB, b_planes, m2, b_plane_rows, kpad, b_planes_n, kT2Rows, f16);
@@ -568,14 +594,15 @@ extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long lon
     }
     static thread_local int configured2_dev = -1;
     if (configured2_dev != dev) {
-      PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemm2Smem));
+      PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc2_kernel<256, EPI_DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kGemm2Smem));
       configured2_dev = dev;
     }
     const long long tiles2 = (long long)ga.g.m_tiles * ga.g.n_tiles;
     long long slots = sms / 2;
     if ((flags & PPS_DIST_RESERVE_SM_PAIR) && slots > 8) slots -= 1;   // leave one SM pair to concurrent small kernels
     const long long pairs = tiles2 < slots ? tiles2 : slots;
-    dist_tc2_kernel<<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga);
+    dist_tc2_kernel<256, EPI_DIST><<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga);
     PPS_LAUNCH_CHECK("dist_tc2_kernel");
     return PPS_OK;
   }
@@ -608,5 +635,89 @@ extern "C" int pps_dist_fp32(const float* a, long long lda, const float* a_sqnor
   dist_fp32_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       a, lda, a_sqnorm, m1, b, ldb, b_sqnorm, m2, dim, flags, dist, ldd);
   PPS_LAUNCH_CHECK("dist_fp32_kernel");
+  return PPS_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Next row: the per-combination embedding between pooling and distance
+// (detectron/modeling/reid_heads.py:34-76 at test time): for every combination k
+//   out[n, k*E + e] = max(0, alpha[k*E+e] * (sum_c pooled[k, n, c] * W[k, e, c]) + beta[k*E+e])
+// i.e. Conv1x1(C -> E) + bias + SpatialBN(test: an affine map) + ReLU with the conv bias and the BN statistics
+// folded into alpha / beta by the caller, written straight into the concatenated [N, K*E] feature
+// (Concat(axis=1), :95-101).  K independent [N, C] x [C, E] products = one grouped launch of the 2-CTA kernel
+// (256 x 128 tiles, tcgen05.mma.cta_group::2 with N = 128), same split-precision operands as the distance.
+// ------------------------------------------------------------------------------------
+extern "C" int pps_embed_tc(const void* x_planes /*[planes][K*N][kpad]*/, int x_planes_n, long long N,
+                            const void* w_planes /*[planes][K*E][kpad]*/, int w_planes_n, int E, int K, int C,
+                            const float* alpha, const float* beta, int precision, float* out /*[N, ldo >= K*E]*/,
+                            long long ldo, void* stream) {
+  if (N < 0 || K <= 0 || C <= 0 || E <= 0 || ldo < (long long)K * E) return PPS_ERR_INVALID_ARG;
+  if (N == 0) return PPS_OK;
+  if (E != 128) return PPS_ERR_UNSUPPORTED;             // cfg.REID.BPM_DIM of every shipped PPS config
+  if (!x_planes || !w_planes || !alpha || !beta || !out) return PPS_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(x_planes) & 15u) || (reinterpret_cast<uintptr_t>(w_planes) & 15u)) return PPS_ERR_ALIGN;
+  if ((ldo & 3) || (reinterpret_cast<uintptr_t>(out) & 15u)) return PPS_ERR_ALIGN;
+  if ((long long)K * N > 0x7fffff00LL) return PPS_ERR_UNSUPPORTED;
+  Gemm2Args ga;
+  GemmArgs& g = ga.g;
+  int need = 1;
+  switch (precision) {
+    case PPS_PREC_BF16X1: g.nterms = 1; g.term_a[0] = 0; g.term_b[0] = 0; need = 1; break;
+    case PPS_PREC_BF16X3: {
+      const int ta[3] = {1, 0, 0}, tb[3] = {0, 1, 0};
+      g.nterms = 3; for (int i = 0; i < 3; ++i) { g.term_a[i] = ta[i]; g.term_b[i] = tb[i]; }
+      need = 2; break;
+    }
+    case PPS_PREC_BF16X6: {
+      const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+      g.nterms = 6; for (int i = 0; i < 6; ++i) { g.term_a[i] = ta[i]; g.term_b[i] = tb[i]; }
+      need = 3; break;
+    }
+    default: return PPS_ERR_INVALID_ARG;
+  }
+  if (x_planes_n < need || w_planes_n < need) return PPS_ERR_INVALID_ARG;
+  const int kpad = pps_kpad(C);
+  g.m1 = N; g.m2 = (long long)K * E;
+  g.kblocks = kpad / kBK;
+  g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  g.a_sqnorm = alpha; g.b_sqnorm = beta;
+  g.out = out; g.ldo = ldo; g.flags = 0;
+  g.m_tiles = (int)((N + 255) / 256);
+  g.n_tiles = 1;
+  ga.planes = need;
+  ga.stages = kRing2Bytes / (need * (kTile2Bytes + 64 * kBK * 2));
+  if (ga.stages > kMaxStages2) ga.stages = kMaxStages2;
+  ga.groups = K; ga.a_group_rows = N; ga.b_group_rows = E; ga.out_group_cols = E;
+
+  CUtensorMap tmA, tmB, tmO;
+  int rc = make_operand_map(&tmA, x_planes, (long long)K * N, (long long)K * N, kpad, x_planes_n, kT2Rows, false);
+  if (rc) return rc;
+  rc = make_operand_map(&tmB, w_planes, (long long)K * E, (long long)K * E, kpad, w_planes_n, 64, false);
+  if (rc) return rc;
+  {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return cuda_fail(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[2] = {(cuuint64_t)((long long)K * E), (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)ldo * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(output) failed");
+  }
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  PPS_CUDA_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc2_kernel<128, EPI_AFFINE_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kGemm2Smem));
+    configured_dev = dev;
+  }
+  const int sms = sm_count();
+  const long long tiles = (long long)g.m_tiles * K;
+  const long long pairs = tiles < sms / 2 ? tiles : sms / 2;
+  dist_tc2_kernel<128, EPI_AFFINE_RELU><<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem,
+                                          static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmO, ga);
+  PPS_LAUNCH_CHECK("dist_tc2_kernel<embed>");
   return PPS_OK;
 }

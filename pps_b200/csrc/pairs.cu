@@ -192,6 +192,96 @@ static void pair_segments(long long ng, long long* seg, int* nseg) {
   if (*nseg < 1) *nseg = 1;
 }
 
+// ------------------------------------------------------------------------------------
+// Compacted same-id gallery ("G'") for the threshold pass of galleries that do not fit one
+// distance block.  The thresholds of the ranking are the distances of the same-id pairs only, so
+// they come from a dense product of the queries with JUST the gallery rows that appear in some pair
+// (a few 10^4 rows however large the gallery is) instead of a first sweep over the whole gallery.
+// All queries of one id share the same gallery list, so G' is the concatenation of the lists of
+// one representative query per id (the first query carrying it), restricted to the row window
+// [row_lo, row_hi) of this gallery shard; pair e of query q then sits at column
+// gp_off[rep(q)] + (e - pair_off[q]) - lo(q) of the product.
+// ------------------------------------------------------------------------------------
+__global__ void compact_rep_kernel(const int64_t* __restrict__ qid, int nq, const int32_t* __restrict__ pair_off,
+                                   const int32_t* __restrict__ pair_g, int row_lo, int row_hi,
+                                   int32_t* __restrict__ rep, int32_t* __restrict__ lo_out, int32_t* __restrict__ cnt) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int64_t id = qid[q];
+  int r = q;
+  for (int j = 0; j < q; ++j)
+    if (qid[j] == id) { r = j; break; }
+  rep[q] = r;
+  // the pair list is ascending in the gallery index: the rows of the window are one sub-range
+  const int e0 = pair_off[q], e1 = pair_off[q + 1];
+  int a = e0, b = e1;
+  while (a < b) { const int m = (a + b) >> 1; if (pair_g[m] < row_lo) a = m + 1; else b = m; }
+  const int lo = a;
+  b = e1;
+  while (a < b) { const int m = (a + b) >> 1; if (pair_g[m] < row_hi) a = m + 1; else b = m; }
+  lo_out[q] = lo - e0;
+  cnt[q] = a - lo;              // rows of q's list inside the window (whether or not q is the representative)
+}
+
+// one CTA: exclusive scan of the representatives' counts -> gp_off[q] (meaningful where rep[q] == q)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const int32_t* __restrict__ rep, const int32_t* __restrict__ cnt,
+                                                            int nq, int32_t* __restrict__ gp_off,
+                                                            int32_t* __restrict__ n_rows) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nq; base += 1024) {
+    const int q = base + tid;
+    const int v = (q < nq && rep[q] == q) ? cnt[q] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (q < nq) gp_off[q] = carry + (warp ? warp_sum[warp - 1] : 0) + incl - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sum[31];
+    __syncthreads();
+  }
+  if (tid == 0) *n_rows = carry_s;
+}
+
+__global__ void compact_fill_kernel(const int32_t* __restrict__ pair_off, const int32_t* __restrict__ pair_q,
+                                    const int32_t* __restrict__ pair_g, long long n_pairs,
+                                    const int32_t* __restrict__ rep, const int32_t* __restrict__ lo,
+                                    const int32_t* __restrict__ cnt, const int32_t* __restrict__ gp_off,
+                                    int32_t* __restrict__ gp_rows, int32_t* __restrict__ pair_col) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pairs) return;
+  const int q = pair_q[e];
+  int col = -1;
+  if (q >= 0) {
+    const int i = (int)(e - pair_off[q]) - lo[q];
+    if (i >= 0 && i < cnt[q]) {
+      const int r = rep[q];
+      col = gp_off[r] + i;
+      if (r == q) gp_rows[col] = pair_g[e];
+    }
+  }
+  pair_col[e] = col;
+}
+
 }  // namespace pps
 
 using namespace pps;
@@ -306,4 +396,38 @@ extern "C" int pps_pairs_fill_device(const int64_t* query_ids, const int64_t* qu
                                      void* stream) {
   return pps_pairs_fill_local(query_ids, query_cams, nq, gallery_ids, gallery_cams, ng, 0, workspace, pair_q, pair_g,
                               pair_pos, nullptr, zero_f32, zero_u32, zero_per_query, capacity, stream);
+}
+
+// ---- compacted same-id gallery for the threshold pass (see compact_rep_kernel) ----
+extern "C" long long pps_pairs_compact_workspace_bytes(long long nq) {
+  if (nq < 0) return PPS_ERR_INVALID_ARG;
+  return (4 * (nq > 0 ? nq : 1) + 4) * 4;
+}
+
+extern "C" int pps_pairs_compact_rows(const int64_t* query_ids, long long nq, const int32_t* pair_off,
+                                      const int32_t* pair_q, const int32_t* pair_g, long long n_pairs, long long row_lo,
+                                      long long row_hi, void* workspace, int32_t* gp_rows, int32_t* pair_col,
+                                      int32_t* n_rows, void* stream) {
+  if (nq < 0 || n_pairs < 0 || row_lo < 0 || row_hi < row_lo || nq > 0x7fffffffLL || row_hi > 0x7fffffffLL)
+    return PPS_ERR_INVALID_ARG;
+  if (!n_rows) return PPS_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nq == 0 || n_pairs == 0) {
+    PPS_CUDA_TRY(cudaMemsetAsync(n_rows, 0, 4, st));
+    return PPS_OK;
+  }
+  if (!query_ids || !pair_off || !pair_q || !pair_g || !workspace || !gp_rows || !pair_col) return PPS_ERR_INVALID_ARG;
+  int32_t* rep = static_cast<int32_t*>(workspace);
+  int32_t* lo = rep + nq;
+  int32_t* cnt = lo + nq;
+  int32_t* gp_off = cnt + nq;
+  compact_rep_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(query_ids, (int)nq, pair_off, pair_g, (int)row_lo,
+                                                                   (int)row_hi, rep, lo, cnt);
+  PPS_LAUNCH_CHECK("compact_rep_kernel");
+  compact_scan_kernel<<<1, 1024, 0, st>>>(rep, cnt, (int)nq, gp_off, n_rows);
+  PPS_LAUNCH_CHECK("compact_scan_kernel");
+  compact_fill_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(pair_off, pair_q, pair_g, n_pairs, rep, lo, cnt,
+                                                                         gp_off, gp_rows, pair_col);
+  PPS_LAUNCH_CHECK("compact_fill_kernel");
+  return PPS_OK;
 }

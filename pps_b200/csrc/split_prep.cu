@@ -14,14 +14,18 @@ __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_kernel(const void
                                                                        long long row_end, long long rows, int dim,
                                                                        long long ld, int kpad,
                                                                        void* __restrict__ out_planes,
-                                                                       float* __restrict__ out_sqnorm) {
+                                                                       float* __restrict__ out_sqnorm,
+                                                                       const int32_t* __restrict__ row_index,
+                                                                       long long index_base) {
+  // output row `row` <- source row `srow` (= row unless a gather list is given)
   const int lane = threadIdx.x & 31;
   const long long row = row_begin + (long long)blockIdx.x * kSplitWarps + (threadIdx.x >> 5);
   if (row >= row_end) return;
+  const long long srow = row_index ? (long long)row_index[row] - index_base : row;
   double acc = 0.0;
   const long long plane_stride = rows * (long long)kpad;   // elements
   if constexpr (F16IN) {
-    const __half* src = reinterpret_cast<const __half*>(feats) + row * ld;
+    const __half* src = reinterpret_cast<const __half*>(feats) + srow * ld;
     __half* dst = out_planes ? reinterpret_cast<__half*>(out_planes) + row * (long long)kpad : nullptr;
     for (int k = lane; k < kpad; k += 32) {
       const __half h = k < dim ? src[k] : __float2half(0.f);
@@ -30,7 +34,7 @@ __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_kernel(const void
       if (dst) dst[k] = h;
     }
   } else {
-    const float* src = reinterpret_cast<const float*>(feats) + row * ld;
+    const float* src = reinterpret_cast<const float*>(feats) + srow * ld;
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out_planes);
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15u) == 0);
     for (int k = lane * 4; k < kpad; k += 128) {
@@ -69,6 +73,43 @@ __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_kernel(const void
   if (lane == 0 && out_sqnorm) out_sqnorm[row] = (float)acc;
 }
 
+// Caffe2 Normalize(axis=1) of the concatenated embedding (reid_heads.py:123-127, triplet_loss.py:18):
+// y = x / max(|x|_2, 1e-12).  One CTA per row; the row (<= tens of KB) is read twice, the second time from L1/L2.
+__global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __restrict__ x, int dim, long long ld,
+                                                                float* __restrict__ out, long long ldo) {
+  __shared__ float part[8];
+  const float* src = x + (long long)blockIdx.x * ld;
+  float* dst = out + (long long)blockIdx.x * ldo;
+  const bool vec = ((dim & 3) == 0) && ((ld & 3) == 0) && ((ldo & 3) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0);
+  float acc = 0.f;
+  if (vec) {
+    for (int k = threadIdx.x * 4; k < dim; k += 1024) {
+      const float4 t = *reinterpret_cast<const float4*>(src + k);
+      acc = fmaf(t.x, t.x, acc); acc = fmaf(t.y, t.y, acc); acc = fmaf(t.z, t.z, acc); acc = fmaf(t.w, t.w, acc);
+    }
+  } else {
+    for (int k = threadIdx.x; k < dim; k += 256) acc = fmaf(src[k], src[k], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += part[w];
+  const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+  if (vec) {
+    for (int k = threadIdx.x * 4; k < dim; k += 1024) {
+      float4 t = *reinterpret_cast<const float4*>(src + k);
+      t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
+      *reinterpret_cast<float4*>(dst + k) = t;
+    }
+  } else {
+    for (int k = threadIdx.x; k < dim; k += 256) dst[k] = src[k] * inv;
+  }
+}
+
 }  // namespace pps
 
 using namespace pps;
@@ -81,7 +122,8 @@ extern "C" long long pps_split_bytes(long long rows, int dim, int planes) {
 }
 
 static int split_dispatch(const void* feats, int dtype, long long row0, long long nrows, long long rows, int dim,
-                          long long ld, int planes, void* out_planes, float* out_sqnorm, void* stream) {
+                          long long ld, int planes, void* out_planes, float* out_sqnorm, void* stream,
+                          const int32_t* row_index = nullptr, long long index_base = 0) {
   if (rows < 0 || dim <= 0 || ld < dim || row0 < 0 || nrows < 0 || row0 + nrows > rows) return PPS_ERR_INVALID_ARG;
   if (nrows == 0) return PPS_OK;
   if (!feats) return PPS_ERR_INVALID_ARG;
@@ -93,12 +135,12 @@ static int split_dispatch(const void* feats, int dtype, long long row0, long lon
   const dim3 grid((unsigned)blocks), block(32 * kSplitWarps);
   if (dtype == PPS_DTYPE_F16) {
     if (planes != 1) return PPS_ERR_INVALID_ARG;
-    split_rows_kernel<1, true><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm);
+    split_rows_kernel<1, true><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm, row_index, index_base);
   } else if (dtype == PPS_DTYPE_F32) {
     switch (planes) {
-      case 1: split_rows_kernel<1, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm); break;
-      case 2: split_rows_kernel<2, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm); break;
-      case 3: split_rows_kernel<3, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm); break;
+      case 1: split_rows_kernel<1, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm, row_index, index_base); break;
+      case 2: split_rows_kernel<2, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm, row_index, index_base); break;
+      case 3: split_rows_kernel<3, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm, row_index, index_base); break;
       default: return PPS_ERR_INVALID_ARG;
     }
   } else {
@@ -125,4 +167,23 @@ extern "C" int pps_row_sqnorm(const void* feats, int dtype, long long rows, int 
                               void* stream) {
   if (!out_sqnorm && rows > 0) return PPS_ERR_INVALID_ARG;
   return split_dispatch(feats, dtype, 0, rows, rows, dim, ld, 1, nullptr, out_sqnorm, stream);
+}
+
+extern "C" int pps_l2_normalize_rows(const float* x, long long rows, int dim, long long ld, float* out, long long ldo,
+                                     void* stream) {
+  if (rows < 0 || dim <= 0 || ld < dim || ldo < dim) return PPS_ERR_INVALID_ARG;
+  if (rows == 0) return PPS_OK;
+  if (!x || !out) return PPS_ERR_INVALID_ARG;
+  if (rows > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  l2_normalize_rows_kernel<<<(unsigned)rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dim, ld, out, ldo);
+  PPS_LAUNCH_CHECK("l2_normalize_rows_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_split_rows_gather(const void* feats, int dtype, const int32_t* row_index, long long index_base,
+                                     long long rows, int dim, long long ld, int planes, void* out_planes,
+                                     float* out_sqnorm, void* stream) {
+  if ((!out_planes || !row_index) && rows > 0) return PPS_ERR_INVALID_ARG;
+  return split_dispatch(feats, dtype, 0, rows, rows, dim, ld, planes, out_planes, out_sqnorm, stream, row_index,
+                        index_base);
 }

@@ -518,6 +518,9 @@ class RankEngine:
         self._cnt_all = None
         self._side = None
         self.h2d_bytes = 0
+        self.compact_thresholds = True   # multi-chunk galleries: thresholds from the compacted same-id gallery
+        self._gp_cap, self._gp_rows, self._pair_col, self._gp_ws = 0, None, None, None
+        self.threshold_rows = 0
 
     # -- helpers --
     def _pair_buffers(self, n_pairs):
@@ -613,6 +616,40 @@ class RankEngine:
                                                self.planes, _lib.ptr(planes_buf), _lib.ptr(sq_buf), _lib.stream_ptr()),
                        "pps_split_rows")
 
+    def _threshold_pass(self, g, pairs, pair_d):
+        """pair_d[e] = d(query, gallery row) for every same-id pair whose row lives in this shard, from the product
+        queries x (the distinct rows that appear in a pair) — pps_pairs_compact_rows + pps_split_rows_gather."""
+        torch, lib = self.torch, self.lib
+        n = pairs.n_pairs
+        if self._gp_cap < n:
+            self._gp_cap = max(int(n * 1.25), 1024)
+            self._gp_rows = torch.empty(self._gp_cap, dtype=torch.int32, device=self.dev)
+            self._pair_col = torch.empty(self._gp_cap, dtype=torch.int32, device=self.dev)
+        if self._gp_ws is None:
+            self._gp_ws = torch.empty(int(lib.pps_pairs_compact_workspace_bytes(self.nq)), dtype=torch.uint8, device=self.dev)
+            self._gp_n_d = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self._gp_n_h = torch.zeros(1, dtype=torch.int32).pin_memory()
+        s = _lib.stream_ptr()
+        _lib.check(lib.pps_pairs_compact_rows(_lib.ptr(pairs.qid), self.nq, _lib.ptr(pairs.dev("off")),
+                                              _lib.ptr(pairs.dev("q")), _lib.ptr(pairs.dev("g")), n, self.offset,
+                                              self.offset + self.ngl, _lib.ptr(self._gp_ws), _lib.ptr(self._gp_rows),
+                                              _lib.ptr(self._pair_col), _lib.ptr(self._gp_n_d), s),
+                   "pps_pairs_compact_rows")
+        self._gp_n_h.copy_(self._gp_n_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # 4 bytes: the row count sizes the product
+        n_rows = int(self._gp_n_h[0])
+        self.threshold_rows = n_rows
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        for c0 in range(0, n_rows, self.chunk):
+            rows = min(self.chunk, n_rows - c0)
+            _lib.check(lib.pps_split_rows_gather(_lib.ptr(g), self.in_code, _lib.ptr(self._gp_rows[c0:]), self.offset, rows,
+                                                 self.dim, int(g.stride(0)), self.planes, _lib.ptr(self.g_planes),
+                                                 _lib.ptr(self.g_sq), s), "pps_split_rows_gather")
+            self._distance(rows)
+            _lib.check(lib.pps_rank_gather(_lib.ptr(self.block), self.ldd, self.nq, rows, c0, _lib.ptr(pairs.dev("q")),
+                                           _lib.ptr(self._pair_col), n, _lib.ptr(pair_d), s), "pps_rank_gather")
+
     def _distance(self, rows):
         torch = self.torch
         ev = None
@@ -656,14 +693,23 @@ class RankEngine:
             first_chunk = True
             pair_d = cnt_le = None
             cnt_first = self.cnt_first
-            for r0, rows in chunks:
-                self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)
-                self._distance(rows)
-                if first_chunk:                 # the pair count came back while the GEMM was queued / running
-                    pair_d, cnt_le = self._finish_pairs(pairs)
-                    first_chunk = False
-                _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
-                            True, False)
+            if self.n_chunks > 1 and self.compact_thresholds:
+                # The thresholds are the distances of the same-id pairs only: one dense product of the queries with
+                # just the gallery rows that appear in a pair (a few 10^4 rows however large the gallery is), with
+                # the same kernel and operands as sweep 2 (bit-identical values), instead of a sweep over every chunk.
+                pair_d, cnt_le = self._finish_pairs(pairs)
+                first_chunk = False
+                if pairs.n_pairs:
+                    self._threshold_pass(g, pairs, pair_d)
+            else:
+                for r0, rows in chunks:
+                    self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)
+                    self._distance(rows)
+                    if first_chunk:                 # the pair count came back while the GEMM was queued / running
+                        pair_d, cnt_le = self._finish_pairs(pairs)
+                        first_chunk = False
+                    _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
+                                True, False)
             if first_chunk:                     # empty gallery shard
                 pair_d, cnt_le = self._finish_pairs(pairs)
             if self.group is not None:

@@ -37,6 +37,11 @@ def _worker(rank, world, port, golden_path, out_dir):
                              gallery_offset=row0, group=dist.group.WORLD)
     # the C step path (no top-k, no neg_before): begin -> all-gather -> distance -> all-reduce -> count -> all-reduce -> end
     fast = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"], gallery_offset=row0, group=dist.group.WORLD)
+    # sharded AND chunked: thresholds from the compacted same-id rows of each shard
+    small = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"], topk=12, gallery_offset=row0,
+                               group=dist.group.WORLD, max_block_bytes=int(q.shape[0]) * 256 * 4)
+    assert np.array_equal(small.ap, res.ap) and np.array_equal(small.first_rank, res.first_rank)
+    assert np.array_equal(small.topk_index, res.topk_index)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), ap=res.ap, valid=res.is_valid, first=res.first_rank,
              neg_before=res.neg_before, ti=res.topk_index, td=res.topk_dist, fast_ap=fast.ap, fast_valid=fast.is_valid,
              fast_first=fast.first_rank)

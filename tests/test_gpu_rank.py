@@ -96,6 +96,68 @@ def test_chunked_gallery_equals_single_block(golden):
     np.testing.assert_array_equal(one.topk_dist, many.topk_dist)
 
 
+def test_compacted_threshold_pass_equals_full_sweep(golden):
+    """Multi-chunk galleries take their thresholds from the product queries x (rows that appear in a pair);
+    it must give the bits of the two-sweep form, including when those rows need several blocks themselves."""
+    import torch
+    from pps_b200 import evaluator
+    for name in ("small_mid", "many_pos", "some_invalid"):
+        d = golden(name)
+        q, g = torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda()
+        out = []
+        for compact in (False, True):
+            eng = evaluator.RankEngine(d["qid"], d["gid"], d["qcam"], d["gcam"], nq=q.shape[0], ng_local=g.shape[0],
+                                       dim=q.shape[1], topk=7, want_neg_before=True, max_block_bytes=q.shape[0] * 256 * 4)
+            eng.compact_thresholds = compact
+            assert eng.n_chunks > 1
+            out.append(eng.run(q, g))
+            if compact:
+                same_id = np.isin(d["gid"], np.unique(d["qid"]))
+                assert eng.threshold_rows == int(same_id.sum())
+        a, b = out
+        np.testing.assert_array_equal(a.ap, b.ap)
+        np.testing.assert_array_equal(a.first_rank, b.first_rank)
+        np.testing.assert_array_equal(a.neg_before, b.neg_before)
+        np.testing.assert_array_equal(a.topk_index, b.topk_index)
+
+
+def test_compact_rows_layout():
+    """pps_pairs_compact_rows: gp_rows = the distinct same-id gallery rows of the window grouped by id (one
+    representative query per id), pair_col = where each pair's row sits in it (or -1 outside the window)."""
+    import torch
+    from pps_b200 import _lib, evaluator
+    rs = np.random.RandomState(3)
+    nq, ng = 300, 4000
+    qid, gid = rs.randint(1, 40, size=nq), rs.randint(0, 60, size=ng)
+    qcam, gcam = rs.randint(0, 3, size=nq), rs.randint(0, 3, size=ng)
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    p = evaluator.DevicePairs(qid, qcam, gid, gcam, dev)
+    p.begin().finish()
+    n = p.n_pairs
+    for lo, hi in ((0, ng), (1000, 2500), (3999, 4000), (10, 10)):
+        ws = torch.empty(int(lib.pps_pairs_compact_workspace_bytes(nq)), dtype=torch.uint8, device=dev)
+        rows = torch.full((n,), -7, dtype=torch.int32, device=dev)
+        col = torch.full((n,), -7, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.pps_pairs_compact_rows(_lib.ptr(p.qid), nq, _lib.ptr(p.off_d), _lib.ptr(p.q_d), _lib.ptr(p.g_d), n,
+                                              lo, hi, _lib.ptr(ws), _lib.ptr(rows), _lib.ptr(col), _lib.ptr(cnt),
+                                              _lib.stream_ptr()), "pps_pairs_compact_rows")
+        torch.cuda.synchronize()
+        n_rows = int(cnt[0])
+        rows, col = rows.cpu().numpy()[:n_rows], col.cpu().numpy()
+        inside = np.isin(gid, np.unique(qid)) & (np.arange(ng) >= lo) & (np.arange(ng) < hi)
+        assert n_rows == int(inside.sum())
+        np.testing.assert_array_equal(np.sort(rows), np.nonzero(inside)[0])       # every such row exactly once
+        pg, pq = p.g[:n], p.q[:n]
+        win = (pg >= lo) & (pg < hi)
+        assert (col[~win] == -1).all()
+        np.testing.assert_array_equal(rows[col[win]], pg[win])                    # the column holds the pair's row
+        # grouped by id in the order of each id's first query
+        first_q = [np.nonzero(qid == i)[0][0] for i in gid[rows]]
+        assert (np.diff(first_q) >= 0).all()
+
+
 def test_more_positives_than_one_window():
     """> 63 positives per query: the count kernel walks several threshold windows."""
     import pps_b200
