@@ -261,10 +261,41 @@ int pps_rank_finalize(long long nq,
  * pps_topk_unpack splits the state into distances / indices (-1 = fewer than k items).
  * ---------------------------------------------------------------------------------- */
 #define PPS_TOPK_MAX 128
+/* Fused form for gallery blocks whose thresholds are already known (multi-block sweeps): the ranking counters are
+ * taken in the EPILOGUE of the tensor-core distance kernel, so the [m1, m2] distance block is never written.
+ *   pps_rank_tab_prep   per query: the positives' distances sorted ascending (ties by gallery index) into
+ *                       thr_tab (+inf padded), their pair indices into tpair_tab, cnt_tab zeroed, the nearest
+ *                       positive into dstar / gstar (NaN / 0 for a query without one).  Tables hold
+ *                       pps_rank_tab_elems(nq, p_cap) elements laid out [rows/128][p_cap][128]; p_cap is a multiple
+ *                       of 8, <= 64, and must be >= the largest number of positives of a query (*overflow counts
+ *                       the queries that break this: the caller then uses pps_rank_count on a materialised block).
+ *   pps_dist_rank_tc    pps_dist_tc's arithmetic (same operands, same kernel mainloop, bit-identical distances)
+ *                       with the counting epilogue: cnt_tab[q][j] += #{columns with exactly j thresholds of q
+ *                       strictly below their distance}, cnt_first as in pps_rank_count.  col0 = global gallery
+ *                       index of the block's first row.  flags: 0 or PPS_DIST_SQUARED.
+ *   pps_rank_tab_finish cnt_le[pair of threshold j] += cnt_tab[q][0] + ... + cnt_tab[q][j]. */
+long long pps_rank_tab_elems(long long nq, int p_cap);
+int pps_rank_tab_prep(long long nq, const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                      const float* pair_d, int p_cap, float* thr_tab, int32_t* tpair_tab, uint32_t* cnt_tab,
+                      float* dstar, int32_t* gstar, int32_t* overflow, void* stream);
+int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n, long long a_plane_rows,
+                     const void* b_planes, const float* b_sqnorm, long long m2, int b_planes_n, long long b_plane_rows,
+                     int dim, int precision, int flags, long long col0, int p_cap,
+                     const float* thr_tab, uint32_t* cnt_tab, const float* dstar, const int32_t* gstar,
+                     uint32_t* cnt_first, void* stream);
+int pps_rank_tab_finish(long long nq, int p_cap, const int32_t* tpair_tab, const uint32_t* cnt_tab,
+                        uint32_t* cnt_le, void* stream);
+
 int pps_topk_init(uint64_t* topk_key, long long nq, int k, void* stream);
 int pps_topk_update(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
                     const int32_t* excl_off, const int32_t* excl_g, const uint8_t* excl_keep,
                     uint64_t* topk_key, int k, void* stream);
+/* pps_rank_count + pps_topk_update in ONE read of the block (one CTA per query): same counters, same top-k state.
+ * pair_off must hold nq + 1 valid offsets (all zero when there is no pair at all). */
+int pps_rank_sweep(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                   const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos, const float* pair_d,
+                   int max_pairs_per_query, uint32_t* cnt_le, uint32_t* cnt_first,
+                   uint64_t* topk_key, int k, int topk_filtered, void* stream);
 int pps_topk_unpack(const uint64_t* topk_key, long long nq, int k,
                     float* out_dist, int32_t* out_index, void* stream);
 

@@ -78,8 +78,14 @@ SIGNATURES = {
     "pps_rank_gather": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _ll, _vp, _vp]),
     "pps_rank_count": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "pps_rank_finalize": (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_rank_tab_elems": (_ll, [_ll, _i]),
+    "pps_rank_tab_prep": (_i, [_ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_dist_rank_tc": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp, _ll, _i, _ll, _i, _i, _i, _ll, _i,
+                              _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_rank_tab_finish": (_i, [_ll, _i, _vp, _vp, _vp, _vp]),
     "pps_topk_init": (_i, [_vp, _ll, _i, _vp]),
     "pps_topk_update": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp]),
+    "pps_rank_sweep": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "pps_topk_unpack": (_i, [_vp, _ll, _i, _vp, _vp, _vp]),
     "pps_ctx_create": (_i, [_i, C.POINTER(_vp)]),
     "pps_ctx_destroy": (_i, [_vp]),

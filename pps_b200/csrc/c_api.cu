@@ -354,6 +354,14 @@ int count_local(pps_ctx* c, cudaStream_t cs) {
   uint32_t* cnt_first = c->counters.as<uint32_t>();
   if (c->world > 1)    // after the exchange every rank holds all pairs; the kernels read the flags as bytes
     PPS_TRY(pps_pairs_unpack_pos(c->pair_pos32(), c->n_pairs, c->pair_pos.as<uint8_t>(), cs));
+  if (e.topk > 0 && c->world == 1) {
+    // counts and the k nearest valid items from ONE read of the distance block
+    PPS_TRY(c->topk.ensure((size_t)e.nq * e.topk * 8));
+    PPS_TRY(pps_topk_init(c->topk.as<uint64_t>(), e.nq, e.topk, cs));
+    return pps_rank_sweep(c->dist.as<float>(), e.ldd, e.nq, e.ng, e.col0, c->pair_off.as<int32_t>(), c->pair_g(),
+                          c->pair_pos.as<uint8_t>(), c->pair_d(), c->max_pairs, cnt_first + e.nq, cnt_first,
+                          c->topk.as<uint64_t>(), e.topk, 1, cs);
+  }
   return pps_rank_count(c->dist.as<float>(), e.ldd, e.nq, e.ng, e.col0, c->pair_off.as<int32_t>(), c->pair_g(),
                         c->pair_pos.as<uint8_t>(), c->pair_d(), c->max_pairs, cnt_first + e.nq, cnt_first, cs);
 }
@@ -373,9 +381,11 @@ int finalize_and_fetch(pps_ctx* c, int cmc_topk, cudaStream_t cs, double* out_ma
     PPS_TRY(c->topk.ensure((size_t)nq * topk * 8));
     PPS_TRY(c->tki.ensure((size_t)nq * topk * 4));
     PPS_TRY(c->tkd.ensure((size_t)nq * topk * 4));
-    PPS_TRY(pps_topk_init(c->topk.as<uint64_t>(), nq, topk, cs));
-    PPS_TRY(pps_topk_update(c->dist.as<float>(), e.ldd, nq, e.ng, e.col0, c->pair_off.as<int32_t>(), c->pair_g(),
-                            c->pair_pos.as<uint8_t>(), c->topk.as<uint64_t>(), topk, cs));
+    if (c->world != 1) {       // (single device: count_local already swept the block for counts and top-k together)
+      PPS_TRY(pps_topk_init(c->topk.as<uint64_t>(), nq, topk, cs));
+      PPS_TRY(pps_topk_update(c->dist.as<float>(), e.ldd, nq, e.ng, e.col0, c->pair_off.as<int32_t>(), c->pair_g(),
+                              c->pair_pos.as<uint8_t>(), c->topk.as<uint64_t>(), topk, cs));
+    }
     PPS_TRY(pps_topk_unpack(c->topk.as<uint64_t>(), nq, topk, c->tkd.as<float>(), c->tki.as<int32_t>(), cs));
   }
   mark(c, 6, cs);

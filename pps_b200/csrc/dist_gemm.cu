@@ -218,25 +218,98 @@ constexpr size_t kGemm2Smem = (size_t)kRing2Bytes + kOutStageBytes + 2 * 256 * 4
 struct Gemm2Args {
   GemmArgs g;
   int planes;       // planes of each operand loaded per k-block (1..3)
-  int stages;       // ring depth = kRing2Bytes / stage bytes
+  int stages;       // ring depth = ring bytes / stage bytes
   // grouped form (embedding head): `groups` independent products; group grp uses A rows [grp*a_group_rows, ...),
   // B rows [grp*b_group_rows, ...) and writes output columns [grp*out_group_cols, ...).  Distance: groups = 1.
   int groups;
   long long a_group_rows, b_group_rows, out_group_cols;
 };
 
-constexpr int EPI_DIST = 0;      // |a|^2 + |b|^2 - 2ab, clamp, sqrt (or squared / raw dot by flags)
+// Fused ranking epilogue (EPI_RANK): the distance tile never leaves the SM.  Per element one lower-bound search
+// among the row's sorted positive distances (shared memory, [threshold][row] so that bank = row for every
+// thread whatever it searches) and one increment of a thread-private 16-bit histogram counter.
+struct RankFuse {
+  const float* thr_tab;     // [row groups of 128][p_cap][128] ascending positive distances of each query, +inf padded
+  uint32_t* cnt_tab;        // same shape: #{columns whose lower bound among the row's thresholds is j}
+  const float* dstar;       // [rows] nearest positive distance (NaN: the query has no positive)
+  const int32_t* gstar;     // [rows] its global gallery index
+  uint32_t* cnt_first;      // [rows] += -#{d == d*} + #{d == d*, column < g*}   (mod 2^32)
+  long long col0;           // global gallery index of column 0 of this block
+  int p_cap;                // thresholds per row in the tables (multiple of 8, <= 64)
+};
+
+constexpr int EPI_DIST = 0;          // |a|^2 + |b|^2 - 2ab, clamp, sqrt (or squared / raw dot by flags) -> matrix
 constexpr int EPI_AFFINE_RELU = 1;   // max(0, dot * alpha[col] + beta[col])   (a_sqnorm = alpha, b_sqnorm = beta)
+constexpr int EPI_RANK = 2;          // distance as EPI_DIST, consumed by the counting epilogue; no matrix
+
+// Tile order.  EPI_DIST / EPI_AFFINE_RELU: tile t = pair, pair + npairs, ... with the m index fastest, so that the
+// CTA pairs running concurrently share B tiles in L2.  EPI_RANK: every CTA pair keeps ONE m tile (its rows'
+// thresholds and counters stay in shared memory) and walks a contiguous range of n tiles; the pairs that own the
+// other m tiles walk the same n range at the same pace, which keeps the L2 sharing of B.  With more m tiles than
+// pairs the schedule repeats per "superblock" of npairs m tiles.
+template <int EPI>
+struct TileWalk {
+  long long t, tiles, tiles_per_group, npairs, pair;
+  int m_tiles, n_tiles;
+  int sb, n_sb, n_cur, n_stop;
+  // outputs
+  long long grp;
+  int m_tile, n_tile;
+  bool run_start, run_end;
+
+  __device__ TileWalk(const Gemm2Args& ga, long long pair_, long long npairs_) {
+    pair = pair_; npairs = npairs_;
+    m_tiles = ga.g.m_tiles; n_tiles = ga.g.n_tiles;
+    tiles_per_group = (long long)m_tiles * n_tiles;
+    tiles = tiles_per_group * ga.groups;
+    t = pair - npairs;
+    sb = -1; n_sb = (int)((m_tiles + npairs - 1) / npairs); n_cur = 0; n_stop = 0;
+    grp = 0; m_tile = 0; n_tile = 0; run_start = run_end = false;
+  }
+  __device__ bool next() {
+    if (EPI != EPI_RANK) {
+      t += npairs;
+      if (t >= tiles) return false;
+      grp = t / tiles_per_group;
+      const long long tt = t % tiles_per_group;
+      m_tile = (int)(tt % m_tiles);
+      n_tile = (int)(tt / m_tiles);
+      return true;
+    }
+    run_start = false;
+    while (n_cur >= n_stop) {                     // next superblock with a non-empty range for this pair
+      if (++sb >= n_sb) return false;
+      const long long m0 = (long long)sb * npairs;
+      const long long mt = (m_tiles - m0) < npairs ? (m_tiles - m0) : npairs;
+      const long long ml = pair % mt, i = pair / mt;
+      const long long owners = npairs / mt + (ml < npairs % mt ? 1 : 0);
+      m_tile = (int)(m0 + ml);
+      n_cur = (int)((long long)n_tiles * i / owners);
+      n_stop = (int)((long long)n_tiles * (i + 1) / owners);
+      run_start = true;
+    }
+    n_tile = n_cur++;
+    run_end = n_cur >= n_stop;
+    return true;
+  }
+};
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Gemm2Args ga) {
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Gemm2Args ga,
+                const __grid_constant__ RankFuse rf) {
   extern __shared__ __align__(1024) unsigned char smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  unsigned char* stage_out = smem + kRing2Bytes;                                   // [4 warps][2][4 KB]
-  float* bn_s = reinterpret_cast<float*>(stage_out + kOutStageBytes);             // [2][256] (or [2][2][128])
   constexpr int kBTile = (BN / 2) * kBK * 2;                 // this CTA's half of a B plane tile
+  const int planes = ga.planes, stages = ga.stages;
+  const uint32_t stage_bytes = (uint32_t)planes * (kTile2Bytes + kBTile);
+  // after the ring: EPI_DIST / EPI_AFFINE_RELU: output staging [4 warps][2][4 KB]; EPI_RANK: threshold and counter tables
+  unsigned char* after_ring = smem + (EPI == EPI_RANK ? (size_t)stages * stage_bytes : (size_t)kRing2Bytes);
+  unsigned char* stage_out = after_ring;
+  float* thr_s = reinterpret_cast<float*>(after_ring);                               // [p_cap][128]
+  uint32_t* cnt_s = reinterpret_cast<uint32_t*>(after_ring + (size_t)rf.p_cap * 512); // [p_cap / 2][128], two u16 per word
+  float* bn_s = reinterpret_cast<float*>(after_ring + (EPI == EPI_RANK ? (size_t)rf.p_cap * 768 : (size_t)kOutStageBytes));
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(bn_s) + 2 * 256 * 4);
   uint64_t* empty = full + kMaxStages2;
   uint64_t* tfull = empty + kMaxStages2;      // [2]
@@ -246,16 +319,12 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const GemmArgs& g = ga.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const long long tiles_per_group = (long long)g.m_tiles * g.n_tiles;   // 256 x BN tiles
-  const long long tiles = tiles_per_group * ga.groups;
   const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int planes = ga.planes, stages = ga.stages;
-  const uint32_t stage_bytes = (uint32_t)planes * (kTile2Bytes + kBTile);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmO);
+    if (EPI != EPI_RANK) tma_prefetch_desc(&tmO);
     for (int s = 0; s < kMaxStages2; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -279,10 +348,10 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long t = pair; t < tiles; t += npairs) {
-        const long long grp = t / tiles_per_group, tt = t % tiles_per_group;
-        const int m0 = (int)(grp * ga.a_group_rows) + (int)(tt % g.m_tiles) * 256 + (int)rank * kT2Rows;
-        const int n0 = (int)(grp * ga.b_group_rows) + (int)(tt / g.m_tiles) * BN + (int)rank * (BN / 2);
+      TileWalk<EPI> w(ga, pair, npairs);
+      while (w.next()) {
+        const int m0 = (int)(w.grp * ga.a_group_rows) + w.m_tile * 256 + (int)rank * kT2Rows;
+        const int n0 = (int)(w.grp * ga.b_group_rows) + w.n_tile * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < g.kblocks; ++kb, ++it) {
           const uint32_t s = it % stages, ph = (it / stages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
@@ -299,7 +368,8 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== MMA issuer (leader CTA, one thread) =====================
     if (rank == 0 && lane == 0) {
       uint32_t it = 0, acc_it = 0;
-      for (long long t = pair; t < tiles; t += npairs, ++acc_it) {
+      TileWalk<EPI> w(ga, pair, npairs);
+      for (; w.next(); ++acc_it) {
         const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
         mbar_wait(&tempty[as], aph ^ 1u);
         tc_fence_after();
@@ -323,8 +393,9 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue (warps 2..5 of both CTAs) =====================
-    // TMEM -> registers (thread = row) -> |a|^2 + |b|^2 - 2ab, clamp, sqrt -> 128B-swizzled staging tile in
-    // shared memory -> one TMA store per 32 x 32 chunk (coalesced, clipped at the matrix edges by the tensor map).
+    // EPI_DIST / EPI_AFFINE_RELU: TMEM -> registers (thread = row) -> value -> 128B-swizzled staging tile in shared
+    // memory -> one TMA store per 32 x 32 chunk (coalesced, clipped at the matrix edges by the tensor map).
+    // EPI_RANK: TMEM -> registers -> distance -> lower bound among the row's thresholds -> private counter.
     const int lane_grp = warp & 3;
     const int row = lane_grp * 32 + lane;
     const int etid = (int)threadIdx.x - 64;     // 0..127 among the epilogue threads
@@ -333,12 +404,35 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool want_dot = (g.flags & PPS_DIST_DOT) != 0;
     unsigned char* my_stage = stage_out + (size_t)lane_grp * (2 * kOutChunkBytes);
     const uint32_t swz = (uint32_t)(lane & 7);
-    for (long long t = pair; t < tiles; t += npairs, ++acc_it) {
-      const long long grp = t / tiles_per_group, tt = t % tiles_per_group;
-      const int m0 = (int)(tt % g.m_tiles) * 256 + (int)rank * kT2Rows;             // output row (within the group's rows)
-      const int n0 = (int)(grp * ga.out_group_cols) + (int)(tt / g.m_tiles) * BN;   // output column
-      const int n_end = EPI == EPI_DIST ? (int)g.m2 : (int)((grp + 1) * ga.out_group_cols);   // first column not ours
+    // EPI_RANK per-row state
+    const int p_cap = rf.p_cap;
+    float dstar = 0.f;
+    long long gstar = 0;
+    uint32_t tie_corr = 0;
+    float piv1 = 0.f, piv2a = 0.f, piv2b = 0.f; // thresholds probed by the first two search levels
+    int tiles_since_flush = 0;                  // a 16-bit counter takes <= 256 increments per tile
+    long long tab_base = 0;                     // element offset of (row group, j = 0, this row) in the global tables
+    TileWalk<EPI> w(ga, pair, npairs);
+    for (; w.next(); ++acc_it) {
+      const int m0 = w.m_tile * 256 + (int)rank * kT2Rows;                          // output row (within the group's rows)
+      const int n0 = (int)(w.grp * ga.out_group_cols) + w.n_tile * BN;              // output column
+      const int n_end = EPI == EPI_AFFINE_RELU ? (int)((w.grp + 1) * ga.out_group_cols) : (int)g.m2;   // first column not ours
       const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+      const long long gi = (long long)m0 + row;
+      if (EPI == EPI_RANK && w.run_start) {
+        // this thread's row of the threshold table -> shared memory (only this thread ever reads it), counters = 0
+        tab_base = ((long long)(m0 >> 7) * p_cap) * 128 + row;
+        for (int j = 0; j < p_cap; ++j) thr_s[j * 128 + row] = __ldg(rf.thr_tab + tab_base + (long long)j * 128);
+        for (int j = 0; j < p_cap / 2; ++j) cnt_s[j * 128 + row] = 0u;
+        dstar = gi < g.m1 ? __ldg(rf.dstar + gi) : __int_as_float(0x7fc00000);
+        gstar = gi < g.m1 ? (long long)__ldg(rf.gstar + gi) : 0;
+        tie_corr = 0;
+        tiles_since_flush = 0;
+        const int h1 = p_cap >> 1, h2 = (p_cap - h1) >> 1;
+        piv1 = thr_s[(h1 - 1) * 128 + row];
+        piv2a = thr_s[(h2 - 1) * 128 + row];
+        piv2b = thr_s[(h1 + h2 - 1) * 128 + row];
+      }
       // per-column operands of the tile -> shared (double-buffered by accumulator stage):
       // |b|^2 of the gallery rows, or alpha / beta of the output channels
       float* bn = bn_s + as * 256;
@@ -352,8 +446,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (BN > 128) bn[etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_sqnorm + gj + 128) : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const long long gi = (long long)m0 + row;
-      const float an = (EPI == EPI_DIST && gi < g.m1 && !want_dot) ? __ldg(g.a_sqnorm + gi) : 0.f;
+      const float an = (EPI != EPI_AFFINE_RELU && gi < g.m1 && !want_dot) ? __ldg(g.a_sqnorm + gi) : 0.f;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + as * BN + ((uint32_t)(lane_grp * 32) << 16);
@@ -361,42 +454,99 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int c = 0; c < BN; c += 32, ++chunk_it) {
         uint32_t r[32];
         tmem_ld_32x32(tbase + c, r);
-        unsigned char* buf = my_stage + (chunk_it & 1u) * kOutChunkBytes;
-        bulk_wait_group_read<1>();               // the store that last read this buffer has drained it
-        __syncwarp();
-        tmem_ld_wait();
-        const float4* bn4 = reinterpret_cast<const float4*>(bn + c);
+        if (EPI == EPI_RANK) {
+          tmem_ld_wait();
+          const int valid_cols = n_end - n0 - c;             // columns of this chunk inside the gallery block
+          const long long colg = rf.col0 + n0 + c;           // global gallery index of the chunk's first column
+          const float4* bn4 = reinterpret_cast<const float4*>(bn + c);
+          float d[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v[4];
-          const float4 b4 = bn4[j];
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-          float cc[4] = {0.f, 0.f, 0.f, 0.f};
-          if (EPI == EPI_AFFINE_RELU) {
-            const float4 c4 = reinterpret_cast<const float4*>(bn + 128 + c)[j];
-            cc[0] = c4.x; cc[1] = c4.y; cc[2] = c4.z; cc[3] = c4.w;
-          }
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = bn4[j];
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float dot = __uint_as_float(r[4 * j + e]);
-            if (EPI == EPI_AFFINE_RELU) {
-              v[e] = fmaxf(fmaf(dot, bb[e], cc[e]), 0.f);
-            } else if (want_dot) {
-              v[e] = dot;
-            } else {
-              // same association as the reference: (-2*ab + |a|^2) + |b|^2   (-2*ab is exact, so the FMA rounds once)
-              float d2 = __fadd_rn(__fmaf_rn(-2.f, dot, an), bb[e]);
+            for (int e = 0; e < 4; ++e) {
+              const float dot = __uint_as_float(r[4 * j + e]);
+              float d2 = __fadd_rn(__fmaf_rn(-2.f, dot, an), bb[e]);      // the EPI_DIST arithmetic, bit for bit
               d2 = fmaxf(d2, 0.f);
-              v[e] = want_sq ? d2 : sqrt_approx(d2);
+              d[4 * j + e] = want_sq ? d2 : sqrt_approx(d2);
             }
           }
-          *reinterpret_cast<float4*>(buf + lane * 128 + (((uint32_t)j ^ swz) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (m0 + lane_grp * 32 < g.m1 && n0 + c < n_end) tma_store_2d(&tmO, buf, n0 + c, m0 + lane_grp * 32);
-          bulk_commit_group();
+          // lower bound of every element among this row's thresholds: 32 independent searches per step, the first
+          // two levels against pivots held in registers
+          int lo[32];
+          const int half1 = p_cap >> 1, half2 = (p_cap - half1) >> 1;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const bool up = piv1 < d[e];
+            lo[e] = up ? half1 : 0;
+            lo[e] += ((up ? piv2b : piv2a) < d[e]) ? half2 : 0;
+          }
+          int len = p_cap - half1 - half2;
+          while (len > 1) {
+            const int half = len >> 1;
+            const float* probe = thr_s + (half - 1) * 128 + row;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) lo[e] += (probe[lo[e] * 128] < d[e]) ? half : 0;
+            len -= half;
+          }
+          bool tie = false;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            lo[e] += (thr_s[lo[e] * 128 + row] < d[e]) ? 1 : 0;
+            tie |= (d[e] == dstar);
+          }
+          // one fire-and-forget shared-memory add per element on the thread's own 16-bit counter (no read-back, so no
+          // dependent chain); columns past the block end and elements beyond every threshold add nothing
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int b = min(lo[e], p_cap - 1);             // branch-free: an uncounted element adds 0
+            const uint32_t inc = (e < valid_cols && lo[e] < p_cap) ? (1u << ((b & 1) << 4)) : 0u;
+            atomicAdd(cnt_s + (b >> 1) * 128 + row, inc);
+          }
+          if (tie) {                                         // exact ties with the nearest positive: rare
+#pragma unroll 1
+            for (int e = 0; e < 32; ++e)
+              if (e < valid_cols && d[e] == dstar) tie_corr += ((colg + e) < gstar ? 1u : 0u) - 1u;
+          }
+        } else {
+          unsigned char* buf = my_stage + (chunk_it & 1u) * kOutChunkBytes;
+          bulk_wait_group_read<1>();               // the store that last read this buffer has drained it
+          __syncwarp();
+          tmem_ld_wait();
+          const float4* bn4 = reinterpret_cast<const float4*>(bn + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v[4];
+            const float4 b4 = bn4[j];
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            float cc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (EPI == EPI_AFFINE_RELU) {
+              const float4 c4 = reinterpret_cast<const float4*>(bn + 128 + c)[j];
+              cc[0] = c4.x; cc[1] = c4.y; cc[2] = c4.z; cc[3] = c4.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float dot = __uint_as_float(r[4 * j + e]);
+              if (EPI == EPI_AFFINE_RELU) {
+                v[e] = fmaxf(fmaf(dot, bb[e], cc[e]), 0.f);
+              } else if (want_dot) {
+                v[e] = dot;
+              } else {
+                // same association as the reference: (-2*ab + |a|^2) + |b|^2   (-2*ab is exact, so the FMA rounds once)
+                float d2 = __fadd_rn(__fmaf_rn(-2.f, dot, an), bb[e]);
+                d2 = fmaxf(d2, 0.f);
+                v[e] = want_sq ? d2 : sqrt_approx(d2);
+              }
+            }
+            *reinterpret_cast<float4*>(buf + lane * 128 + (((uint32_t)j ^ swz) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (m0 + lane_grp * 32 < g.m1 && n0 + c < n_end) tma_store_2d(&tmO, buf, n0 + c, m0 + lane_grp * 32);
+            bulk_commit_group();
+          }
         }
       }
       tc_fence_before();
@@ -405,8 +555,24 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (rank == 0) mbar_arrive(&tempty[as]);
         else mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[as]), 0));
       }
+      if (EPI == EPI_RANK && (w.run_end || ++tiles_since_flush == 255)) {
+        // counters -> global table at the end of the run (a handful of CTA pairs share a row: atomics), and every 255
+        // tiles in between so that no 16-bit counter can wrap
+        tiles_since_flush = 0;
+        for (int j = 0; j < p_cap / 2; ++j) {
+          const uint32_t v = cnt_s[j * 128 + row];
+          if (v) {
+            cnt_s[j * 128 + row] = 0u;
+            if (gi < g.m1) {
+              if (v & 0xffffu) atomicAdd(rf.cnt_tab + tab_base + (long long)(2 * j) * 128, v & 0xffffu);
+              if (v >> 16) atomicAdd(rf.cnt_tab + tab_base + (long long)(2 * j + 1) * 128, v >> 16);
+            }
+          }
+        }
+        if (w.run_end && gi < g.m1 && tie_corr) atomicAdd(rf.cnt_first + gi, tie_corr);
+      }
     }
-    bulk_wait_group_read<0>();
+    if (EPI != EPI_RANK) bulk_wait_group_read<0>();
   }
 
   tc_fence_before();
@@ -506,6 +672,28 @@ static int make_operand_map(CUtensorMap* tm, const void* planes, long long rows,
   return PPS_OK;
 }
 
+// plane-pair terms of a precision: returns the planes needed per operand, 0 if the precision is not a tensor-core one
+static int setup_terms(int precision, GemmArgs& g, bool* f16) {
+  *f16 = false;
+  switch (precision) {
+    case PPS_PREC_BF16X1:
+      g.nterms = 1; g.term_a[0] = 0; g.term_b[0] = 0; return 1;
+    case PPS_PREC_BF16X3: {
+      const int ta[3] = {1, 0, 0}, tb[3] = {0, 1, 0};   // small terms first
+      g.nterms = 3; for (int i = 0; i < 3; ++i) { g.term_a[i] = ta[i]; g.term_b[i] = tb[i]; }
+      return 2;
+    }
+    case PPS_PREC_BF16X6: {
+      const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+      g.nterms = 6; for (int i = 0; i < 6; ++i) { g.term_a[i] = ta[i]; g.term_b[i] = tb[i]; }
+      return 3;
+    }
+    case PPS_PREC_F16X1:
+      g.nterms = 1; g.term_a[0] = 0; g.term_b[0] = 0; *f16 = true; return 1;
+    default: return 0;
+  }
+}
+
 }  // namespace pps
 
 using namespace pps;
@@ -602,7 +790,7 @@ extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long lon
     long long slots = sms / 2;
     if ((flags & PPS_DIST_RESERVE_SM_PAIR) && slots > 8) slots -= 1;   // leave one SM pair to concurrent small kernels
     const long long pairs = tiles2 < slots ? tiles2 : slots;
-    dist_tc2_kernel<256, EPI_DIST><<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga);
+    dist_tc2_kernel<256, EPI_DIST><<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga, RankFuse{});
     PPS_LAUNCH_CHECK("dist_tc2_kernel");
     return PPS_OK;
   }
@@ -717,7 +905,80 @@ extern "C" int pps_embed_tc(const void* x_planes /*[planes][K*N][kpad]*/, int x_
   const long long tiles = (long long)g.m_tiles * K;
   const long long pairs = tiles < sms / 2 ? tiles : sms / 2;
   dist_tc2_kernel<128, EPI_AFFINE_RELU><<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem,
-                                          static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmO, ga);
+                                          static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmO, ga, RankFuse{});
   PPS_LAUNCH_CHECK("dist_tc2_kernel<embed>");
+  return PPS_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Distance + ranking counters in one kernel (EPI_RANK): for gallery blocks of a multi-block sweep whose thresholds
+// are already known (pps_rank_tab_prep).  The [m1, m2] distance block is never written: the epilogue turns every
+// distance into one increment of cnt_tab and, for exact ties with the nearest positive, of cnt_first.
+// ------------------------------------------------------------------------------------
+extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
+                                long long a_plane_rows, const void* b_planes, const float* b_sqnorm, long long m2,
+                                int b_planes_n, long long b_plane_rows, int dim, int precision, int flags,
+                                long long col0, int p_cap, const float* thr_tab, uint32_t* cnt_tab, const float* dstar,
+                                const int32_t* gstar, uint32_t* cnt_first, void* stream) {
+  if (m1 < 0 || m2 < 0 || dim <= 0 || col0 < 0) return PPS_ERR_INVALID_ARG;
+  if (p_cap < 8 || p_cap > 64 || (p_cap & 7)) return PPS_ERR_INVALID_ARG;
+  if (flags & ~PPS_DIST_SQUARED) return PPS_ERR_INVALID_ARG;
+  if (a_plane_rows == 0) a_plane_rows = m1;
+  if (b_plane_rows == 0) b_plane_rows = m2;
+  if (a_plane_rows < m1 || b_plane_rows < m2) return PPS_ERR_INVALID_ARG;
+  if (m1 == 0 || m2 == 0) return PPS_OK;
+  if (!a_planes || !b_planes || !a_sqnorm || !b_sqnorm || !thr_tab || !cnt_tab || !dstar || !gstar || !cnt_first)
+    return PPS_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(a_planes) & 15u) || (reinterpret_cast<uintptr_t>(b_planes) & 15u))
+    return PPS_ERR_ALIGN;
+  if (m1 > 0x7fffff00LL || m2 > 0x7fffff00LL) return PPS_ERR_UNSUPPORTED;
+  Gemm2Args ga;
+  GemmArgs& g = ga.g;
+  bool f16 = false;
+  const int need = setup_terms(precision, g, &f16);
+  if (need == 0 || a_planes_n < need || b_planes_n < need) return PPS_ERR_INVALID_ARG;
+  const int sms = sm_count();
+  if (sms < 2) return PPS_ERR_UNSUPPORTED;
+  const int kpad = pps_kpad(dim);
+  const uint32_t fmt = f16 ? 0u : 1u;
+  g.m1 = m1; g.m2 = m2;
+  g.kblocks = kpad / kBK;
+  g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  g.a_sqnorm = a_sqnorm; g.b_sqnorm = b_sqnorm;
+  g.out = nullptr; g.ldo = 0; g.flags = flags;
+  g.m_tiles = (int)((m1 + 255) / 256);
+  g.n_tiles = (int)((m2 + 255) / 256);
+  ga.planes = need;
+  ga.groups = 1; ga.a_group_rows = 0; ga.b_group_rows = 0; ga.out_group_cols = 0;
+  // shared memory: ring | thresholds [p_cap][128] f32 | counters [p_cap/2][128] u32 | |b|^2 [2][256] | barriers
+  const int stage_bytes = 2 * need * kTile2Bytes;
+  const int tail = p_cap * 768 + 2 * 256 * 4 + 256;
+  int stages = (227 * 1024 - tail) / stage_bytes;
+  if (stages > kMaxStages2) stages = kMaxStages2;
+  if (stages < 2) return PPS_ERR_UNSUPPORTED;
+  ga.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + tail;
+  CUtensorMap tmA, tmB;
+  int rc = make_operand_map(&tmA, a_planes, m1, a_plane_rows, kpad, a_planes_n, kT2Rows, f16);
+  if (rc) return rc;
+  rc = make_operand_map(&tmB, b_planes, m2, b_plane_rows, kpad, b_planes_n, kT2Rows, f16);
+  if (rc) return rc;
+  RankFuse rf;
+  rf.thr_tab = thr_tab; rf.cnt_tab = cnt_tab; rf.dstar = dstar; rf.gstar = gstar; rf.cnt_first = cnt_first;
+  rf.col0 = col0; rf.p_cap = p_cap;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  PPS_CUDA_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc2_kernel<256, EPI_RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
+    configured_dev = dev;
+  }
+  const long long tiles = (long long)g.m_tiles * g.n_tiles;
+  const long long slots = sms / 2;
+  const long long pairs = tiles < slots ? tiles : slots;
+  dist_tc2_kernel<256, EPI_RANK><<<(unsigned)(2 * pairs), kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      tmA, tmB, tmA /*no output map*/, ga, rf);
+  PPS_LAUNCH_CHECK("dist_tc2_kernel<rank>");
   return PPS_OK;
 }

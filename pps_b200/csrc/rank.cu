@@ -28,6 +28,25 @@ __device__ __forceinline__ int fkey(float x) {
   return k ^ ((k >> 31) & 0x7fffffff);
 }
 
+constexpr int kTopkThreads = 256;
+constexpr int kCand = 2048;
+
+__device__ __forceinline__ void bitonic_sort_smem(unsigned long long* a, int n /*pow2*/, int tid, int nthreads) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n; i += nthreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = a[i], y = a[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // step 1: gather the pair distances out of the block
 // ------------------------------------------------------------------------------------
@@ -65,6 +84,13 @@ __global__ void rank_gather_kernel(const float* __restrict__ dist, long long ldd
 // dynamic smem: thr[maxp] sorted positive distances, tpair[maxp] their pair index, sd/sg[maxp] the
 //               staged pair list, exact[maxp]
 // ------------------------------------------------------------------------------------
+// TOPK = true (one CTA per query, no column splits): the same sweep also keeps the query's k nearest valid gallery
+// items.  A column is admitted only if its key beats the current k-th best (one compare per element), candidates
+// collect in a 2048-entry shared buffer that is re-selected by bitonic sort when it fills; junk items (same id, same
+// camera) are skipped through the staged pair list.  One read of the block serves counts and top-k.
+constexpr int kCandC = 2048;
+
+template <bool TOPK>
 __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float* __restrict__ dist, long long ldd,
                                                                      long long ncols, long long col0, long long seg,
                                                                      const int32_t* __restrict__ pair_off,
@@ -72,18 +98,24 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
                                                                      const uint8_t* __restrict__ pair_pos,
                                                                      const float* __restrict__ pair_d, int maxp,
                                                                      uint32_t* __restrict__ cnt_le,
-                                                                     uint32_t* __restrict__ cnt_first) {
+                                                                     uint32_t* __restrict__ cnt_first,
+                                                                     unsigned long long* __restrict__ topk_key, int k,
+                                                                     int topk_filtered) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* thr = reinterpret_cast<float*>(smem_raw);                          // [maxp]
   int32_t* tpair = reinterpret_cast<int32_t*>(thr + maxp);                  // [maxp]
   float* sd = reinterpret_cast<float*>(tpair + maxp);                       // [maxp] pair distances
   int32_t* sg = reinterpret_cast<int32_t*>(sd + maxp);                      // [maxp] gallery index, -1 = junk
   uint32_t* exact = reinterpret_cast<uint32_t*>(sg + maxp);                 // [maxp]
+  int32_t* sj = reinterpret_cast<int32_t*>(exact + maxp);                   // [maxp] junk gallery indices (TOPK)
   __shared__ uint32_t hist[kNB];          // bit 31: the bin holds a threshold
   __shared__ uint32_t binfo[kNB];         // (index of the bin's first threshold << 16) | thresholds in the bin
   __shared__ uint32_t part[kCntThreads];
-  __shared__ int s_np;
+  __shared__ int s_np, s_nj;
   __shared__ uint32_t s_below, s_first_cnt;
+  __shared__ unsigned long long cand[TOPK ? kCandC : 1];
+  __shared__ int s_n;
+  __shared__ unsigned long long s_bound;
 
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -91,14 +123,24 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
 
   // --- positives of this query, rank-sorted by (distance, gallery index) into thr[] ---
   // stage the pair list in shared memory first (coalesced): the O(P^2) ranking must not chase global latency
-  if (tid == 0) { s_np = 0; s_below = 0; s_first_cnt = 0; }
+  if (tid == 0) { s_np = 0; s_nj = 0; s_below = 0; s_first_cnt = 0; }
   const int npair = e1 - e0;
   for (int i = tid; i < npair; i += kCntThreads) {
     sd[i] = pair_d[e0 + i];
     sg[i] = pair_pos[e0 + i] ? pair_g[e0 + i] : -1;
   }
   for (int i = tid; i < kNB; i += kCntThreads) { hist[i] = 0; binfo[i] = 0; }
+  unsigned long long* state = nullptr;
+  if (TOPK) {
+    state = topk_key + (long long)q * k;
+    for (int i = tid; i < kCandC; i += kCntThreads) cand[i] = i < k ? state[i] : ~0ull;
+    if (tid == 0) { s_n = k; s_bound = state[k - 1]; }
+  }
   __syncthreads();
+  if (TOPK && topk_filtered) {
+    for (int i = tid; i < npair; i += kCntThreads)
+      if (sg[i] < 0) sj[atomicAdd(&s_nj, 1)] = pair_g[e0 + i];
+  }
   for (int i = tid; i < npair; i += kCntThreads) {
     const int g = sg[i];
     if (g < 0) continue;
@@ -115,13 +157,15 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
   }
   __syncthreads();
   const int np = s_np;
-  if (np == 0) return;                                     // query without a valid match: nothing to count
-  const float dstar = thr[0];
-  const long long gstar = pair_g[tpair[0]];
-  const int key_min = fkey(thr[0]);
-  const unsigned key_span = (unsigned)fkey(thr[np - 1]) - (unsigned)key_min;
+  if (!TOPK && np == 0) return;                            // query without a valid match: nothing to count
+  const bool count_on = np > 0;                            // (TOPK: the sweep still runs for the nearest items)
+  const float dstar = count_on ? thr[0] : 0.f;
+  const long long gstar = count_on ? pair_g[tpair[0]] : 0;
+  const int key_min = count_on ? fkey(thr[0]) : 0;
+  const unsigned key_span = count_on ? (unsigned)fkey(thr[np - 1]) - (unsigned)key_min : 0u;
   int shift = 0;
   while ((key_span >> shift) >= (unsigned)kNB) ++shift;
+  const int nj = TOPK ? s_nj : 0;
 
   const long long c_begin = (long long)blockIdx.y * seg;
   const long long c_end = min(ncols, c_begin + seg);
@@ -142,12 +186,13 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
   uint32_t below = 0;                                      // elements under every threshold
   uint32_t tie_corr = 0;                                   // signed: -#{d == d*} + #{d == d*, col < g*}
 
+  unsigned long long bound = ~0ull;                        // TOPK: key of the current k-th best (sampled per half pass)
   auto visit = [&](float d, long long col) {
     const int key = fkey(d);
     const bool lt = key < key_min;
     below += lt ? 1u : 0u;
     const unsigned b = ((unsigned)key - (unsigned)key_min) >> shift;
-    if (!lt && b < (unsigned)kNB) {
+    if (count_on && !lt && b < (unsigned)kNB) {
       const uint32_t old = atomicAdd(&hist[b], 1u);
       if (old & 0x80000000u) {                             // the bin holds thresholds: exact comparison
         const uint32_t info = binfo[b];
@@ -158,9 +203,60 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
         if (d == dstar) tie_corr += ((col0 + col) < gstar ? 1u : 0u) - 1u;
       }
     }
+    if (TOPK) {
+      if (__float_as_uint(d) <= (uint32_t)(bound >> 32)) {
+        const unsigned long long ukey = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(uint32_t)(col0 + col);
+        if (ukey < bound) {
+          bool skip = false;
+          for (int x = 0; x < nj; ++x) skip |= ((long long)sj[x] == col0 + col);
+          if (!skip) cand[atomicAdd(&s_n, 1)] = ukey;      // s_n <= kCandC - 1024 when a half pass starts
+        }
+      }
+    }
   };
 
-  if (vec) {
+  if (TOPK) {
+    // passes of 2048 columns (four 128-bit loads in flight per thread), admission bound re-sampled and the candidate
+    // buffer checked after every 1024 columns
+    constexpr long long kStep = 4LL * kCntThreads;
+    for (long long base = c_begin; base < c_end; base += 4 * kStep) {
+      float4 v[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long cu = base + u * kStep + 4LL * tid;
+        ok[u] = vec && cu + 3 < c_end;
+        if (ok[u]) v[u] = ld_stream_f4(reinterpret_cast<const float4*>(drow + cu));
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        bound = s_bound;
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+          const int u = 2 * h + uu;
+          const long long cu = base + u * kStep + 4LL * tid;
+          if (ok[u]) {
+            visit(v[u].x, cu); visit(v[u].y, cu + 1); visit(v[u].z, cu + 2); visit(v[u].w, cu + 3);
+          } else {
+            for (int e = 0; e < 4; ++e)
+              if (cu + e < c_end) visit(drow[cu + e], cu + e);
+          }
+        }
+        __syncthreads();
+        const int n_now = s_n;
+        __syncthreads();           // every thread has sampled s_n before anyone appends again
+        if (n_now > kCandC - 1024) {
+          bitonic_sort_smem(cand, kCandC, tid, kCntThreads);
+          for (int i = k + tid; i < kCandC; i += kCntThreads) cand[i] = ~0ull;
+          if (tid == 0) { s_n = k; s_bound = cand[k - 1]; }
+          __syncthreads();
+        }
+      }
+    }
+    bitonic_sort_smem(cand, kCandC, tid, kCntThreads);
+    for (int i = tid; i < k; i += kCntThreads) state[i] = cand[i];
+    if (!count_on) return;                                 // uniform: no positives, only the top-k was wanted
+  } else if (vec) {
     const long long c4_end = c_begin + ((c_end - c_begin) & ~3LL);
     constexpr long long kStep = 4LL * kCntThreads;         // columns per pass of the CTA
     long long c = c_begin + 4LL * tid;
@@ -306,25 +402,6 @@ __global__ void __launch_bounds__(128) rank_finalize_kernel(long long nq, const 
 // key = (float bits << 32) | global gallery index: unsigned order == (distance, index) order
 // for the non-negative distances this path produces.
 // ------------------------------------------------------------------------------------
-constexpr int kTopkThreads = 256;
-constexpr int kCand = 2048;
-
-__device__ __forceinline__ void bitonic_sort_smem(unsigned long long* a, int n /*pow2*/, int tid, int nthreads) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < n; i += nthreads) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long x = a[i], y = a[ixj];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) { a[i] = y; a[ixj] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kTopkThreads) topk_update_kernel(const float* __restrict__ dist, long long ldd,
                                                                     long long ncols, long long col0,
                                                                     const int32_t* __restrict__ excl_off,
@@ -390,6 +467,75 @@ __global__ void topk_unpack_kernel(const unsigned long long* __restrict__ key, l
   if (oi) oi[i] = none ? -1 : (int32_t)(uint32_t)(kk & 0xffffffffu);
 }
 
+// ------------------------------------------------------------------------------------
+// Tables for the fused ranking epilogue of the distance kernel (dist_gemm.cu, EPI_RANK).
+// Row groups of 128 queries; element (group, j, r) at ((group * p_cap) + j) * 128 + r:
+//   thr_tab   j-th smallest positive distance of query 128*group + r (ties by gallery index), +inf beyond the last
+//   tpair_tab its pair index, -1 beyond the last
+//   cnt_tab   zeroed here; the epilogue adds #{columns with exactly j thresholds below them}
+// so that n_le(threshold j) = cnt_tab[0] + ... + cnt_tab[j]   (rank_tab_finish_kernel).
+// One warp per query; rows up to the next multiple of 256 are padded.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) rank_tab_prep_kernel(long long nq, long long rows_pad,
+                                                            const int32_t* __restrict__ pair_off,
+                                                            const int32_t* __restrict__ pair_g,
+                                                            const uint8_t* __restrict__ pair_pos,
+                                                            const float* __restrict__ pair_d, int p_cap,
+                                                            float* __restrict__ thr_tab, int32_t* __restrict__ tpair_tab,
+                                                            uint32_t* __restrict__ cnt_tab, float* __restrict__ dstar,
+                                                            int32_t* __restrict__ gstar, int* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= rows_pad) return;
+  const long long base = ((q >> 7) * p_cap) * 128 + (q & 127);
+  for (int j = lane; j < p_cap; j += 32) {
+    thr_tab[base + (long long)j * 128] = __int_as_float(0x7f800000);
+    tpair_tab[base + (long long)j * 128] = -1;
+    cnt_tab[base + (long long)j * 128] = 0u;
+  }
+  __syncwarp();
+  if (q >= nq) return;
+  const int e0 = pair_off[q], e1 = pair_off[q + 1];
+  int np = 0;
+  for (int e = e0 + lane; e < e1; e += 32) {
+    if (!pair_pos[e]) continue;
+    const float d = pair_d[e];
+    const int g = pair_g[e];
+    int pos = 0;
+    for (int f = e0; f < e1; ++f) {
+      const float df = pair_d[f];
+      pos += pair_pos[f] && ((df < d) || (df == d && pair_g[f] < g));
+    }
+    if (pos < p_cap) {
+      thr_tab[base + (long long)pos * 128] = d;
+      tpair_tab[base + (long long)pos * 128] = e;
+    }
+    if (pos == 0) { dstar[q] = d; gstar[q] = g; }
+    ++np;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
+  if (lane == 0) {
+    if (np == 0) { dstar[q] = __int_as_float(0x7fc00000); gstar[q] = 0; }
+    if (np > p_cap) atomicAdd(overflow, 1);
+  }
+}
+
+__global__ void __launch_bounds__(128) rank_tab_finish_kernel(long long nq, int p_cap, const int32_t* __restrict__ tpair_tab,
+                                                              const uint32_t* __restrict__ cnt_tab,
+                                                              uint32_t* __restrict__ cnt_le) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const long long base = ((q >> 7) * p_cap) * 128 + (q & 127);
+  uint32_t run = 0;
+  for (int j = 0; j < p_cap; ++j) {
+    const int e = tpair_tab[base + (long long)j * 128];
+    if (e < 0) break;
+    run += cnt_tab[base + (long long)j * 128];
+    cnt_le[e] += run;
+  }
+}
+
 }  // namespace pps
 
 using namespace pps;
@@ -408,6 +554,42 @@ extern "C" int pps_rank_gather(const float* dist, long long ldd, long long nq, l
   return PPS_OK;
 }
 
+static int rank_count_launch(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                             const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                             const float* pair_d, int max_pairs_per_query, uint32_t* cnt_le, uint32_t* cnt_first,
+                             unsigned long long* topk_key, int k, int topk_filtered, void* stream) {
+  const bool topk = topk_key != nullptr;
+  const int maxp = ((max_pairs_per_query > 0 ? max_pairs_per_query : 1) + 3) & ~3;
+  const size_t smem = (size_t)maxp * 24;                      // thr, tpair, staged distances / indices, exact, junk
+  if (smem > 150 * 1024) return PPS_ERR_UNSUPPORTED;          // > ~6k same-id items for one query
+  // column splits: enough CTAs to fill the GPU when there are few queries (not with top-k: one CTA owns a query's state)
+  const int sms = sm_count();
+  long long splits = 1;
+  if (!topk && nq < 4LL * sms) splits = (4LL * sms + nq - 1) / nq;
+  long long seg = (ncols + splits - 1) / splits;
+  seg = (seg + 1023) & ~1023LL;                               // keeps 16-byte alignment of segment starts
+  splits = (ncols + seg - 1) / seg;
+  if (splits > 65535) return PPS_ERR_UNSUPPORTED;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  PPS_CUDA_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    PPS_CUDA_TRY(cudaFuncSetAttribute(rank_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+    PPS_CUDA_TRY(cudaFuncSetAttribute(rank_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+    configured_dev = dev;
+  }
+  const dim3 grid((unsigned)nq, (unsigned)splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (topk)
+    rank_count_kernel<true><<<grid, kCntThreads, smem, st>>>(dist, ldd, ncols, col0, seg, pair_off, pair_g, pair_pos,
+                                                             pair_d, maxp, cnt_le, cnt_first, topk_key, k, topk_filtered);
+  else
+    rank_count_kernel<false><<<grid, kCntThreads, smem, st>>>(dist, ldd, ncols, col0, seg, pair_off, pair_g, pair_pos,
+                                                              pair_d, maxp, cnt_le, cnt_first, nullptr, 0, 0);
+  PPS_LAUNCH_CHECK("rank_count_kernel");
+  return PPS_OK;
+}
+
 extern "C" int pps_rank_count(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
                               const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
                               const float* pair_d, int max_pairs_per_query, uint32_t* cnt_le, uint32_t* cnt_first,
@@ -418,28 +600,22 @@ extern "C" int pps_rank_count(const float* dist, long long ldd, long long nq, lo
   if (max_pairs_per_query == 0) return PPS_OK;               // no query has any same-id gallery item
   if (!pair_g || !pair_pos || !pair_d || !cnt_le) return PPS_ERR_INVALID_ARG;
   if (nq > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
-  const int maxp = (max_pairs_per_query + 3) & ~3;
-  const size_t smem = (size_t)maxp * 20;                      // thr, tpair, staged distances / indices, exact
-  if (smem > 160 * 1024) return PPS_ERR_UNSUPPORTED;          // > ~8k same-id items for one query
-  // column splits: enough CTAs to fill the GPU when there are few queries
-  const int sms = sm_count();
-  long long splits = 1;
-  if (nq < 4LL * sms) splits = (4LL * sms + nq - 1) / nq;
-  long long seg = (ncols + splits - 1) / splits;
-  seg = (seg + 1023) & ~1023LL;                               // keeps 16-byte alignment of segment starts
-  splits = (ncols + seg - 1) / seg;
-  if (splits > 65535) return PPS_ERR_UNSUPPORTED;
-  static thread_local int configured_dev = -1;
-  int dev = 0;
-  PPS_CUDA_TRY(cudaGetDevice(&dev));
-  if (configured_dev != dev) {
-    PPS_CUDA_TRY(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured_dev = dev;
-  }
-  rank_count_kernel<<<dim3((unsigned)nq, (unsigned)splits), kCntThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      dist, ldd, ncols, col0, seg, pair_off, pair_g, pair_pos, pair_d, maxp, cnt_le, cnt_first);
-  PPS_LAUNCH_CHECK("rank_count_kernel");
-  return PPS_OK;
+  return rank_count_launch(dist, ldd, nq, ncols, col0, pair_off, pair_g, pair_pos, pair_d, max_pairs_per_query, cnt_le,
+                           cnt_first, nullptr, 0, 0, stream);
+}
+
+// counts + first-match counter + valid-filtered top-k in ONE read of the block
+extern "C" int pps_rank_sweep(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                              const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                              const float* pair_d, int max_pairs_per_query, uint32_t* cnt_le, uint32_t* cnt_first,
+                              uint64_t* topk_key, int k, int topk_filtered, void* stream) {
+  if (nq < 0 || ncols < 0 || ldd < ncols || max_pairs_per_query < 0 || k < 1 || k > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
+  if (nq == 0 || ncols == 0) return PPS_OK;
+  if (!dist || !pair_off || !cnt_first || !topk_key) return PPS_ERR_INVALID_ARG;
+  if (max_pairs_per_query > 0 && (!pair_g || !pair_pos || !pair_d || !cnt_le)) return PPS_ERR_INVALID_ARG;
+  if (nq > 0x7fffffffLL || col0 + ncols > 0xffffffffLL) return PPS_ERR_UNSUPPORTED;
+  return rank_count_launch(dist, ldd, nq, ncols, col0, pair_off, pair_g, pair_pos, pair_d, max_pairs_per_query, cnt_le,
+                           cnt_first, reinterpret_cast<unsigned long long*>(topk_key), k, topk_filtered, stream);
 }
 
 extern "C" int pps_rank_finalize(long long nq, const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
@@ -490,5 +666,38 @@ extern "C" int pps_topk_unpack(const uint64_t* topk_key, long long nq, int k, fl
   topk_unpack_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const unsigned long long*>(topk_key), n, out_dist, out_index);
   PPS_LAUNCH_CHECK("topk_unpack_kernel");
+  return PPS_OK;
+}
+
+// ---- tables of the fused ranking epilogue (pps_dist_rank_tc) ----
+extern "C" long long pps_rank_tab_elems(long long nq, int p_cap) {
+  if (nq < 0 || p_cap < 8 || p_cap > 64 || (p_cap & 7)) return PPS_ERR_INVALID_ARG;
+  const long long rows_pad = (nq + 255) / 256 * 256;
+  return rows_pad * p_cap;
+}
+
+extern "C" int pps_rank_tab_prep(long long nq, const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                                 const float* pair_d, int p_cap, float* thr_tab, int32_t* tpair_tab, uint32_t* cnt_tab,
+                                 float* dstar, int32_t* gstar, int32_t* overflow, void* stream) {
+  if (nq < 0 || p_cap < 8 || p_cap > 64 || (p_cap & 7)) return PPS_ERR_INVALID_ARG;
+  if (nq == 0) return PPS_OK;
+  if (!pair_off || !thr_tab || !tpair_tab || !cnt_tab || !dstar || !gstar || !overflow) return PPS_ERR_INVALID_ARG;
+  const long long rows_pad = (nq + 255) / 256 * 256;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PPS_CUDA_TRY(cudaMemsetAsync(overflow, 0, 4, st));
+  rank_tab_prep_kernel<<<(unsigned)(rows_pad / 4), 128, 0, st>>>(nq, rows_pad, pair_off, pair_g, pair_pos, pair_d, p_cap,
+                                                                thr_tab, tpair_tab, cnt_tab, dstar, gstar, overflow);
+  PPS_LAUNCH_CHECK("rank_tab_prep_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_rank_tab_finish(long long nq, int p_cap, const int32_t* tpair_tab, const uint32_t* cnt_tab,
+                                   uint32_t* cnt_le, void* stream) {
+  if (nq < 0 || p_cap < 8 || p_cap > 64 || (p_cap & 7)) return PPS_ERR_INVALID_ARG;
+  if (nq == 0) return PPS_OK;
+  if (!tpair_tab || !cnt_tab || !cnt_le) return PPS_ERR_INVALID_ARG;
+  rank_tab_finish_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(nq, p_cap, tpair_tab,
+                                                                                                      cnt_tab, cnt_le);
+  PPS_LAUNCH_CHECK("rank_tab_finish_kernel");
   return PPS_OK;
 }

@@ -244,18 +244,20 @@ def _rank_block(lib, dist, ldd, nq, ncols, col0, pairs: PairLists, pair_d, cnt_l
                                        _lib.ptr(pairs.dev("g")), pairs.n_pairs, _lib.ptr(pair_d), s),
                    "pps_rank_gather")
     if do_count:
-        if pairs.n_pairs:
+        if topk_key is not None:
+            # counts + first-match counter + top-k in one read of the block
+            use = pairs.n_pairs > 0
+            _lib.check(lib.pps_rank_sweep(_lib.ptr(dist), ldd, nq, ncols, col0, _lib.ptr(pairs.dev("off")),
+                                          _lib.ptr(pairs.dev("g")) if use else None,
+                                          _lib.ptr(pairs.dev("pos")) if use else None, _lib.ptr(pair_d) if use else None,
+                                          pairs.max_pairs if use else 0, _lib.ptr(cnt_le) if use else None,
+                                          _lib.ptr(cnt_first), _lib.ptr(topk_key), topk, 1 if topk_filtered else 0, s),
+                       "pps_rank_sweep")
+        elif pairs.n_pairs:
             _lib.check(lib.pps_rank_count(_lib.ptr(dist), ldd, nq, ncols, col0, _lib.ptr(pairs.dev("off")),
                                           _lib.ptr(pairs.dev("g")), _lib.ptr(pairs.dev("pos")), _lib.ptr(pair_d),
                                           pairs.max_pairs, _lib.ptr(cnt_le), _lib.ptr(cnt_first), s),
                        "pps_rank_count")
-        if topk_key is not None:
-            use = topk_filtered and pairs.n_pairs > 0
-            eo = pairs.dev("off") if use else None
-            eg = pairs.dev("g") if use else None
-            ek = pairs.dev("pos") if use else None
-            _lib.check(lib.pps_topk_update(_lib.ptr(dist), ldd, nq, ncols, col0, _lib.ptr(eo), _lib.ptr(eg),
-                                           _lib.ptr(ek), _lib.ptr(topk_key), topk, s), "pps_topk_update")
 
 
 def _finalize(lib, nq, pairs: PairLists, pair_d, cnt_le, cnt_first, want_neg_before):
@@ -519,6 +521,11 @@ class RankEngine:
         self._side = None
         self.h2d_bytes = 0
         self.compact_thresholds = True   # multi-chunk galleries: thresholds from the compacted same-id gallery
+        self.fused_rank = False          # counters in the epilogue of the distance kernel (no distance block written):
+                                         # bit-identical, saves the block's memory, but measured slower than block +
+                                         # count kernel on B200 (the MMA mainloop already saturates shared-memory bandwidth)
+        self.used_fused_rank = False
+        self._tab = None
         self._gp_cap, self._gp_rows, self._pair_col, self._gp_ws = 0, None, None, None
         self.threshold_rows = 0
 
@@ -615,6 +622,36 @@ class RankEngine:
             _lib.check(self.lib.pps_split_rows(_lib.ptr(feats), self.in_code, rows, self.dim, int(feats.stride(0)),
                                                self.planes, _lib.ptr(planes_buf), _lib.ptr(sq_buf), _lib.stream_ptr()),
                        "pps_split_rows")
+
+    def _fused_count_sweep(self, g, chunks, pairs, pair_d, cnt_le, cnt_first):
+        torch, lib = self.torch, self.lib
+        nq = self.nq
+        p_cap = max(8, (pairs.max_pairs + 7) // 8 * 8)
+        elems = int(lib.pps_rank_tab_elems(nq, p_cap))
+        if self._tab is None or self._tab[0] < elems:
+            mk = lambda dt, n: torch.empty(n, dtype=dt, device=self.dev)
+            self._tab = (elems, mk(torch.float32, elems), mk(torch.int32, elems), mk(torch.int32, elems),
+                         mk(torch.float32, max(nq, 1)), mk(torch.int32, max(nq, 1)), mk(torch.int32, 1))
+        _, thr, tpair, cnt, dstar, gstar, ovf = self._tab
+        s = _lib.stream_ptr()
+        _lib.check(lib.pps_rank_tab_prep(nq, _lib.ptr(pairs.dev("off")), _lib.ptr(pairs.dev("g")), _lib.ptr(pairs.dev("pos")),
+                                         _lib.ptr(pair_d), p_cap, _lib.ptr(thr), _lib.ptr(tpair), _lib.ptr(cnt),
+                                         _lib.ptr(dstar), _lib.ptr(gstar), _lib.ptr(ovf), s), "pps_rank_tab_prep")
+        for r0, rows in chunks:
+            self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)
+            ev = None
+            if self.kernel_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            _lib.check(lib.pps_dist_rank_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), nq, self.planes, 0,
+                                            _lib.ptr(self.g_planes), _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
+                                            self.prec, 0, self.offset + r0, p_cap, _lib.ptr(thr), _lib.ptr(cnt),
+                                            _lib.ptr(dstar), _lib.ptr(gstar), _lib.ptr(cnt_first), s), "pps_dist_rank_tc")
+            if ev is not None:
+                ev[1].record()
+                self.kernel_events.append(ev)
+        _lib.check(lib.pps_rank_tab_finish(nq, p_cap, _lib.ptr(tpair), _lib.ptr(cnt), _lib.ptr(cnt_le), s),
+                   "pps_rank_tab_finish")
 
     def _threshold_pass(self, g, pairs, pair_d):
         """pair_d[e] = d(query, gallery row) for every same-id pair whose row lives in this shard, from the product
@@ -715,6 +752,14 @@ class RankEngine:
             if self.group is not None:
                 dist_mod.all_reduce(pair_d, op=dist_mod.ReduceOp.SUM, group=self.group)
             # sweep 2: counts (+ top-k); a single chunk is still resident in the block
+            fused = (self.fused_rank and self.n_chunks > 1 and not self.topk and pairs.n_pairs > 0
+                     and pairs.max_pairs <= 64)
+            self.used_fused_rank = bool(fused)
+            if fused:
+                # thresholds are known: the counters are taken in the epilogue of the distance kernel and the
+                # distance blocks are never written (pps_dist_rank_tc)
+                self._fused_count_sweep(g, chunks, pairs, pair_d, cnt_le, cnt_first)
+                chunks = []
             for r0, rows in chunks:
                 if self.n_chunks > 1:
                     self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)

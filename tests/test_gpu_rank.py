@@ -101,7 +101,7 @@ def test_compacted_threshold_pass_equals_full_sweep(golden):
     it must give the bits of the two-sweep form, including when those rows need several blocks themselves."""
     import torch
     from pps_b200 import evaluator
-    for name in ("small_mid", "many_pos", "some_invalid"):
+    for name in ("small_mid", "many_pos", "ragged_dim", "dup_ties"):
         d = golden(name)
         q, g = torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda()
         out = []
@@ -119,6 +119,52 @@ def test_compacted_threshold_pass_equals_full_sweep(golden):
         np.testing.assert_array_equal(a.first_rank, b.first_rank)
         np.testing.assert_array_equal(a.neg_before, b.neg_before)
         np.testing.assert_array_equal(a.topk_index, b.topk_index)
+
+
+@pytest.mark.parametrize("name", ["small_mid", "ragged_dim", "dup_ties"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x1"])
+def test_fused_rank_epilogue_equals_count_kernel(golden, name, precision):
+    """pps_dist_rank_tc (counters in the GEMM epilogue, no distance block) == pps_dist_tc + pps_rank_count, bit for
+    bit: AP, first-match ranks (exact duplicate ties included) and per-positive negatives-before counts."""
+    import torch
+    from pps_b200 import evaluator
+    d = golden(name)
+    q, g = torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda()
+    out = []
+    for fused in (False, True):
+        eng = evaluator.RankEngine(d["qid"], d["gid"], d["qcam"], d["gcam"], nq=q.shape[0], ng_local=g.shape[0],
+                                   dim=q.shape[1], want_neg_before=True, precision=precision,
+                                   max_block_bytes=q.shape[0] * 256 * 4)
+        eng.fused_rank = fused
+        assert eng.n_chunks > 1
+        out.append(eng.run(q, g))
+        assert eng.used_fused_rank == fused
+    a, b = out
+    np.testing.assert_array_equal(a.is_valid, b.is_valid)
+    np.testing.assert_array_equal(a.ap, b.ap)
+    np.testing.assert_array_equal(a.first_rank, b.first_rank)
+    np.testing.assert_array_equal(a.neg_before, b.neg_before)
+
+
+def test_fused_rank_epilogue_shapes():
+    """Row / column edges of the fused kernel: queries not a multiple of 256 (and > 256 so that several m tiles and
+    the superblock schedule are exercised), gallery blocks not a multiple of 256, fp16 inputs."""
+    import torch
+    import pps_b200
+    from pps_b200 import evaluator, synthetic
+    for nq, ng, dim, dt in ((300, 3001, 192, torch.float32), (1, 700, 64, torch.float32), (2600, 1500, 128, torch.float16)):
+        d = synthetic.make_reid_set(nq=nq, ng=ng, dim=dim, n_ids=max(nq // 6, 1), n_cams=3, n_distractors=ng // 5,
+                                    sigma=3.0, seed=nq)
+        q, g = torch.from_numpy(d["q"]).cuda().to(dt), torch.from_numpy(d["g"]).cuda().to(dt)
+        out = []
+        for fused in (False, True):
+            eng = evaluator.RankEngine(d["qid"], d["gid"], d["qcam"], d["gcam"], nq=nq, ng_local=ng, dim=dim,
+                                       max_block_bytes=max(nq, 1) * 700 * 4, in_dtype=dt)
+            eng.fused_rank = fused
+            out.append(eng.run(q, g))
+            assert eng.used_fused_rank == (fused and eng.n_chunks > 1)
+        np.testing.assert_array_equal(out[0].ap, out[1].ap)
+        np.testing.assert_array_equal(out[0].first_rank, out[1].first_rank)
 
 
 def test_compact_rows_layout():
