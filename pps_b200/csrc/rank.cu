@@ -31,7 +31,7 @@ __device__ __forceinline__ int fkey(float x) {
 constexpr int kTopkThreads = 256;
 constexpr int kCand = 2048;
 
-__device__ __forceinline__ void bitonic_sort_smem(unsigned long long* a, int n /*pow2*/, int tid, int nthreads) {
+__device__ __noinline__ void bitonic_sort_smem(unsigned long long* a, int n /*pow2*/, int tid, int nthreads) {
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = tid; i < n; i += nthreads) {
@@ -45,6 +45,48 @@ __device__ __forceinline__ void bitonic_sort_smem(unsigned long long* a, int n /
       __syncthreads();
     }
   }
+}
+
+// Keep the k smallest of the n_buf keys in a[] (unused slots hold ~0) WITHOUT sorting: a 32-step bisection on the
+// high word (the distance bits) finds the smallest v with #{hi <= v} >= k, every key with hi <= v moves to the front
+// (all ties at v included, in no particular order), the rest becomes ~0.  Returns the number kept (same in every
+// thread) and sets *bound_out (thread 0) to the largest key that can still enter.  ~1/8 of the instructions of the
+// full bitonic sort it replaces.  NPT = n_buf / nthreads keys per thread live in registers.
+template <int NPT>
+__device__ __noinline__ int select_k_smallest(unsigned long long* a, int k, int tid, int nthreads, int* s_part /*[2][32]*/,
+                                                 int* s_cnt, unsigned long long* bound_out) {
+  unsigned long long key[NPT];
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) key[j] = a[tid + j * nthreads];
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+  uint32_t lo = 0u, hi = 0xffffffffu;
+  int it = 0;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) c += ((uint32_t)(key[j] >> 32) <= mid) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    int* part = s_part + (it & 1) * 32;
+    if (lane == 0) part[warp] = c;
+    __syncthreads();
+    int tot = 0;
+    for (int w = 0; w < nwarps; ++w) tot += part[w];
+    if (tot >= k) hi = mid; else lo = mid + 1;
+    ++it;
+  }
+  if (tid == 0) *s_cnt = 0;
+  __syncthreads();                      // every key is in registers: the buffer can be rewritten
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) a[tid + j * nthreads] = ~0ull;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NPT; ++j)
+    if ((uint32_t)(key[j] >> 32) <= lo && key[j] != ~0ull) a[atomicAdd(s_cnt, 1)] = key[j];
+  __syncthreads();
+  if (tid == 0) *bound_out = ((unsigned long long)lo << 32) | 0xffffffffull;
+  return *s_cnt;
 }
 
 // ------------------------------------------------------------------------------------
@@ -84,6 +126,17 @@ __global__ void rank_gather_kernel(const float* __restrict__ dist, long long ldd
 // dynamic smem: thr[maxp] sorted positive distances, tpair[maxp] their pair index, sd/sg[maxp] the
 //               staged pair list, exact[maxp]
 // ------------------------------------------------------------------------------------
+// rare path of the top-k sweep: one column whose distance bits do not exceed the admission bound
+__device__ __noinline__ void topk_admit(float d, unsigned long long gcol, unsigned long long bound, const int32_t* sj, int nj,
+                                        unsigned long long* cand, int* s_n, int* app_ctr) {
+  const unsigned long long ukey = ((unsigned long long)__float_as_uint(d) << 32) | (gcol & 0xffffffffull);
+  if (ukey >= bound) return;
+  for (int x = 0; x < nj; ++x)
+    if ((unsigned long long)(long long)sj[x] == gcol) return;       // junk: same id, same camera
+  cand[atomicAdd(s_n, 1)] = ukey;                                    // *s_n <= kCandC - 1024 when a half pass starts
+  atomicAdd(app_ctr, 1);
+}
+
 // TOPK = true (one CTA per query, no column splits): the same sweep also keeps the query's k nearest valid gallery
 // items.  A column is admitted only if its key beats the current k-th best (one compare per element), candidates
 // collect in a 2048-entry shared buffer that is re-selected by bitonic sort when it fills; junk items (same id, same
@@ -115,6 +168,8 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
   __shared__ uint32_t s_below, s_first_cnt;
   __shared__ unsigned long long cand[TOPK ? kCandC : 1];
   __shared__ int s_n;
+  __shared__ int s_app[3];                // appends of half pass h in s_app[h % 3]
+  __shared__ int s_sel[64];               // partial counts of select_k_smallest
   __shared__ unsigned long long s_bound;
 
   const int q = blockIdx.x;
@@ -134,7 +189,7 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
   if (TOPK) {
     state = topk_key + (long long)q * k;
     for (int i = tid; i < kCandC; i += kCntThreads) cand[i] = i < k ? state[i] : ~0ull;
-    if (tid == 0) { s_n = k; s_bound = state[k - 1]; }
+    if (tid == 0) { s_n = k; s_bound = state[k - 1]; s_app[0] = s_app[1] = s_app[2] = 0; }
   }
   __syncthreads();
   if (TOPK && topk_filtered) {
@@ -187,6 +242,7 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
   uint32_t tie_corr = 0;                                   // signed: -#{d == d*} + #{d == d*, col < g*}
 
   unsigned long long bound = ~0ull;                        // TOPK: key of the current k-th best (sampled per half pass)
+  int* app_ctr = s_app;                                    // TOPK: this half pass's append counter
   auto visit = [&](float d, long long col) {
     const int key = fkey(d);
     const bool lt = key < key_min;
@@ -203,57 +259,82 @@ __global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float*
         if (d == dstar) tie_corr += ((col0 + col) < gstar ? 1u : 0u) - 1u;
       }
     }
-    if (TOPK) {
-      if (__float_as_uint(d) <= (uint32_t)(bound >> 32)) {
-        const unsigned long long ukey = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(uint32_t)(col0 + col);
-        if (ukey < bound) {
-          bool skip = false;
-          for (int x = 0; x < nj; ++x) skip |= ((long long)sj[x] == col0 + col);
-          if (!skip) cand[atomicAdd(&s_n, 1)] = ukey;      // s_n <= kCandC - 1024 when a half pass starts
-        }
-      }
-    }
   };
 
   if (TOPK) {
-    // passes of 2048 columns (four 128-bit loads in flight per thread), admission bound re-sampled and the candidate
-    // buffer checked after every 1024 columns
+    // passes of 2048 columns; the loads of the next pass are issued before the current one is consumed, so the stream
+    // never drains at the barriers.  After every 1024 columns one barrier: it sums the threads that appended, which
+    // bounds the fill of the candidate buffer (<= 8 appends per thread and half pass) identically in every thread.
     constexpr long long kStep = 4LL * kCntThreads;
-    for (long long base = c_begin; base < c_end; base += 4 * kStep) {
-      float4 v[4];
-      bool ok[4];
+    float4 v[4], vn[4];
+    auto load_pass = [&](long long base, float4 (&dst)[4]) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long long cu = base + u * kStep + 4LL * tid;
-        ok[u] = vec && cu + 3 < c_end;
-        if (ok[u]) v[u] = ld_stream_f4(reinterpret_cast<const float4*>(drow + cu));
+        if (vec && cu + 3 < c_end) dst[u] = ld_stream_f4(reinterpret_cast<const float4*>(drow + cu));
       }
+    };
+    load_pass(c_begin, v);
+    int fill = k;                                            // entries in the candidate buffer, the same in every thread
+    int hp = 0;                                              // half pass index mod 3
+    for (long long base = c_begin; base < c_end; base += 4 * kStep) {
+      if (base + 4 * kStep < c_end) load_pass(base + 4 * kStep, vn);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         bound = s_bound;
+        app_ctr = s_app + hp;
 #pragma unroll
         for (int uu = 0; uu < 2; ++uu) {
           const int u = 2 * h + uu;
           const long long cu = base + u * kStep + 4LL * tid;
-          if (ok[u]) {
+          const uint32_t bh = (uint32_t)(bound >> 32);
+          if (vec && cu + 3 < c_end) {
             visit(v[u].x, cu); visit(v[u].y, cu + 1); visit(v[u].z, cu + 2); visit(v[u].w, cu + 3);
+            const float dv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            if ((__float_as_uint(dv[0]) <= bh) | (__float_as_uint(dv[1]) <= bh) | (__float_as_uint(dv[2]) <= bh) |
+                (__float_as_uint(dv[3]) <= bh)) {
+#pragma unroll 1
+              for (int e = 0; e < 4; ++e)
+                if (__float_as_uint(dv[e]) <= bh)
+                  topk_admit(dv[e], (unsigned long long)(col0 + cu + e), bound, sj, nj, cand, &s_n, app_ctr);
+            }
           } else {
+#pragma unroll 1
             for (int e = 0; e < 4; ++e)
-              if (cu + e < c_end) visit(drow[cu + e], cu + e);
+              if (cu + e < c_end) {
+                const float d = drow[cu + e];
+                visit(d, cu + e);
+                if (__float_as_uint(d) <= bh)
+                  topk_admit(d, (unsigned long long)(col0 + cu + e), bound, sj, nj, cand, &s_n, app_ctr);
+              }
           }
         }
         __syncthreads();
-        const int n_now = s_n;
-        __syncthreads();           // every thread has sampled s_n before anyone appends again
-        if (n_now > kCandC - 1024) {
-          bitonic_sort_smem(cand, kCandC, tid, kCntThreads);
-          for (int i = k + tid; i < kCandC; i += kCntThreads) cand[i] = ~0ull;
-          if (tid == 0) { s_n = k; s_bound = cand[k - 1]; }
+        // s_app[hp] is complete and nobody writes it again before it is reset two half passes from now, so every
+        // thread reads the same value without a second barrier
+        fill += s_app[hp];
+        const int hp_reset = hp == 0 ? 2 : hp - 1;           // the counter half pass h + 2 will use (last read: h - 1)
+        if (tid == 0) s_app[hp_reset] = 0;
+        hp = hp == 2 ? 0 : hp + 1;
+        if (fill > kCandC - 1024) {
+          fill = select_k_smallest<kCandC / kCntThreads>(cand, k, tid, kCntThreads, s_sel, &s_n, &s_bound);
+          if (fill > kCandC - 1024) {                      // > 1000 exact distance ties at the k-th place: full sort
+            bitonic_sort_smem(cand, kCandC, tid, kCntThreads);
+            for (int i = k + tid; i < kCandC; i += kCntThreads) cand[i] = ~0ull;
+            if (tid == 0) { s_n = k; s_bound = cand[k - 1]; }
+            fill = k;
+          }
           __syncthreads();
         }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = vn[u];
     }
-    bitonic_sort_smem(cand, kCandC, tid, kCntThreads);
+    // final state: the k smallest, sorted.  Select first, then sort only what was kept (k plus ties).
+    const int kept = select_k_smallest<kCandC / kCntThreads>(cand, k, tid, kCntThreads, s_sel, &s_n, &s_bound);
+    __syncthreads();
+    if (kept <= 256) bitonic_sort_smem(cand, 256, tid, kCntThreads);
+    else bitonic_sort_smem(cand, kCandC, tid, kCntThreads);
     for (int i = tid; i < k; i += kCntThreads) state[i] = cand[i];
     if (!count_on) return;                                 // uniform: no positives, only the top-k was wanted
   } else if (vec) {
