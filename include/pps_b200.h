@@ -198,6 +198,19 @@ int pps_pairs_fill_local(const int64_t* query_ids, const int64_t* query_cams, lo
                          long long capacity, void* stream);
 int pps_pairs_unpack_pos(const int32_t* pair_pos32, long long n_pairs, uint8_t* pair_pos, void* stream);
 
+/* Candidate pre-filter for very large galleries (millions of distractor rows): keeps, in ascending order, only
+ * the gallery rows whose id is the id of some query (hash set of the query ids + ordered compaction), so that the
+ * pair sweeps above run on a few 10^4 rows instead of the whole gallery:
+ *   pps_pairs_prefilter(...) -> cand_rows[*n_cand] (gallery rows), cand_gid / cand_gcam (their ids / cameras)
+ *   pps_pairs_count_device / pps_pairs_fill_device on (cand_gid, cand_gcam, *n_cand)   [caller reads *n_cand back]
+ *   pps_pairs_remap(pair_g, n_pairs, cand_rows, offset): pair_g[e] = cand_rows[pair_g[e]] + offset.
+ * cand_* arrays need room for ng entries in the worst case (every row matches). */
+long long pps_pairs_prefilter_workspace_bytes(long long nq, long long ng);
+int pps_pairs_prefilter(const int64_t* query_ids, long long nq, const int64_t* gallery_ids,
+                        const int64_t* gallery_cams, long long ng, void* workspace,
+                        int32_t* cand_rows, int64_t* cand_gid, int64_t* cand_gcam, int32_t* n_cand, void* stream);
+int pps_pairs_remap(int32_t* pair_g, long long n_pairs, const int32_t* cand_rows, long long offset, void* stream);
+
 /* Compacted same-id gallery for the threshold pass of a gallery that does not fit one distance block.
  * The thresholds of the ranking are the distances of the same-id pairs only; all queries of one id share one
  * gallery list, so the rows needed are the lists of one representative query per id, restricted to the

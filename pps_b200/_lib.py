@@ -73,6 +73,9 @@ SIGNATURES = {
     "pps_pairs_offsets": (_i, [_vp, _i, _i, _ll, _ll, _vp, _vp, _vp, _vp]),
     "pps_pairs_fill_local": (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "pps_pairs_unpack_pos": (_i, [_vp, _ll, _vp, _vp]),
+    "pps_pairs_prefilter_workspace_bytes": (_ll, [_ll, _ll]),
+    "pps_pairs_prefilter": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_pairs_remap": (_i, [_vp, _ll, _vp, _ll, _vp]),
     "pps_pairs_compact_workspace_bytes": (_ll, [_ll]),
     "pps_pairs_compact_rows": (_i, [_vp, _ll, _vp, _vp, _vp, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _vp]),
     "pps_rank_gather": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _ll, _vp, _vp]),

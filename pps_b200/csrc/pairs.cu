@@ -282,6 +282,139 @@ __global__ void compact_fill_kernel(const int32_t* __restrict__ pair_off, const 
   pair_col[e] = col;
 }
 
+// ------------------------------------------------------------------------------------
+// Candidate pre-filter for very large galleries.  The pair sweeps compare every query id with every gallery id; with
+// millions of distractor rows almost all of that is wasted, so first keep only the gallery rows whose id is the id
+// of SOME query: a hash set of the query ids (open addressing, built once), one membership probe per gallery row,
+// and an ORDERED compaction (block counts -> scan -> fill) so that the candidate list stays ascending in the
+// gallery index.  The sweeps then run on the compact (id, camera) arrays and pps_pairs_remap turns their pair_g
+// (an index into the candidate list) back into gallery rows.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_id(int64_t id, uint32_t mask) {
+  uint64_t x = (uint64_t)id * 0x9E3779B97F4A7C15ull;
+  return (uint32_t)(x >> 32) & mask;
+}
+
+__global__ void qset_build_kernel(const int64_t* __restrict__ qid, int nq, int64_t* __restrict__ keys,
+                                  int32_t* __restrict__ occ, uint32_t mask) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int64_t id = qid[q];
+  uint32_t s = hash_id(id, mask);
+  while (true) {
+    const int old = atomicCAS(&occ[s], 0, 1);
+    if (old == 0) { keys[s] = id; return; }      // claimed an empty slot (duplicates of an id may take several: harmless)
+    s = (s + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ bool qset_has(int64_t id, const int64_t* __restrict__ keys, const int32_t* __restrict__ occ,
+                                         uint32_t mask) {
+  uint32_t s = hash_id(id, mask);
+  while (occ[s]) {
+    if (keys[s] == id) return true;
+    s = (s + 1) & mask;
+  }
+  return false;
+}
+
+constexpr int kFilterRows = 2048;      // gallery rows per CTA (256 threads x 8)
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) prefilter_kernel(const int64_t* __restrict__ gid, const int64_t* __restrict__ gcam,
+                                                        long long ng, const int64_t* __restrict__ keys,
+                                                        const int32_t* __restrict__ occ, uint32_t mask,
+                                                        int32_t* __restrict__ blk_cnt /*count: out; fill: exclusive offsets*/,
+                                                        int32_t* __restrict__ cand_rows, int64_t* __restrict__ cand_gid,
+                                                        int64_t* __restrict__ cand_gcam) {
+  __shared__ int warp_cnt[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long row0 = (long long)blockIdx.x * kFilterRows;
+  // thread t owns 8 CONSECUTIVE rows, so ranks inside the block follow the gallery order
+  const long long r0 = row0 + (long long)tid * 8;
+  int64_t id[8];
+  unsigned hit = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    id[e] = 0;
+    if (r0 + e < ng) {
+      id[e] = gid[r0 + e];
+      if (qset_has(id[e], keys, occ, mask)) hit |= 1u << e;
+    }
+  }
+  const int mine = __popc(hit);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_cnt[warp] = incl;
+  __syncthreads();
+  int before = incl - mine, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < warp) before += warp_cnt[w];
+    total += warp_cnt[w];
+  }
+  if (!FILL) {
+    if (tid == 0) blk_cnt[blockIdx.x] = total;
+    return;
+  }
+  int pos = blk_cnt[blockIdx.x] + before;
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (hit & (1u << e)) {
+      cand_rows[pos] = (int32_t)(r0 + e);
+      cand_gid[pos] = id[e];
+      cand_gcam[pos] = gcam[r0 + e];
+      ++pos;
+    }
+}
+
+// one CTA: in-place exclusive scan of n block counts, total -> *n_out
+__global__ void __launch_bounds__(1024) prefilter_scan_kernel(int32_t* __restrict__ cnt, int n, int32_t* __restrict__ n_out) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const int v = i < n ? cnt[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (i < n) cnt[i] = carry + (warp ? warp_sum[warp - 1] : 0) + incl - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sum[31];
+    __syncthreads();
+  }
+  if (tid == 0) *n_out = carry_s;
+}
+
+__global__ void pairs_remap_kernel(int32_t* __restrict__ pair_g, long long n, const int32_t* __restrict__ cand_rows,
+                                   long long offset) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pair_g[i] = (int32_t)(cand_rows[pair_g[i]] + offset);
+}
+
 }  // namespace pps
 
 using namespace pps;
@@ -429,5 +562,61 @@ extern "C" int pps_pairs_compact_rows(const int64_t* query_ids, long long nq, co
   compact_fill_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(pair_off, pair_q, pair_g, n_pairs, rep, lo, cnt,
                                                                          gp_off, gp_rows, pair_col);
   PPS_LAUNCH_CHECK("compact_fill_kernel");
+  return PPS_OK;
+}
+
+// ---- candidate pre-filter (see qset_build_kernel) ----
+static uint32_t qset_slots(long long nq) {
+  uint32_t n = 64;
+  while ((long long)n < 2 * nq) n <<= 1;
+  return n;
+}
+
+extern "C" long long pps_pairs_prefilter_workspace_bytes(long long nq, long long ng) {
+  if (nq < 0 || ng < 0) return PPS_ERR_INVALID_ARG;
+  const long long slots = qset_slots(nq);
+  const long long nblk = (ng + kFilterRows - 1) / kFilterRows;
+  return slots * 12 + (nblk + 4) * 4 + 64;
+}
+
+extern "C" int pps_pairs_prefilter(const int64_t* query_ids, long long nq, const int64_t* gallery_ids,
+                                   const int64_t* gallery_cams, long long ng, void* workspace, int32_t* cand_rows,
+                                   int64_t* cand_gid, int64_t* cand_gcam, int32_t* n_cand, void* stream) {
+  if (nq < 0 || ng < 0 || nq > 0x3fffffffLL || ng > 0x7fffffffLL) return PPS_ERR_INVALID_ARG;
+  if (!n_cand) return PPS_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nq == 0 || ng == 0) {
+    PPS_CUDA_TRY(cudaMemsetAsync(n_cand, 0, 4, st));
+    return PPS_OK;
+  }
+  if (!query_ids || !gallery_ids || !gallery_cams || !workspace || !cand_rows || !cand_gid || !cand_gcam)
+    return PPS_ERR_INVALID_ARG;
+  const uint32_t slots = qset_slots(nq);
+  int64_t* keys = static_cast<int64_t*>(workspace);
+  int32_t* occ = reinterpret_cast<int32_t*>(keys + slots);
+  int32_t* blk = occ + slots;
+  const long long nblk = (ng + kFilterRows - 1) / kFilterRows;
+  PPS_CUDA_TRY(cudaMemsetAsync(occ, 0, (size_t)slots * 4, st));
+  qset_build_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(query_ids, (int)nq, keys, occ, slots - 1);
+  PPS_LAUNCH_CHECK("qset_build_kernel");
+  prefilter_kernel<false><<<(unsigned)nblk, 256, 0, st>>>(gallery_ids, gallery_cams, ng, keys, occ, slots - 1, blk, nullptr,
+                                                          nullptr, nullptr);
+  PPS_LAUNCH_CHECK("prefilter_kernel<count>");
+  prefilter_scan_kernel<<<1, 1024, 0, st>>>(blk, (int)nblk, n_cand);
+  PPS_LAUNCH_CHECK("prefilter_scan_kernel");
+  prefilter_kernel<true><<<(unsigned)nblk, 256, 0, st>>>(gallery_ids, gallery_cams, ng, keys, occ, slots - 1, blk, cand_rows,
+                                                         cand_gid, cand_gcam);
+  PPS_LAUNCH_CHECK("prefilter_kernel<fill>");
+  return PPS_OK;
+}
+
+extern "C" int pps_pairs_remap(int32_t* pair_g, long long n_pairs, const int32_t* cand_rows, long long offset,
+                               void* stream) {
+  if (n_pairs < 0) return PPS_ERR_INVALID_ARG;
+  if (n_pairs == 0) return PPS_OK;
+  if (!pair_g || !cand_rows) return PPS_ERR_INVALID_ARG;
+  pairs_remap_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(pair_g, n_pairs,
+                                                                                                       cand_rows, offset);
+  PPS_LAUNCH_CHECK("pairs_remap_kernel");
   return PPS_OK;
 }

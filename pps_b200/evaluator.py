@@ -62,6 +62,9 @@ def _ids64(a, name):
     return a
 
 
+PREFILTER_MIN_ROWS = 131072      # galleries at least this long get the candidate pre-filter before the pair sweeps
+
+
 class PairLists:
     """Same-id (query, gallery) pairs in CSR form (C ABI part 2c); host arrays + device copies."""
 
@@ -140,10 +143,37 @@ class DevicePairs:
         self.q_d = self.g_d = self.pos_d = None
         self.n_pairs = self.max_pairs = 0
         self._host = None
+        # very large galleries: the sweeps run on the rows whose id is some query's id (pps_pairs_prefilter)
+        self.prefilter = self.ng >= PREFILTER_MIN_ROWS and self.nq > 0
+        self.n_cand = self.ng
+        if self.prefilter:
+            self.pf_ws = torch.empty(int(self.lib.pps_pairs_prefilter_workspace_bytes(self.nq, self.ng)), dtype=torch.uint8,
+                                     device=self.device)
+            self.cand_rows = torch.empty(self.ng, dtype=torch.int32, device=self.device)
+            self.cand_gid = torch.empty(self.ng, dtype=torch.int64, device=self.device)
+            self.cand_gcam = torch.empty(self.ng, dtype=torch.int64, device=self.device)
+            self.n_cand_d = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.n_cand_h = torch.zeros(1, dtype=torch.int32).pin_memory()
+
+    def _sweep_arrays(self):
+        """(gallery ids, gallery cameras, rows) the pair sweeps run on."""
+        if self.prefilter:
+            return self.cand_gid, self.cand_gcam, self.n_cand
+        return self.gid, self.gcam, self.ng
 
     def begin(self):
         lib = self.lib
-        _lib.check(lib.pps_pairs_count_device(_lib.ptr(self.qid), self.nq, _lib.ptr(self.gid), self.ng, _lib.ptr(self.ws),
+        if self.prefilter:
+            torch = _torch()
+            _lib.check(lib.pps_pairs_prefilter(_lib.ptr(self.qid), self.nq, _lib.ptr(self.gid), _lib.ptr(self.gcam), self.ng,
+                                               _lib.ptr(self.pf_ws), _lib.ptr(self.cand_rows), _lib.ptr(self.cand_gid),
+                                               _lib.ptr(self.cand_gcam), _lib.ptr(self.n_cand_d), _lib.stream_ptr()),
+                       "pps_pairs_prefilter")
+            self.n_cand_h.copy_(self.n_cand_d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # 4 bytes: the candidate count sizes the sweeps
+            self.n_cand = int(self.n_cand_h[0])
+        gid, _, rows = self._sweep_arrays()
+        _lib.check(lib.pps_pairs_count_device(_lib.ptr(self.qid), self.nq, _lib.ptr(gid), rows, _lib.ptr(self.ws),
                                               _lib.ptr(self.off_d), _lib.ptr(self.totals_d), _lib.stream_ptr()),
                    "pps_pairs_count_device")
         self.totals_h.copy_(self.totals_d, non_blocking=True)
@@ -167,11 +197,15 @@ class DevicePairs:
             zero_f32 = zero_f32(self.n_pairs)
         if callable(zero_u32):
             zero_u32 = zero_u32(self.n_pairs)
-        _lib.check(self.lib.pps_pairs_fill_device(_lib.ptr(self.qid), _lib.ptr(self.qcam), self.nq, _lib.ptr(self.gid),
-                                                  _lib.ptr(self.gcam), self.ng, _lib.ptr(self.ws),
+        gid, gcam, rows = self._sweep_arrays()
+        _lib.check(self.lib.pps_pairs_fill_device(_lib.ptr(self.qid), _lib.ptr(self.qcam), self.nq, _lib.ptr(gid),
+                                                  _lib.ptr(gcam), rows, _lib.ptr(self.ws),
                                                   _lib.ptr(self.q_d), _lib.ptr(self.g_d), _lib.ptr(self.pos_d),
                                                   _lib.ptr(zero_f32), _lib.ptr(zero_u32), _lib.ptr(zero_per_query),
                                                   self.n_pairs, _lib.stream_ptr()), "pps_pairs_fill_device")
+        if self.prefilter and self.n_pairs:
+            _lib.check(self.lib.pps_pairs_remap(_lib.ptr(self.g_d), self.n_pairs, _lib.ptr(self.cand_rows), 0,
+                                                _lib.stream_ptr()), "pps_pairs_remap")
         return self
 
     def dev(self, name):

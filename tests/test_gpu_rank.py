@@ -167,6 +167,39 @@ def test_fused_rank_epilogue_shapes():
         np.testing.assert_array_equal(out[0].first_rank, out[1].first_rank)
 
 
+def test_prefiltered_pair_lists_equal_plain(monkeypatch):
+    """pps_pairs_prefilter + sweeps on the candidates + pps_pairs_remap == the plain sweeps over the whole gallery
+    (ids far apart, negative ids, an id shared by many queries, block edges of the ordered compaction)."""
+    import torch
+    from pps_b200 import evaluator
+    rs = np.random.RandomState(11)
+    nq, ng = 500, 20000
+    qid = rs.randint(-50, 200, size=nq).astype(np.int64) * 1000003
+    gid = np.where(rs.rand(ng) < 0.1, rs.randint(-50, 200, size=ng) * 1000003, rs.randint(10 ** 9, 2 * 10 ** 9, size=ng)).astype(np.int64)
+    gid[2047] = gid[2048] = gid[4095] = qid[0]
+    gid[ng - 1] = qid[1]
+    qcam, gcam = rs.randint(0, 4, size=nq), rs.randint(0, 4, size=ng)
+    dev = torch.device("cuda")
+    plain = evaluator.DevicePairs(qid, qcam, gid, gcam, dev)
+    assert not plain.prefilter
+    plain.begin().finish()
+    monkeypatch.setattr(evaluator, "PREFILTER_MIN_ROWS", 1000)
+    filt = evaluator.DevicePairs(qid, qcam, gid, gcam, dev)
+    assert filt.prefilter
+    filt.begin().finish()
+    assert filt.n_cand == int(np.isin(gid, np.unique(qid)).sum())
+    assert filt.n_pairs == plain.n_pairs and filt.max_pairs == plain.max_pairs
+    n = plain.n_pairs
+    np.testing.assert_array_equal(filt.off, plain.off)
+    np.testing.assert_array_equal(filt.q[:n], plain.q[:n])
+    np.testing.assert_array_equal(filt.g[:n], plain.g[:n])
+    np.testing.assert_array_equal(filt.pos[:n], plain.pos[:n])
+    # no query id at all in the gallery
+    none = evaluator.DevicePairs(qid, qcam, np.arange(ng, dtype=np.int64) + 10 ** 12, gcam, dev)
+    none.begin().finish()
+    assert none.n_cand == 0 and none.n_pairs == 0
+
+
 def test_compact_rows_layout():
     """pps_pairs_compact_rows: gp_rows = the distinct same-id gallery rows of the window grouped by id (one
     representative query per id), pair_col = where each pair's row sits in it (or -1 outside the window)."""
