@@ -436,6 +436,39 @@ int pps_embed_tc(const void* x_planes, int x_planes_n, long long N,
 int pps_l2_normalize_rows(const float* x, long long rows, int dim, long long ld,
                           float* out, long long ldo, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Next row — k-reciprocal re-ranking, reid_dataset_evaluator.py:442-519
+ * `re_ranking(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3)` (evaluate() :161-207;
+ * cfg.REID.RERANK defaults to True, config.py:1022).  M is the assembled [n, n] matrix
+ * [[q_q, q_g], [q_g^T, g_g]] (n = nq + ng), images 0 .. nq-1 are the queries.  Steps, each one call:
+ *   pps_rerank_normalize  od[i][j] = M[j][i]^2 / max_r M[r][i]^2                       (:447-454)
+ *   initial_rank          = the k1 + 1 nearest columns of every row of od: pps_topk_init / pps_topk_update
+ *                           (no exclusion list) / pps_topk_unpack on od                 (:456)
+ *   pps_rerank_krecip     k-reciprocal set + expansion, V row = exp(-od) normalised     (:462-487)
+ *                         rows as ELL: v_idx / v_val [n][pps_rerank_vcap()], v_cnt [n]
+ *   pps_rerank_expand     V row <- mean of the V rows of the k2 nearest images          (:489-494)
+ *                         q_idx / q_val [n][qe_cap], qe_cap >= k2 * pps_rerank_vcap()
+ *   pps_rerank_invert     inverted index (by column) of the gallery rows                (:496-498)
+ *   pps_rerank_jaccard    out[i][g] = (1 - t/(2 - t)) (1 - lambda) + od[i][nq + g] lambda,
+ *                         t = sum_c min(V[i][c], V[nq + g][c])                          (:500-513)
+ * All arithmetic is float32 in the reference's order (columns ascending, no atomics on floats).
+ * ---------------------------------------------------------------------------------- */
+int pps_rerank_vcap(void);
+int pps_rerank_normalize(const float* m, long long ld, long long n, float* colmax, float* od, long long ldo,
+                         void* stream);
+int pps_rerank_krecip(const int32_t* initial_rank, int rank_cols, long long n, int k1,
+                      const float* od, long long ldo, int32_t* v_idx, float* v_val, int32_t* v_cnt, void* stream);
+int pps_rerank_expand(const int32_t* initial_rank, int rank_cols, long long n, int k2,
+                      const int32_t* v_idx, const float* v_val, const int32_t* v_cnt,
+                      int qe_cap, int32_t* q_idx, float* q_val, int32_t* q_cnt, void* stream);
+int pps_rerank_invert(const int32_t* q_idx, const float* q_val, const int32_t* q_cnt, int qe_cap,
+                      long long nq, long long n, int32_t* col_cnt, int32_t* col_off, int32_t* cursor,
+                      int32_t* inv_row, float* inv_val, void* stream);
+int pps_rerank_jaccard(const int32_t* q_idx, const float* q_val, const int32_t* q_cnt, int qe_cap,
+                       const int32_t* col_off, const int32_t* inv_row, const float* inv_val,
+                       long long nq, long long ng, const float* od, long long ldo, float lambda_value,
+                       float* out, long long ld_out, void* stream);
+
 /* instrumentation: number of kernels this library has launched in this process
  * (bench.py reports the delta over the timed region as `gpu_launches`). */
 unsigned long long pps_kernel_launch_count(void);

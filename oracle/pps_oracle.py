@@ -349,3 +349,66 @@ def reid_embed(pooled, weight, conv_bias, bn_scale, bn_bias, bn_mean, bn_var, ep
     if normalize:
         feat = feat / np.maximum(np.sqrt((feat * feat).sum(axis=1, keepdims=True)), 1e-12)
     return feat
+
+
+# ------------------------------------------------------------------------------------
+# k-reciprocal re-ranking — pinned against the reference's own re_ranking
+# (tests/golden/rerank_*.npz made by oracle/make_golden_rerank.py)
+# ------------------------------------------------------------------------------------
+
+
+def re_ranking(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3):
+    """reid_dataset_evaluator.py:442-519, restated step by step (float32 throughout, like the reference).
+
+    Differences from the reference text: only the first k1 + 1 columns of the argsort are kept (all it reads),
+    the inverted index covers gallery rows only (all that survives the final slice), `np.argsort(kind='stable')`
+    pins the order of exact ties (the reference's default sort leaves it undefined).
+    """
+    q_g = np.asarray(q_g_dist, dtype=np.float32)
+    nq, ng = q_g.shape
+    m = np.concatenate([np.concatenate([np.asarray(q_q_dist, np.float32), q_g], axis=1),
+                        np.concatenate([q_g.T, np.asarray(g_g_dist, np.float32)], axis=1)], axis=0)      # :447-452
+    m = np.power(m, 2).astype(np.float32)                                                                # :453
+    od = np.transpose(1. * m / np.max(m, axis=0)).astype(np.float32)                                     # :454
+    n = nq + ng
+    rank = np.argsort(od, axis=1, kind="stable")[:, :k1 + 1].astype(np.int32)                            # :456
+    kh = int(np.around(k1 / 2.)) + 1
+    rows = []                                            # sparse V: (indices ascending, float32 values) per image
+    for i in range(n):
+        fwd = rank[i, :k1 + 1]
+        back = rank[fwd, :k1 + 1]
+        kr = fwd[np.where(back == i)[0]]                                                                 # :463-466
+        exp = kr
+        for cand in kr:
+            cf = rank[cand, :kh]
+            cb = rank[cf, :kh]
+            ck = cf[np.where(cb == cand)[0]]
+            if len(np.intersect1d(ck, kr)) > 2. / 3 * len(ck):                                           # :477-481
+                exp = np.append(exp, ck)
+        exp = np.unique(exp)                                                                             # :485
+        w = np.exp(-od[i, exp])                                                                          # :486
+        rows.append((exp.astype(np.int64), (1. * w / np.sum(w)).astype(np.float32)))                     # :487
+    if k2 != 1:                                                                                          # :489-494
+        dense = np.zeros((n, n), dtype=np.float32)
+        for i, (idx, val) in enumerate(rows):
+            dense[i, idx] = val
+        qe = np.zeros_like(dense)
+        for i in range(n):
+            qe[i, :] = np.mean(dense[rank[i, :k2], :], axis=0)
+        dense = qe
+    else:
+        dense = np.zeros((n, n), dtype=np.float32)
+        for i, (idx, val) in enumerate(rows):
+            dense[i, idx] = val
+    inv = [np.where(dense[nq:, c] != 0)[0] for c in range(n)]                                            # :496-498 (gallery rows)
+    out = np.zeros((nq, ng), dtype=np.float32)
+    lam = np.float32(lambda_value)
+    for i in range(nq):                                                                                  # :502-509
+        temp = np.zeros(ng, dtype=np.float32)
+        nz = np.where(dense[i, :] != 0)[0]
+        for c in nz:
+            r = inv[c]
+            temp[r] = temp[r] + np.minimum(dense[i, c], dense[nq + r, c])
+        jac = 1 - temp / (2. - temp)
+        out[i] = jac * (1 - lambda_value) + od[i, nq:] * lambda_value                                    # :511-512
+    return out.astype(np.float32)

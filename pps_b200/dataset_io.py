@@ -53,6 +53,7 @@ def main(argv=None):
     ap.add_argument("--features", required=True, help="features.npy written by the reference's test engine")
     ap.add_argument("--annotations", required=True, help="COCO-style json of the test split (with per-annotation 'mark')")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x1", "bf16x3", "bf16x6"])
+    ap.add_argument("--rerank", action="store_true", help="k-reciprocal re-ranking (the reference's cfg.REID.RERANK)")
     ap.add_argument("--output", default=None, help="write the result dict as json here")
     args = ap.parse_args(argv)
     from . import evaluator
@@ -60,7 +61,7 @@ def main(argv=None):
     feats = load_features(args.features)
     if feats.shape[0] != len(ds.get_roidb()):
         raise RuntimeError("%d feature rows but %d images in %s" % (feats.shape[0], len(ds.get_roidb()), args.annotations))
-    result = evaluator.evaluate(ds, feats, None, precision=args.precision, verbose=True)
+    result = evaluator.evaluate(ds, feats, None, precision=args.precision, verbose=True, to_re_rank=args.rerank)
     res = evaluator.reid_results(result, ds.name)
     if args.output:
         with open(args.output, "w") as f:

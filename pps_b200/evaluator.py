@@ -894,11 +894,13 @@ def get_info(entry):
     return parse_im_name(im_name, "id"), parse_im_name(im_name, "cam"), im_name, entry["mark"], entry["image"]
 
 
-def evaluate_arrays(all_feats, ids, cams, marks, precision: str = DEFAULT_PRECISION, verbose: bool = False):
-    """The body of ``evaluate`` after the roidb has been flattened to arrays (:57-159, :209).
+def evaluate_arrays(all_feats, ids, cams, marks, precision: str = DEFAULT_PRECISION, verbose: bool = False,
+                    to_re_rank: bool = False):
+    """The body of ``evaluate`` after the roidb has been flattened to arrays (:57-209).
 
     marks: 0 = query, 1 = gallery, 2 = multi-query (json_dataset.py:149,188-189).
-    Returns (mAP, cmc_scores[10], mq_mAP, mq_cmc_scores) like the reference.
+    Returns (mAP, cmc_scores[10], mq_mAP, mq_cmc_scores) like the reference; with ``to_re_rank`` (the reference's
+    ``cfg.REID.RERANK``, :30) these are the scores of the k-reciprocal re-ranked distances (:161-207), as there.
     """
     torch = _torch()
     ids, cams, marks = _ids64(ids, "ids"), _ids64(cams, "cams"), _ids64(marks, "marks")
@@ -943,11 +945,30 @@ def evaluate_arrays(all_feats, ids, cams, marks, precision: str = DEFAULT_PRECIS
         if verbose:
             print("{:<30}".format("Multi Query:"), end="")
             print_scores(mq_mAP, mq_cmc_scores)
+    if to_re_rank:
+        from . import rerank as _rerank
+
+        def rerank_score(qf, query_ids, query_cams):
+            d = _rerank.re_ranking_from_features(qf, gf, precision=precision)          # :165-171
+            res = rank_distmat(d, query_ids, ids[g_inds], query_cams, cams[g_inds])
+            return res.mean_ap(), res.cmc(topk=10, first_match_break=True)             # :174-175
+
+        mAP, cmc_scores = rerank_score(feat_dev[qsel.to(feat_dev.device)], ids[q_inds], cams[q_inds])
+        if verbose:
+            print("{:<30}".format("Re-ranked Single Query:"), end="")
+            print_scores(mAP, cmc_scores)
+        if np.any(mq_inds):
+            mq_mAP, mq_cmc_scores = rerank_score(pooled, np.array([k[0] for k in keys]), np.array([k[1] for k in keys]))
+            if verbose:
+                print("{:<30}".format("Re-ranked Multi Query:"), end="")
+                print_scores(mq_mAP, mq_cmc_scores)
     return mAP, cmc_scores, mq_mAP, mq_cmc_scores
 
 
-def evaluate(json_dataset, all_feats, output_dir=None, precision: str = DEFAULT_PRECISION, verbose: bool = True):
-    """reid_dataset_evaluator.py:29-209 (re-ranking, :161-207, is not part of this build).
+def evaluate(json_dataset, all_feats, output_dir=None, precision: str = DEFAULT_PRECISION, verbose: bool = True,
+             to_re_rank: bool = False):
+    """reid_dataset_evaluator.py:29-209.  ``to_re_rank`` is the reference's ``cfg.REID.RERANK`` (:30; there it
+    defaults to True through the config, here the caller passes it).
 
     ``json_dataset`` only needs ``get_roidb(gt=True)`` returning entries with 'image' and 'mark'.
     """
@@ -958,7 +979,7 @@ def evaluate(json_dataset, all_feats, output_dir=None, precision: str = DEFAULT_
         ids.append(pid)
         cams.append(cam)
         marks.append(mark)
-    return evaluate_arrays(all_feats, np.asarray(ids), np.asarray(cams), np.asarray(marks), precision, verbose)
+    return evaluate_arrays(all_feats, np.asarray(ids), np.asarray(cams), np.asarray(marks), precision, verbose, to_re_rank)
 
 
 def reid_results(coco_eval, name="reid"):

@@ -102,3 +102,29 @@ def test_oracle_against_live_reference():
     np.testing.assert_array_equal(O.compute_dist(d["q"], d["g"]), dist_ref)
     assert O.mean_ap(dist_ref, **ids) == map_ref
     np.testing.assert_array_equal(O.cmc(dist_ref, topk=10, first_match_break=True, **ids), cmc_ref)
+
+
+RERANK_CASES = ["rerank_small", "rerank_tiny", "rerank_wide"]
+
+
+@pytest.mark.parametrize("name", RERANK_CASES)
+def test_re_ranking_restatement_matches_reference_fixture(golden, name):
+    """oracle.re_ranking == the reference's re_ranking (reid_dataset_evaluator.py:442-519) bit for bit, for the
+    default parameters and for k1=7, k2=1 (no query expansion), lambda=0.5."""
+    d = golden(name)
+    np.testing.assert_array_equal(O.re_ranking(d["q_g"], d["q_q"], d["g_g"]), d["rerank"])
+    np.testing.assert_array_equal(O.re_ranking(d["q_g"], d["q_q"], d["g_g"], k1=7, k2=1, lambda_value=0.5),
+                                  d["rerank_k7_k2_1"])
+    ids = dict(query_ids=d["qid"], gallery_ids=d["gid"], query_cams=d["qcam"], gallery_cams=d["gcam"])
+    assert abs(O.mean_ap(d["rerank"], **ids) - float(d["mAP"])) < 1e-12
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs /root/reference (authoring container)")
+def test_re_ranking_restatement_matches_live_reference():
+    from pps_b200 import synthetic
+    ref = ref_loader.load()
+    d = synthetic.make_reid_set(nq=25, ng=150, dim=48, n_ids=8, n_cams=3, n_distractors=10, sigma=2.5, seed=31)
+    with contextlib.redirect_stdout(io.StringIO()):
+        q_g, q_q, g_g = (ref.compute_dist(a, b) for a, b in ((d["q"], d["g"]), (d["q"], d["q"]), (d["g"], d["g"])))
+        want = ref.re_ranking(q_g, q_q, g_g, k1=12, k2=4, lambda_value=0.2)
+    np.testing.assert_array_equal(O.re_ranking(q_g, q_q, g_g, k1=12, k2=4, lambda_value=0.2), want)
