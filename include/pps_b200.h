@@ -73,6 +73,14 @@ int pps_pool_fwd(const float* x, int N, int C, int H, int W,
                  float* y, long long y_stride_n, long long y_stride_k,
                  void* stream);
 
+/* same pooling, written straight into the bf16 operand planes pps_embed_tc consumes: output k of image n is row
+ * k*N + n of out_planes [planes][K*N][pps_kpad(C)] (the [K, N, C] layout, split like pps_split_rows splits it), so the
+ * fp32 pooled intermediate and its split pass never touch HBM. */
+int pps_pool_planes_fwd(const float* x, int N, int C, int H, int W,
+                        int n_parts, const int* split, int mode,
+                        const int* combos, int n_combos,
+                        void* out_planes, int planes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Part 2a — operand preparation for the tensor-core distance.
  *

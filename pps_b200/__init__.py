@@ -7,7 +7,7 @@ from .pooling import (ReIDPoolCfg, add_pps_part_head, add_pps_part_head_, blob_n
                       pps_pool, pyramid_combs, uniform_partition_split)
 from .evaluator import (PairLists, RankEngine, RankResult, cmc, compute_dist, evaluate, evaluate_arrays, evaluate_host, mean_ap,
                         rank_distmat, rank_eval, reid_results)
-from .embedding import ReidEmbedHead, add_reid_outputs, fold_bn, l2_normalize_rows
+from .embedding import ReidEmbedHead, add_reid_outputs, embed_maps, fold_bn, l2_normalize_rows
 from .rerank import re_ranking, re_ranking_from_features
 
 __all__ = [
@@ -15,7 +15,7 @@ __all__ = [
     "pps_pool", "pyramid_combs", "uniform_partition_split",
     "PairLists", "RankEngine", "RankResult", "cmc", "compute_dist", "evaluate", "evaluate_arrays", "evaluate_host", "mean_ap",
     "rank_distmat", "rank_eval", "reid_results",
-    "ReidEmbedHead", "add_reid_outputs", "fold_bn", "l2_normalize_rows",
+    "ReidEmbedHead", "add_reid_outputs", "embed_maps", "fold_bn", "l2_normalize_rows",
     "re_ranking", "re_ranking_from_features",
 ]
 __version__ = "0.1.0"

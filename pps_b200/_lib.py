@@ -56,6 +56,7 @@ SIGNATURES = {
     "pps_strerror": (C.c_char_p, [_i]),
     "pps_last_cuda_error": (C.c_char_p, []),
     "pps_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i), _i, _vp, _ll, _ll, _vp]),
+    "pps_pool_planes_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i), _i, _vp, _i, _vp]),
     "pps_kpad": (_i, [_i]),
     "pps_split_bytes": (_ll, [_ll, _i, _i]),
     "pps_split_rows": (_i, [_vp, _i, _ll, _i, _ll, _i, _vp, _vp, _vp]),

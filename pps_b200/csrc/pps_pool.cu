@@ -27,6 +27,7 @@ constexpr int kStageBytes = 32 * 1024;   // bytes per ring slot
 constexpr int kConsumerWarps = 8;
 constexpr int kPoolThreads = 32 * (1 + kConsumerWarps);
 constexpr int kMaxComboList = 512;
+constexpr int kPoolPlanesOut = 2;       // template MODE bit: write bf16 operand planes instead of fp32 values
 
 struct PoolArgs {
   const float* x;
@@ -37,6 +38,12 @@ struct PoolArgs {
   int use_list;         // 1: masks come from combos[]
   int planes_per_stage;
   long long ysn, ysk;
+  // operand-plane output (pps_pool_planes_fwd): instead of fp32 values, write the bf16 residual planes the tensor-core
+  // embedding consumes (plane p = bf16(v - sum of the planes before it), as split_rows_kernel does), same element
+  // offsets, plane p at y_planes + p * plane_stride
+  __nv_bfloat16* y_planes;
+  int out_planes;
+  long long plane_stride;
   int row0[PPS_POOL_MAX_PARTS + 1];
   float inv_cnt[PPS_POOL_MAX_PARTS + 1];   // 1.0f / k  (Caffe2 Mean scales the sum by 1.0f/InputSize())
   int combos[kMaxComboList];
@@ -48,17 +55,18 @@ struct PoolArgs {
 // Caffe2 Mean (sum in input order, then one multiply by 1.0f / count).
 template <int NP, int MODE>
 __device__ __forceinline__ void combine_unit(const PoolArgs& a, const float* pavg, const float* pmax, int cw,
-                                             int nwarps, int lane, int nch, float* ybase) {
+                                             int nwarps, int lane, int nch, long long yoff) {
+  float* ybase = a.y + yoff;
   float av[NP], mv[NP];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     av[j] = pavg[j * kCB + lane];
-    mv[j] = MODE == PPS_POOL_MAX_AVE ? pmax[j * kCB + lane] : 0.f;
+    mv[j] = (MODE & 1) == PPS_POOL_MAX_AVE ? pmax[j * kCB + lane] : 0.f;
   }
   for (int idx = cw; idx < a.n_out; idx += nwarps) {
     const int m = a.use_list ? a.combos[idx] : idx + 1;
     float val;
-    if (MODE == PPS_POOL_MAX_AVE) {
+    if ((MODE & 1) == PPS_POOL_MAX_AVE) {
       float s = 0.f, mx = -FLT_MAX;
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
@@ -74,7 +82,17 @@ __device__ __forceinline__ void combine_unit(const PoolArgs& a, const float* pav
       for (int j = 0; j < NP; ++j) mx = ((m >> j) & 1) ? fmaxf(mx, av[j]) : mx;
       val = mx;
     }
-    if (lane < nch) st_stream_f32(ybase + (long long)idx * a.ysk + lane, val);
+    if (!(MODE & kPoolPlanesOut)) {
+      if (lane < nch) st_stream_f32(ybase + (long long)idx * a.ysk + lane, val);
+    } else if (lane < nch) {
+      float r = val;
+      __nv_bfloat16* dst = a.y_planes + yoff + (long long)idx * a.ysk + lane;
+      for (int p = 0; p < a.out_planes; ++p) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(r);
+        dst[(long long)p * a.plane_stride] = h;
+        r -= __bfloat162float(h);                          // exact in fp32
+      }
+    }
   }
 }
 
@@ -160,15 +178,14 @@ __global__ void __launch_bounds__(kPoolThreads, 2) pool_tma_kernel(const __grid_
           }
           const float sum = (acc.x + acc.y) + (acc.z + acc.w);
           ua[j * kCB + p0 + pl] = __fdiv_rn(sum, (float)((r1 - r0) * a.W));
-          if (MODE == PPS_POOL_MAX_AVE) um[j * kCB + p0 + pl] = fmaxf(fmaxf(mx.x, mx.y), fmaxf(mx.z, mx.w));
+          if ((MODE & 1) == PPS_POOL_MAX_AVE) um[j * kCB + p0 + pl] = fmaxf(fmaxf(mx.x, mx.y), fmaxf(mx.z, mx.w));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);   // slot may be refilled
       }
       // all strip results of this unit are in ua/um
       asm volatile("bar.sync 1, %0;" ::"r"(32 * kConsumerWarps) : "memory");
-      float* ybase = a.y + n * a.ysn + c0;
-      combine_unit<NP, MODE>(a, ua, um, cw, kConsumerWarps, lane, nch, ybase);
+      combine_unit<NP, MODE>(a, ua, um, cw, kConsumerWarps, lane, nch, n * a.ysn + c0);
       ubuf ^= 1;
     }
   }
@@ -210,8 +227,7 @@ __global__ void __launch_bounds__(256) pool_generic_kernel(const __grid_constant
     }
   }
   __syncthreads();
-  float* ybase = a.y + n * a.ysn + c0;
-  combine_unit<NP, MODE>(a, pavg, pmax, warp, 8, lane, nch, ybase);
+  combine_unit<NP, MODE>(a, pavg, pmax, warp, 8, lane, nch, n * a.ysn + c0);
 }
 
 template <int NP, int MODE>
@@ -256,9 +272,9 @@ static int dispatch_parts(const PoolArgs& a, bool fast, long long units, size_t 
 
 using namespace pps;
 
-extern "C" int pps_pool_fwd(const float* x, int N, int C, int H, int W, int n_parts, const int* split, int mode,
-                            const int* combos, int n_combos, float* y, long long y_stride_n, long long y_stride_k,
-                            void* stream) {
+static int pool_launch(const float* x, int N, int C, int H, int W, int n_parts, const int* split, int mode,
+                       const int* combos, int n_combos, float* y, void* y_planes, int out_planes, long long plane_stride,
+                       long long y_stride_n, long long y_stride_k, void* stream) {
   if (N < 0 || C <= 0 || H <= 0 || W <= 0 || !split) return PPS_ERR_INVALID_ARG;
   if (mode != PPS_POOL_AVG_MAX && mode != PPS_POOL_MAX_AVE) return PPS_ERR_INVALID_ARG;
   if (n_parts < 1 || n_parts > PPS_POOL_MAX_PARTS) return PPS_ERR_SHAPE;
@@ -286,8 +302,9 @@ extern "C" int pps_pool_fwd(const float* x, int N, int C, int H, int W, int n_pa
     a.n_out = full_mask;
   }
   if (N == 0) return PPS_OK;
-  if (!x || !y) return PPS_ERR_INVALID_ARG;
+  if (!x || (!y && !y_planes)) return PPS_ERR_INVALID_ARG;
   a.x = x; a.y = y; a.N = N; a.C = C; a.H = H; a.W = W;
+  a.y_planes = static_cast<__nv_bfloat16*>(y_planes); a.out_planes = y_planes ? out_planes : 0; a.plane_stride = plane_stride;
   a.n_parts = n_parts; a.mode = mode;
   a.ysn = y_stride_n; a.ysk = y_stride_k;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -300,6 +317,33 @@ extern "C" int pps_pool_fwd(const float* x, int N, int C, int H, int W, int n_pa
   a.planes_per_stage = fast ? (int)((kStageBytes / plane_bytes) < kCB ? (kStageBytes / plane_bytes) : kCB) : 0;
   const size_t smem = (size_t)kPoolStages * kStageBytes + 4 * PPS_POOL_MAX_PARTS * kCB * sizeof(float) +
                       2 * kPoolStages * sizeof(uint64_t);
+  if (a.out_planes)
+    return mode == PPS_POOL_MAX_AVE ? dispatch_parts<PPS_POOL_MAX_AVE | kPoolPlanesOut>(a, fast, units, smem, st)
+                                    : dispatch_parts<PPS_POOL_AVG_MAX | kPoolPlanesOut>(a, fast, units, smem, st);
   return mode == PPS_POOL_MAX_AVE ? dispatch_parts<PPS_POOL_MAX_AVE>(a, fast, units, smem, st)
                                   : dispatch_parts<PPS_POOL_AVG_MAX>(a, fast, units, smem, st);
+}
+
+extern "C" int pps_pool_fwd(const float* x, int N, int C, int H, int W, int n_parts, const int* split, int mode,
+                            const int* combos, int n_combos, float* y, long long y_stride_n, long long y_stride_k,
+                            void* stream) {
+  return pool_launch(x, N, C, H, W, n_parts, split, mode, combos, n_combos, y, nullptr, 0, 0, y_stride_n, y_stride_k, stream);
+}
+
+// Pooling straight into the operand planes of the tensor-core embedding (pps_embed_tc): output k of image n is row
+// k * N + n of a [planes][K * N][kpad] bf16 buffer, i.e. the [K, N, C] layout already split the way pps_split_rows
+// would split it - the fp32 pooled intermediate and its split pass never touch HBM.
+extern "C" int pps_pool_planes_fwd(const float* x, int N, int C, int H, int W, int n_parts, const int* split, int mode,
+                                   const int* combos, int n_combos, void* out_planes, int planes, void* stream) {
+  if (planes < 1 || planes > 3) return PPS_ERR_INVALID_ARG;
+  if (N > 0 && !out_planes) return PPS_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(out_planes) & 15u) return PPS_ERR_ALIGN;
+  if (n_parts < 1 || n_parts > PPS_POOL_MAX_PARTS) return PPS_ERR_SHAPE;
+  const int kpad = pps_kpad(C);
+  const long long K = combos ? n_combos : ((1LL << n_parts) - 1);
+  const long long rows = K * (long long)N;
+  if (kpad != C && rows > 0)       // K padding of every row must read as zero
+    PPS_CUDA_TRY(cudaMemsetAsync(out_planes, 0, (size_t)planes * rows * kpad * 2, static_cast<cudaStream_t>(stream)));
+  return pool_launch(x, N, C, H, W, n_parts, split, mode, combos, n_combos, nullptr, out_planes, planes, rows * kpad,
+                     (long long)kpad, (long long)N * kpad, stream);
 }

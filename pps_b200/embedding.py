@@ -89,6 +89,49 @@ class ReidEmbedHead:
         return out
 
 
+def embed_maps(head: "ReidEmbedHead", x, n_parts: int = 6, split=None, mode="max_ave", combos=None,
+               normalize: bool = True, out=None):
+    """conv5 maps [N, C, H, W] -> normalised ``reid_feature_concat`` [N, K*E] without the fp32 pooled intermediate:
+    the pooling kernel writes the bf16 operand planes of the embedding product directly (``pps_pool_planes_fwd``),
+    then one grouped tcgen05 launch (``pps_embed_tc``) and the row normalisation.  Same result as
+    ``head(pps_pool(x, layout='knc'))`` bit for bit (the planes are the same numbers either way)."""
+    import ctypes as C
+    from . import pooling
+    torch = _torch()
+    lib = _lib.load()
+    pooling._check_input(x)
+    n, c, h, _ = (int(v) for v in x.shape)
+    if c != head.C:
+        raise RuntimeError("embed_maps: maps have %d channels, the head expects %d" % (c, head.C))
+    if split is None:
+        split = [h // n_parts] * n_parts
+    k_out = (1 << n_parts) - 1 if combos is None else len(combos)
+    if k_out != head.K:
+        raise RuntimeError("embed_maps: %d combinations pooled, the head has %d branches" % (k_out, head.K))
+    feat_dim = head.K * head.E
+    if out is None:
+        out = torch.empty((n, feat_dim), dtype=torch.float32, device=x.device)
+    elif tuple(out.shape) != (n, feat_dim) or out.dtype != torch.float32 or out.stride(1) != 1:
+        raise RuntimeError("out: expected a float32 [N, K*E] tensor with unit column stride")
+    if n == 0:
+        return out
+    planes_n = head.w.planes_n
+    split_arr = (C.c_int * n_parts)(*[int(v) for v in split])
+    combos_arr, n_combos = (None, 0) if combos is None else ((C.c_int * len(combos))(*[int(m) for m in combos]), len(combos))
+    with torch.cuda.device(x.device):
+        nbytes = int(lib.pps_split_bytes(head.K * n, head.C, planes_n))
+        planes = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.check(lib.pps_pool_planes_fwd(_lib.ptr(x), n, c, h, int(x.shape[3]), n_parts, split_arr, pooling._mode_code(mode),
+                                           combos_arr, n_combos, _lib.ptr(planes), planes_n, _lib.stream_ptr()),
+                   "pps_pool_planes_fwd")
+        _lib.check(lib.pps_embed_tc(_lib.ptr(planes), planes_n, n, _lib.ptr(head.w.planes), head.w.planes_n, head.E, head.K,
+                                    head.C, _lib.ptr(head.alpha), _lib.ptr(head.beta), head.prec, _lib.ptr(out),
+                                    int(out.stride(0)), _lib.stream_ptr()), "pps_embed_tc")
+        if normalize:
+            l2_normalize_rows(out, out=out)
+    return out
+
+
 def l2_normalize_rows(x, out=None):
     """Caffe2 ``Normalize(axis=1)``: x / max(|x|_2, 1e-12) per row (triplet_loss.py:18)."""
     torch = _torch()

@@ -79,6 +79,25 @@ def test_pool_then_embed_pipeline(torch):
     np.testing.assert_allclose(feat, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
 
 
+@pytest.mark.parametrize("shape,n_parts,split,mode", [((6, 256, 24, 8), 6, None, "max_ave"), ((3, 128, 24, 8), 5, [5, 5, 4, 5, 5], "avg_max"),
+                                                     ((2, 100, 12, 4), 3, None, "max_ave")])
+def test_pool_into_planes_equals_pool_then_split(torch, shape, n_parts, split, mode):
+    """embed_maps (pooling kernel writes the bf16 operand planes itself) == pps_pool -> split -> embed, bit for bit;
+    C = 100 exercises the zero K padding of the planes."""
+    import pps_b200
+    rs = np.random.RandomState(shape[0])
+    x = torch.from_numpy(np.maximum(rs.randn(*shape), 0).astype(np.float32)).cuda()
+    K = (1 << n_parts) - 1
+    w, p = _params(K, 128, shape[1], seed=3)
+    head = _head(w, p)
+    pooled = pps_b200.pps_pool(x, n_parts=n_parts, split=split, mode=mode, layout="knc")
+    want = head(pooled, normalize=True)
+    got = pps_b200.embed_maps(head, x, n_parts=n_parts, split=split, mode=mode, normalize=True)
+    assert torch.equal(got, want)
+    ref = O.reid_embed(np.transpose(O.pps_pool(x.cpu().numpy(), n_parts, split=split, mode=mode), (1, 0, 2)), w, normalize=True, **p)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+
+
 def test_normalize_rows_edge_cases(torch):
     import pps_b200
     x = torch.zeros((3, 10), device="cuda")
