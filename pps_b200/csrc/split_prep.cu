@@ -27,11 +27,28 @@ __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_kernel(const void
   if constexpr (F16IN) {
     const __half* src = reinterpret_cast<const __half*>(feats) + srow * ld;
     __half* dst = out_planes ? reinterpret_cast<__half*>(out_planes) + row * (long long)kpad : nullptr;
-    for (int k = lane; k < kpad; k += 32) {
-      const __half h = k < dim ? src[k] : __float2half(0.f);
-      const float v = __half2float(h);
-      acc += (double)v * (double)v;
-      if (dst) dst[k] = h;
+    const bool vec8 = ((dim & 7) == 0) && ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15u) == 0);
+    if (vec8) {
+      // 128-bit loads: 8 halves per lane and step; the K padding (kpad - dim < 64 halves) is zero-filled below
+      for (int k = lane * 8; k < dim; k += 256) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + k);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h2[e]);
+          acc += (double)(f.x * f.x) + (double)(f.y * f.y);   // squares of fp16 values are exact in fp32
+        }
+        if (dst) *reinterpret_cast<uint4*>(dst + k) = u;
+      }
+      if (dst)
+        for (int k = dim + lane; k < kpad; k += 32) dst[k] = __float2half(0.f);
+    } else {
+      for (int k = lane; k < kpad; k += 32) {
+        const __half h = k < dim ? src[k] : __float2half(0.f);
+        const float v = __half2float(h);
+        acc += (double)v * (double)v;
+        if (dst) dst[k] = h;
+      }
     }
   } else {
     const float* src = reinterpret_cast<const float*>(feats) + srow * ld;

@@ -555,6 +555,7 @@ class RankEngine:
         self._side = None
         self.h2d_bytes = 0
         self.compact_thresholds = True   # multi-chunk galleries: thresholds from the compacted same-id gallery
+        self._g_ptr, self._g_keepalive = None, None
         self.fused_rank = False          # counters in the epilogue of the distance kernel (no distance block written):
                                          # bit-identical, saves the block's memory, but measured slower than block +
                                          # count kernel on B200 (the MMA mainloop already saturates shared-memory bandwidth)
@@ -650,9 +651,19 @@ class RankEngine:
         return RankResult(ap, valid, first, None, None, ti, td)
 
     def _split(self, feats, rows, planes_buf, sq_buf):
+        if planes_buf is self.g_planes:
+            self._g_ptr = _lib.ptr(self.g_planes)
         if rows:
             if feats.stride(1) != 1:
                 feats = feats.contiguous()
+            if (planes_buf is self.g_planes and self.is_f16 and self.dim % 64 == 0 and int(feats.stride(0)) == self.dim
+                    and feats.data_ptr() % 16 == 0):
+                # fp16 rows that already are a K-major operand plane: no copy, only the row norms
+                self._g_ptr = _lib.ptr(feats)
+                self._g_keepalive = feats
+                _lib.check(self.lib.pps_row_sqnorm(_lib.ptr(feats), self.in_code, rows, self.dim, self.dim, _lib.ptr(sq_buf),
+                                                   _lib.stream_ptr()), "pps_row_sqnorm")
+                return
             _lib.check(self.lib.pps_split_rows(_lib.ptr(feats), self.in_code, rows, self.dim, int(feats.stride(0)),
                                                self.planes, _lib.ptr(planes_buf), _lib.ptr(sq_buf), _lib.stream_ptr()),
                        "pps_split_rows")
@@ -678,7 +689,7 @@ class RankEngine:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
             _lib.check(lib.pps_dist_rank_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), nq, self.planes, 0,
-                                            _lib.ptr(self.g_planes), _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
+                                            self._g_ptr, _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
                                             self.prec, 0, self.offset + r0, p_cap, _lib.ptr(thr), _lib.ptr(cnt),
                                             _lib.ptr(dstar), _lib.ptr(gstar), _lib.ptr(cnt_first), s), "pps_dist_rank_tc")
             if ev is not None:
@@ -714,6 +725,7 @@ class RankEngine:
             g = g.contiguous()
         for c0 in range(0, n_rows, self.chunk):
             rows = min(self.chunk, n_rows - c0)
+            self._g_ptr = _lib.ptr(self.g_planes)
             _lib.check(lib.pps_split_rows_gather(_lib.ptr(g), self.in_code, _lib.ptr(self._gp_rows[c0:]), self.offset, rows,
                                                  self.dim, int(g.stride(0)), self.planes, _lib.ptr(self.g_planes),
                                                  _lib.ptr(self.g_sq), s), "pps_split_rows_gather")
@@ -728,7 +740,7 @@ class RankEngine:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         _lib.check(self.lib.pps_dist_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), self.nq, self.planes, 0,
-                                        _lib.ptr(self.g_planes), _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
+                                        self._g_ptr, _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
                                         self.prec, DIST_KERNEL_FLAGS, _lib.ptr(self.block), self.ldd,
                                         _lib.stream_ptr()), "pps_dist_tc")
         if ev is not None:
