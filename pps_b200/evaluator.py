@@ -603,6 +603,22 @@ class RankEngine:
         if sharded:
             import torch.distributed as dist_mod
             world, rank = dist_mod.get_world_size(self.group), dist_mod.get_rank(self.group)
+        if not sharded:
+            # one C call: begin -> thresholds -> count -> end (no exchange points needed)
+            out_map = C.c_double(0.0)
+            out_cmc = np.zeros(10, dtype=np.float64)
+            ap = np.zeros(nq, dtype=np.float64)
+            valid = np.zeros(nq, dtype=np.uint8)
+            first = np.zeros(nq, dtype=np.int32)
+            ti = np.zeros((nq, topk), dtype=np.int32) if topk else None
+            td = np.zeros((nq, topk), dtype=np.float32) if topk else None
+            rc = self.lib.pps_evaluate_device_ctx(ctx, _lib.ptr(q), nq, _lib.ptr(g), self.ngl, self.dim, _lib.ptr(p.qid),
+                                                  _lib.ptr(p.qcam), _lib.ptr(p.gid), _lib.ptr(p.gcam), self.prec, 10, topk, s,
+                                                  C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc), _lib.ptr(ap),
+                                                  _lib.ptr(valid), _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
+            if rc != _lib.PPS_ERR_NO_VALID_QUERY:
+                _lib.check(rc, "pps_evaluate_device_ctx")
+            return RankResult(ap, valid, first, None, None, ti, td)
         gid_l = p.gid[self.offset:self.offset + self.ngl] if sharded else p.gid
         gcam_l = p.gcam[self.offset:self.offset + self.ngl] if sharded else p.gcam
         d_lc = C.c_void_p(0)
