@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--check-queries", type=int, default=8)
     ap.add_argument("--max-block-gib", type=float, default=8.0)
+    ap.add_argument("--sigma", type=float, default=4.0, help="noise of the identity model (4: hard, mAP ~0.01-0.05 at this scale)")
     ap.add_argument("--two-sweep", action="store_true", help="thresholds from a full first sweep (the old form)")
     a = ap.parse_args()
 
@@ -75,7 +76,7 @@ def main():
         ids_t = torch.from_numpy(ids_np).to(dev)
         for r0 in range(0, len(ids_np), 65536):
             sl = ids_t[r0:r0 + 65536]
-            x = centers[sl] + 4.0 * torch.randn((len(sl), a.dim), device=dev, generator=g)
+            x = centers[sl] + a.sigma * torch.randn((len(sl), a.dim), device=dev, generator=g)
             x = x / x.norm(dim=1, keepdim=True)
             out[r0:r0 + 65536] = x.to(tdt)
         return out
@@ -157,7 +158,7 @@ def main():
     if rank == 0:
         pairs = float(a.nq) * float(a.ng)
         flops = 2.0 * a.dim * pairs
-        line = {"tool": "large_gallery_bench", "n_gpus": world, "nq": a.nq, "ng": a.ng, "dim": a.dim, "dtype": a.dtype,
+        line = {"tool": "large_gallery_bench", "n_gpus": world, "nq": a.nq, "ng": a.ng, "dim": a.dim, "dtype": a.dtype, "sigma": a.sigma,
                 "precision": "f16x1" if a.dtype == "fp16" else a.precision, "topk": a.topk,
                 "rows_per_gpu": ngl, "chunks_per_gpu": eng.n_chunks, "chunk_rows": eng.chunk,
                 "threshold_pass": "two-sweep" if a.two_sweep else "compacted same-id rows (%d on rank 0)" % eng.threshold_rows,
