@@ -144,7 +144,7 @@ __device__ __noinline__ void topk_admit(float d, unsigned long long gcol, unsign
 constexpr int kCandC = 2048;
 
 template <bool TOPK>
-__global__ void __launch_bounds__(kCntThreads, 8) rank_count_kernel(const float* __restrict__ dist, long long ldd,
+__global__ void __launch_bounds__(kCntThreads, TOPK ? 8 : 16) rank_count_kernel(const float* __restrict__ dist, long long ldd,
                                                                      long long ncols, long long col0, long long seg,
                                                                      const int32_t* __restrict__ pair_off,
                                                                      const int32_t* __restrict__ pair_g,
