@@ -54,7 +54,41 @@ __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_kernel(const void
     const float* src = reinterpret_cast<const float*>(feats) + srow * ld;
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out_planes);
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15u) == 0);
-    for (int k = lane * 4; k < kpad; k += 128) {
+    // four 128-bit loads of the row in flight per lane before any is consumed (the rows are streamed once)
+    int kfast = lane * 4;
+    if (vec) {
+      for (; kfast + 3 * 128 + 3 < dim; kfast += 4 * 128) {
+        float4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] = ld_stream_f4(reinterpret_cast<const float4*>(src + kfast + u * 128));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = kfast + u * 128;
+          const float v[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+          __nv_bfloat16 p[3][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc += (double)v[e] * (double)v[e];
+            float r = v[e];
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl) {
+              p[pl][e] = __float2bfloat16_rn(r);
+              r -= __bfloat162float(p[pl][e]);   // exact in fp32
+            }
+          }
+          if (dst) {
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl) {
+              uint2 w;
+              w.x = (uint32_t)__bfloat16_as_ushort(p[pl][0]) | ((uint32_t)__bfloat16_as_ushort(p[pl][1]) << 16);
+              w.y = (uint32_t)__bfloat16_as_ushort(p[pl][2]) | ((uint32_t)__bfloat16_as_ushort(p[pl][3]) << 16);
+              *reinterpret_cast<uint2*>(dst + pl * plane_stride + row * (long long)kpad + k) = w;
+            }
+          }
+        }
+      }
+    }
+    for (int k = kfast; k < kpad; k += 128) {
       float v[4];
       if (vec && k + 3 < dim) {
         const float4 t = ld_stream_f4(reinterpret_cast<const float4*>(src + k));
