@@ -104,28 +104,66 @@ __global__ void batch_hard_kernel(const float* __restrict__ xd, const int* __res
   hardest_of_row([r](int j) { return r[j]; }, labels, a, N, threadIdx.x & 31, ap, an, idx_p, idx_n);
 }
 
-// fused: squared distances of anchor a to every item straight from the features (anchor row in shared memory)
-__global__ void batch_hard_fused_kernel(const float* __restrict__ x, const int* __restrict__ labels, int N, int D,
-                                        float* __restrict__ ap, float* __restrict__ an, int* __restrict__ idx_p,
-                                        int* __restrict__ idx_n) {
-  extern __shared__ float srow[];                       // [warps][D]
+// fused: squared distances of 8 anchors (one per warp) to every item straight from the features, no [N, N] matrix.
+// The CTA stages a 128-wide slice of its 8 anchor rows and of 32 item rows in shared memory (coalesced loads, rows
+// padded by one word: conflict-free), thread (warp = anchor, lane = item) accumulates its pair over d in ascending
+// order - the same fmaf chain as pairwise_sqdist_kernel, so the mined values equal the two-step result.
+constexpr int kFA = 8;          // anchors per CTA
+constexpr int kFD = 128;        // feature slice
+
+__global__ void __launch_bounds__(32 * kFA) batch_hard_fused_kernel(const float* __restrict__ x, const int* __restrict__ labels,
+                                                                     int N, int D, float* __restrict__ ap,
+                                                                     float* __restrict__ an, int* __restrict__ idx_p,
+                                                                     int* __restrict__ idx_n) {
+  __shared__ float sa[kFA][kFD + 1];
+  __shared__ float sj[32][kFD + 1];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int a = blockIdx.x * (blockDim.x >> 5) + w;
-  if (a >= N) return;
-  float* xa = srow + (size_t)w * D;
-  for (int d = lane; d < D; d += 32) xa[d] = x[(long long)a * D + d];
-  __syncwarp();
-  hardest_of_row(
-      [&](int j) {
-        const float* xj = x + (long long)j * D;
-        float acc = 0.f;
-        for (int d = 0; d < D; ++d) {
-          const float sub = xa[d] - xj[d];
-          acc = fmaf(sub, sub, acc);
-        }
-        return acc;
-      },
-      labels, a, N, lane, ap, an, idx_p, idx_n);
+  const int a = blockIdx.x * kFA + w;
+  const int la = a < N ? labels[a] : 0;
+  float best_p = 0.f, best_n = FLT_MAX;          // initial values of batch_hard_op.cc:33,45
+  int ip = -1, in = -1;
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    const int j = j0 + lane;
+    float acc = 0.f;
+    for (int d0 = 0; d0 < D; d0 += kFD) {
+      const int dn = min(kFD, D - d0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < kFA * kFD; i += 32 * kFA) {
+        const int r = i / kFD, c = i % kFD, row = blockIdx.x * kFA + r;
+        sa[r][c] = (row < N && c < dn) ? x[(long long)row * D + d0 + c] : 0.f;
+      }
+      for (int i = threadIdx.x; i < 32 * kFD; i += 32 * kFA) {
+        const int r = i / kFD, c = i % kFD, row = j0 + r;
+        sj[r][c] = (row < N && c < dn) ? x[(long long)row * D + d0 + c] : 0.f;
+      }
+      __syncthreads();
+      for (int c = 0; c < dn; ++c) {
+        const float sub = sa[w][c] - sj[lane][c];
+        acc = fmaf(sub, sub, acc);
+      }
+    }
+    if (a < N && j < N) {
+      if (labels[j] == la) {
+        if (best_p < acc) { best_p = acc; ip = j; }
+      } else {
+        if (best_n > acc) { best_n = acc; in = j; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float op = __shfl_xor_sync(0xffffffffu, best_p, o), on = __shfl_xor_sync(0xffffffffu, best_n, o);
+    const int oip = __shfl_xor_sync(0xffffffffu, ip, o), oin = __shfl_xor_sync(0xffffffffu, in, o);
+    // strict compares in index order == the lowest index among equal extrema wins
+    if (oip >= 0 && (op > best_p || (op == best_p && (ip < 0 || oip < ip)))) { best_p = op; ip = oip; }
+    if (oin >= 0 && (on < best_n || (on == best_n && (in < 0 || oin < in)))) { best_n = on; in = oin; }
+  }
+  if (lane == 0 && a < N) {
+    ap[a] = best_p;
+    an[a] = best_n;
+    if (idx_p) idx_p[a] = ip;
+    if (idx_n) idx_n[a] = in;
+  }
 }
 
 __global__ void batch_hard_grad_kernel(const int* __restrict__ idx_p, const int* __restrict__ idx_n,
@@ -175,19 +213,11 @@ extern "C" int pps_batch_hard_fwd(const float* xdist, const int32_t* labels, int
 
 extern "C" int pps_batch_hard_fused_fwd(const float* x, const int32_t* labels, int N, int D, float* ap, float* an,
                                         int32_t* idx_p, int32_t* idx_n, void* stream) {
-  if (N < 0 || D <= 0 || D > 8192) return PPS_ERR_SHAPE;
+  if (N < 0 || D <= 0) return PPS_ERR_SHAPE;
   if (N == 0) return PPS_OK;
   if (!x || !labels || !ap || !an) return PPS_ERR_INVALID_ARG;
-  const size_t smem = (size_t)4 * D * sizeof(float);
-  static thread_local int configured_dev = -1;
-  int dev = 0;
-  PPS_CUDA_TRY(cudaGetDevice(&dev));
-  if (configured_dev != dev) {
-    PPS_CUDA_TRY(cudaFuncSetAttribute(batch_hard_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8192 * 4));
-    configured_dev = dev;
-  }
-  batch_hard_fused_kernel<<<(unsigned)((N + 3) / 4), 128, smem, static_cast<cudaStream_t>(stream)>>>(x, labels, N, D, ap, an,
-                                                                                                    idx_p, idx_n);
+  batch_hard_fused_kernel<<<(unsigned)((N + kFA - 1) / kFA), 32 * kFA, 0, static_cast<cudaStream_t>(stream)>>>(x, labels, N, D, ap,
+                                                                                                             an, idx_p, idx_n);
   PPS_LAUNCH_CHECK("batch_hard_fused_kernel");
   return PPS_OK;
 }
