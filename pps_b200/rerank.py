@@ -35,7 +35,11 @@ def _rerank_device(m, nq, k1, k2, lambda_value):
     rk = k1 + 1
     key = torch.empty((n, rk), dtype=torch.int64, device=dev)
     _lib.check(lib.pps_topk_init(_lib.ptr(key), n, rk, s), "pps_topk_init")
-    _lib.check(lib.pps_topk_update(_lib.ptr(od), n, n, n, 0, None, None, None, _lib.ptr(key), rk, s), "pps_topk_update")
+    # (the one-read sweep kernel with no pair lists: only its top-k half runs)
+    no_pairs = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    no_first = torch.zeros(n, dtype=torch.int32, device=dev)
+    _lib.check(lib.pps_rank_sweep(_lib.ptr(od), n, n, n, 0, _lib.ptr(no_pairs), None, None, None, 0, None, _lib.ptr(no_first),
+                                  _lib.ptr(key), rk, 0, s), "pps_rank_sweep")
     rank = torch.empty((n, rk), dtype=torch.int32, device=dev)
     _lib.check(lib.pps_topk_unpack(_lib.ptr(key), n, rk, None, _lib.ptr(rank), s), "pps_topk_unpack")
     v_idx = torch.empty((n, vcap), dtype=torch.int32, device=dev)
