@@ -474,3 +474,46 @@ def test_features_npy_cli_roundtrip(tmp_path, golden):
     r = res["split"]["ReID"]
     assert abs(r["mAP"] - float(d["mAP"])) < 1e-6 and abs(r["CMC1"] - d["cmc_fmb"][0]) < 1e-12 and r["mq_mAP"] == -1
     assert json.loads((tmp_path / "out.json").read_text())["split"]["ReID"]["CMC10"] == r["CMC10"]
+
+
+def test_new_entry_points_degenerate_inputs():
+    """Empty / tiny inputs of the large-gallery entry points: nothing launched, sane outputs, argument errors."""
+    import torch
+    from pps_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    s = _lib.stream_ptr()
+    n_out = torch.full((1,), 7, dtype=torch.int32, device=dev)
+    # pre-filter with no queries / no gallery rows -> zero candidates
+    assert lib.pps_pairs_prefilter(None, 0, None, None, 0, None, None, None, None, _lib.ptr(n_out), s) == 0
+    torch.cuda.synchronize()
+    assert int(n_out[0]) == 0
+    assert lib.pps_pairs_prefilter(None, 0, None, None, 0, None, None, None, None, None, s) == _lib.PPS_ERR_INVALID_ARG
+    # compaction with no pairs
+    n_out.fill_(7)
+    assert lib.pps_pairs_compact_rows(None, 5, None, None, None, 0, 0, 10, None, None, None, _lib.ptr(n_out), s) == 0
+    torch.cuda.synchronize()
+    assert int(n_out[0]) == 0
+    assert lib.pps_pairs_remap(None, 0, None, 0, s) == 0
+    # gather split / fused distance with zero rows are no-ops; bad table widths are rejected
+    assert lib.pps_split_rows_gather(None, _lib.DTYPE_F32, None, 0, 0, 64, 64, 2, None, None, s) == 0
+    assert lib.pps_rank_tab_elems(300, 12) == _lib.PPS_ERR_INVALID_ARG and lib.pps_rank_tab_elems(300, 72) == _lib.PPS_ERR_INVALID_ARG
+    assert lib.pps_rank_tab_elems(300, 16) == 512 * 16
+    assert lib.pps_dist_rank_tc(None, None, 0, 1, 0, None, None, 0, 1, 0, 64, _lib.PREC_BF16X3, 0, 0, 16, None, None, None, None,
+                                None, s) == 0
+    # sweep with k out of range
+    assert lib.pps_rank_sweep(None, 0, 1, 1, 0, None, None, None, None, 0, None, None, None, 0, 1, s) == _lib.PPS_ERR_INVALID_ARG
+    assert lib.pps_rank_sweep(None, 0, 0, 0, 0, None, None, None, None, 0, None, None, None, 10, 1, s) == 0
+
+
+def test_rank_eval_topk_without_any_pair():
+    """No query id occurs in the gallery: nothing to count, but the top-k sweep still has to run."""
+    import torch
+    import pps_b200
+    rs = np.random.RandomState(2)
+    q, g = rs.randn(5, 64).astype(np.float32), rs.randn(900, 64).astype(np.float32)
+    res = pps_b200.rank_eval(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), np.arange(5) + 1000, np.arange(900),
+                             np.zeros(5, np.int64), np.zeros(900, np.int64), topk=9)
+    assert res.is_valid.sum() == 0
+    d = O.compute_dist(q, g)
+    np.testing.assert_array_equal(res.topk_index, np.argsort(d, axis=1, kind="stable")[:, :9])

@@ -84,3 +84,27 @@ def test_re_ranking_larger_set_runs_and_is_consistent():
     res = pps_b200.rank_distmat(a, d["qid"], d["gid"], d["qcam"], d["gcam"])
     plain = pps_b200.rank_eval(q, g, d["qid"], d["gid"], d["qcam"], d["gcam"])
     assert res.mean_ap() > plain.mean_ap()                 # re-ranking helps on this clustered synthetic set
+
+
+def test_rerank_c_abi_degenerate_inputs():
+    from pps_b200 import _lib
+    lib = _lib.load()
+    s = _lib.stream_ptr()
+    assert lib.pps_rerank_vcap() == 256
+    assert lib.pps_rerank_normalize(None, 0, 0, None, None, 0, s) == 0
+    assert lib.pps_rerank_krecip(None, 21, 0, 20, None, 0, None, None, None, s) == 0
+    assert lib.pps_rerank_krecip(None, 10, 0, 20, None, 0, None, None, None, s) == _lib.PPS_ERR_INVALID_ARG      # rank_cols < k1 + 1
+    assert lib.pps_rerank_krecip(None, 40, 0, 39, None, 0, None, None, None, s) == _lib.PPS_ERR_UNSUPPORTED      # k1 + 1 > 32
+    assert lib.pps_rerank_expand(None, 21, 0, 9, None, None, None, 2304, None, None, None, s) == _lib.PPS_ERR_INVALID_ARG
+    assert lib.pps_rerank_jaccard(None, None, None, 256, None, None, None, 0, 5, None, 5, 0.3, None, 5, s) == 0
+
+
+def test_re_ranking_no_query_expansion_and_small_k():
+    import pps_b200
+    rs = np.random.RandomState(8)
+    f = rs.randn(60, 16).astype(np.float32)
+    q, g = f[:10], f[10:]
+    mats = (O.compute_dist(q, g), O.compute_dist(q, q), O.compute_dist(g, g))
+    for k1, k2, lam in ((5, 1, 0.0), (3, 2, 1.0), (12, 3, 0.3)):
+        got = pps_b200.re_ranking(*mats, k1=k1, k2=k2, lambda_value=lam)
+        np.testing.assert_allclose(got, O.re_ranking(*mats, k1=k1, k2=k2, lambda_value=lam), rtol=2e-5, atol=2e-6)
