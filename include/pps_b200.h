@@ -317,6 +317,24 @@ int pps_rank_sweep(const float* dist, long long ldd, long long nq, long long nco
                    const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos, const float* pair_d,
                    int max_pairs_per_query, uint32_t* cnt_le, uint32_t* cnt_first,
                    uint64_t* topk_key, int k, int topk_filtered, void* stream);
+/* Top-k admission in the EPILOGUE of the distance kernel (blocks after the first of a multi-block sweep):
+ *   pps_topk_bound    tk_bound[q] = distance bits of the current k-th best of the state (all ones: unbounded),
+ *                     tk_cnt[q] = 0
+ *   pps_dist_topk_tc  pps_dist_tc (identical block) + per element one compare against tk_bound[row]; the few
+ *                     that pass are appended to tk_cand[row][tk_cap] (tk_cnt counts them, also past tk_cap)
+ *   pps_topk_merge    state + candidates -> new state (junk dropped through the pair lists), new tk_bound,
+ *                     tk_cnt = 0; *overflow = 1 if some buffer ran over (repeat the pass with pps_rank_sweep).
+ * The block is then only COUNTED (pps_rank_count), not swept for top-k as well. */
+int pps_topk_bound(const uint64_t* topk_key, long long nq, int k, uint32_t* tk_bound, uint32_t* tk_cnt, void* stream);
+int pps_dist_topk_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n, long long a_plane_rows,
+                     const void* b_planes, const float* b_sqnorm, long long m2, int b_planes_n, long long b_plane_rows,
+                     int dim, int precision, int flags, float* dist, long long ldd,
+                     long long col0, const uint32_t* tk_bound, uint32_t* tk_cnt, uint64_t* tk_cand, int tk_cap,
+                     void* stream);
+int pps_topk_merge(uint64_t* topk_key, long long nq, int k, const uint64_t* tk_cand, int tk_cap,
+                   uint32_t* tk_cnt, uint32_t* tk_bound,
+                   const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                   int max_pairs_per_query, int topk_filtered, int32_t* overflow, void* stream);
 int pps_topk_unpack(const uint64_t* topk_key, long long nq, int k,
                     float* out_dist, int32_t* out_index, void* stream);
 

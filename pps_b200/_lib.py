@@ -90,6 +90,10 @@ SIGNATURES = {
     "pps_topk_init": (_i, [_vp, _ll, _i, _vp]),
     "pps_topk_update": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp]),
     "pps_rank_sweep": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "pps_topk_bound": (_i, [_vp, _ll, _i, _vp, _vp, _vp]),
+    "pps_dist_topk_tc": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp, _ll, _i, _ll, _i, _i, _i, _vp, _ll,
+                              _ll, _vp, _vp, _vp, _i, _vp]),
+    "pps_topk_merge": (_i, [_vp, _ll, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "pps_topk_unpack": (_i, [_vp, _ll, _i, _vp, _vp, _vp]),
     "pps_ctx_create": (_i, [_i, C.POINTER(_vp)]),
     "pps_ctx_destroy": (_i, [_vp]),

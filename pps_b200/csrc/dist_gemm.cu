@@ -236,11 +236,17 @@ struct RankFuse {
   uint32_t* cnt_first;      // [rows] += -#{d == d*} + #{d == d*, column < g*}   (mod 2^32)
   long long col0;           // global gallery index of column 0 of this block
   int p_cap;                // thresholds per row in the tables (multiple of 8, <= 64)
+  // EPI_DIST_TOPK: admission of top-k candidates while the distance block is being written
+  const uint32_t* tk_bound; // [rows] distance bits of the current k-th best of each query (0xffffffff: unbounded)
+  uint32_t* tk_cnt;         // [rows] candidates appended so far (may run past tk_cap: the excess is dropped and detected)
+  unsigned long long* tk_cand;   // [rows][tk_cap] keys (distance bits << 32 | global gallery index)
+  int tk_cap;
 };
 
 constexpr int EPI_DIST = 0;          // |a|^2 + |b|^2 - 2ab, clamp, sqrt (or squared / raw dot by flags) -> matrix
 constexpr int EPI_AFFINE_RELU = 1;   // max(0, dot * alpha[col] + beta[col])   (a_sqnorm = alpha, b_sqnorm = beta)
 constexpr int EPI_RANK = 2;          // distance as EPI_DIST, consumed by the counting epilogue; no matrix
+constexpr int EPI_DIST_TOPK = 3;     // EPI_DIST + one compare per element against the row's top-k admission bound
 
 // Tile order.  EPI_DIST / EPI_AFFINE_RELU: tile t = pair, pair + npairs, ... with the m index fastest, so that the
 // CTA pairs running concurrently share B tiles in L2.  EPI_RANK: every CTA pair keeps ONE m tile (its rows'
@@ -447,6 +453,8 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const float an = (EPI != EPI_AFFINE_RELU && gi < g.m1 && !want_dot) ? __ldg(g.a_sqnorm + gi) : 0.f;
+      uint32_t tk_bound = 0u;                  // EPI_DIST_TOPK: nothing is admitted for padding rows
+      if (EPI == EPI_DIST_TOPK && gi < g.m1) tk_bound = __ldg(rf.tk_bound + gi);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + as * BN + ((uint32_t)(lane_grp * 32) << 16);
@@ -540,6 +548,22 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
             *reinterpret_cast<float4*>(buf + lane * 128 + (((uint32_t)j ^ swz) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+            if (EPI == EPI_DIST_TOPK) {
+              // distances are >= 0: their bits order like the values.  Almost never true once a bound exists.
+              if ((__float_as_uint(v[0]) <= tk_bound) | (__float_as_uint(v[1]) <= tk_bound) |
+                  (__float_as_uint(v[2]) <= tk_bound) | (__float_as_uint(v[3]) <= tk_bound)) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {             // (unrolled: v[] must stay in registers)
+                  const int col = n0 + c + 4 * j + e;
+                  if (__float_as_uint(v[e]) <= tk_bound && col < n_end) {
+                    const uint32_t slot = atomicAdd(rf.tk_cnt + gi, 1u);
+                    if (slot < (uint32_t)rf.tk_cap)
+                      rf.tk_cand[(long long)gi * rf.tk_cap + slot] =
+                          ((unsigned long long)__float_as_uint(v[e]) << 32) | (unsigned long long)(uint32_t)(rf.col0 + col);
+                  }
+                }
+              }
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -698,10 +722,10 @@ static int setup_terms(int precision, GemmArgs& g, bool* f16) {
 
 using namespace pps;
 
-extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
-                           long long a_plane_rows, const void* b_planes, const float* b_sqnorm, long long m2,
-                           int b_planes_n, long long b_plane_rows, int dim, int precision, int flags, float* dist,
-                           long long ldd, void* stream) {
+static int dist_tc_impl(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
+                        long long a_plane_rows, const void* b_planes, const float* b_sqnorm, long long m2,
+                        int b_planes_n, long long b_plane_rows, int dim, int precision, int flags, float* dist,
+                        long long ldd, void* stream, const RankFuse* topk) {
   if (m1 < 0 || m2 < 0 || dim <= 0 || ldd < m2) return PPS_ERR_INVALID_ARG;
   if (a_plane_rows == 0) a_plane_rows = m1;
   if (b_plane_rows == 0) b_plane_rows = m2;
@@ -790,10 +814,22 @@ extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long lon
     long long slots = sms / 2;
     if ((flags & PPS_DIST_RESERVE_SM_PAIR) && slots > 8) slots -= 1;   // leave one SM pair to concurrent small kernels
     const long long pairs = tiles2 < slots ? tiles2 : slots;
+    if (topk) {
+      static thread_local int configured3_dev = -1;
+      if (configured3_dev != dev) {
+        PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc2_kernel<256, EPI_DIST_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kGemm2Smem));
+        configured3_dev = dev;
+      }
+      dist_tc2_kernel<256, EPI_DIST_TOPK><<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga, *topk);
+      PPS_LAUNCH_CHECK("dist_tc2_kernel<topk>");
+      return PPS_OK;
+    }
     dist_tc2_kernel<256, EPI_DIST><<<(unsigned)(2 * pairs), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga, RankFuse{});
     PPS_LAUNCH_CHECK("dist_tc2_kernel");
     return PPS_OK;
   }
+  if (topk) return PPS_ERR_UNSUPPORTED;        // the admission epilogue exists in the 2-CTA kernel only
 
   int rc = make_operand_map(&tmA, a_planes, m1, a_plane_rows, kpad, a_planes_n, kBM, f16);
   if (rc) return rc;
@@ -809,6 +845,31 @@ extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long lon
   dist_tc_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, g);
   PPS_LAUNCH_CHECK("dist_tc_kernel");
   return PPS_OK;
+}
+
+extern "C" int pps_dist_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
+                           long long a_plane_rows, const void* b_planes, const float* b_sqnorm, long long m2,
+                           int b_planes_n, long long b_plane_rows, int dim, int precision, int flags, float* dist,
+                           long long ldd, void* stream) {
+  return dist_tc_impl(a_planes, a_sqnorm, m1, a_planes_n, a_plane_rows, b_planes, b_sqnorm, m2, b_planes_n, b_plane_rows, dim,
+                      precision, flags, dist, ldd, stream, nullptr);
+}
+
+// pps_dist_tc + top-k admission in the epilogue: while the block is written, every distance is compared with its
+// query's current k-th best (tk_bound) and the few that pass are appended to the query's candidate buffer; a later
+// pps_topk_merge folds them into the top-k state.  The block itself is identical to pps_dist_tc's.
+extern "C" int pps_dist_topk_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
+                                long long a_plane_rows, const void* b_planes, const float* b_sqnorm, long long m2,
+                                int b_planes_n, long long b_plane_rows, int dim, int precision, int flags, float* dist,
+                                long long ldd, long long col0, const uint32_t* tk_bound, uint32_t* tk_cnt,
+                                uint64_t* tk_cand, int tk_cap, void* stream) {
+  if (!tk_bound || !tk_cnt || !tk_cand || tk_cap < 1 || col0 < 0 || col0 + m2 > 0xffffffffLL) return PPS_ERR_INVALID_ARG;
+  if (flags & PPS_DIST_DOT) return PPS_ERR_INVALID_ARG;      // keys order by the bits of a non-negative distance
+  RankFuse rf{};
+  rf.col0 = col0;
+  rf.tk_bound = tk_bound; rf.tk_cnt = tk_cnt; rf.tk_cand = reinterpret_cast<unsigned long long*>(tk_cand); rf.tk_cap = tk_cap;
+  return dist_tc_impl(a_planes, a_sqnorm, m1, a_planes_n, a_plane_rows, b_planes, b_sqnorm, m2, b_planes_n, b_plane_rows, dim,
+                      precision, flags, dist, ldd, stream, &rf);
 }
 
 extern "C" int pps_dist_fp32(const float* a, long long lda, const float* a_sqnorm, long long m1, const float* b,

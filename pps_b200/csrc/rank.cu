@@ -617,6 +617,82 @@ __global__ void __launch_bounds__(128) rank_tab_finish_kernel(long long nq, int 
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Top-k candidates admitted by the distance kernel's epilogue (dist_gemm.cu, EPI_DIST_TOPK) -> top-k state.
+// One CTA per query: state (k sorted keys) + the query's candidate buffer go through the same 2048-entry shared
+// buffer and bisection select as the sweep kernel; junk items (same id, same camera) are dropped here.  Writes the
+// new state, the new admission bound and resets the candidate count; a buffer that overflowed raises *overflow
+// (the caller then repeats the pass with the one-read sweep).
+// ------------------------------------------------------------------------------------
+__global__ void topk_bound_kernel(const unsigned long long* __restrict__ key, long long nq, int k,
+                                  uint32_t* __restrict__ tk_bound, uint32_t* __restrict__ tk_cnt) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const unsigned long long kk = key[q * k + k - 1];
+  tk_bound[q] = kk == ~0ull ? 0xffffffffu : (uint32_t)(kk >> 32);
+  tk_cnt[q] = 0u;
+}
+
+__global__ void __launch_bounds__(kCntThreads) topk_merge_kernel(unsigned long long* __restrict__ topk_key, int k,
+                                                                 const unsigned long long* __restrict__ tk_cand, int tk_cap,
+                                                                 uint32_t* __restrict__ tk_cnt, uint32_t* __restrict__ tk_bound,
+                                                                 const int32_t* __restrict__ pair_off,
+                                                                 const int32_t* __restrict__ pair_g,
+                                                                 const uint8_t* __restrict__ pair_pos, int filtered,
+                                                                 int* __restrict__ overflow) {
+  extern __shared__ int32_t sj_dyn[];                    // junk gallery indices of this query
+  __shared__ unsigned long long cand[kCandC];
+  __shared__ int s_n, s_nj;
+  __shared__ int s_sel[64];
+  __shared__ unsigned long long s_bound;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  unsigned long long* state = topk_key + (long long)q * k;
+  const uint32_t raw = tk_cnt[q];
+  if (raw == 0u) return;                                 // nothing was admitted for this query in the block
+  if (raw > (uint32_t)tk_cap && tid == 0) atomicExch(overflow, 1);
+  const int cnt = raw < (uint32_t)tk_cap ? (int)raw : tk_cap;
+  for (int i = tid; i < kCandC; i += kCntThreads) cand[i] = i < k ? state[i] : ~0ull;
+  if (tid == 0) { s_n = k; s_nj = 0; }
+  __syncthreads();
+  if (filtered && pair_off) {
+    const int e0 = pair_off[q], e1 = pair_off[q + 1];
+    for (int e = e0 + tid; e < e1; e += kCntThreads)
+      if (!pair_pos[e]) sj_dyn[atomicAdd(&s_nj, 1)] = pair_g[e];
+  }
+  __syncthreads();
+  const int nj = s_nj;
+  const unsigned long long* src = tk_cand + (long long)q * tk_cap;
+  int fill = k;
+  for (int base = 0; base < cnt;) {
+    const int take = min(cnt - base, kCandC - fill);
+    for (int i = tid; i < take; i += kCntThreads) {
+      const unsigned long long key = src[base + i];
+      const long long gcol = (long long)(key & 0xffffffffull);
+      bool skip = false;
+      for (int x = 0; x < nj; ++x) skip |= ((long long)sj_dyn[x] == gcol);
+      if (!skip) cand[atomicAdd(&s_n, 1)] = key;
+    }
+    base += take;
+    __syncthreads();
+    fill = select_k_smallest<kCandC / kCntThreads>(cand, k, tid, kCntThreads, s_sel, &s_n, &s_bound);
+    if (fill > kCandC - 1024) {                          // > 1000 exact ties at the k-th place: full sort, keep k
+      bitonic_sort_smem(cand, kCandC, tid, kCntThreads);
+      for (int i = k + tid; i < kCandC; i += kCntThreads) cand[i] = ~0ull;
+      if (tid == 0) s_n = k;
+      fill = k;
+    }
+    __syncthreads();
+  }
+  if (fill <= 256) bitonic_sort_smem(cand, 256, tid, kCntThreads);
+  else bitonic_sort_smem(cand, kCandC, tid, kCntThreads);
+  for (int i = tid; i < k; i += kCntThreads) state[i] = cand[i];
+  if (tid == 0) {
+    const unsigned long long kk = cand[k - 1];
+    tk_bound[q] = kk == ~0ull ? 0xffffffffu : (uint32_t)(kk >> 32);
+    tk_cnt[q] = 0u;
+  }
+}
+
 }  // namespace pps
 
 using namespace pps;
@@ -780,5 +856,43 @@ extern "C" int pps_rank_tab_finish(long long nq, int p_cap, const int32_t* tpair
   rank_tab_finish_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(nq, p_cap, tpair_tab,
                                                                                                       cnt_tab, cnt_le);
   PPS_LAUNCH_CHECK("rank_tab_finish_kernel");
+  return PPS_OK;
+}
+
+// ---- top-k admission in the distance epilogue (pps_dist_topk_tc): bound initialisation and candidate merge ----
+extern "C" int pps_topk_bound(const uint64_t* topk_key, long long nq, int k, uint32_t* tk_bound, uint32_t* tk_cnt,
+                              void* stream) {
+  if (nq < 0 || k < 1 || k > PPS_TOPK_MAX) return PPS_ERR_INVALID_ARG;
+  if (nq == 0) return PPS_OK;
+  if (!topk_key || !tk_bound || !tk_cnt) return PPS_ERR_INVALID_ARG;
+  topk_bound_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(topk_key), nq, k, tk_bound, tk_cnt);
+  PPS_LAUNCH_CHECK("topk_bound_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_topk_merge(uint64_t* topk_key, long long nq, int k, const uint64_t* tk_cand, int tk_cap,
+                              uint32_t* tk_cnt, uint32_t* tk_bound, const int32_t* pair_off, const int32_t* pair_g,
+                              const uint8_t* pair_pos, int max_pairs_per_query, int topk_filtered, int32_t* overflow,
+                              void* stream) {
+  if (nq < 0 || k < 1 || k > PPS_TOPK_MAX || tk_cap < 1 || max_pairs_per_query < 0) return PPS_ERR_INVALID_ARG;
+  if (nq == 0) return PPS_OK;
+  if (!topk_key || !tk_cand || !tk_cnt || !tk_bound || !overflow) return PPS_ERR_INVALID_ARG;
+  if (nq > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  const bool filt = topk_filtered && max_pairs_per_query > 0;
+  if (filt && (!pair_off || !pair_g || !pair_pos)) return PPS_ERR_INVALID_ARG;
+  const size_t smem = (size_t)(max_pairs_per_query > 0 ? max_pairs_per_query : 1) * 4;
+  if (smem > 100 * 1024) return PPS_ERR_UNSUPPORTED;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  PPS_CUDA_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    PPS_CUDA_TRY(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured_dev = dev;
+  }
+  topk_merge_kernel<<<(unsigned)nq, kCntThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<unsigned long long*>(topk_key), k, reinterpret_cast<const unsigned long long*>(tk_cand), tk_cap, tk_cnt,
+      tk_bound, filt ? pair_off : nullptr, pair_g, pair_pos, filt ? 1 : 0, overflow);
+  PPS_LAUNCH_CHECK("topk_merge_kernel");
   return PPS_OK;
 }

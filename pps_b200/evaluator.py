@@ -557,6 +557,9 @@ class RankEngine:
         self.compact_thresholds = True   # multi-chunk galleries: thresholds from the compacted same-id gallery
         self._g_ptr, self._g_keepalive = None, None
         self._c_fixed = {}
+        self.fused_topk = True           # blocks after the first: top-k admission in the distance epilogue
+        self.used_fused_topk = False
+        self._tk = None
         self.fused_rank = False          # counters in the epilogue of the distance kernel (no distance block written):
                                          # bit-identical, saves the block's memory, but measured slower than block +
                                          # count kernel on B200 (the MMA mainloop already saturates shared-memory bandwidth)
@@ -755,16 +758,46 @@ class RankEngine:
             _lib.check(lib.pps_rank_gather(_lib.ptr(self.block), self.ldd, self.nq, rows, c0, _lib.ptr(pairs.dev("q")),
                                            _lib.ptr(self._pair_col), n, _lib.ptr(pair_d), s), "pps_rank_gather")
 
-    def _distance(self, rows):
+    TOPK_CAND_CAP = 2048             # candidates per query and block the distance epilogue may append
+
+    def _topk_epilogue_begin(self, key):
+        torch = self.torch
+        if self._tk is None:
+            nq_ = max(self.nq, 1)
+            self._tk = (torch.empty(nq_, dtype=torch.int32, device=self.dev), torch.empty(nq_, dtype=torch.int32, device=self.dev),
+                        torch.empty((nq_, self.TOPK_CAND_CAP), dtype=torch.int64, device=self.dev),
+                        torch.zeros(1, dtype=torch.int32, device=self.dev))
+        bound, cnt, _, ovf = self._tk
+        ovf.zero_()
+        _lib.check(self.lib.pps_topk_bound(_lib.ptr(key), self.nq, self.topk, _lib.ptr(bound), _lib.ptr(cnt), _lib.stream_ptr()),
+                   "pps_topk_bound")
+
+    def _topk_epilogue_merge(self, key, pairs):
+        bound, cnt, cand, ovf = self._tk
+        use = self.topk_filtered and pairs.n_pairs > 0
+        _lib.check(self.lib.pps_topk_merge(_lib.ptr(key), self.nq, self.topk, _lib.ptr(cand), self.TOPK_CAND_CAP, _lib.ptr(cnt),
+                                           _lib.ptr(bound), _lib.ptr(pairs.dev("off")), _lib.ptr(pairs.dev("g")) if use else None,
+                                           _lib.ptr(pairs.dev("pos")) if use else None, pairs.max_pairs if use else 0,
+                                           1 if use else 0, _lib.ptr(ovf), _lib.stream_ptr()), "pps_topk_merge")
+
+    def _distance(self, rows, topk_col0=None):
         torch = self.torch
         ev = None
         if self.kernel_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        _lib.check(self.lib.pps_dist_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), self.nq, self.planes, 0,
-                                        self._g_ptr, _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
-                                        self.prec, DIST_KERNEL_FLAGS, _lib.ptr(self.block), self.ldd,
-                                        _lib.stream_ptr()), "pps_dist_tc")
+        if topk_col0 is not None:
+            bound, cnt, cand, _ = self._tk
+            _lib.check(self.lib.pps_dist_topk_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), self.nq, self.planes, 0,
+                                                 self._g_ptr, _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
+                                                 self.prec, DIST_KERNEL_FLAGS, _lib.ptr(self.block), self.ldd, topk_col0,
+                                                 _lib.ptr(bound), _lib.ptr(cnt), _lib.ptr(cand), self.TOPK_CAND_CAP,
+                                                 _lib.stream_ptr()), "pps_dist_topk_tc")
+        else:
+            _lib.check(self.lib.pps_dist_tc(_lib.ptr(self.q_planes), _lib.ptr(self.q_sq), self.nq, self.planes, 0,
+                                            self._g_ptr, _lib.ptr(self.g_sq), rows, self.planes, 0, self.dim,
+                                            self.prec, DIST_KERNEL_FLAGS, _lib.ptr(self.block), self.ldd,
+                                            _lib.stream_ptr()), "pps_dist_tc")
         if ev is not None:
             ev[1].record()
             self.kernel_events.append(ev)
@@ -830,12 +863,32 @@ class RankEngine:
                 # distance blocks are never written (pps_dist_rank_tc)
                 self._fused_count_sweep(g, chunks, pairs, pair_d, cnt_le, cnt_first)
                 chunks = []
-            for r0, rows in chunks:
+            # Blocks after the first: the top-k candidates are admitted by the EPILOGUE of the distance kernel (one
+            # compare per element against the bound the first block's sweep established) and the block is only
+            # counted, instead of being swept for counts and top-k together.
+            epi_topk = bool(self.fused_topk and self.topk and self.n_chunks > 1 and chunks and DIST_KERNEL_FLAGS == 0)
+            self.used_fused_topk = epi_topk
+            for ci, (r0, rows) in enumerate(chunks):
                 if self.n_chunks > 1:
                     self._split(g[r0:r0 + rows], rows, self.g_planes, self.g_sq)
+                    if epi_topk and ci >= 1:
+                        if ci == 1:
+                            self._topk_epilogue_begin(key)
+                        self._distance(rows, topk_col0=self.offset + r0)
+                        _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
+                                    False, True)
+                        self._topk_epilogue_merge(key, pairs)
+                        continue
                     self._distance(rows)
                 _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
                             False, True, key, self.topk, self.topk_filtered)
+            if epi_topk and len(chunks) > 1 and int(self._tk[3].item()) != 0:
+                # a candidate buffer ran over (adversarial column order): repeat the pass with the one-read sweep
+                self.fused_topk = False
+                try:
+                    return self.run(q, g)
+                finally:
+                    self.fused_topk = True
             if self.group is not None:
                 dist_mod.all_reduce(cnt_le, op=dist_mod.ReduceOp.SUM, group=self.group)
                 dist_mod.all_reduce(cnt_first, op=dist_mod.ReduceOp.SUM, group=self.group)

@@ -517,3 +517,41 @@ def test_rank_eval_topk_without_any_pair():
     assert res.is_valid.sum() == 0
     d = O.compute_dist(q, g)
     np.testing.assert_array_equal(res.topk_index, np.argsort(d, axis=1, kind="stable")[:, :9])
+
+
+def test_topk_admission_in_distance_epilogue(golden):
+    """Blocks after the first take their top-k candidates in the epilogue of the distance kernel; the result must be
+    the bits of the one-read sweep, with and without the junk filter, and an overflowing candidate buffer must fall
+    back to the sweep (forced here by a 4-entry buffer and a gallery whose nearest rows come last)."""
+    import torch
+    from pps_b200 import evaluator
+    for name in ("small_mid", "dup_ties", "many_pos"):
+        d = golden(name)
+        q, g = torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda()
+        for filtered in (True, False):
+            out = []
+            for fused in (False, True):
+                eng = evaluator.RankEngine(d["qid"], d["gid"], d["qcam"], d["gcam"], nq=q.shape[0], ng_local=g.shape[0],
+                                           dim=q.shape[1], topk=13, topk_filtered=filtered, max_block_bytes=q.shape[0] * 256 * 4)
+                eng.fused_topk = fused
+                assert eng.n_chunks > 1
+                out.append(eng.run(q, g))
+                assert eng.used_fused_topk == fused
+            np.testing.assert_array_equal(out[0].topk_index, out[1].topk_index)
+            np.testing.assert_array_equal(out[0].topk_dist, out[1].topk_dist)
+            np.testing.assert_array_equal(out[0].ap, out[1].ap)
+    # overflow -> fallback
+    d = golden("small_mid")
+    order = np.argsort(-O.compute_dist(d["q"][:1], d["g"])[0])            # farthest rows first
+    g = torch.from_numpy(np.ascontiguousarray(d["g"][order])).cuda()
+    q = torch.from_numpy(d["q"]).cuda()
+    gid, gcam = d["gid"][order], d["gcam"][order]
+    ref = evaluator.RankEngine(d["qid"], gid, d["qcam"], gcam, nq=q.shape[0], ng_local=g.shape[0], dim=q.shape[1], topk=13)
+    want = ref.run(q, g)
+    eng = evaluator.RankEngine(d["qid"], gid, d["qcam"], gcam, nq=q.shape[0], ng_local=g.shape[0], dim=q.shape[1], topk=13,
+                               max_block_bytes=q.shape[0] * 256 * 4)
+    eng.TOPK_CAND_CAP = 4
+    got = eng.run(q, g)
+    assert eng.fused_topk and not eng.used_fused_topk                    # the repeat ran without the epilogue path
+    np.testing.assert_array_equal(got.topk_index, want.topk_index)
+    np.testing.assert_array_equal(got.ap, want.ap)
