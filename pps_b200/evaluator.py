@@ -760,6 +760,25 @@ class RankEngine:
 
     TOPK_CAND_CAP = 2048             # candidates per query and block the distance epilogue may append
 
+    def _chunk_list(self):
+        """(row0, rows) of the gallery blocks of one pass.  With top-k admission in the distance epilogue the FIRST block
+        is kept short: it is the one that still takes the one-read sweep, and all it has to do is establish a bound
+        tight enough that a full block admits well under TOPK_CAND_CAP candidates per query (rows in random order:
+        a block of R rows after F swept rows admits ~ k * R / F)."""
+        if self.n_chunks <= 1:
+            return [(0, self.ngl)] if self.n_chunks else []
+        first = self.chunk
+        if self.fused_topk and self.topk and DIST_KERNEL_FLAGS == 0:
+            want = int(2.2 * self.topk * self.chunk / self.TOPK_CAND_CAP)
+            first = min(self.chunk, max(32768, (want + 255) // 256 * 256))
+        out, r0 = [], 0
+        rows = min(first, self.ngl)
+        while r0 < self.ngl:
+            out.append((r0, rows))
+            r0 += rows
+            rows = min(self.chunk, self.ngl - r0)
+        return out
+
     def _topk_epilogue_begin(self, key):
         torch = self.torch
         if self._tk is None:
@@ -828,7 +847,7 @@ class RankEngine:
             if self.topk:
                 _lib.check(lib.pps_topk_init(_lib.ptr(key), nq, self.topk, _lib.stream_ptr()), "pps_topk_init")
             self._split(q, nq, self.q_planes, self.q_sq)
-            chunks = [(c * self.chunk, min(self.chunk, self.ngl - c * self.chunk)) for c in range(self.n_chunks)]
+            chunks = self._chunk_list()
             # sweep 1: thresholds
             first_chunk = True
             pair_d = cnt_le = None

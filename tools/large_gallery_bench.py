@@ -160,7 +160,7 @@ def main():
         flops = 2.0 * a.dim * pairs
         line = {"tool": "large_gallery_bench", "n_gpus": world, "nq": a.nq, "ng": a.ng, "dim": a.dim, "dtype": a.dtype, "sigma": a.sigma,
                 "precision": "f16x1" if a.dtype == "fp16" else a.precision, "topk": a.topk,
-                "rows_per_gpu": ngl, "chunks_per_gpu": eng.n_chunks, "chunk_rows": eng.chunk,
+                "rows_per_gpu": ngl, "chunks_per_gpu": len(eng._chunk_list()), "chunk_rows": eng.chunk,
                 "threshold_pass": "two-sweep" if a.two_sweep else "compacted same-id rows (%d on rank 0)" % eng.threshold_rows,
                 "ms_per_pass": ms, "pairs_per_s": pairs / (ms * 1e-3), "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
                 "gpu_launches_per_pass": launches / max(a.steps, 1), "gallery_gen_s": gen_s,
