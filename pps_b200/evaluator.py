@@ -761,23 +761,9 @@ class RankEngine:
     TOPK_CAND_CAP = 2048             # candidates per query and block the distance epilogue may append
 
     def _chunk_list(self):
-        """(row0, rows) of the gallery blocks of one pass.  With top-k admission in the distance epilogue the FIRST block
-        is kept short: it is the one that still takes the one-read sweep, and all it has to do is establish a bound
-        tight enough that a full block admits well under TOPK_CAND_CAP candidates per query (rows in random order:
-        a block of R rows after F swept rows admits ~ k * R / F)."""
-        if self.n_chunks <= 1:
-            return [(0, self.ngl)] if self.n_chunks else []
-        first = self.chunk
-        if self.fused_topk and self.topk and DIST_KERNEL_FLAGS == 0:
-            want = int(2.2 * self.topk * self.chunk / self.TOPK_CAND_CAP)
-            first = min(self.chunk, max(32768, (want + 255) // 256 * 256))
-        out, r0 = [], 0
-        rows = min(first, self.ngl)
-        while r0 < self.ngl:
-            out.append((r0, rows))
-            r0 += rows
-            rows = min(self.chunk, self.ngl - r0)
-        return out
+        """(row0, rows) of the gallery blocks of one pass (see plan_blocks)."""
+        short_first = bool(self.fused_topk and self.topk and DIST_KERNEL_FLAGS == 0)
+        return plan_blocks(self.ngl, self.chunk, self.topk if short_first else 0, self.TOPK_CAND_CAP)
 
     def _topk_epilogue_begin(self, key):
         torch = self.torch
@@ -932,6 +918,30 @@ class RankEngine:
             g = g_host.to(self.dev, non_blocking=True)
             self.h2d_bytes = q_host.numel() * q_host.element_size() + g_host.numel() * g_host.element_size()
             return self.run(q, g)
+
+
+def plan_blocks(ng_local, block_rows, topk=0, cand_cap=2048):
+    """Gallery blocks [(row0, rows), ...] of one pass over ``ng_local`` rows in blocks of at most ``block_rows``.
+
+    With top-k admission in the distance epilogue (``topk`` > 0) the FIRST block is kept short: it is the one that still
+    takes the one-read sweep, and all it has to do is establish a bound tight enough that a full block admits well
+    under ``cand_cap`` candidates per query (rows in random order: a block of R rows after F swept rows admits about
+    k * R / F per query, so F >= 2.2 * k * R / cap, at least 32 768 rows)."""
+    ng_local, block_rows = int(ng_local), int(block_rows)
+    if ng_local <= 0:
+        return []
+    if ng_local <= block_rows:
+        return [(0, ng_local)]
+    first = block_rows
+    if topk:
+        want = int(2.2 * topk * block_rows / cand_cap)
+        first = min(block_rows, max(32768, (want + 255) // 256 * 256))
+    out, r0, rows = [], 0, min(first, ng_local)
+    while r0 < ng_local:
+        out.append((r0, rows))
+        r0 += rows
+        rows = min(block_rows, ng_local - r0)
+    return out
 
 
 def rank_eval(q_feats, g_feats, query_ids, gallery_ids, query_cams, gallery_cams, topk: int = 0,

@@ -143,3 +143,22 @@ def test_json_dataset_reader_orders_by_image_id_and_reads_marks(tmp_path):
     path.write_text(json.dumps(dict(images=images, annotations=anns[:2])))
     with pytest.raises(RuntimeError, match="no annotation"):
         dataset_io.JsonReidDataset(str(path))
+
+
+def test_plan_blocks_covers_the_gallery_exactly():
+    """Host logic of the multi-block pass: blocks tile [0, ng) without gaps, the first one is short only when the
+    top-k bound has to be established, and a gallery that fits one block is one block."""
+    assert evaluator.plan_blocks(0, 1000) == []
+    assert evaluator.plan_blocks(700, 1000, topk=100) == [(0, 700)]
+    assert evaluator.plan_blocks(2500, 1000) == [(0, 1000), (1000, 1000), (2000, 500)]
+    for ng, blk, k in ((10_000_000, 637_440, 100), (1_250_000, 637_440, 100), (2_000_000, 637_440, 128), (900, 256, 7)):
+        blocks = evaluator.plan_blocks(ng, blk, topk=k)
+        assert blocks[0][0] == 0 and sum(r for _, r in blocks) == ng
+        assert all(a[0] + a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert all(0 < r <= blk for _, r in blocks)
+        if blk >= 65536:
+            first = blocks[0][1]
+            assert first % 256 == 0 and 32768 <= first < blk
+            assert k * blk / first <= 2048 / 2.0                      # expected admissions per query and block
+        else:
+            assert blocks[0][1] == blk                                # tiny blocks (tests): nothing to shorten
