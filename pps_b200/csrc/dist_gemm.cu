@@ -555,7 +555,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {             // (unrolled: v[] must stay in registers)
                   const int col = n0 + c + 4 * j + e;
-                  if (__float_as_uint(v[e]) <= tk_bound && col < n_end) {
+                  if (__float_as_uint(v[e]) <= tk_bound && col < n_end && gi < g.m1) {   // (an exact 0 passes even a 0 bound)
                     const uint32_t slot = atomicAdd(rf.tk_cnt + gi, 1u);
                     if (slot < (uint32_t)rf.tk_cap)
                       rf.tk_cand[(long long)gi * rf.tk_cap + slot] =
