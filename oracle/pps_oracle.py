@@ -9,10 +9,12 @@ Pinning status
     these functions.  The restatement is pinned instead against outputs of
     the unmodified reference functions run in the authoring container (oracle/ref_loader.py,
     fixtures in tests/golden/ made by oracle/make_golden.py): numpy 2.3.5, scikit-learn 1.9.0.
-  * pooling: **parity unpinned** — the reference's pooling exists only as a Caffe2 graph
-    (pytorch v1.0.1 `Split/AveragePool/MaxPool/Mean/Max/Add`, not vendored, not importable here),
-    so this restates the published semantics of those ops at the call sites
-    bpm_heads.py:45-55 and pps_heads.py:58-76.
+  * pooling: the reference's pooling exists only as a Caffe2 graph (pytorch v1.0.1 `Split/AveragePool/MaxPool/
+    Mean/Max/Add`, not vendored, not importable here).  The GRAPH is pinned: oracle/ref_pool_loader.py executes the
+    unmodified builders (bpm_heads.py:18-55, pps_heads.py:38-142) with eagerly evaluated operators and
+    tests/golden/pool_*.npz (oracle/make_golden_pool.py) hold what they return; this file reproduces them bit for
+    bit.  The arithmetic inside the six stock operators stays a restatement of their published semantics
+    (**parity unpinned** in that sense).
 
 Third-party arithmetic the reference leans on: scikit-learn ``average_precision_score``
 (reid_dataset_evaluator.py:434; the code asks for 0.18.1 at :398-407, the installed 1.9.0

@@ -171,3 +171,27 @@ def test_full_size_property_linearity_in_batch(torch):
         assert torch.equal(y[i:i + 1], yi)
     ref = O.pps_pool(x[:2].cpu().numpy(), 6, mode="max_ave")
     np.testing.assert_allclose(y[:2].cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+
+
+from conftest import POOL_GOLDEN_CASES, pool_fixture_expected  # noqa: E402
+
+
+@pytest.mark.parametrize("name", POOL_GOLDEN_CASES)
+def test_heads_match_reference_graph_fixture(torch, golden, name):
+    """pps_b200.add_pps_part_head (fused CUDA kernel) against the blobs the reference's own graph builders return
+    (tests/golden/pool_*.npz, oracle/make_golden_pool.py): count, order, shapes, values to 1e-5."""
+    import pps_b200
+    d = golden(name)
+    cfg = pps_b200.ReIDPoolCfg(BPM_STRIP_NUM=int(d["strip_num"]), MAX_AVE_FEATURE=bool(int(d["max_ave"])),
+                               FPN_ON=bool(int(d["fpn_on"])), FPN_SHARED=bool(int(d["fpn_shared"])), train=bool(int(d["train"])))
+    levels = [torch.from_numpy(d["x%d" % j]).cuda() for j in range(int(d["n_levels"]))]
+    scales = [float(v) for v in d["spatial_scale"]]
+    if cfg.FPN_ON:
+        blobs, dims = pps_b200.add_pps_part_head(levels, [int(x.shape[1]) for x in levels], scales, cfg)
+    else:
+        blobs, dims = pps_b200.add_pps_part_head(levels[0], int(levels[0].shape[1]), scales[0], cfg)
+    want = [d["y%03d" % k] for k in range(int(d["n_out"]))]
+    assert len(blobs) == len(want) and [int(v) for v in dims] == [int(v) for v in d["dims"]]
+    for got, ref in zip(blobs, want):
+        assert tuple(got.shape) == ref.shape
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)

@@ -8,7 +8,7 @@ import pytest
 
 from oracle import pps_oracle as O
 from oracle import ref_loader
-from conftest import GOLDEN_CASES
+from conftest import GOLDEN_CASES, POOL_GOLDEN_CASES, pool_fixture_expected
 
 
 def _ids(d):
@@ -128,3 +128,33 @@ def test_re_ranking_restatement_matches_live_reference():
         q_g, q_q, g_g = (ref.compute_dist(a, b) for a, b in ((d["q"], d["g"]), (d["q"], d["q"]), (d["g"], d["g"])))
         want = ref.re_ranking(q_g, q_q, g_g, k1=12, k2=4, lambda_value=0.2)
     np.testing.assert_array_equal(O.re_ranking(q_g, q_q, g_g, k1=12, k2=4, lambda_value=0.2), want)
+
+
+@pytest.mark.parametrize("name", POOL_GOLDEN_CASES)
+def test_pooling_restatement_matches_reference_graph_fixture(golden, name):
+    """oracle.pps_pool == the blobs the reference's OWN graph builders (bpm_heads.py + pps_heads.py, executed eagerly by
+    oracle/ref_pool_loader.py) return: same count, same order, same bits; names follow the reference's scheme."""
+    from pps_b200 import pooling
+    d = golden(name)
+    want = [d["y%03d" % k] for k in range(int(d["n_out"]))]
+    got = pool_fixture_expected(d, lambda x, n, split, mode: O.pps_pool(x, n, split=split, mode=mode), O.uniform_partition_split)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    names = [str(s) for s in d["names"]]
+    n = int(d["strip_num"])
+    if not int(d["fpn_on"]) or not int(d["train"]):
+        assert names == pooling.blob_names(n, "pps")
+    elif not int(d["fpn_shared"]):
+        assert names == [nm for i in range(int(d["n_levels"])) for nm in pooling.blob_names(n, "pps_%d_" % i)]
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_pool_loader", fromlist=["x"]).available(), reason="needs /root/reference")
+def test_pooling_restatement_matches_live_reference_graph():
+    from oracle import ref_pool_loader as R
+    x = np.maximum(np.random.RandomState(77).randn(2, 24, 24, 8), 0).astype(np.float32)
+    for n, max_ave in ((6, True), (9, False), (10, True), (3, True)):
+        names, arrs, dims, ops = R.run_pps_head(x, n, max_ave)
+        want = O.pps_pool(x, n, split=O.uniform_partition_split(n), mode="max_ave" if max_ave else "avg_max")
+        assert len(arrs) == (1 << n) - 1 and dims == [24] * len(arrs)
+        np.testing.assert_array_equal(np.stack([a.reshape(2, 24) for a in arrs], 1), want)
