@@ -324,8 +324,9 @@ def batch_hard_grad(idx_p, idx_n, dap, dan):
 
 
 # ------------------------------------------------------------------------------------
-# per-combination embedding + concat + normalise — parity unpinned: a Caffe2 graph
-# (Conv, SpatialBN, Relu, Concat, Normalize of pytorch v1.0.1) with no reference test
+# per-combination embedding + concat + normalise: a Caffe2 graph (Conv, SpatialBN, Relu, Concat,
+# Normalize of pytorch v1.0.1) with no reference test.  The graph is pinned by executing the reference's own builder
+# eagerly (oracle/ref_pool_loader.run_reid_outputs -> tests/golden/embed_*.npz); the operator arithmetic is restated.
 # ------------------------------------------------------------------------------------
 
 

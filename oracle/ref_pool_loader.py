@@ -155,3 +155,113 @@ def run_pps_head(maps, strip_num=6, max_ave=True, scale=(128, 384), spatial_scal
     with contextlib.redirect_stdout(io.StringIO()):                 # the builder print()s every combination
         blobs_out, dims_out = pps.add_pps_part_head(model, blob_in, dim_in, ss, preprefix=preprefix)
     return [str(b) for b in blobs_out], [model.ws[str(b)] for b in blobs_out], list(dims_out), model.ops
+
+
+# ------------------------------------------------------------------------------------
+# the embedding head between pooling and distance: reid_heads.add_reid_outputs at test time
+# ------------------------------------------------------------------------------------
+class _EmbedNet(_Net):
+    """+ the operators detectron/modeling/reid_heads.py:34-127 emits (Conv 1x1, SpatialBN in test mode, Relu,
+    DropoutIfTraining, FC, Reshape, Normalize), with parameters looked up by the blob names Caffe2's helpers give them:
+    '<out>_w' / '<out>_b' for Conv and FC, '<out>_s' / '_b' / '_rm' / '_riv' for SpatialBN."""
+
+    def __init__(self, blobs, params, num_classes, train=False):
+        super().__init__(blobs, train)
+        self.params = params
+        self.num_classes = num_classes
+
+    def Conv(self, blob_in, blob_out, dim_in, dim_out, kernel, stride=1, pad=0, no_bias=0, **kw):
+        assert kernel == 1 and stride == 1 and pad == 0
+        x = self._get(blob_in)                                        # [N, C, 1, 1]
+        w, b = self.params[blob_out + "_w"], self.params[blob_out + "_b"]
+        assert w.shape == (dim_out, dim_in, 1, 1)
+        y = np.einsum("nchw,ec->nehw", x.astype(np.float64), w[:, :, 0, 0].astype(np.float64)) + b.astype(np.float64)[None, :, None, None]
+        self.ws[blob_out] = y                                         # float64 through the branch, rounded at the end
+        self.ops.append(("Conv", [str(blob_in)], [blob_out]))
+        return blob_out
+
+    def SpatialBN(self, blob_in, blob_out, dim, is_test=True, epsilon=1e-5, **kw):
+        assert is_test
+        x = self._get(blob_in)
+        p = lambda s: self.params[blob_out + s].astype(np.float64)[None, :, None, None]
+        self.ws[blob_out] = (x - p("_rm")) / np.sqrt(p("_riv") + epsilon) * p("_s") + p("_b")
+        self.ops.append(("SpatialBN", [str(blob_in)], [blob_out]))
+        return blob_out
+
+    def Relu(self, blob_in, blob_out):
+        self.ws[str(blob_out)] = np.maximum(self._get(blob_in), 0)
+        self.ops.append(("Relu", [str(blob_in)], [str(blob_out)]))
+        return blob_out
+
+    def DropoutIfTraining(self, blob_in, ratio):
+        return blob_in
+
+    def FC(self, blob_in, blob_out, dim_in, dim_out, **kw):
+        x = self._get(blob_in)
+        self.ws[blob_out] = np.zeros((x.shape[0], dim_out))           # classifier logits: not on the retrieval path
+        self.ops.append(("FC", [str(blob_in)], [blob_out]))
+        return blob_out
+
+    def Reshape(self, blob_in, blobs_out, shape=None):
+        self.ws[blobs_out[0]] = self._get(blob_in).reshape(shape)
+        self.ops.append(("Reshape", [str(blob_in)], list(blobs_out)))
+        return blobs_out[0], blobs_out[1]
+
+    def Normalize(self, blob_in, blob_out, axis=-1):
+        x = self._get(blob_in)
+        nrm = np.maximum(np.sqrt((x * x).sum(axis=axis, keepdims=True)), 1e-12)      # caffe2 normalize_op.h: kEps = 1e-12
+        self.ws[blob_out] = x / nrm
+        self.ops.append(("Normalize", [str(blob_in)], [blob_out]))
+        return blob_out
+
+
+def run_reid_outputs(pooled_blobs, names, params, bpm_dim=128, normalize=True, num_classes=751):
+    """Execute the unmodified ``add_reid_outputs`` (reid_heads.py:34-127, model.train = False) on ONE image's pooled
+    blobs (the reference extracts features with batch size 1, and its Reshape(shape=[1, -1]) flattens whatever batch it
+    gets).  pooled_blobs: list of [1, C, 1, 1] arrays named ``names``.  Returns (feature [1, K*bpm_dim] float64, ops)."""
+    if not available():
+        raise RuntimeError("reference not found under %s" % MODELING)
+    cfg = types.SimpleNamespace(
+        REID=types.SimpleNamespace(BPM_DIM=bpm_dim, DROPOUT_FEATURE=False, NORMALIZE_FEATURE=normalize, CRM=False),
+        MODEL=types.SimpleNamespace(USE_GN=False))
+    stubs = {
+        "detectron": {}, "detectron.core": {}, "detectron.core.config": {"cfg": cfg},
+        "detectron.utils": {}, "detectron.utils.c2": {"const_fill": lambda *a, **k: None, "gauss_fill": lambda *a, **k: None,
+                                                     "UnscopeName": lambda s: s[s.rfind("/") + 1:]},
+        "detectron.utils.blob": {}, "detectron.utils.reid": {}, "detectron.modeling": {}, "detectron.modeling.init": {},
+        "detectron.modeling.crm_heads": {},
+    }
+    saved = {}
+    for name, attrs in stubs.items():
+        saved[name] = sys.modules.get(name)
+        mod = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(mod, k, v)
+        sys.modules[name] = mod
+    loaded = []
+
+    def load_file(modname, fname):
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(MODELING, fname))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[modname] = mod
+        loaded.append(modname)
+        spec.loader.exec_module(mod)
+        return mod
+
+    try:
+        load_file("detectron.modeling.triplet_loss", "triplet_loss.py")
+        heads = load_file("detectron.modeling.reid_heads", "reid_heads.py")      # fresh module: its feature_list is a global
+    finally:
+        for name, old in saved.items():
+            if old is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = old
+        for name in loaded:
+            sys.modules.pop(name, None)
+    model = _EmbedNet({n: np.asarray(b, np.float32) for n, b in zip(names, pooled_blobs)}, params, num_classes, train=False)
+    dims = [int(b.shape[1]) for b in pooled_blobs]
+    with contextlib.redirect_stdout(io.StringIO()):
+        heads.add_reid_outputs(model, list(names), dims, preprefix="reid")
+    out = model.ws["reid_feature_concat_norm" if normalize else "reid_feature_concat"]
+    return np.asarray(out, np.float64), model.ops

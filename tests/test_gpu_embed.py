@@ -120,3 +120,23 @@ def test_embed_argument_errors(torch):
     w2, p2 = _params(2, 64, 64, seed=1)
     with pytest.raises(RuntimeError):
         _head(w2, p2)(torch.zeros((2, 4, 64), device="cuda"))                 # E != 128 -> PPS_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("name", ["embed_n3_c48", "embed_n6_c64", "embed_n4_raw"])
+def test_embed_matches_reference_graph_fixture(torch, golden, name):
+    """conv5 maps -> pool -> embed (-> normalise) on the device against what the reference's own add_reid_outputs
+    builder produces for the same parameters (tests/golden/embed_*.npz, oracle/make_golden_embed.py)."""
+    import pps_b200
+    d = golden(name)
+    n = int(d["n_parts"])
+    p = {k: d[k] for k in ("conv_bias", "bn_scale", "bn_bias", "bn_mean", "bn_var")}
+    head = _head(d["weight"], p)
+    x = torch.from_numpy(d["x"]).cuda()
+    normalize = bool(int(d["normalize"]))
+    want = d["feature"]
+    tol = 1e-5 * np.abs(want).max()
+    got = pps_b200.embed_maps(head, x, n_parts=n, mode="max_ave", normalize=normalize).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=tol)
+    blobs, _ = pps_b200.add_pps_part_head(x, int(x.shape[1]), 1.0 / 16, pps_b200.ReIDPoolCfg(BPM_STRIP_NUM=n, MAX_AVE_FEATURE=True))
+    got2 = pps_b200.add_reid_outputs(blobs, head, normalize=normalize).cpu().numpy()
+    np.testing.assert_allclose(got2, want, rtol=1e-5, atol=tol)

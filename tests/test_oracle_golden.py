@@ -158,3 +158,18 @@ def test_pooling_restatement_matches_live_reference_graph():
         want = O.pps_pool(x, n, split=O.uniform_partition_split(n), mode="max_ave" if max_ave else "avg_max")
         assert len(arrs) == (1 << n) - 1 and dims == [24] * len(arrs)
         np.testing.assert_array_equal(np.stack([a.reshape(2, 24) for a in arrs], 1), want)
+
+
+EMBED_CASES = ["embed_n3_c48", "embed_n6_c64", "embed_n4_raw"]
+
+
+@pytest.mark.parametrize("name", EMBED_CASES)
+def test_embedding_restatement_matches_reference_graph_fixture(golden, name):
+    """oracle.reid_embed == what the reference's own add_reid_outputs builder (reid_heads.py:34-127, executed eagerly
+    one image at a time by oracle/ref_pool_loader.run_reid_outputs) produces."""
+    d = golden(name)
+    n = int(d["n_parts"])
+    pooled = np.transpose(O.pps_pool(d["x"], n, split=[24 // n] * n, mode="max_ave"), (1, 0, 2))
+    p = {k: d[k] for k in ("conv_bias", "bn_scale", "bn_bias", "bn_mean", "bn_var")}
+    got = O.reid_embed(pooled, d["weight"], normalize=bool(int(d["normalize"])), **p)
+    np.testing.assert_allclose(got, d["feature"], rtol=1e-12, atol=1e-14)
