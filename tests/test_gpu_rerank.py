@@ -108,3 +108,27 @@ def test_re_ranking_no_query_expansion_and_small_k():
     for k1, k2, lam in ((5, 1, 0.0), (3, 2, 1.0), (12, 3, 0.3)):
         got = pps_b200.re_ranking(*mats, k1=k1, k2=k2, lambda_value=lam)
         np.testing.assert_allclose(got, O.re_ranking(*mats, k1=k1, k2=k2, lambda_value=lam), rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["evaluate_small", "evaluate_mixed_order"])
+def test_evaluate_matches_reference_evaluate_fixture(golden, name):
+    """pps_b200.evaluate(json_dataset, all_feats, output_dir) against the UNMODIFIED reference evaluate()
+    (reid_dataset_evaluator.py:29-209; oracle/make_golden_evaluate.py): image-name parsing, mark split, single-query
+    scores with cfg.REID.RERANK = False and the re-ranked scores with True."""
+    import pps_b200
+    d = golden(name)
+
+    class Dataset:
+        def get_roidb(self, gt=True):
+            return [{"image": str(im), "mark": int(m)} for im, m in zip(d["images"], d["marks"])]
+
+    nq = int((d["marks"] == 0).sum())
+    mAP, cmc, mq_mAP, mq_cmc = pps_b200.evaluate(Dataset(), d["feats"], None, verbose=False)
+    assert mq_mAP is None and mq_cmc is None
+    assert abs(mAP - float(d["mAP"])) < 1e-6
+    assert np.max(np.abs(cmc - d["cmc"])) <= 1.0 / nq + 1e-12
+    mAP, cmc, _, _ = pps_b200.evaluate(Dataset(), d["feats"], None, verbose=False, to_re_rank=True)
+    assert abs(mAP - float(d["mAP_rerank"])) < 2e-3
+    assert np.max(np.abs(cmc - d["cmc_rerank"])) <= 2.0 / nq + 1e-12
+    res = pps_b200.reid_results((mAP, cmc, None, None), name="toy")
+    assert res["toy"]["ReID"]["mAP"] == mAP and res["toy"]["ReID"]["CMC5"] == cmc[4] and res["toy"]["ReID"]["mq_mAP"] == -1
