@@ -462,6 +462,11 @@ int pps_embed_tc(const void* x_planes, int x_planes_n, long long N,
 int pps_l2_normalize_rows(const float* x, long long rows, int dim, long long ld,
                           float* out, long long ldo, void* stream);
 
+/* Multi-query pooling (reid_dataset_evaluator.py:131-143): out[g] = np.mean(feats[row_idx[group_off[g] :
+ * group_off[g+1]]], axis=0) - a float32 sum of the listed rows in order, then one division by their count. */
+int pps_group_mean_rows(const float* feats, long long ld, int dim, const int32_t* group_off, const int32_t* row_idx,
+                        long long n_groups, float* out, long long ldo, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Next row — k-reciprocal re-ranking, reid_dataset_evaluator.py:442-519
  * `re_ranking(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3)` (evaluate() :161-207;

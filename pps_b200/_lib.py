@@ -116,6 +116,7 @@ SIGNATURES = {
     "pps_batch_hard_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "pps_embed_tc": (_i, [_vp, _i, _ll, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _vp]),
     "pps_l2_normalize_rows": (_i, [_vp, _ll, _i, _ll, _vp, _ll, _vp]),
+    "pps_group_mean_rows": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _vp, _ll, _vp]),
     "pps_rerank_vcap": (_i, []),
     "pps_rerank_normalize": (_i, [_vp, _ll, _ll, _vp, _vp, _ll, _vp]),
     "pps_rerank_krecip": (_i, [_vp, _i, _ll, _i, _vp, _ll, _vp, _vp, _vp, _vp]),

@@ -161,6 +161,23 @@ __global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __r
   }
 }
 
+// Multi-query pooling (reid_dataset_evaluator.py:131-143): the features of the mark-2 images of one (id, camera) group
+// are averaged, `np.mean(mq_feat[rows], axis=0)` - a float32 sum of the rows in list order, then one division by the
+// count.  One CTA per group, thread = feature columns, rows added in order (bit-identical to NumPy's axis-0 reduction).
+__global__ void __launch_bounds__(256) group_mean_rows_kernel(const float* __restrict__ feats, long long ld, int dim,
+                                                              const int32_t* __restrict__ group_off,
+                                                              const int32_t* __restrict__ row_idx, float* __restrict__ out,
+                                                              long long ldo) {
+  const int gidx = blockIdx.x;
+  const int e0 = group_off[gidx], e1 = group_off[gidx + 1];
+  const float cnt = (float)(e1 - e0);
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    float acc = 0.f;
+    for (int e = e0; e < e1; ++e) acc = __fadd_rn(acc, feats[(long long)row_idx[e] * ld + c]);
+    out[(long long)gidx * ldo + c] = e1 > e0 ? __fdiv_rn(acc, cnt) : 0.f;
+  }
+}
+
 }  // namespace pps
 
 using namespace pps;
@@ -237,4 +254,16 @@ extern "C" int pps_split_rows_gather(const void* feats, int dtype, const int32_t
   if ((!out_planes || !row_index) && rows > 0) return PPS_ERR_INVALID_ARG;
   return split_dispatch(feats, dtype, 0, rows, rows, dim, ld, planes, out_planes, out_sqnorm, stream, row_index,
                         index_base);
+}
+
+extern "C" int pps_group_mean_rows(const float* feats, long long ld, int dim, const int32_t* group_off,
+                                   const int32_t* row_idx, long long n_groups, float* out, long long ldo, void* stream) {
+  if (n_groups < 0 || dim <= 0 || ld < dim || ldo < dim) return PPS_ERR_INVALID_ARG;
+  if (n_groups == 0) return PPS_OK;
+  if (!feats || !group_off || !row_idx || !out) return PPS_ERR_INVALID_ARG;
+  if (n_groups > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  group_mean_rows_kernel<<<(unsigned)n_groups, 256, 0, static_cast<cudaStream_t>(stream)>>>(feats, ld, dim, group_off, row_idx,
+                                                                                          out, ldo);
+  PPS_LAUNCH_CHECK("group_mean_rows_kernel");
+  return PPS_OK;
 }

@@ -1012,6 +1012,27 @@ def get_info(entry):
     return parse_im_name(im_name, "id"), parse_im_name(im_name, "cam"), im_name, entry["mark"], entry["image"]
 
 
+def group_mean_rows(feats, groups):
+    """np.stack([np.mean(feats[rows], axis=0) for rows in groups]) on the device (pps_group_mean_rows): float32 sums
+    of the listed rows in order, one division by the count - the reference's multi-query pooling (:131-143)."""
+    torch = _torch()
+    lib = _lib.load()
+    if not feats.is_cuda or feats.dtype != torch.float32 or feats.dim() != 2 or feats.stride(1) != 1:
+        raise RuntimeError("group_mean_rows: expected a 2-D float32 CUDA tensor with unit column stride")
+    off = np.zeros(len(groups) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(g) for g in groups])
+    idx = np.asarray([r for g in groups for r in g], dtype=np.int32)
+    out = torch.empty((len(groups), int(feats.shape[1])), dtype=torch.float32, device=feats.device)
+    if len(groups):
+        off_d = torch.from_numpy(off).to(feats.device)
+        idx_d = torch.from_numpy(idx if idx.size else np.zeros(1, np.int32)).to(feats.device)
+        with torch.cuda.device(feats.device):
+            _lib.check(lib.pps_group_mean_rows(_lib.ptr(feats), int(feats.stride(0)), int(feats.shape[1]), _lib.ptr(off_d),
+                                               _lib.ptr(idx_d), len(groups), _lib.ptr(out), int(out.stride(0)),
+                                               _lib.stream_ptr()), "pps_group_mean_rows")
+    return out
+
+
 def evaluate_arrays(all_feats, ids, cams, marks, precision: str = DEFAULT_PRECISION, verbose: bool = False,
                     to_re_rank: bool = False):
     """The body of ``evaluate`` after the roidb has been flattened to arrays (:57-209).
@@ -1046,19 +1067,13 @@ def evaluate_arrays(all_feats, ids, cams, marks, precision: str = DEFAULT_PRECIS
     if np.any(mq_inds):
         # multi-query: average the mark==2 features of each (id, cam) group (:131-143)
         mq_ids, mq_cams = ids[mq_inds], cams[mq_inds]
-        mq_feat = feat_dev[torch.from_numpy(np.nonzero(mq_inds)[0]).to(feat_dev.device)].float()
+        mq_rows = np.nonzero(mq_inds)[0]
         groups = OrderedDict()
-        for ind, (i, c) in enumerate(zip(mq_ids.tolist(), mq_cams.tolist())):
-            groups.setdefault((i, c), []).append(ind)
+        for row, (i, c) in zip(mq_rows.tolist(), zip(mq_ids.tolist(), mq_cams.tolist())):
+            groups.setdefault((i, c), []).append(row)
         keys = list(groups.keys())
-        seg = torch.empty(len(mq_ids), dtype=torch.int64)
-        for k, key in enumerate(keys):
-            seg[groups[key]] = k
-        seg = seg.to(feat_dev.device)
-        pooled = torch.zeros((len(keys), mq_feat.shape[1]), dtype=torch.float32, device=feat_dev.device)
-        pooled.index_add_(0, seg, mq_feat)
-        counts = torch.bincount(seg, minlength=len(keys)).clamp_min(1).unsqueeze(1)
-        pooled = pooled / counts
+        src = feat_dev if feat_dev.dtype == torch.float32 and feat_dev.stride(1) == 1 else feat_dev.float().contiguous()
+        pooled = group_mean_rows(src, [groups[k] for k in keys])         # rows of the full feature array, in place
         mq_mAP, mq_cmc_scores = compute_score(pooled, np.array([k[0] for k in keys]), np.array([k[1] for k in keys]))
         if verbose:
             print("{:<30}".format("Multi Query:"), end="")

@@ -555,3 +555,17 @@ def test_topk_admission_in_distance_epilogue(golden):
     assert eng.fused_topk and not eng.used_fused_topk                    # the repeat ran without the epilogue path
     np.testing.assert_array_equal(got.topk_index, want.topk_index)
     np.testing.assert_array_equal(got.ap, want.ap)
+
+
+def test_group_mean_rows_is_numpy_mean():
+    """pps_group_mean_rows == np.stack([np.mean(feats[rows], axis=0) ...]) bit for bit (float32 sum in list order, then
+    one division), the multi-query pooling of reid_dataset_evaluator.py:131-143."""
+    import torch
+    from pps_b200 import evaluator
+    rs = np.random.RandomState(4)
+    f = rs.randn(50, 77).astype(np.float32)
+    groups = [[3], [0, 49, 7], list(range(10, 40)), [5, 5, 6]]
+    got = evaluator.group_mean_rows(torch.from_numpy(f).cuda(), groups).cpu().numpy()
+    want = np.stack([np.mean(f[g], axis=0) for g in groups])
+    np.testing.assert_array_equal(got, want)
+    assert evaluator.group_mean_rows(torch.from_numpy(f).cuda(), []).shape == (0, 77)
