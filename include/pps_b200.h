@@ -307,6 +307,18 @@ int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, long long m1, 
 int pps_rank_tab_finish(long long nq, int p_cap, const int32_t* tpair_tab, const uint32_t* cnt_tab,
                         uint32_t* cnt_le, void* stream);
 
+/* Secondary metric: AP as scikit-learn 0.18.1 computed it (trapezoidal area under the precision-recall curve) - the
+ * version reid_dataset_evaluator.py:398-407 asks for; pps_rank_finalize gives the step-wise AP of scikit-learn >= 0.19.
+ *   pps_rank_count_eq            cnt_eq[e] += #{columns of the block with distance EXACTLY pair_d[e]}
+ *   pps_rank_finalize_trapezoid  ap[q] = sum over the distinct positive distances v of
+ *                                (tp(v) - tp(<v)) / P * (tp(v) / n_le(v) + P_prev(v)) / 2,
+ *                                P_prev(v) = tp(<v) / n_lt(v) if n_lt(v) > 0 else 1, n_lt = n_le - n_eq (valid items only). */
+int pps_rank_count_eq(const float* dist, long long ldd, long long nq, long long ncols, const int32_t* pair_off,
+                      const float* pair_d, int max_pairs_per_query, uint32_t* cnt_eq, void* stream);
+int pps_rank_finalize_trapezoid(long long nq, const int32_t* pair_off, const int32_t* pair_g, const uint8_t* pair_pos,
+                                const float* pair_d, const uint32_t* cnt_le, const uint32_t* cnt_eq, double* ap,
+                                void* stream);
+
 int pps_topk_init(uint64_t* topk_key, long long nq, int k, void* stream);
 int pps_topk_update(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
                     const int32_t* excl_off, const int32_t* excl_g, const uint8_t* excl_keep,

@@ -87,6 +87,8 @@ SIGNATURES = {
     "pps_dist_rank_tc": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp, _ll, _i, _ll, _i, _i, _i, _ll, _i,
                               _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_rank_tab_finish": (_i, [_ll, _i, _vp, _vp, _vp, _vp]),
+    "pps_rank_count_eq": (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _i, _vp, _vp]),
+    "pps_rank_finalize_trapezoid": (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_topk_init": (_i, [_vp, _ll, _i, _vp]),
     "pps_topk_update": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp]),
     "pps_rank_sweep": (_i, [_vp, _ll, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),

@@ -693,6 +693,91 @@ __global__ void __launch_bounds__(kCntThreads) topk_merge_kernel(unsigned long l
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Secondary metric: AP as scikit-learn 0.18.1 defined it (the version reid_dataset_evaluator.py:398-407 asks for):
+// area under the precision-recall curve by the trapezoidal rule.  From counts, with v the distinct positive distances:
+//   AP = sum_v (tp(v) - tp(<v)) / P * ( tp(v) / n_le(v) + P_prev(v) ) / 2,
+//   P_prev(v) = tp(<v) / n_lt(v) if n_lt(v) > 0 else 1        (the curve's prepended (recall 0, precision 1) point)
+// n_lt = n_le - n_eq needs, besides the <=-counts of the main sweep, the number of items at EXACTLY each pair's
+// distance: rank_count_eq_kernel (a second, unhurried pass over the block; only run when this metric is asked for).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rank_count_eq_kernel(const float* __restrict__ dist, long long ldd, long long ncols,
+                                                            const int32_t* __restrict__ pair_off,
+                                                            const float* __restrict__ pair_d, int maxp,
+                                                            uint32_t* __restrict__ cnt_eq) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sd = reinterpret_cast<float*>(smem_raw);                  // [maxp]
+  uint32_t* se = reinterpret_cast<uint32_t*>(sd + maxp);           // [maxp]
+  __shared__ float s_min, s_max;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int e0 = pair_off[q], np = pair_off[q + 1] - e0;
+  if (np == 0) return;
+  for (int i = tid; i < np; i += blockDim.x) { sd[i] = pair_d[e0 + i]; se[i] = 0u; }
+  __syncthreads();
+  if (tid == 0) {
+    float mn = sd[0], mx = sd[0];
+    for (int i = 1; i < np; ++i) { mn = fminf(mn, sd[i]); mx = fmaxf(mx, sd[i]); }
+    s_min = mn; s_max = mx;
+  }
+  __syncthreads();
+  const float mn = s_min, mx = s_max;
+  const float* drow = dist + (long long)q * ldd;
+  for (long long c = tid; c < ncols; c += blockDim.x) {
+    const float d = drow[c];
+    if (d < mn || d > mx) continue;
+    for (int i = 0; i < np; ++i)
+      if (sd[i] == d) atomicAdd(&se[i], 1u);
+  }
+  __syncthreads();
+  for (int i = tid; i < np; i += blockDim.x)
+    if (se[i]) atomicAdd(&cnt_eq[e0 + i], se[i]);
+}
+
+__global__ void __launch_bounds__(128) rank_finalize_trapezoid_kernel(long long nq, const int32_t* __restrict__ pair_off,
+                                                                      const int32_t* __restrict__ pair_g,
+                                                                      const uint8_t* __restrict__ pair_pos,
+                                                                      const float* __restrict__ pair_d,
+                                                                      const uint32_t* __restrict__ cnt_le,
+                                                                      const uint32_t* __restrict__ cnt_eq,
+                                                                      double* __restrict__ ap) {
+  const int lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const int e0 = pair_off[q], e1 = pair_off[q + 1];
+  double acc = 0.0;
+  int npos = 0;
+  for (int e = e0 + lane; e < e1; e += 32) {
+    if (!pair_pos[e]) continue;
+    ++npos;
+    const float d = pair_d[e];
+    int tp = 0, tp_lt = 0, junk_le = 0, junk_eq = 0;
+    bool rep = true;                         // one term per distinct positive distance: its lowest pair index
+    for (int f = e0; f < e1; ++f) {
+      const float df = pair_d[f];
+      if (pair_pos[f]) {
+        tp += df <= d;
+        tp_lt += df < d;
+        rep &= !(df == d && f < e);
+      } else {
+        junk_le += df <= d;
+        junk_eq += df == d;
+      }
+    }
+    if (!rep) continue;
+    const double n_le = (double)((int)cnt_le[e] - junk_le);
+    const double n_lt = n_le - (double)((int)cnt_eq[e] - junk_eq);
+    const double p_prev = n_lt > 0.0 ? (double)tp_lt / n_lt : 1.0;
+    acc += (double)(tp - tp_lt) * ((double)tp / n_le + p_prev) * 0.5;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    npos += __shfl_xor_sync(0xffffffffu, npos, o);
+  }
+  if (lane == 0) ap[q] = npos > 0 ? acc / (double)npos : 0.0;
+  (void)pair_g;
+}
+
 }  // namespace pps
 
 using namespace pps;
@@ -894,5 +979,41 @@ extern "C" int pps_topk_merge(uint64_t* topk_key, long long nq, int k, const uin
       reinterpret_cast<unsigned long long*>(topk_key), k, reinterpret_cast<const unsigned long long*>(tk_cand), tk_cap, tk_cnt,
       tk_bound, filt ? pair_off : nullptr, pair_g, pair_pos, filt ? 1 : 0, overflow);
   PPS_LAUNCH_CHECK("topk_merge_kernel");
+  return PPS_OK;
+}
+
+// ---- secondary metric: trapezoidal AP (scikit-learn 0.18.1) ----
+extern "C" int pps_rank_count_eq(const float* dist, long long ldd, long long nq, long long ncols, const int32_t* pair_off,
+                                 const float* pair_d, int max_pairs_per_query, uint32_t* cnt_eq, void* stream) {
+  if (nq < 0 || ncols < 0 || ldd < ncols || max_pairs_per_query < 0) return PPS_ERR_INVALID_ARG;
+  if (nq == 0 || ncols == 0 || max_pairs_per_query == 0) return PPS_OK;
+  if (!dist || !pair_off || !pair_d || !cnt_eq) return PPS_ERR_INVALID_ARG;
+  if (nq > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)max_pairs_per_query * 8;
+  if (smem > 150 * 1024) return PPS_ERR_UNSUPPORTED;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  PPS_CUDA_TRY(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    PPS_CUDA_TRY(cudaFuncSetAttribute(rank_count_eq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+    configured_dev = dev;
+  }
+  rank_count_eq_kernel<<<(unsigned)nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(dist, ldd, ncols, pair_off, pair_d,
+                                                                                      max_pairs_per_query, cnt_eq);
+  PPS_LAUNCH_CHECK("rank_count_eq_kernel");
+  return PPS_OK;
+}
+
+extern "C" int pps_rank_finalize_trapezoid(long long nq, const int32_t* pair_off, const int32_t* pair_g,
+                                           const uint8_t* pair_pos, const float* pair_d, const uint32_t* cnt_le,
+                                           const uint32_t* cnt_eq, double* ap, void* stream) {
+  if (nq < 0) return PPS_ERR_INVALID_ARG;
+  if (nq == 0) return PPS_OK;
+  if (!pair_off || !ap) return PPS_ERR_INVALID_ARG;
+  const long long blocks = (nq + 3) / 4;
+  if (blocks > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  rank_finalize_trapezoid_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      nq, pair_off, pair_g, pair_pos, pair_d, cnt_le, cnt_eq, ap);
+  PPS_LAUNCH_CHECK("rank_finalize_trapezoid_kernel");
   return PPS_OK;
 }

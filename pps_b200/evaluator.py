@@ -309,8 +309,14 @@ def _finalize(lib, nq, pairs: PairLists, pair_d, cnt_le, cnt_first, want_neg_bef
 
 
 def rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams, want_neg_before=False, topk=0,
-                 topk_filtered=True) -> RankResult:
-    """Ranking outputs for a materialised [m, n] distance matrix (numpy or CUDA tensor)."""
+                 topk_filtered=True, ap_definition="step") -> RankResult:
+    """Ranking outputs for a materialised [m, n] distance matrix (numpy or CUDA tensor).
+
+    ap_definition: 'step' = scikit-learn >= 0.19 ``average_precision_score`` (what an unpinned install runs today);
+    'trapezoid' = scikit-learn 0.18.1 (the version reid_dataset_evaluator.py:398-407 asks for; needs one more pass
+    over the matrix for the exact-tie counts)."""
+    if ap_definition not in ("step", "trapezoid"):
+        raise RuntimeError("ap_definition must be 'step' or 'trapezoid'")
     torch = _torch()
     lib = _lib.load()
     dist, _ = _as_cuda_f32(distmat, "distmat")
@@ -333,6 +339,15 @@ def rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams, want
         _rank_block(lib, dist, int(dist.stride(0)), m, n, 0, pairs, pair_d, cnt_le, cnt_first, True, True, key, topk,
                     topk_filtered)
         ap, valid, first, negb = _finalize(lib, m, pairs, pair_d, cnt_le, cnt_first, want_neg_before)
+        if ap_definition == "trapezoid" and pairs.n_pairs:
+            cnt_eq = torch.zeros(E, dtype=torch.int32, device=dist.device)
+            _lib.check(lib.pps_rank_count_eq(_lib.ptr(dist), int(dist.stride(0)), m, n, _lib.ptr(pairs.dev("off")),
+                                             _lib.ptr(pair_d), pairs.max_pairs, _lib.ptr(cnt_eq), _lib.stream_ptr()),
+                       "pps_rank_count_eq")
+            _lib.check(lib.pps_rank_finalize_trapezoid(m, _lib.ptr(pairs.dev("off")), _lib.ptr(pairs.dev("g")),
+                                                       _lib.ptr(pairs.dev("pos")), _lib.ptr(pair_d), _lib.ptr(cnt_le),
+                                                       _lib.ptr(cnt_eq), _lib.ptr(ap), _lib.stream_ptr()),
+                       "pps_rank_finalize_trapezoid")
         ti = td = None
         if topk:
             td = torch.empty((m, topk), dtype=torch.float32, device=dist.device)
@@ -418,8 +433,15 @@ def compute_dist(array1, array2, type="euclidean", precision: str = DEFAULT_PREC
     m1, m2, dim = int(a.shape[0]), int(b.shape[0]), int(a.shape[1])
     with torch.cuda.device(a.device):
         if type == "cosine":
-            a = a.float() / torch.linalg.norm(a.float(), dim=1, keepdim=True).clamp_min(1e-12)
-            b = b.float() / torch.linalg.norm(b.float(), dim=1, keepdim=True).clamp_min(1e-12)
+            def unit_rows(x):
+                x = x.float().contiguous()
+                out = torch.empty_like(x)
+                if x.shape[0]:
+                    _lib.check(lib.pps_l2_normalize_rows(_lib.ptr(x), int(x.shape[0]), int(x.shape[1]), int(x.stride(0)),
+                                                         _lib.ptr(out), int(out.stride(0)), _lib.stream_ptr()),
+                               "pps_l2_normalize_rows")
+                return out
+            a, b = unit_rows(a), unit_rows(b)
         flags = _lib.DIST_DOT if type == "cosine" else 0
         out = torch.empty((m1, m2), dtype=torch.float32, device=a.device)
         if m1 and m2:
@@ -472,10 +494,12 @@ def cmc(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_cams
     return res.cmc(topk=topk, first_match_break=first_match_break, average=average)
 
 
-def mean_ap(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_cams=None, average=True):
-    """reid_dataset_evaluator.py:366-439 with the installed scikit-learn's (>= 0.19) AP definition."""
+def mean_ap(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_cams=None, average=True,
+            ap_definition="step"):
+    """reid_dataset_evaluator.py:366-439.  ``ap_definition='step'``: the AP of scikit-learn >= 0.19 (what an unpinned
+    install computes); ``'trapezoid'``: the scikit-learn 0.18.1 AP the reference asks for at :398-407."""
     _ensure_arrays(distmat, query_ids, gallery_ids, query_cams, gallery_cams)
-    res = rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams)
+    res = rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams, ap_definition=ap_definition)
     if average:
         return res.mean_ap()
     return res.ap, res.is_valid.astype(np.float64)

@@ -569,3 +569,19 @@ def test_group_mean_rows_is_numpy_mean():
     want = np.stack([np.mean(f[g], axis=0) for g in groups])
     np.testing.assert_array_equal(got, want)
     assert evaluator.group_mean_rows(torch.from_numpy(f).cuda(), []).shape == (0, 77)
+
+
+@pytest.mark.parametrize("name", ["small_mid", "ragged_dim", "many_pos", "dup_ties", "some_invalid"])
+def test_trapezoid_ap_definition(golden, name):
+    """mean_ap(ap_definition='trapezoid') == the scikit-learn 0.18.1 definition the reference asks for (:398-407),
+    restated in the oracle; exact duplicate distances (dup_ties) go through the exact-tie counts."""
+    import pps_b200
+    d = golden(name)
+    ids = dict(query_ids=d["qid"], gallery_ids=d["gid"], query_cams=d["qcam"], gallery_cams=d["gcam"])
+    want_aps, want_valid = O.mean_ap(d["dist"], average=False, ap_fn=O.average_precision_trapezoid, **ids)
+    aps, valid = pps_b200.mean_ap(d["dist"], average=False, ap_definition="trapezoid", **ids)
+    np.testing.assert_array_equal(valid, want_valid)
+    np.testing.assert_allclose(aps, want_aps, rtol=0, atol=1e-12)
+    step = pps_b200.mean_ap(d["dist"], **ids)
+    trap = pps_b200.mean_ap(d["dist"], ap_definition="trapezoid", **ids)
+    assert abs(step - float(d["mAP"])) < 1e-12 and trap != step
