@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PPS_ABI_VERSION 3
+#define PPS_ABI_VERSION 4
 
 /* ---- error codes (the Python mirror turns every non-zero code into RuntimeError,
  * like CAFFE_ENFORCE does: detectron/tests/test_zero_even_op.py:50-53) ---- */
