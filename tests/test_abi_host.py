@@ -162,3 +162,47 @@ def test_plan_blocks_covers_the_gallery_exactly():
             assert k * blk / first <= 2048 / 2.0                      # expected admissions per query and block
         else:
             assert blocks[0][1] == blk                                # tiny blocks (tests): nothing to shorten
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    lib = _lib.lib_path() if os.path.exists(_lib.lib_path()) else None
+    _lib.load()
+    libdir = os.path.dirname(_lib.lib_path())
+    exe = os.path.join(str(tmp_path), "evaluate_host")
+    cmd = [gcc, "-O2", "-Wall", "-Werror", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "evaluate_host.c"),
+           "-L", libdir, "-lpps_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert proc.returncode == 0, proc.stdout
+    return exe
+
+
+def test_header_is_plain_c_and_the_example_links(tmp_path):
+    """include/pps_b200.h compiles as C99 with -Wall -Werror, examples/evaluate_host.c links against the shared library
+    through the C ABI alone; without a CUDA device the call fails loudly (no CPU path)."""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    try:
+        import torch
+        has_cuda = torch.cuda.is_available()
+    except Exception:
+        has_cuda = False
+    if not has_cuda:
+        proc = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert proc.returncode != 0 and "pps_evaluate_host" in proc.stdout
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_the_device(tmp_path):
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    proc = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert proc.returncode == 0, proc.stdout
+    first = proc.stdout.splitlines()[0]
+    assert first.startswith("ABI %d" % _lib.ABI_VERSION) and "mAP" in first
+    m_ap = float(first.split("mAP")[1].split()[0])
+    assert 0.05 < m_ap <= 1.0
