@@ -206,3 +206,42 @@ def test_c_example_runs_on_the_device(tmp_path):
     assert first.startswith("ABI %d" % _lib.ABI_VERSION) and "mAP" in first
     m_ap = float(first.split("mAP")[1].split()[0])
     assert 0.05 < m_ap <= 1.0
+
+
+def test_host_partition_helpers_properties():
+    """Property tests (hypothesis) of the host-side partition logic: gallery shards and gallery blocks tile their range
+    exactly, in order, for any sizes; the strip tables always cover the map height."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 5_000_000), st.integers(1, 16))
+    def shards(ng, world):
+        parts = [evaluator.gallery_shard(ng, r, world) for r in range(world)]
+        assert parts[0][0] == 0 and sum(rows for _, rows in parts) == ng
+        assert all(a[0] + a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        sizes = [rows for _, rows in parts]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)      # np.array_split rule
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 20_000_000), st.integers(256, 2_000_000), st.integers(0, 128), st.sampled_from([4, 1024, 2048, 8192]))
+    def blocks(ng, blk, k, cap):
+        out = evaluator.plan_blocks(ng, blk, topk=k, cand_cap=cap)
+        assert sum(rows for _, rows in out) == ng
+        assert all(a[0] + a[1] == b[0] for a, b in zip(out, out[1:]))
+        assert all(0 < rows <= blk for _, rows in out)
+        assert (not out) or out[0][0] == 0
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.sampled_from([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12]), st.sampled_from([1 / 16., 1 / 8., 1 / 32.]))
+    def strips(n, scale):
+        split = pooling.uniform_partition_split(n, 384, scale)
+        assert len(split) == n and all(s == int(s) for s in split)
+        h = int(384 * scale)
+        tabled = n in (5, 7, 9, 10)                      # bpm_heads.py:25-40: rows of the 24-row tables times 16 * scale
+        if (tabled and scale in (1 / 16., 1 / 8.)) or (not tabled and h % n == 0):
+            assert sum(split) == h                       # otherwise Caffe2's Split refuses, as the reference's graph would
+        assert split == list(O.uniform_partition_split(n, 384, scale))
+
+    shards()
+    blocks()
+    strips()
