@@ -513,7 +513,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             atomicAdd(cnt_s + (b >> 1) * 128 + row, inc);
           }
           if (tie) {                                         // exact ties with the nearest positive: rare
-#pragma unroll 1
+#pragma unroll                                               // (unrolled: a runtime index would push d[] to local memory)
             for (int e = 0; e < 32; ++e)
               if (e < valid_cols && d[e] == dstar) tie_corr += ((colg + e) < gstar ? 1u : 0u) - 1u;
           }
