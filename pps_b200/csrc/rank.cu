@@ -144,7 +144,7 @@ __device__ __noinline__ void topk_admit(float d, unsigned long long gcol, unsign
 constexpr int kCandC = 2048;
 
 template <bool TOPK>
-__global__ void __launch_bounds__(kCntThreads, TOPK ? 8 : 16) rank_count_kernel(const float* __restrict__ dist, long long ldd,
+__global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 16) rank_count_kernel(const float* __restrict__ dist, long long ldd,
                                                                      long long ncols, long long col0, long long seg,
                                                                      const int32_t* __restrict__ pair_off,
                                                                      const int32_t* __restrict__ pair_g,
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kCntThreads, TOPK ? 8 : 16) rank_count_kernel(
             const float dv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
             if ((__float_as_uint(dv[0]) <= bh) | (__float_as_uint(dv[1]) <= bh) | (__float_as_uint(dv[2]) <= bh) |
                 (__float_as_uint(dv[3]) <= bh)) {
-#pragma unroll 1
+#pragma unroll                                               // (a runtime index would put dv[] in local memory)
               for (int e = 0; e < 4; ++e)
                 if (__float_as_uint(dv[e]) <= bh)
                   topk_admit(dv[e], (unsigned long long)(col0 + cu + e), bound, sj, nj, cand, &s_n, app_ctr);
