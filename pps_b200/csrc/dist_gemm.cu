@@ -263,7 +263,7 @@ struct TileWalk {
   int m_tile, n_tile;
   bool run_start, run_end;
 
-  __device__ TileWalk(const Gemm2Args& ga, long long pair_, long long npairs_) {
+  __host__ __device__ TileWalk(const Gemm2Args& ga, long long pair_, long long npairs_) {
     pair = pair_; npairs = npairs_;
     m_tiles = ga.g.m_tiles; n_tiles = ga.g.n_tiles;
     tiles_per_group = (long long)m_tiles * n_tiles;
@@ -272,7 +272,7 @@ struct TileWalk {
     sb = -1; n_sb = (int)((m_tiles + npairs - 1) / npairs); n_cur = 0; n_stop = 0;
     grp = 0; m_tile = 0; n_tile = 0; run_start = run_end = false;
   }
-  __device__ bool next() {
+  __host__ __device__ bool next() {
     if (EPI != EPI_RANK) {
       t += npairs;
       if (t >= tiles) return false;
@@ -1042,4 +1042,31 @@ extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, lon
       tmA, tmB, tmA /*no output map*/, ga, rf);
   PPS_LAUNCH_CHECK("dist_tc2_kernel<rank>");
   return PPS_OK;
+}
+
+// Instrumentation: the tile schedule of the 2-CTA kernel, replayed on the host (the same TileWalk the producer, MMA and
+// epilogue warps run).  out[i] = {group, m tile, n tile | run_start << 30 | run_end << 31} for the i-th tile of CTA pair
+// `pair` out of `npairs`; returns the number of tiles (also when it exceeds cap).  rank_order != 0: the EPI_RANK walk.
+extern "C" long long pps_debug_tile_walk(int rank_order, int m_tiles, int n_tiles, int groups, long long npairs,
+                                         long long pair, int32_t* out, long long cap) {
+  if (m_tiles < 0 || n_tiles < 0 || groups < 1 || npairs < 1 || pair < 0 || pair >= npairs) return PPS_ERR_INVALID_ARG;
+  Gemm2Args ga{};
+  ga.g.m_tiles = m_tiles; ga.g.n_tiles = n_tiles; ga.groups = groups;
+  long long n = 0;
+  auto emit = [&](long long grp, int m, int nt, bool rs, bool re) {
+    if (out && n < cap) {
+      out[3 * n + 0] = (int32_t)grp;
+      out[3 * n + 1] = m;
+      out[3 * n + 2] = (int32_t)((uint32_t)nt | (rs ? 0x40000000u : 0u) | (re ? 0x80000000u : 0u));
+    }
+    ++n;
+  };
+  if (rank_order) {
+    TileWalk<EPI_RANK> w(ga, pair, npairs);
+    while (w.next()) emit(w.grp, w.m_tile, w.n_tile, w.run_start, w.run_end);
+  } else {
+    TileWalk<EPI_DIST> w(ga, pair, npairs);
+    while (w.next()) emit(w.grp, w.m_tile, w.n_tile, false, false);
+  }
+  return n;
 }

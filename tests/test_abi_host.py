@@ -245,3 +245,39 @@ def test_host_partition_helpers_properties():
     shards()
     blocks()
     strips()
+
+
+def test_tile_schedules_visit_every_tile_exactly_once():
+    """The persistent tile walks of the 2-CTA distance kernel (replayed on the host by pps_debug_tile_walk): over all
+    CTA pairs every (group, m, n) tile appears exactly once; in the counting-epilogue order a pair's runs keep one m
+    tile, their n tiles are consecutive and run_start / run_end bracket them."""
+    lib = _lib.load()
+    rs = np.random.RandomState(0)
+    shapes = [(14, 78, 1, 74), (14, 2490, 1, 74), (1, 1, 1, 1), (3, 5, 1, 74), (100, 7, 1, 74), (75, 3, 1, 74), (1, 500, 1, 8),
+              (91, 63, 1, 74)] + [(int(rs.randint(1, 200)), int(rs.randint(1, 300)), 1, int(rs.randint(1, 80))) for _ in range(40)]
+    shapes += [(3, 1, 63, 74), (91, 1, 63, 74), (2, 1, 7, 5)]                    # grouped (embedding head): plain order only
+    for m_tiles, n_tiles, groups, npairs in shapes:
+        for rank_order in ((0,) if groups > 1 else (0, 1)):
+            seen = {}
+            total = m_tiles * n_tiles * groups
+            buf = np.zeros((total + 1, 3), dtype=np.int32)
+            for pair in range(npairs):
+                cnt = int(lib.pps_debug_tile_walk(rank_order, m_tiles, n_tiles, groups, npairs, pair, _lib.ptr(buf), total + 1))
+                assert 0 <= cnt <= total
+                prev = None
+                for i in range(cnt):
+                    grp, m, packed = int(buf[i, 0]), int(buf[i, 1]), int(buf[i, 2]) & 0xffffffff
+                    n, start, end = packed & 0x3fffffff, bool(packed & 0x40000000), bool(packed & 0x80000000)
+                    assert 0 <= grp < groups and 0 <= m < m_tiles and 0 <= n < n_tiles
+                    key = (grp, m, n)
+                    assert key not in seen, (m_tiles, n_tiles, npairs, rank_order, key)
+                    seen[key] = pair
+                    if rank_order:
+                        if prev is None or prev[2]:
+                            assert start
+                        else:
+                            assert not start and m == prev[0] and n == prev[1] + 1
+                        prev = (m, n, end)
+                if rank_order and cnt:
+                    assert prev[2]                                              # the last tile closes its run
+            assert len(seen) == total, (m_tiles, n_tiles, groups, npairs, rank_order, len(seen), total)
