@@ -147,3 +147,15 @@ def test_single_cta_kernel_still_agrees(monkeypatch):
     d1 = pps_b200.compute_dist(a, b)
     np.testing.assert_allclose(d1, d2, rtol=2e-6, atol=1e-6)
     np.testing.assert_allclose(d1, _f64_dist(a, b), rtol=1e-5)
+
+
+def test_full_concat_width_d8064():
+    """D = 8 064 = 63 x 128, the real reid_feature_concat length (reid_heads.py:95-101): 126 k-blocks per tile."""
+    import pps_b200
+    rs = np.random.RandomState(63)
+    a = rs.randn(70, 8064).astype(np.float32)
+    b = rs.randn(333, 8064).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    got = pps_b200.compute_dist(a, b)
+    np.testing.assert_allclose(got, O.compute_dist(a, b), rtol=1e-4, atol=1e-6)
