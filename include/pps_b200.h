@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PPS_ABI_VERSION 4
+#define PPS_ABI_VERSION 5
 
 /* ---- error codes (the Python mirror turns every non-zero code into RuntimeError,
  * like CAFFE_ENFORCE does: detectron/tests/test_zero_even_op.py:50-53) ---- */
@@ -81,6 +81,19 @@ int pps_pool_planes_fwd(const float* x, int N, int C, int H, int W,
                         const int* combos, int n_combos,
                         void* out_planes, int planes, void* stream);
 
+/* Backward of pps_pool_fwd: dx[N, C, H, W] = d loss / d x given dy = d loss / d y, addressed like y
+ * (element (n, k, c) at dy[n*dy_stride_n + k*dy_stride_k + c]).  The reference trains through this sub-graph (the
+ * multi-scale branch exists only at train time, pps_heads.py:88-142); a custom op would register it the way
+ * detectron/ops/pairwise_distance_op.cc:14-24 registers PairWiseDistanceGradient (inputs {X, dY} -> dX).  Gradients of
+ * the stock operators it fuses: AveragePool spreads d avg_j / (h_j W) over strip j; MaxPool routes d max_j to the first
+ * maximal element of the strip; Mean divides by |S|; Max passes dY to EVERY input equal to the maximum (Caffe2's
+ * MaxGradient), Add to both.  dx is written in full (no accumulation into an existing gradient). */
+int pps_pool_bwd(const float* x, const float* dy, int N, int C, int H, int W,
+                 int n_parts, const int* split, int mode,
+                 const int* combos, int n_combos,
+                 long long dy_stride_n, long long dy_stride_k,
+                 float* dx, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Part 2a — operand preparation for the tensor-core distance.
  *
@@ -90,9 +103,15 @@ int pps_pool_planes_fwd(const float* x, int N, int C, int H, int W,
  * fp64.  out_planes : [planes][rows][kpad] bf16 with kpad = pps_kpad(dim).
  * For PPS_DTYPE_F16 input there is no split: planes must be 1 and the rows are copied
  * (padded) as fp16.
+ * planes = 2 | PPS_SPLIT_F16_SCALED (fp32 input; what PPS_PREC_F16X3 consumes): the two planes are fp16
+ * roundings of the residual of the row SCALED by a power of two s (max|x| s in [2^14, 2^15)), i.e. 22
+ * significant bits per element instead of the 16 of two bf16 planes, at the same cost.  out_sqnorm then has
+ * 2 * rows entries: |x|^2 of every row, followed by the inverse scales 1 / s (exact powers of two); with the
+ * _slab form the second half starts at out_sqnorm + total_rows.
  * ---------------------------------------------------------------------------------- */
 #define PPS_DTYPE_F32 0
 #define PPS_DTYPE_F16 1
+#define PPS_SPLIT_F16_SCALED 0x100
 
 int       pps_kpad(int dim);
 long long pps_split_bytes(long long rows, int dim, int planes);
@@ -119,6 +138,10 @@ int pps_split_rows_gather(const void* feats, int dtype, const int32_t* row_index
  *   PPS_PREC_BF16X3  p0.p0 + p0.p1 + p1.p0, fp32 accumulate in TMEM   (default; ~3e-7 rel)
  *   PPS_PREC_BF16X6  all products down to 2^-24                       (fp32-exact grade)
  *   PPS_PREC_F16X1   operands are fp16 planes (dtype F16), one pass, exact products
+ *   PPS_PREC_F16X3   fp32 rows split into two power-of-two-scaled fp16 planes (PPS_SPLIT_F16_SCALED), the three
+ *                    terms of BF16X3; dot-product error ~2^-22 |a||b| / sqrt(K), below a float32 sgemm's own
+ *                    rounding (measured: tools/split_precision_sim.py).  a_sqnorm / b_sqnorm hold
+ *                    2 * plane_rows floats (norms, then inverse scales) and are required even with PPS_DIST_DOT
  *   PPS_PREC_FP32    CUDA-core fp32 FMA kernel on the original fp32 rows (a_f32/b_f32)
  * a_planes/b_planes come from pps_split_rows (need >= the planes the precision uses).
  * a_plane_rows / b_plane_rows: rows between consecutive planes of the buffer (0 = m1 / m2); a row
@@ -134,6 +157,7 @@ int pps_split_rows_gather(const void* feats, int dtype, const int32_t* row_index
 #define PPS_PREC_BF16X3 3
 #define PPS_PREC_BF16X6 6
 #define PPS_PREC_F16X1  16
+#define PPS_PREC_F16X3  19
 #define PPS_PREC_FP32   32
 
 #define PPS_DIST_SQUARED 1

@@ -415,3 +415,50 @@ def re_ranking(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3):
         jac = 1 - temp / (2. - temp)
         out[i] = jac * (1 - lambda_value) + od[i, nq:] * lambda_value                                    # :511-512
     return out.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------
+# pooling backward — gradients of the stock Caffe2 operators of the pooling sub-graph, restated (float64):
+# AveragePoolGradient (global) spreads dY / (h W); MaxPoolGradient routes dY to the maximal element (first one in
+# row-major order on ties); MeanGradient = dY / N to every input; MaxGradient passes dY to every input equal to the output;
+# Add passes dY to both.  **parity unpinned** like the forward operator arithmetic (Caffe2 is not importable); the test
+# pins it against float64 finite differences of pps_pool instead (the reference's own gradient-check style,
+# detectron/tests/test_batch_permutation_op.py:43-50).
+# ------------------------------------------------------------------------------------
+
+
+def pps_pool_grad(x, dy, n_parts=6, split=None, mode="max_ave", combos=None):
+    """dX [N, C, H, W] (float64) for dY [N, K, C]."""
+    x = np.asarray(x, dtype=np.float64)
+    dy = np.asarray(dy, dtype=np.float64)
+    N, C, H, W = x.shape
+    if split is None:
+        split = [H // n_parts] * n_parts
+    avg, mx = strip_pools(x, split, np.float64)                      # [n, N, C]
+    masks = list(combos) if combos is not None else list(range(1, 1 << n_parts))
+    d_avg = np.zeros_like(avg)
+    d_max = np.zeros_like(mx)
+    for k, m in enumerate(masks):
+        parts = [j for j in range(n_parts) if m & (1 << j)]
+        g = dy[:, k, :]
+        if mode == "max_ave":
+            top = np.max(mx[parts], axis=0)
+            for j in parts:
+                d_avg[j] += g / len(parts)
+                d_max[j] += g * (mx[j] == top)
+        else:
+            top = np.max(avg[parts], axis=0)
+            for j in parts:
+                d_avg[j] += g * (avg[j] == top)
+    dx = np.zeros_like(x)
+    r = 0
+    for j, h in enumerate(split):
+        dx[:, :, r:r + h, :] += (d_avg[j] / (h * W))[:, :, None, None]
+        if mode == "max_ave":
+            flat = x[:, :, r:r + h, :].reshape(N, C, h * W)
+            arg = np.argmax(flat, axis=2)                            # first maximum
+            sub = np.zeros((N, C, h * W))
+            np.put_along_axis(sub, arg[:, :, None], d_max[j][:, :, None], axis=2)
+            dx[:, :, r:r + h, :] += sub.reshape(N, C, h, W)
+        r += h
+    return dx

@@ -4,7 +4,7 @@ Python here is the thin host layer over ``libpps_b200.so`` (hand-written sm_100a
 the C ABI of ``include/pps_b200.h``); PyTorch only hands tensors and streams across.
 """
 from .pooling import (ReIDPoolCfg, add_pps_part_head, add_pps_part_head_, blob_names, comb_to_mask, mask_to_comb,
-                      pps_pool, pyramid_combs, uniform_partition_split)
+                      pps_pool, pps_pool_autograd, pps_pool_backward, pyramid_combs, uniform_partition_split)
 from .evaluator import (PairLists, RankEngine, RankResult, cmc, compute_dist, evaluate, evaluate_arrays, evaluate_host, mean_ap,
                         rank_distmat, rank_eval, reid_results)
 from .embedding import ReidEmbedHead, add_reid_outputs, embed_maps, fold_bn, l2_normalize_rows
@@ -12,7 +12,7 @@ from .rerank import re_ranking, re_ranking_from_features
 
 __all__ = [
     "ReIDPoolCfg", "add_pps_part_head", "add_pps_part_head_", "blob_names", "comb_to_mask", "mask_to_comb",
-    "pps_pool", "pyramid_combs", "uniform_partition_split",
+    "pps_pool", "pps_pool_autograd", "pps_pool_backward", "pyramid_combs", "uniform_partition_split",
     "PairLists", "RankEngine", "RankResult", "cmc", "compute_dist", "evaluate", "evaluate_arrays", "evaluate_host", "mean_ap",
     "rank_distmat", "rank_eval", "reid_results",
     "ReidEmbedHead", "add_reid_outputs", "embed_maps", "fold_bn", "l2_normalize_rows",

@@ -13,7 +13,7 @@ import threading
 from . import build as _build
 
 # ---- constants (keep in sync with include/pps_b200.h) ----
-ABI_VERSION = 4
+ABI_VERSION = 5
 PPS_OK = 0
 PPS_ERR_INVALID_ARG = -1
 PPS_ERR_SHAPE = -2
@@ -29,11 +29,13 @@ POOL_MAX_PARTS = 10
 
 DTYPE_F32 = 0
 DTYPE_F16 = 1
+SPLIT_F16_SCALED = 0x100
 
 PREC_BF16X1 = 1
 PREC_BF16X3 = 3
 PREC_BF16X6 = 6
 PREC_F16X1 = 16
+PREC_F16X3 = 19
 PREC_FP32 = 32
 
 DIST_SQUARED = 1
@@ -44,9 +46,14 @@ TOPK_MAX = 128
 N_PHASES = 7
 PHASE_NAMES = ["pairs_enqueue", "split", "dist_gemm", "pairs_wait_gather", "rank_count", "finalize", "d2h"]
 
-PRECISIONS = {"bf16x1": PREC_BF16X1, "bf16x3": PREC_BF16X3, "bf16x6": PREC_BF16X6,
+PRECISIONS = {"bf16x1": PREC_BF16X1, "bf16x3": PREC_BF16X3, "bf16x6": PREC_BF16X6, "f16x3": PREC_F16X3,
               "fp16": PREC_F16X1, "fp32": PREC_FP32}
-PLANES_FOR = {PREC_BF16X1: 1, PREC_BF16X3: 2, PREC_BF16X6: 3, PREC_F16X1: 1}
+PLANES_FOR = {PREC_BF16X1: 1, PREC_BF16X3: 2, PREC_BF16X6: 3, PREC_F16X1: 1, PREC_F16X3: 2}
+
+
+def split_planes_arg(prec: int) -> int:
+    """`planes` argument of pps_split_rows for a precision code (PPS_PREC_F16X3 wants scaled fp16 planes)."""
+    return (2 | SPLIT_F16_SCALED) if prec == PREC_F16X3 else PLANES_FOR[prec]
 
 _vp, _ll, _i = C.c_void_p, C.c_longlong, C.c_int
 
@@ -57,6 +64,7 @@ SIGNATURES = {
     "pps_last_cuda_error": (C.c_char_p, []),
     "pps_pool_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i), _i, _vp, _ll, _ll, _vp]),
     "pps_pool_planes_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i), _i, _vp, _i, _vp]),
+    "pps_pool_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i), _i, _ll, _ll, _vp, _vp]),
     "pps_kpad": (_i, [_i]),
     "pps_split_bytes": (_ll, [_ll, _i, _i]),
     "pps_split_rows": (_i, [_vp, _i, _ll, _i, _ll, _i, _vp, _vp, _vp]),

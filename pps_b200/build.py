@@ -20,8 +20,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
-    "-shared",
 ]
+OBJ_DIR = os.path.join(OUT_DIR, "obj")
 
 
 def nvcc_path():
@@ -39,24 +39,47 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def _compile_one(nvcc, src, obj, verbose):
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    proc = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return src, proc.returncode, proc.stdout
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into one shared library; returns its path."""
+    """Compile every CUDA source for sm_100a (one object per source, in parallel; objects newer than their source and
+    the shared headers are reused) and link them into one shared library; returns its path."""
     if not force and not is_stale():
         return LIB_PATH
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libpps_b200.so (set NVCC or install the CUDA toolkit)")
-    os.makedirs(OUT_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in HEADERS if os.path.exists(h))
+    jobs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        src_t = max(os.path.getmtime(os.path.join(CSRC, src)), hdr_t)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < src_t:
+            jobs.append((src, obj))
+    log = []
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            for src, rc, out in pool.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs):
+                log.append("== %s ==\n%s" % (src, out))
+                if rc != 0:
+                    raise RuntimeError("nvcc failed on %s (%d):\n%s" % (src, rc, out))
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs
     proc = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         if os.path.exists(tmp):
             os.remove(tmp)
-        raise RuntimeError("nvcc failed (%d):\n%s" % (proc.returncode, proc.stdout))
+        raise RuntimeError("nvcc link failed (%d):\n%s" % (proc.returncode, proc.stdout))
     os.replace(tmp, LIB_PATH)
     if verbose:
-        print(proc.stdout)
+        print("\n".join(log))
     return LIB_PATH
 
 

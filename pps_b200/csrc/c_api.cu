@@ -162,6 +162,7 @@ namespace {
 struct EvalShape {
   long long nq, ng /*rows of the local gallery block (and of its id arrays)*/, col0 /*its first global row*/, ldd;
   int dim, kpad, planes, precision, topk;
+  int split_planes;      // `planes` argument of pps_split_rows: planes, or 2 | PPS_SPLIT_F16_SCALED for PPS_PREC_F16X3
 };
 struct Staging {   // pinned: totals, per-query results
   int32_t* totals; double* ap; int32_t* first; uint8_t* valid;
@@ -258,8 +259,10 @@ int eval_shape(long long nq, long long ng, long long col0, int dim, int precisio
     case PPS_PREC_BF16X1: e->planes = 1; break;
     case PPS_PREC_BF16X3: e->planes = 2; break;
     case PPS_PREC_BF16X6: e->planes = 3; break;
+    case PPS_PREC_F16X3: e->planes = 2; break;
     default: return PPS_ERR_INVALID_ARG;
   }
+  e->split_planes = precision == PPS_PREC_F16X3 ? (2 | PPS_SPLIT_F16_SCALED) : e->planes;
   e->nq = nq; e->ng = ng; e->col0 = col0; e->dim = dim; e->precision = precision; e->topk = topk;
   e->ldd = (ng + 3) & ~3LL;
   e->kpad = pps_kpad(dim);
@@ -272,8 +275,8 @@ int eval_shape(long long nq, long long ng, long long col0, int dim, int precisio
 int ensure_common(pps_ctx* c, const EvalShape& e) {
   PPS_TRY(c->qs.ensure((size_t)pps_split_bytes(e.nq, e.dim, e.planes)));
   PPS_TRY(c->gs.ensure((size_t)pps_split_bytes(e.ng, e.dim, e.planes)));
-  PPS_TRY(c->qn.ensure((size_t)e.nq * 4));
-  PPS_TRY(c->gn.ensure((size_t)e.ng * 4));
+  PPS_TRY(c->qn.ensure((size_t)e.nq * 8));      // |x|^2 [rows] (+ the inverse row scales [rows] of PPS_PREC_F16X3)
+  PPS_TRY(c->gn.ensure((size_t)e.ng * 8));
   PPS_TRY(c->dist.ensure((size_t)e.nq * e.ldd * 4));
   PPS_TRY(c->pair_ws.ensure((size_t)pps_pairs_workspace_bytes(e.nq, e.ng)));
   PPS_TRY(c->pair_off.ensure(((size_t)e.nq + 1) * 4));
@@ -471,7 +474,7 @@ extern "C" int pps_evaluate_host_ctx(pps_ctx* c, const float* q_feats, long long
 
   // ---- queries up + split ----
   PPS_CUDA_TRY(cudaMemcpyAsync(c->qf.p, q_feats, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, cs));
-  PPS_TRY(pps_split_rows(c->qf.p, PPS_DTYPE_F32, nq, dim, dim, planes, c->qs.p, c->qn.as<float>(), cs));
+  PPS_TRY(pps_split_rows(c->qf.p, PPS_DTYPE_F32, nq, dim, dim, e.split_planes, c->qs.p, c->qn.as<float>(), cs));
 
   // ---- gallery in row slabs: H2D on the copy stream; split + distance of slab s overlap the copy of s+1 ----
   long long slab = ((ng + 7) / 8 + 255) & ~255LL;              // ~8 slabs, whole 256-column tiles
@@ -485,7 +488,7 @@ extern "C" int pps_evaluate_host_ctx(pps_ctx* c, const float* q_feats, long long
                                  cudaMemcpyHostToDevice, ps));
     PPS_CUDA_TRY(cudaEventRecord(c->ev_slab[si], ps));
     PPS_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_slab[si], 0));
-    PPS_TRY(pps_split_rows_slab(c->gf.p, PPS_DTYPE_F32, r0, nr, ng, dim, dim, planes, c->gs.p, c->gn.as<float>(), cs));
+    PPS_TRY(pps_split_rows_slab(c->gf.p, PPS_DTYPE_F32, r0, nr, ng, dim, dim, e.split_planes, c->gs.p, c->gn.as<float>(), cs));
     PPS_TRY(pps_dist_tc(c->qs.p, c->qn.as<float>(), nq, planes, 0,
                         c->gs.as<unsigned char>() + (size_t)r0 * kpad * esz, c->gn.as<float>() + r0, nr, planes, ng, dim,
                         precision, 0, c->dist.as<float>() + r0, ldd, cs));
@@ -529,8 +532,8 @@ extern "C" int pps_rank_begin(pps_ctx* c, const float* d_q, long long nq, const 
   if (d_local_cnt) *d_local_cnt = c->local_cnt;
   mark(c, 1, cs);
   // the distance block is enqueued NOW, so that the caller's all-gather (host latency included) hides under it
-  PPS_TRY(pps_split_rows(d_q, PPS_DTYPE_F32, e.nq, e.dim, e.dim, e.planes, c->qs.p, c->qn.as<float>(), cs));
-  PPS_TRY(pps_split_rows(d_g, PPS_DTYPE_F32, e.ng, e.dim, e.dim, e.planes, c->gs.p, c->gn.as<float>(), cs));
+  PPS_TRY(pps_split_rows(d_q, PPS_DTYPE_F32, e.nq, e.dim, e.dim, e.split_planes, c->qs.p, c->qn.as<float>(), cs));
+  PPS_TRY(pps_split_rows(d_g, PPS_DTYPE_F32, e.ng, e.dim, e.dim, e.split_planes, c->gs.p, c->gn.as<float>(), cs));
   mark(c, 2, cs);
   PPS_TRY(pps_dist_tc(c->qs.p, c->qn.as<float>(), e.nq, e.planes, 0, c->gs.p, c->gn.as<float>(), e.ng, e.planes, 0,
                       e.dim, e.precision, world > 1 ? PPS_DIST_RESERVE_SM_PAIR : 0, c->dist.as<float>(), e.ldd, cs));

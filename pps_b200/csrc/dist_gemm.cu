@@ -40,6 +40,8 @@ struct GemmArgs {
   uint32_t idesc;
   const float* a_sqnorm;
   const float* b_sqnorm;
+  const float* a_scale;       // PPS_PREC_F16X3: inverse power-of-two row scales of the operands (else nullptr)
+  const float* b_scale;
   float* out;
   long long ldo;
   int flags;
@@ -147,6 +149,8 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long gi = (long long)m0 + row;
       const bool row_ok = gi < g.m1;
       const float an = (row_ok && !want_dot) ? __ldg(g.a_sqnorm + gi) : 0.f;
+      const bool scaled = g.a_scale != nullptr;
+      const float cs = (scaled && row_ok) ? -2.f * __ldg(g.a_scale + gi) : -2.f;
       float* orow = g.out + (row_ok ? gi : 0) * g.ldo;
       const uint32_t tbase = tmem_base + as * kBN + ((uint32_t)(lane_grp * 32) << 16);
 #pragma unroll 1
@@ -160,13 +164,14 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const float dot = __uint_as_float(r[e]);
+            const long long gj = gj0 + e;
+            const float sc = (scaled && gj < g.m2) ? cs * __ldg(g.b_scale + gj) : cs;   // -2 / (s_a s_b): exact
             if (want_dot) {
-              v[e] = dot;
+              v[e] = scaled ? dot * (-0.5f * sc) : dot;
             } else {
-              const long long gj = gj0 + e;
               const float bn = gj < g.m2 ? __ldg(g.b_sqnorm + gj) : 0.f;
               // same association as the reference: (-2*ab + |a|^2) + |b|^2
-              float d2 = __fadd_rn(__fadd_rn(__fmul_rn(-2.f, dot), an), bn);
+              float d2 = __fadd_rn(__fadd_rn(__fmul_rn(sc, dot), an), bn);
               d2 = d2 < 0.f ? 0.f : d2;
               v[e] = want_sq ? d2 : __fsqrt_rn(d2);
             }
@@ -441,18 +446,29 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       // per-column operands of the tile -> shared (double-buffered by accumulator stage):
       // |b|^2 of the gallery rows, or alpha / beta of the output channels
-      float* bn = bn_s + as * 256;
+      // (scaled operands: |b|^2 and the column scales share the two buffers, so they are single-buffered and a
+      // second barrier at the end of the tile keeps a fast warp from refilling them early)
+      const bool scaled = EPI != EPI_AFFINE_RELU && EPI != EPI_RANK && g.a_scale != nullptr;
+      float* bn = bn_s + (scaled ? 0 : as * 256);
+      const float* sc_s = bn_s + 256;
       if (EPI == EPI_AFFINE_RELU) {
         const long long gj = (long long)n0 + etid;            // BN == 128 == number of epilogue threads
         bn[etid] = gj < n_end ? __ldg(g.a_sqnorm + gj) : 0.f;
         bn[etid + 128] = gj < n_end ? __ldg(g.b_sqnorm + gj) : 0.f;
-      } else if (!want_dot) {
+      } else {
         const long long gj = (long long)n0 + etid;
-        bn[etid] = gj < g.m2 ? __ldg(g.b_sqnorm + gj) : 0.f;
-        if (BN > 128) bn[etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_sqnorm + gj + 128) : 0.f;
+        if (!want_dot) {
+          bn[etid] = gj < g.m2 ? __ldg(g.b_sqnorm + gj) : 0.f;
+          if (BN > 128) bn[etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_sqnorm + gj + 128) : 0.f;
+        }
+        if (scaled) {
+          bn_s[256 + etid] = gj < g.m2 ? __ldg(g.b_scale + gj) : 0.f;
+          if (BN > 128) bn_s[256 + etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_scale + gj + 128) : 0.f;
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const float an = (EPI != EPI_AFFINE_RELU && gi < g.m1 && !want_dot) ? __ldg(g.a_sqnorm + gi) : 0.f;
+      const float cs = (scaled && gi < g.m1) ? -2.f * __ldg(g.a_scale + gi) : -2.f;    // -2 / s_a
       uint32_t tk_bound = 0u;                  // EPI_DIST_TOPK: nothing is admitted for padding rows
       if (EPI == EPI_DIST_TOPK && gi < g.m1) tk_bound = __ldg(rf.tk_bound + gi);
       mbar_wait(&tfull[as], aph);
@@ -533,16 +549,22 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const float4 c4 = reinterpret_cast<const float4*>(bn + 128 + c)[j];
               cc[0] = c4.x; cc[1] = c4.y; cc[2] = c4.z; cc[3] = c4.w;
             }
+            float sc[4] = {cs, cs, cs, cs};
+            if (scaled) {                       // -2 / (s_a s_b): a product of powers of two, exact
+              const float4 q4 = reinterpret_cast<const float4*>(sc_s + c)[j];
+              sc[0] = cs * q4.x; sc[1] = cs * q4.y; sc[2] = cs * q4.z; sc[3] = cs * q4.w;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float dot = __uint_as_float(r[4 * j + e]);
               if (EPI == EPI_AFFINE_RELU) {
                 v[e] = fmaxf(fmaf(dot, bb[e], cc[e]), 0.f);
               } else if (want_dot) {
-                v[e] = dot;
+                v[e] = scaled ? dot * (-0.5f * sc[e]) : dot;
               } else {
-                // same association as the reference: (-2*ab + |a|^2) + |b|^2   (-2*ab is exact, so the FMA rounds once)
-                float d2 = __fadd_rn(__fmaf_rn(-2.f, dot, an), bb[e]);
+                // same association as the reference: (-2*ab + |a|^2) + |b|^2   (-2*ab is exact, so the FMA rounds once;
+                // with scaled operands sc = -2 / (s_a s_b) and sc * dot is the same exact product)
+                float d2 = __fadd_rn(__fmaf_rn(sc[e], dot, an), bb[e]);
                 d2 = fmaxf(d2, 0.f);
                 v[e] = want_sq ? d2 : sqrt_approx(d2);
               }
@@ -579,6 +601,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (rank == 0) mbar_arrive(&tempty[as]);
         else mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[as]), 0));
       }
+      if (scaled) asm volatile("bar.sync 1, 128;" ::: "memory");   // every warp is done with bn / sc of this tile
       if (EPI == EPI_RANK && (w.run_end || ++tiles_since_flush == 255)) {
         // counters -> global table at the end of the run (a handful of CTA pairs share a row: atomics), and every 255
         // tiles in between so that no 16-bit counter can wrap
@@ -714,6 +737,11 @@ static int setup_terms(int precision, GemmArgs& g, bool* f16) {
     }
     case PPS_PREC_F16X1:
       g.nterms = 1; g.term_a[0] = 0; g.term_b[0] = 0; *f16 = true; return 1;
+    case PPS_PREC_F16X3: {
+      const int ta[3] = {1, 0, 0}, tb[3] = {0, 1, 0};
+      g.nterms = 3; for (int i = 0; i < 3; ++i) { g.term_a[i] = ta[i]; g.term_b[i] = tb[i]; }
+      *f16 = true; return 2;
+    }
     default: return 0;
   }
 }
@@ -738,25 +766,11 @@ static int dist_tc_impl(const void* a_planes, const float* a_sqnorm, long long m
   if (m1 > 0x7fffff00LL || m2 > 0x7fffff00LL) return PPS_ERR_UNSUPPORTED;   // TMA coordinates are int32
 
   GemmArgs g;
-  int need = 1;
   bool f16 = false;
-  switch (precision) {
-    case PPS_PREC_BF16X1:
-      g.nterms = 1; g.term_a[0] = 0; g.term_b[0] = 0; need = 1; break;
-    case PPS_PREC_BF16X3: {
-      const int ta[3] = {1, 0, 0}, tb[3] = {0, 1, 0};   // small terms first
-      g.nterms = 3; for (int i = 0; i < 3; ++i) { g.term_a[i] = ta[i]; g.term_b[i] = tb[i]; }
-      need = 2; break;
-    }
-    case PPS_PREC_BF16X6: {
-      const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
-      g.nterms = 6; for (int i = 0; i < 6; ++i) { g.term_a[i] = ta[i]; g.term_b[i] = tb[i]; }
-      need = 3; break;
-    }
-    case PPS_PREC_F16X1:
-      g.nterms = 1; g.term_a[0] = 0; g.term_b[0] = 0; need = 1; f16 = true; break;
-    default: return PPS_ERR_INVALID_ARG;
-  }
+  const int need = setup_terms(precision, g, &f16);
+  if (need == 0) return PPS_ERR_INVALID_ARG;
+  const bool scaled = precision == PPS_PREC_F16X3;
+  if (scaled && (!a_sqnorm || !b_sqnorm)) return PPS_ERR_INVALID_ARG;     // they carry the row scales too
   if (a_planes_n < need || b_planes_n < need) return PPS_ERR_INVALID_ARG;
 
   const int kpad = pps_kpad(dim);
@@ -765,6 +779,8 @@ static int dist_tc_impl(const void* a_planes, const float* a_sqnorm, long long m
   const uint32_t fmt = f16 ? 0u : 1u;   // F16F32Format: F16 = 0, BF16 = 1
   g.idesc = (1u << 4) /*D = f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
   g.a_sqnorm = a_sqnorm; g.b_sqnorm = b_sqnorm;
+  g.a_scale = scaled ? a_sqnorm + a_plane_rows : nullptr;
+  g.b_scale = scaled ? b_sqnorm + b_plane_rows : nullptr;
   g.out = dist; g.ldo = ldd; g.flags = flags;
   g.m_tiles = (int)((m1 + kBM - 1) / kBM);
   g.n_tiles = (int)((m2 + kBN - 1) / kBN);
@@ -930,6 +946,7 @@ extern "C" int pps_embed_tc(const void* x_planes /*[planes][K*N][kpad]*/, int x_
   g.kblocks = kpad / kBK;
   g.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   g.a_sqnorm = alpha; g.b_sqnorm = beta;
+  g.a_scale = nullptr; g.b_scale = nullptr;
   g.out = out; g.ldo = ldo; g.flags = 0;
   g.m_tiles = (int)((N + 255) / 256);
   g.n_tiles = 1;
@@ -996,6 +1013,7 @@ extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, lon
   Gemm2Args ga;
   GemmArgs& g = ga.g;
   bool f16 = false;
+  if (precision == PPS_PREC_F16X3) return PPS_ERR_UNSUPPORTED;   // the counting epilogue has no row-scale path
   const int need = setup_terms(precision, g, &f16);
   if (need == 0 || a_planes_n < need || b_planes_n < need) return PPS_ERR_INVALID_ARG;
   const int sms = sm_count();
@@ -1006,6 +1024,7 @@ extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, lon
   g.kblocks = kpad / kBK;
   g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   g.a_sqnorm = a_sqnorm; g.b_sqnorm = b_sqnorm;
+  g.a_scale = nullptr; g.b_scale = nullptr;
   g.out = nullptr; g.ldo = 0; g.flags = flags;
   g.m_tiles = (int)((m1 + 255) / 256);
   g.n_tiles = (int)((m2 + 255) / 256);

@@ -230,6 +230,131 @@ __global__ void __launch_bounds__(256) pool_generic_kernel(const __grid_constant
   combine_unit<NP, MODE>(a, pavg, pmax, warp, 8, lane, nch, n * a.ysn + c0);
 }
 
+// ------------------------------------------------------------------------------------
+// Backward of the fused pooling (the reference's multi-scale branch is train-only, pps_heads.py:88-142; a custom op
+// registers its gradient like detectron/ops/pairwise_distance_op.cc:14-24).  Gradients of the stock Caffe2 operators
+// the sub-graph is made of:
+//   Mean(avg_j, j in S)      d avg_j += dY_S / |S|
+//   Max(v_j, j in S)         d v_j   += dY_S where v_j == max          (Caffe2 MaxGradient: EVERY tied input gets dY)
+//   Add                      both inputs get dY
+//   AveragePool(global)      dX[e] = d avg_j / (h_j W) for every element of strip j
+//   MaxPool(global)          dX[arg max] = d max_j  (first maximal element in row-major order on ties)
+// One CTA per unit (image x 32 channels): (1) strip average / max / arg-max of every plane from x, (2) lane = channel walks
+// the combinations and accumulates d avg_j, d max_j from dY, (3) dX written once, coalesced.  HBM traffic per image:
+// x read once + dY read once + dX written once = 2 * 4 C H W + 4 K C bytes.
+// ------------------------------------------------------------------------------------
+struct PoolBwdArgs {
+  const float* dy;
+  float* dx;
+  long long dysn, dysk;
+};
+
+template <int NP, int MODE>
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const __grid_constant__ PoolArgs a, const __grid_constant__ PoolBwdArgs b) {
+  __shared__ float pavg[NP * kCB];
+  __shared__ float pmax[NP * kCB];
+  __shared__ int parg[NP * kCB];
+  __shared__ float d_avg[NP * kCB];      // gradient w.r.t. the strip average, already divided by the strip size
+  __shared__ float d_max[NP * kCB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = a.H * a.W;
+  const int cblocks = (a.C + kCB - 1) / kCB;
+  const long long u = blockIdx.x;
+  const long long n = u / cblocks;
+  const int c0 = (int)(u % cblocks) * kCB;
+  const int nch = min(kCB, a.C - c0);
+  for (int i = threadIdx.x; i < NP * kCB; i += 256) { d_avg[i] = 0.f; d_max[i] = 0.f; }
+  // (1) forward statistics of every plane
+  for (int pl = warp; pl < nch; pl += 8) {
+    const float* plane = a.x + (n * a.C + c0 + pl) * (long long)HW;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int e0 = a.row0[j] * a.W, e1 = a.row0[j + 1] * a.W;
+      float s = 0.f, mx = -FLT_MAX;
+      int arg = e1;
+      for (int e = e0 + lane; e < e1; e += 32) {
+        const float v = __ldg(plane + e);
+        s += v;
+        if (v > mx) { mx = v; arg = e; }        // ascending e per lane: the first maximum of the lane
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+      }
+      if (lane == 0) {
+        pavg[j * kCB + pl] = __fdiv_rn(s, (float)(e1 - e0));
+        pmax[j * kCB + pl] = mx;
+        parg[j * kCB + pl] = arg;
+      }
+    }
+  }
+  __syncthreads();
+  // (2) lane = channel: gradients of the strip statistics from the combinations' gradients
+  if (lane < nch) {
+    float av[NP], mv[NP], ga[NP], gm[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      av[j] = pavg[j * kCB + lane];
+      mv[j] = pmax[j * kCB + lane];
+      ga[j] = 0.f; gm[j] = 0.f;
+    }
+    const float* dyb = b.dy + n * b.dysn + c0 + lane;
+    for (int idx = warp; idx < a.n_out; idx += 8) {
+      const int m = a.use_list ? a.combos[idx] : idx + 1;
+      const float g = __ldg(dyb + (long long)idx * b.dysk);
+      if (MODE == PPS_POOL_MAX_AVE) {
+        float mx = -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) mx = ((m >> j) & 1) ? fmaxf(mx, mv[j]) : mx;
+        const int cnt = __popc(m);
+        const float gs = cnt > 1 ? g * a.inv_cnt[cnt] : g;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const bool on = (m >> j) & 1;
+          ga[j] += on ? gs : 0.f;
+          gm[j] += (on && mv[j] == mx) ? g : 0.f;
+        }
+      } else {
+        float mx = -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) mx = ((m >> j) & 1) ? fmaxf(mx, av[j]) : mx;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) ga[j] += (((m >> j) & 1) && av[j] == mx) ? g : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const float inv = 1.0f / (float)((a.row0[j + 1] - a.row0[j]) * a.W);
+      atomicAdd(&d_avg[j * kCB + lane], ga[j] * inv);
+      if (MODE == PPS_POOL_MAX_AVE) atomicAdd(&d_max[j * kCB + lane], gm[j]);
+    }
+  }
+  __syncthreads();
+  // (3) dX
+  for (int pl = warp; pl < nch; pl += 8) {
+    float* dplane = b.dx + (n * a.C + c0 + pl) * (long long)HW;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int e0 = a.row0[j] * a.W, e1 = a.row0[j + 1] * a.W;
+      const float base = d_avg[j * kCB + pl];
+      const float gmx = MODE == PPS_POOL_MAX_AVE ? d_max[j * kCB + pl] : 0.f;
+      const int arg = parg[j * kCB + pl];
+      for (int e = e0 + lane; e < e1; e += 32) st_stream_f32(dplane + e, base + (e == arg ? gmx : 0.f));
+    }
+  }
+}
+
+template <int NP>
+static int launch_pool_bwd(const PoolArgs& a, const PoolBwdArgs& b, long long units, cudaStream_t st) {
+  if (a.mode == PPS_POOL_MAX_AVE) pool_bwd_kernel<NP, PPS_POOL_MAX_AVE><<<(int)units, 256, 0, st>>>(a, b);
+  else pool_bwd_kernel<NP, PPS_POOL_AVG_MAX><<<(int)units, 256, 0, st>>>(a, b);
+  PPS_LAUNCH_CHECK("pool_bwd_kernel");
+  return PPS_OK;
+}
+
 template <int NP, int MODE>
 static int launch_pool(const PoolArgs& a, bool fast, long long units, size_t smem, cudaStream_t st) {
   if (fast) {
@@ -272,13 +397,12 @@ static int dispatch_parts(const PoolArgs& a, bool fast, long long units, size_t 
 
 using namespace pps;
 
-static int pool_launch(const float* x, int N, int C, int H, int W, int n_parts, const int* split, int mode,
-                       const int* combos, int n_combos, float* y, void* y_planes, int out_planes, long long plane_stride,
-                       long long y_stride_n, long long y_stride_k, void* stream) {
+// shape checks + strip table + combination list shared by the forward and the backward
+static int pool_setup(PoolArgs& a, int N, int C, int H, int W, int n_parts, const int* split, int mode, const int* combos,
+                      int n_combos) {
   if (N < 0 || C <= 0 || H <= 0 || W <= 0 || !split) return PPS_ERR_INVALID_ARG;
   if (mode != PPS_POOL_AVG_MAX && mode != PPS_POOL_MAX_AVE) return PPS_ERR_INVALID_ARG;
   if (n_parts < 1 || n_parts > PPS_POOL_MAX_PARTS) return PPS_ERR_SHAPE;
-  PoolArgs a;
   a.row0[0] = 0;
   for (int j = 0; j < n_parts; ++j) {
     if (split[j] <= 0) return PPS_ERR_SHAPE;
@@ -301,11 +425,23 @@ static int pool_launch(const float* x, int N, int C, int H, int W, int n_parts, 
     a.use_list = 0;
     a.n_out = full_mask;
   }
+  a.N = N; a.C = C; a.H = H; a.W = W;
+  a.n_parts = n_parts; a.mode = mode;
+  a.x = nullptr; a.y = nullptr; a.y_planes = nullptr; a.out_planes = 0; a.plane_stride = 0; a.ysn = 0; a.ysk = 0;
+  a.planes_per_stage = 0;
+  return PPS_OK;
+}
+
+static int pool_launch(const float* x, int N, int C, int H, int W, int n_parts, const int* split, int mode,
+                       const int* combos, int n_combos, float* y, void* y_planes, int out_planes, long long plane_stride,
+                       long long y_stride_n, long long y_stride_k, void* stream) {
+  PoolArgs a;
+  const int rc = pool_setup(a, N, C, H, W, n_parts, split, mode, combos, n_combos);
+  if (rc != PPS_OK) return rc;
   if (N == 0) return PPS_OK;
   if (!x || (!y && !y_planes)) return PPS_ERR_INVALID_ARG;
-  a.x = x; a.y = y; a.N = N; a.C = C; a.H = H; a.W = W;
+  a.x = x; a.y = y;
   a.y_planes = static_cast<__nv_bfloat16*>(y_planes); a.out_planes = y_planes ? out_planes : 0; a.plane_stride = plane_stride;
-  a.n_parts = n_parts; a.mode = mode;
   a.ysn = y_stride_n; a.ysk = y_stride_k;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -346,4 +482,35 @@ extern "C" int pps_pool_planes_fwd(const float* x, int N, int C, int H, int W, i
     PPS_CUDA_TRY(cudaMemsetAsync(out_planes, 0, (size_t)planes * rows * kpad * 2, static_cast<cudaStream_t>(stream)));
   return pool_launch(x, N, C, H, W, n_parts, split, mode, combos, n_combos, nullptr, out_planes, planes, rows * kpad,
                      (long long)kpad, (long long)N * kpad, stream);
+}
+
+// dX of pps_pool_fwd (see pool_bwd_kernel): x the forward input, dy the gradient of the forward output addressed like y
+// (element (n, k, c) at dy[n*dy_stride_n + k*dy_stride_k + c]), dx [N, C, H, W] written in full.
+extern "C" int pps_pool_bwd(const float* x, const float* dy, int N, int C, int H, int W, int n_parts, const int* split,
+                            int mode, const int* combos, int n_combos, long long dy_stride_n, long long dy_stride_k,
+                            float* dx, void* stream) {
+  PoolArgs a;
+  const int rc = pool_setup(a, N, C, H, W, n_parts, split, mode, combos, n_combos);
+  if (rc != PPS_OK) return rc;
+  if (N == 0) return PPS_OK;
+  if (!x || !dy || !dx) return PPS_ERR_INVALID_ARG;
+  a.x = x;
+  PoolBwdArgs b;
+  b.dy = dy; b.dx = dx; b.dysn = dy_stride_n; b.dysk = dy_stride_k;
+  const long long units = (long long)N * ((C + kCB - 1) / kCB);
+  if (units > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (n_parts) {
+    case 1: return launch_pool_bwd<1>(a, b, units, st);
+    case 2: return launch_pool_bwd<2>(a, b, units, st);
+    case 3: return launch_pool_bwd<3>(a, b, units, st);
+    case 4: return launch_pool_bwd<4>(a, b, units, st);
+    case 5: return launch_pool_bwd<5>(a, b, units, st);
+    case 6: return launch_pool_bwd<6>(a, b, units, st);
+    case 7: return launch_pool_bwd<7>(a, b, units, st);
+    case 8: return launch_pool_bwd<8>(a, b, units, st);
+    case 9: return launch_pool_bwd<9>(a, b, units, st);
+    case 10: return launch_pool_bwd<10>(a, b, units, st);
+    default: return PPS_ERR_SHAPE;
+  }
 }

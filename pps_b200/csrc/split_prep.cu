@@ -124,6 +124,95 @@ __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_kernel(const void
   if (lane == 0 && out_sqnorm) out_sqnorm[row] = (float)acc;
 }
 
+// fp32 rows -> TWO fp16 residual planes of the row scaled by a power of two (PPS_SPLIT_F16_SCALED): with
+// s = 2^e chosen per row so that max|x| * s lies in [2^14, 2^15), p0 = fp16(x s), p1 = fp16(x s - p0).  fp16 carries
+// 11 significant bits, so p0 + p1 holds 22 bits of every element (bf16 planes: 16) at the same two-plane cost, and
+// the scaling keeps p1 out of the fp16 subnormals.  The distance epilogue multiplies the accumulator by the two
+// inverse scales - exact, they are powers of two.  out_sqnorm[row] = |x|^2, out_sqnorm[rows + row] = 1 / s.
+// The first 16 float4 of a lane (k < 2048) stay in registers between the max pass and the split pass; longer rows
+// re-read their tail (L1 / L2).
+constexpr int kF16Cache4 = 16;
+
+__global__ void __launch_bounds__(32 * kSplitWarps) split_rows_f16s_kernel(const float* __restrict__ feats, long long row_begin,
+                                                                            long long row_end, long long rows, int dim,
+                                                                            long long ld, int kpad,
+                                                                            __half* __restrict__ out_planes,
+                                                                            float* __restrict__ out_sqnorm,
+                                                                            const int32_t* __restrict__ row_index,
+                                                                            long long index_base) {
+  const int lane = threadIdx.x & 31;
+  const long long row = row_begin + (long long)blockIdx.x * kSplitWarps + (threadIdx.x >> 5);
+  if (row >= row_end) return;
+  const long long srow = row_index ? (long long)row_index[row] - index_base : row;
+  const float* src = feats + srow * ld;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(feats) & 15u) == 0);
+  auto load4 = [&](int k, bool stream) -> float4 {
+    if (vec && k + 3 < dim)
+      return stream ? ld_stream_f4(reinterpret_cast<const float4*>(src + k)) : *reinterpret_cast<const float4*>(src + k);
+    float4 t;
+    t.x = k < dim ? src[k] : 0.f;
+    t.y = k + 1 < dim ? src[k + 1] : 0.f;
+    t.z = k + 2 < dim ? src[k + 2] : 0.f;
+    t.w = k + 3 < dim ? src[k + 3] : 0.f;
+    return t;
+  };
+  double acc = 0.0;
+  float mx = 0.f;
+  auto note = [&](const float4& t) {
+    acc += (double)t.x * (double)t.x + (double)t.y * (double)t.y + (double)t.z * (double)t.z + (double)t.w * (double)t.w;
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+  };
+  float4 cache[kF16Cache4];
+#pragma unroll
+  for (int u = 0; u < kF16Cache4; ++u) {
+    const int k = lane * 4 + u * 128;
+    cache[u] = k < kpad ? load4(k, true) : make_float4(0.f, 0.f, 0.f, 0.f);
+    note(cache[u]);
+  }
+  for (int k = lane * 4 + kF16Cache4 * 128; k < kpad; k += 128) note(load4(k, false));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  int e = 0;
+  if (mx > 0.f && mx <= 3.0e38f) {          // (NaN / inf rows keep s = 1: their distances are NaN / inf either way)
+    int ex;
+    frexpf(mx, &ex);                        // mx = m * 2^ex, m in [0.5, 1)
+    e = 15 - ex;
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  }
+  const float s = ldexpf(1.f, e), inv = ldexpf(1.f, -e);
+  const long long plane_stride = rows * (long long)kpad;
+  __half* dst = out_planes + row * (long long)kpad;
+  auto emit = [&](int k, const float4& t) {
+    const float v[4] = {t.x * s, t.y * s, t.z * s, t.w * s};
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hi[i] = __float2half_rn(v[i]);
+      lo[i] = __float2half_rn(v[i] - __half2float(hi[i]));     // the residual is exact in fp32
+    }
+    uint2 w0, w1;
+    w0.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
+    w0.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
+    w1.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
+    w1.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
+    *reinterpret_cast<uint2*>(dst + k) = w0;
+    *reinterpret_cast<uint2*>(dst + plane_stride + k) = w1;
+  };
+#pragma unroll
+  for (int u = 0; u < kF16Cache4; ++u) {
+    const int k = lane * 4 + u * 128;
+    if (k < kpad) emit(k, cache[u]);
+  }
+  for (int k = lane * 4 + kF16Cache4 * 128; k < kpad; k += 128) emit(k, load4(k, false));
+  if (lane == 0 && out_sqnorm) {
+    out_sqnorm[row] = (float)acc;
+    out_sqnorm[rows + row] = inv;
+  }
+}
+
 // Caffe2 Normalize(axis=1) of the concatenated embedding (reid_heads.py:123-127, triplet_loss.py:18):
 // y = x / max(|x|_2, 1e-12).  One CTA per row; the row (<= tens of KB) is read twice, the second time from L1/L2.
 __global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __restrict__ x, int dim, long long ld,
@@ -185,6 +274,7 @@ using namespace pps;
 extern "C" int pps_kpad(int dim) { return dim <= 0 ? 0 : ((dim + 63) / 64) * 64; }
 
 extern "C" long long pps_split_bytes(long long rows, int dim, int planes) {
+  if (planes & PPS_SPLIT_F16_SCALED) planes = 2;
   if (rows < 0 || dim <= 0 || planes < 1 || planes > 3) return PPS_ERR_INVALID_ARG;
   return rows * (long long)pps_kpad(dim) * 2 * planes;
 }
@@ -204,6 +294,10 @@ static int split_dispatch(const void* feats, int dtype, long long row0, long lon
   if (dtype == PPS_DTYPE_F16) {
     if (planes != 1) return PPS_ERR_INVALID_ARG;
     split_rows_kernel<1, true><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm, row_index, index_base);
+  } else if (dtype == PPS_DTYPE_F32 && (planes & PPS_SPLIT_F16_SCALED)) {
+    if ((planes & ~PPS_SPLIT_F16_SCALED) != 2 || !out_planes || !out_sqnorm) return PPS_ERR_INVALID_ARG;
+    split_rows_f16s_kernel<<<grid, block, 0, st>>>(static_cast<const float*>(feats), row0, row0 + nrows, rows, dim, ld, kpad,
+                                                   static_cast<__half*>(out_planes), out_sqnorm, row_index, index_base);
   } else if (dtype == PPS_DTYPE_F32) {
     switch (planes) {
       case 1: split_rows_kernel<1, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm, row_index, index_base); break;

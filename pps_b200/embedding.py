@@ -55,7 +55,7 @@ class ReidEmbedHead:
         if self.alpha.numel() != self.K * self.E or self.beta.numel() != self.K * self.E:
             raise RuntimeError("alpha / beta: expected %d values" % (self.K * self.E))
         self.prec = _prec_code(precision)
-        if self.prec not in _lib.PLANES_FOR or self.prec == _lib.PREC_F16X1:
+        if self.prec not in (_lib.PREC_BF16X1, _lib.PREC_BF16X3, _lib.PREC_BF16X6):
             raise RuntimeError("embedding precision must be one of bf16x1 / bf16x3 / bf16x6")
         self.device = dev
         with torch.cuda.device(dev):

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 
-DEFAULT_PRECISION = "bf16x3"
+DEFAULT_PRECISION = "f16x3"         # two scaled fp16 planes, three terms: see DESIGN.md 4.3
 # extra PPS_DIST_* flags OR-ed into every tensor-core distance call (tests / profiling use
 # _lib.DIST_KERNEL_1CTA to select the single-CTA kernel; 0 = the 2-CTA default)
 DIST_KERNEL_FLAGS = _lib.DIST_KERNEL_1CTA if os.environ.get("PPS_DIST_KERNEL", "") == "1cta" else 0
@@ -365,11 +365,13 @@ def rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams, want
 class SplitOperand:
     """Rows prepared for the tensor-core distance: bf16 residual planes (or fp16 rows) + |x|^2."""
 
-    def __init__(self, feats, planes: int):
+    def __init__(self, feats, planes: int, f16_scaled: bool = False):
+        """``f16_scaled``: two power-of-two-scaled fp16 planes (what the 'f16x3' precision consumes) instead of bf16
+        planes; ``sqnorm`` then carries the inverse row scales after the norms."""
         torch = _torch()
         lib = _lib.load()
         if feats.dtype == torch.float16:
-            dtype, planes = _lib.DTYPE_F16, 1
+            dtype, planes, f16_scaled = _lib.DTYPE_F16, 1, False
         elif feats.dtype == torch.float32:
             dtype = _lib.DTYPE_F32
         else:
@@ -377,17 +379,17 @@ class SplitOperand:
         if feats.stride(1) != 1:
             feats = feats.contiguous()
         self.rows, self.dim = int(feats.shape[0]), int(feats.shape[1])
-        self.planes_n, self.is_f16 = planes, dtype == _lib.DTYPE_F16
+        self.planes_n, self.is_f16, self.f16_scaled = planes, dtype == _lib.DTYPE_F16, bool(f16_scaled)
+        if f16_scaled and planes != 2:
+            raise RuntimeError("scaled fp16 operands have two planes")
         nbytes = int(lib.pps_split_bytes(self.rows, self.dim, planes)) if self.rows else 0
         self.planes = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=feats.device)
-        self.sqnorm = torch.empty(max(self.rows, 1), dtype=torch.float32, device=feats.device)
+        self.sqnorm = torch.empty(2 * max(self.rows, 1), dtype=torch.float32, device=feats.device)
         if self.rows:
-            _lib.check(lib.pps_split_rows(_lib.ptr(feats), dtype, self.rows, self.dim, int(feats.stride(0)), planes,
+            _lib.check(lib.pps_split_rows(_lib.ptr(feats), dtype, self.rows, self.dim, int(feats.stride(0)),
+                                          planes | (_lib.SPLIT_F16_SCALED if f16_scaled else 0),
                                           _lib.ptr(self.planes), _lib.ptr(self.sqnorm), _lib.stream_ptr()),
                        "pps_split_rows")
-
-    def rows_slice_ptr(self, r0):
-        raise NotImplementedError
 
 
 def _prec_code(precision):
@@ -404,6 +406,8 @@ def dist_block(a: SplitOperand, b: SplitOperand, prec: int, out, flags=0, b_row0
         raise RuntimeError("query and gallery features must have the same dtype")
     if a.is_f16:
         prec = _lib.PREC_F16X1
+    if (prec == _lib.PREC_F16X3) != (a.f16_scaled and b.f16_scaled):
+        raise RuntimeError("precision 'f16x3' needs (and only it takes) scaled fp16 operands")
     if b_row0 != 0 or b_rows != b.rows:
         # a row window of every plane: planes are [planes][rows][kpad], the TMA map needs the full
         # plane stride, so windows are expressed by a shifted base and the full row count upstream.
@@ -457,7 +461,8 @@ def compute_dist(array1, array2, type="euclidean", precision: str = DEFAULT_PREC
                                              m2, dim, flags, _lib.ptr(out), m2, _lib.stream_ptr()), "pps_dist_fp32")
             else:
                 planes = _lib.PLANES_FOR[prec]
-                sa, sb = SplitOperand(a, planes), SplitOperand(b, planes)
+                scaled = prec == _lib.PREC_F16X3 and a.dtype == torch.float32 and b.dtype == torch.float32
+                sa, sb = SplitOperand(a, planes, scaled), SplitOperand(b, planes, scaled)
                 dist_block(sa, sb, prec, out, flags)
     if a_np and b_np:
         return out.cpu().numpy()
@@ -554,6 +559,7 @@ class RankEngine:
         if self.prec == _lib.PREC_FP32:
             raise RuntimeError("rank_eval runs the distance on the tensor cores; use bf16x1/bf16x3/bf16x6 (or fp16 inputs)")
         self.planes = _lib.PLANES_FOR[self.prec]
+        self.split_arg = _lib.split_planes_arg(self.prec)        # `planes` argument of the split calls
         self.in_code = _lib.DTYPE_F16 if self.is_f16 else _lib.DTYPE_F32
         nq_, ngl_ = max(self.nq, 1), self.ngl
         chunk = ngl_ if self.nq == 0 else max(256, min(ngl_, max_block_bytes // (4 * nq_)))
@@ -566,8 +572,8 @@ class RankEngine:
             e8 = lambda n: torch.empty(max(int(n), 16), dtype=torch.uint8, device=dev)
             self.q_planes = e8(lib.pps_split_bytes(nq_, self.dim, self.planes))
             self.g_planes = e8(lib.pps_split_bytes(max(chunk, 1), self.dim, self.planes))
-            self.q_sq = torch.empty(nq_, dtype=torch.float32, device=dev)
-            self.g_sq = torch.empty(max(chunk, 1), dtype=torch.float32, device=dev)
+            self.q_sq = torch.empty(2 * nq_, dtype=torch.float32, device=dev)           # norms (+ 'f16x3' row scales)
+            self.g_sq = torch.empty(2 * max(chunk, 1), dtype=torch.float32, device=dev)
             self.block = torch.empty((nq_, self.ldd), dtype=torch.float32, device=dev)
             self.cnt_first = torch.zeros(nq_, dtype=torch.int32, device=dev)
             self.key = torch.empty((nq_, self.topk), dtype=torch.int64, device=dev) if self.topk else None
@@ -714,7 +720,7 @@ class RankEngine:
                                                    _lib.stream_ptr()), "pps_row_sqnorm")
                 return
             _lib.check(self.lib.pps_split_rows(_lib.ptr(feats), self.in_code, rows, self.dim, int(feats.stride(0)),
-                                               self.planes, _lib.ptr(planes_buf), _lib.ptr(sq_buf), _lib.stream_ptr()),
+                                               self.split_arg, _lib.ptr(planes_buf), _lib.ptr(sq_buf), _lib.stream_ptr()),
                        "pps_split_rows")
 
     def _fused_count_sweep(self, g, chunks, pairs, pair_d, cnt_le, cnt_first):
@@ -776,7 +782,7 @@ class RankEngine:
             rows = min(self.chunk, n_rows - c0)
             self._g_ptr = _lib.ptr(self.g_planes)
             _lib.check(lib.pps_split_rows_gather(_lib.ptr(g), self.in_code, _lib.ptr(self._gp_rows[c0:]), self.offset, rows,
-                                                 self.dim, int(g.stride(0)), self.planes, _lib.ptr(self.g_planes),
+                                                 self.dim, int(g.stride(0)), self.split_arg, _lib.ptr(self.g_planes),
                                                  _lib.ptr(self.g_sq), s), "pps_split_rows_gather")
             self._distance(rows)
             _lib.check(lib.pps_rank_gather(_lib.ptr(self.block), self.ldd, self.nq, rows, c0, _lib.ptr(pairs.dev("q")),
@@ -885,7 +891,7 @@ class RankEngine:
                 dist_mod.all_reduce(pair_d, op=dist_mod.ReduceOp.SUM, group=self.group)
             # sweep 2: counts (+ top-k); a single chunk is still resident in the block
             fused = (self.fused_rank and self.n_chunks > 1 and not self.topk and pairs.n_pairs > 0
-                     and pairs.max_pairs <= 64)
+                     and pairs.max_pairs <= 64 and self.prec != _lib.PREC_F16X3)
             self.used_fused_rank = bool(fused)
             if fused:
                 # thresholds are known: the counters are taken in the epilogue of the distance kernel and the

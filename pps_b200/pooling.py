@@ -132,6 +132,64 @@ def pps_pool(x, n_parts: int = 6, split: Optional[Sequence[int]] = None, mode="m
     return out
 
 
+def pps_pool_backward(x, dy, n_parts: int = 6, split: Optional[Sequence[int]] = None, mode="max_ave",
+                      combos: Optional[Sequence[int]] = None, layout: str = "nkc"):
+    """Gradient of ``pps_pool`` w.r.t. ``x`` (pps_pool_bwd of the C ABI): ``dy`` has the shape / layout of the forward
+    output.  Operator gradients as in Caffe2 (see include/pps_b200.h): ties between strips in ``Max`` all receive dY, the
+    max pool routes to the first maximal element of the strip."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    _check_input(x)
+    N, Cc, H, W = (int(v) for v in x.shape)
+    if split is None:
+        split = [H // n_parts] * n_parts
+    split = [int(s) for s in split]
+    if len(split) != n_parts:
+        raise RuntimeError("pps_pool: len(split) == n_parts required")
+    K = (1 << n_parts) - 1 if combos is None else len(combos)
+    if layout == "nkc":
+        shape, sn, sk = (N, K, Cc), K * Cc, Cc
+    elif layout == "knc":
+        shape, sn, sk = (K, N, Cc), Cc, N * Cc
+    else:
+        raise RuntimeError("pps_pool: layout must be 'nkc' or 'knc'")
+    if (not isinstance(dy, torch.Tensor) or not dy.is_cuda or dy.dtype != torch.float32 or tuple(dy.shape) != shape
+            or dy.device != x.device):
+        raise RuntimeError("pps_pool_backward: dy must be a float32 CUDA tensor of shape %s" % (shape,))
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    split_arr = (C.c_int * n_parts)(*split)
+    if combos is None:
+        combos_arr, n_combos = None, 0
+    else:
+        combos_arr, n_combos = (C.c_int * len(combos))(*[int(m) for m in combos]), len(combos)
+    with torch.cuda.device(x.device):
+        rc = lib.pps_pool_bwd(_lib.ptr(x), _lib.ptr(dy), N, Cc, H, W, n_parts, split_arr, _mode_code(mode), combos_arr,
+                              n_combos, int(sn), int(sk), _lib.ptr(dx), _lib.stream_ptr())
+    _lib.check(rc, "pps_pool_bwd")
+    return dx
+
+
+def pps_pool_autograd(x, n_parts: int = 6, split: Optional[Sequence[int]] = None, mode="max_ave",
+                      combos: Optional[Sequence[int]] = None, layout: str = "nkc"):
+    """``pps_pool`` as a differentiable torch op (forward pps_pool_fwd, backward pps_pool_bwd) - what the train-time
+    multi-scale branch (pps_heads.py:106-135) needs."""
+    torch = _lib.require_cuda()
+
+    class _Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, inp):
+            ctx.save_for_backward(inp)
+            return pps_pool(inp, n_parts, split, mode, combos, layout)
+
+        @staticmethod
+        def backward(ctx, grad):
+            (inp,) = ctx.saved_tensors
+            return pps_pool_backward(inp, grad, n_parts, split, mode, combos, layout)
+
+    return _Fn.apply(x)
+
+
 def add_uniform_partition_split(cfg: ReIDPoolCfg, spatial_scale: float) -> List[int]:
     return uniform_partition_split(cfg.BPM_STRIP_NUM, cfg.SCALE[1], spatial_scale)
 
@@ -145,7 +203,8 @@ def add_pps_part_head_(blob_in, dim_in, spatial_scale, cfg: Optional[ReIDPoolCfg
         # Caffe2 Split enforces that the split sizes cover the axis
         raise RuntimeError("Split: sum(split) == input.dim(axis) failed: %d vs %d" % (sum(split), blob_in.shape[2]))
     combos = [comb_to_mask(c) for c in pyramid_combs] if cfg.PYRAMID_COMBS_ONLY else None
-    y = pps_pool(blob_in, n, split, "max_ave" if cfg.MAX_AVE_FEATURE else "avg_max", combos=combos, layout="knc")
+    pool = pps_pool_autograd if getattr(blob_in, "requires_grad", False) else pps_pool   # train: gradients flow to the map
+    y = pool(blob_in, n, split, "max_ave" if cfg.MAX_AVE_FEATURE else "avg_max", combos=combos, layout="knc")
     blobs_out = [y[k].view(y.shape[1], y.shape[2], 1, 1) for k in range(y.shape[0])]
     dims_out = [dim_in] * len(blobs_out)
     return blobs_out, dims_out
@@ -182,6 +241,17 @@ def add_pps_part_head(blob_in, dim_in, spatial_scale, cfg: Optional[ReIDPoolCfg]
             if int(b.shape[1]) != Cc:
                 raise RuntimeError("Concat: all levels must have the same channel count when REID.FPN_SHARED")
         n_total = sum(int(b.shape[0]) for b in blob_in)
+        if any(b.requires_grad for b in blob_in):
+            # differentiable form: one autograd node per level, Concat(axis=0) of the batch slices
+            mode = "max_ave" if cfg.MAX_AVE_FEATURE else "avg_max"
+            ys = []
+            for i, b in enumerate(blob_in):
+                split = add_uniform_partition_split(cfg, spatial_scale[i])
+                if sum(split) != int(b.shape[2]):
+                    raise RuntimeError("Split: sum(split) == input.dim(axis) failed: %d vs %d" % (sum(split), b.shape[2]))
+                ys.append(pps_pool_autograd(b, n, split, mode, combos=combos, layout="knc"))
+            y = torch.cat(ys, dim=1)
+            return [y[k].reshape(n_total, Cc, 1, 1) for k in range(K)], [dim_in[0]] * K
         y = torch.empty((K, n_total, Cc), dtype=torch.float32, device=blob_in[0].device)
         row = 0
         for i, b in enumerate(blob_in):

@@ -54,3 +54,35 @@ def make_conv5(n, c=2048, h=24, w=8, seed=0):
     """Post-ReLU conv5 maps (ResNet.py:195 ends res5 with a ReLU, so values are non-negative)."""
     rs = np.random.RandomState(seed)
     return np.maximum(rs.randn(n, c, h, w), 0.0).astype(np.float32)
+
+
+def make_distractor_ids(nq, ng, n_real=16932, n_ids=750, n_cams=6, seed=0):
+    """Global id / camera arrays of BASELINE configs[3] / configs[4]: ``n_real`` gallery rows scattered over the
+    gallery carry Market-like identities, every other row is an id-0 distractor that matches no query."""
+    rs = np.random.RandomState(seed)
+    qid = rs.randint(1, n_ids + 1, size=nq).astype(np.int64)
+    qcam = rs.randint(0, n_cams, size=nq).astype(np.int64)
+    gid = np.zeros(ng, dtype=np.int64)
+    real_rows = np.sort(rs.permutation(ng)[:min(n_real, ng)])
+    gid[real_rows] = rs.randint(1, n_ids + 1, size=len(real_rows))
+    gcam = rs.randint(0, n_cams, size=ng).astype(np.int64)
+    return qid, qcam, gid, gcam
+
+
+def make_features_device(ids, dim, n_ids, sigma, seed, device, dtype, block_rows=65536):
+    """Identity-model features generated ON THE DEVICE in row blocks (a 41 GB gallery never exists on the host):
+    centers (seed 1234, shared by queries and gallery) + sigma * noise (``seed``), L2-normalised, cast to ``dtype``.
+    The result depends only on (ids, seed), so a gallery shard can be generated on its own with ``seed`` = shard seed."""
+    import torch
+    gen = torch.Generator(device=device).manual_seed(1234)
+    centers = torch.randn((n_ids + 1, dim), device=device, generator=gen)
+    centers[0] = 0
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    out = torch.empty((len(ids), dim), dtype=dtype, device=device)
+    ids_t = torch.from_numpy(np.ascontiguousarray(ids)).to(device)
+    for r0 in range(0, len(ids), block_rows):
+        sl = ids_t[r0:r0 + block_rows]
+        x = centers[sl] + sigma * torch.randn((len(sl), dim), device=device, generator=g)
+        x = x / x.norm(dim=1, keepdim=True)
+        out[r0:r0 + block_rows] = x.to(dtype)
+    return out

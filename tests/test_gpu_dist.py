@@ -18,7 +18,7 @@ def _f64_dist(a, b):
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16x6", "fp32"])
+@pytest.mark.parametrize("precision", ["f16x3", "bf16x3", "bf16x6", "fp32"])
 def test_compute_dist_matches_reference_fixture(golden, name, precision):
     import pps_b200
     d = golden(name)
@@ -40,13 +40,14 @@ def test_precision_ladder_against_float64():
     b = rs.randn(700, 520).astype(np.float32)
     exact = _f64_dist(a, b)
     err = {}
-    for p in ("bf16x1", "bf16x3", "bf16x6", "fp32"):
+    for p in ("bf16x1", "bf16x3", "bf16x6", "f16x3", "fp32"):
         got = pps_b200.compute_dist(a, b, precision=p).astype(np.float64)
         err[p] = float(np.max(np.abs(got - exact) / exact))
     ref_err = float(np.max(np.abs(O.compute_dist(a, b).astype(np.float64) - exact) / exact))
-    assert err["bf16x3"] < 1e-5 and err["bf16x6"] < 2e-6 and err["fp32"] < 2e-6
-    assert err["bf16x1"] > err["bf16x3"]
+    assert err["bf16x3"] < 1e-5 and err["bf16x6"] < 2e-6 and err["fp32"] < 2e-6 and err["f16x3"] < 2e-6
+    assert err["bf16x1"] > err["bf16x3"] > err["f16x3"]
     assert err["bf16x3"] < 20 * max(ref_err, 1e-7)
+    assert err["f16x3"] < 4 * max(ref_err, 1e-7)          # the default split is at the level of a float32 sgemm
 
 
 @pytest.mark.parametrize("m1,m2,dim", [
@@ -98,7 +99,7 @@ def test_self_distance_clamps_at_zero():
     # for identical operands is a positive bias of ~1.3e-6 |a|^2; the tensor-core paths also carry the fp32
     # accumulator rounding of interleaved large and small plane terms (~2e-6 |a|^2); fp32 is at the reference level.
     na = float(np.sqrt((a.astype(np.float64) ** 2).sum(1)).max())
-    for p, bound in (("bf16x3", 3e-3), ("bf16x6", 3e-3), ("fp32", 1e-3)):
+    for p, bound in (("f16x3", 3e-3), ("bf16x3", 3e-3), ("bf16x6", 3e-3), ("fp32", 1e-3)):
         d = pps_b200.compute_dist(a, a, precision=p)
         assert np.all(d >= 0) and np.all(np.isfinite(d))
         assert np.max(np.diag(d)) < bound * na, p
@@ -159,3 +160,30 @@ def test_full_concat_width_d8064():
     b /= np.linalg.norm(b, axis=1, keepdims=True)
     got = pps_b200.compute_dist(a, b)
     np.testing.assert_allclose(got, O.compute_dist(a, b), rtol=1e-4, atol=1e-6)
+
+
+def test_f16x3_row_scaling_covers_the_dynamic_range():
+    """'f16x3' scales every row by its own power of two before the fp16 split: rows of wildly different magnitude (1e-6
+    ... 1e6), rows with a huge spread inside, zero rows and the cosine branch all stay at the fp32 level."""
+    import pps_b200
+    rs = np.random.RandomState(17)
+    a = rs.randn(130, 300).astype(np.float32) * np.exp(rs.uniform(-14, 14, size=(130, 1))).astype(np.float32)
+    b = rs.randn(270, 300).astype(np.float32) * np.exp(rs.uniform(-14, 14, size=(270, 1))).astype(np.float32)
+    b[5] = 0.0
+    b[6] *= np.exp(rs.uniform(-20, 0, size=300)).astype(np.float32)       # elements far below the row maximum
+    exact = _f64_dist(a, b)
+    for kernel in ("2cta", "1cta"):
+        from pps_b200 import _lib, evaluator
+        old = evaluator.DIST_KERNEL_FLAGS
+        evaluator.DIST_KERNEL_FLAGS = _lib.DIST_KERNEL_1CTA if kernel == "1cta" else 0
+        try:
+            got = pps_b200.compute_dist(a, b, precision="f16x3")
+            cos = pps_b200.compute_dist(a, b, type="cosine", precision="f16x3")
+        finally:
+            evaluator.DIST_KERNEL_FLAGS = old
+        ref = O.compute_dist(a, b)
+        scale = np.maximum(np.linalg.norm(a.astype(np.float64), axis=1)[:, None], np.linalg.norm(b.astype(np.float64), axis=1)[None, :])
+        # error relative to the larger of the two norms (what a float32 |a|^2 + |b|^2 - 2ab can resolve at all)
+        assert np.max(np.abs(got - exact) / scale) < 4 * max(np.max(np.abs(ref - exact) / scale), 1e-7), kernel
+        keep = np.ones(270, bool); keep[5] = False
+        np.testing.assert_allclose(cos[:, keep], O.compute_dist(a, b[keep], type="cosine"), rtol=1e-4, atol=2e-6)

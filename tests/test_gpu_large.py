@@ -1,0 +1,71 @@
+"""BASELINE configs[3] / configs[4] shapes against the oracle (the reference's CPU path restated, oracle/pps_oracle.py):
+Market-shaped queries x a gallery of real identities + hundreds of thousands of id-0 distractors, top-100 retrieval +
+exact positive ranks.  The oracle runs on a 64-query slice x the FULL gallery (its argsort index matrix is infeasible for
+all 3 368 queries), exactly as BASELINE.md section 3 prescribes for these configs.
+
+Every output is held to north_star's tolerances: mean AP of the slice 1e-6 absolute, valid flags identical, first-match
+ranks and top-k indices identical except where the oracle's own distances tie within 1e-4 relative (each difference is
+proven to be such a tie, tests/parity_util.py), distances 1e-4 relative; the integer machinery is checked bit-exactly on
+the GPU's own distance rows; single block == forced multi-chunk bit for bit."""
+import numpy as np
+import pytest
+
+import parity_util as P
+from oracle import pps_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NQ, DIM, TOPK = 3368, 2048, 100
+
+
+def _large_case(ng, dtype_name, block_bytes_list, sigma=4.0, n_slice=64):
+    import torch
+    import pps_b200
+    from pps_b200 import evaluator, synthetic
+    dev = torch.device("cuda")
+    tdt = torch.float16 if dtype_name == "fp16" else torch.float32
+    qid, qcam, gid, gcam = synthetic.make_distractor_ids(NQ, ng)
+    q = synthetic.make_features_device(qid, DIM, 750, sigma, 7, dev, tdt)
+    g = synthetic.make_features_device(gid, DIM, 750, sigma, 1000, dev, tdt)
+    results = []
+    for bb in block_bytes_list:
+        eng = evaluator.RankEngine(qid, gid, qcam, gcam, nq=NQ, ng_local=ng, dim=DIM, topk=TOPK, device=dev,
+                                   max_block_bytes=bb, in_dtype=tdt)
+        results.append((eng.n_chunks, eng.run(q, g)))
+        del eng
+    assert results[0][0] == 1 and all(n > 1 for n, _ in results[1:]), [n for n, _ in results]
+    one = results[0][1]
+    for _, other in results[1:]:
+        np.testing.assert_array_equal(one.ap, other.ap)
+        np.testing.assert_array_equal(one.is_valid, other.is_valid)
+        np.testing.assert_array_equal(one.first_rank, other.first_rank)
+        np.testing.assert_array_equal(one.topk_index, other.topk_index)
+        np.testing.assert_array_equal(one.topk_dist, other.topk_dist)
+    # ---- the oracle on a query slice x the full gallery (features cast to float32 on the host) ----
+    sel = np.arange(0, NQ, NQ // n_slice)[:n_slice]
+    qh = q[torch.from_numpy(sel).to(dev)].float().cpu().numpy()
+    gh = g.float().cpu().numpy()
+    dist = O.compute_dist(qh, gh)
+    ap, valid, first, _ = O.rank_counts(dist, qid[sel], gid, qcam[sel], gcam)
+    np.testing.assert_array_equal(one.is_valid[sel], valid)
+    assert valid.sum() >= 0.9 * n_slice
+    assert abs(float(one.ap[sel].sum()) - float(ap.sum())) / valid.sum() < 1e-6
+    moved = P.assert_first_rank_parity(one.first_rank[sel], dist, qid[sel], qcam[sel], gid, gcam, what="ng=%d" % ng)
+    assert moved <= 3
+    P.assert_topk_parity(one.topk_index[sel], one.topk_dist[sel], dist, qid[sel], qcam[sel], gid, gcam, what="ng=%d" % ng)
+    # ---- integer outputs bit-exact on the GPU's own distance rows ----
+    own = pps_b200.compute_dist(q[torch.from_numpy(sel).to(dev)], g).cpu().numpy()
+    np.testing.assert_allclose(own, dist, rtol=1e-4, atol=1e-6)
+    P.assert_counts_exact_on_own_distances(one, own, qid, qcam, gid, gcam, O, sel=sel, topk=TOPK)
+    return one
+
+
+def test_config3_market_plus_500k_distractors_fp32():
+    """BASELINE configs[3] on one GPU: 3 368 x 519 732 x 2048 fp32, top-100; one 7 GB block and 1 GiB blocks."""
+    _large_case(519732, "fp32", [8 << 30, 1 << 30])
+
+
+def test_config4_shape_fp16_gallery_600k_rows():
+    """BASELINE configs[4]'s arithmetic (fp16 features, single exact-product pass, top-100 + exact positive ranks) on a
+    600 000-row gallery: one block, 2 GiB blocks (epilogue top-k admission after a short first block) and 512 MiB blocks."""
+    _large_case(600000, "fp16", [9 << 30, 2 << 30, 512 << 20])

@@ -195,3 +195,81 @@ def test_heads_match_reference_graph_fixture(torch, golden, name):
     for got, ref in zip(blobs, want):
         assert tuple(got.shape) == ref.shape
         np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+
+
+# ---- backward (pps_pool_bwd): the reference trains through this sub-graph; its multi-scale branch is train-only ----
+@pytest.mark.parametrize("mode", ["max_ave", "avg_max"])
+@pytest.mark.parametrize("shape,n_parts,split", [
+    ((3, 70, 24, 8), 6, None), ((2, 33, 24, 8), 5, [5, 5, 4, 5, 5]), ((2, 40, 48, 16), 6, [8] * 6), ((1, 5, 7, 3), 3, [2, 4, 1]),
+])
+def test_pool_backward_matches_oracle_gradient(torch, mode, shape, n_parts, split):
+    """dX of the fused kernel against the oracle's restated operator gradients (float64), 1e-5 relative to the gradient
+    scale; the oracle gradient itself is pinned to finite differences in tests/test_oracle_golden.py."""
+    import pps_b200
+    rs = np.random.RandomState(sum(shape) + n_parts)
+    x = rs.randn(*shape).astype(np.float32)
+    K = (1 << n_parts) - 1
+    dy = rs.randn(shape[0], K, shape[1]).astype(np.float32)
+    dx = pps_b200.pps_pool_backward(torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda(), n_parts=n_parts, split=split,
+                                    mode=mode).cpu().numpy()
+    want = O.pps_pool_grad(x, dy, n_parts, split, mode)
+    np.testing.assert_allclose(dx, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
+def test_pool_backward_numeric_gradient_check(torch):
+    """Gradient check in the style of detectron/tests/test_batch_permutation_op.py:43-50 (GradientChecker.CheckSimple):
+    central differences of the float64 oracle forward against the CUDA backward, on the shipped configuration
+    (n = 6, max_ave) and on the explicit pyramid list."""
+    import pps_b200
+    rs = np.random.RandomState(9)
+    x = rs.randn(1, 4, 24, 8).astype(np.float32)
+    for combos in (None, [pps_b200.comb_to_mask(c) for c in pps_b200.pyramid_combs]):
+        K = 63 if combos is None else len(combos)
+        dy = rs.randn(1, K, 4).astype(np.float32)
+        dx = pps_b200.pps_pool_backward(torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda(), n_parts=6, mode="max_ave",
+                                        combos=combos).cpu().numpy()
+        f = lambda z: float((O.pps_pool(z, 6, mode="max_ave", combos=combos, dtype=np.float64) * dy).sum())
+        x64 = x.astype(np.float64)
+        num = np.zeros_like(x64)
+        eps = 1e-4
+        for idx in np.ndindex(*x.shape):
+            xp, xm = x64.copy(), x64.copy()
+            xp[idx] += eps
+            xm[idx] -= eps
+            num[idx] = (f(xp) - f(xm)) / (2 * eps)
+        np.testing.assert_allclose(dx, num, rtol=1e-3, atol=1e-3 * np.abs(num).max())
+
+
+def test_pool_autograd_through_the_multiscale_head(torch):
+    """The train-time multi-scale branch (pps_heads.py:106-135) with gradients: the three pyramid levels, FPN_SHARED
+    Concat(axis=0), loss = sum of all blobs weighted; dX per level equals the oracle gradient of that level."""
+    import pps_b200
+    rs = np.random.RandomState(13)
+    shapes = [(2, 64, 24, 8), (2, 64, 24, 8), (2, 64, 48, 16)]
+    scales = [1. / 16, 1. / 16, 1. / 8]
+    xs = [rs.randn(*s).astype(np.float32) for s in shapes]
+    for shared in (False, True):
+        cfg = pps_b200.ReIDPoolCfg(BPM_STRIP_NUM=6, MAX_AVE_FEATURE=True, FPN_ON=True, FPN_SHARED=shared, train=True)
+        ts = [torch.from_numpy(x).cuda().requires_grad_(True) for x in xs]
+        blobs, _ = pps_b200.add_pps_part_head(ts, [64] * 3, scales, cfg)
+        assert len(blobs) == (63 if shared else 189)
+        w = [torch.from_numpy(rs.randn(*tuple(b.shape)).astype(np.float32)).cuda() for b in blobs]
+        loss = sum((b * wi).sum() for b, wi in zip(blobs, w))
+        loss.backward()
+        for lvl, (x, t) in enumerate(zip(xs, ts)):
+            split = O.uniform_partition_split(6, 384, scales[lvl])
+            if shared:          # blob k = Concat over levels along the batch axis
+                dy = np.stack([wi.cpu().numpy()[2 * lvl:2 * lvl + 2, :, 0, 0] for wi in w], axis=1)
+            else:               # level-major list
+                dy = np.stack([w[63 * lvl + k].cpu().numpy()[:, :, 0, 0] for k in range(63)], axis=1)
+            want = O.pps_pool_grad(x, dy, 6, split, "max_ave")
+            np.testing.assert_allclose(t.grad.cpu().numpy(), want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
+def test_pool_backward_error_contract(torch):
+    import pps_b200
+    x = torch.zeros((1, 4, 24, 8), device="cuda")
+    with pytest.raises(RuntimeError, match="dy must be"):
+        pps_b200.pps_pool_backward(x, torch.zeros((1, 62, 4), device="cuda"))
+    with pytest.raises(RuntimeError, match="shape check"):
+        pps_b200.pps_pool_backward(x, torch.zeros((1, 63, 4), device="cuda"), split=[4, 4, 4, 4, 4, 5])

@@ -173,3 +173,23 @@ def test_embedding_restatement_matches_reference_graph_fixture(golden, name):
     p = {k: d[k] for k in ("conv_bias", "bn_scale", "bn_bias", "bn_mean", "bn_var")}
     got = O.reid_embed(pooled, d["weight"], normalize=bool(int(d["normalize"])), **p)
     np.testing.assert_allclose(got, d["feature"], rtol=1e-12, atol=1e-14)
+
+
+def test_pool_gradient_restatement_equals_finite_differences():
+    """oracle.pps_pool_grad (the Caffe2 operator gradients restated) against central differences of the float64 forward:
+    the CPU half of the gradient check of tests/test_gpu_pool.py (test_batch_permutation_op.py:43-50 style)."""
+    rs = np.random.RandomState(0)
+    for mode in ("max_ave", "avg_max"):
+        for n, split in ((6, None), (5, [5, 5, 4, 5, 5])):
+            x = rs.randn(1, 2, 24, 8)
+            dy = rs.randn(1, (1 << n) - 1, 2)
+            g = O.pps_pool_grad(x, dy, n, split, mode)
+            f = lambda z: float((O.pps_pool(z, n, split, mode, dtype=np.float64) * dy).sum())
+            num = np.zeros_like(x)
+            eps = 1e-6
+            for idx in np.ndindex(*x.shape):
+                xp, xm = x.copy(), x.copy()
+                xp[idx] += eps
+                xm[idx] -= eps
+                num[idx] = (f(xp) - f(xm)) / (2 * eps)
+            np.testing.assert_allclose(g, num, rtol=0, atol=1e-6 * max(1.0, np.abs(num).max()))
