@@ -16,12 +16,20 @@ counters cross NVLink (NCCL all-reduce).
 `e2e`    : the same metric through the host-buffer entry point (N = 1: the C ABI's pps_evaluate_host;
            N > 1: pinned host -> device copies + the sharded path), H2D and D2H inside the timed region.
 `roofline`: the distance GEMM (dominant kernel), timed with CUDA events inside the timed steps.
-`cpu_baseline`: the oracle port of the reference's CPU path on this box's host cores (rank 0, N = 1).
+`cpu_baseline`: the reference's CPU path on this box's host cores (rank 0, N = 1): the UNMODIFIED
+           reid_dataset_evaluator.py staged under baseline/_ref/ (kind "reference"), else the oracle port (kind "port").
 `--impl reference`: only that CPU path, on a bounded query sample per step.
+`large_gallery`: BASELINE configs[3] (Market + 500 k distractors, fp32) and configs[4] (10 M x 2048 fp16) - top-100 +
+           exact positive ranks, the gallery sharded over the N GPUs of the run (STRONG scaling: total rows fixed), each
+           with an oracle check on a query slice x the whole gallery (reference arithmetic on the host).
+`dim8064`: the Market shape at the real concat width D = 8 064 = 63 x 128.
+`checks`:  at N > 1 the headline result is checked against the oracle on a 64-query slice of the GLOBAL gallery.
+The process exits non-zero (after printing the line) if any oracle check is outside north_star's tolerances.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -163,8 +171,8 @@ def make_workload(rank, world, gallery_per_gpu=None, dim=None):
         return out
 
     row0 = rank * ngl
-    d = dict(q=feats(qid, 1), g_local=feats(gid[row0:row0 + ngl], 100 + rank), qid=qid, gid=gid, qcam=qcam, gcam=gcam,
-             row0=row0)
+    shard = lambda r: feats(gid[r * ngl:(r + 1) * ngl], 100 + r)       # any rank's shard, regenerated for the oracle check
+    d = dict(q=feats(qid, 1), g_local=shard(rank), qid=qid, gid=gid, qcam=qcam, gcam=gcam, row0=row0, shard=shard)
     cfg = dict(cfg, ng=ng)
     return d, cfg
 
@@ -172,20 +180,48 @@ def make_workload(rank, world, gallery_per_gpu=None, dim=None):
 # ------------------------------------------------------------------------------------------------
 # CPU path (oracle port of the reference) — cpu_baseline and --impl reference
 # ------------------------------------------------------------------------------------------------
+_CPU_IMPL = None
+
+
+def cpu_impl():
+    """(kind, module): the unmodified reference evaluator if it is available (/root/reference in the authoring container,
+    baseline/_ref/ on the GPU box), else the oracle port."""
+    global _CPU_IMPL
+    if _CPU_IMPL is None:
+        from oracle import ref_loader
+        if ref_loader.available():
+            with contextlib.redirect_stdout(sys.stderr):
+                _CPU_IMPL = ("reference", ref_loader.load(), ref_loader.EVALUATOR)
+        else:
+            from oracle import pps_oracle as O
+            _CPU_IMPL = ("port", O, "oracle/pps_oracle.py")
+    return _CPU_IMPL
+
+
 def cpu_eval(d, nq_sample):
-    """compute_dist -> mean_ap + cmc(topk=10, first_match_break) on the first nq_sample queries x full gallery."""
-    from oracle import pps_oracle as O
+    """compute_dist -> mean_ap + cmc(topk=10, first_match_break) on the first nq_sample queries x full gallery, exactly as
+    the reference's evaluate() closure calls them (reid_dataset_evaluator.py:70-93)."""
+    kind, M, _ = cpu_impl()
     q = d["q"][:nq_sample]
     ids = dict(query_ids=d["qid"][:nq_sample], gallery_ids=d["gid"], query_cams=d["qcam"][:nq_sample],
                gallery_cams=d["gcam"])
-    t0 = time.perf_counter()
-    dist = O.compute_dist(q, d["g"])
-    t1 = time.perf_counter()
-    m = O.mean_ap(dist, **ids)
-    t2 = time.perf_counter()
-    c = O.cmc(dist, topk=10, first_match_break=True, **ids)
-    t3 = time.perf_counter()
-    return dict(total=t3 - t0, dist=t1 - t0, mean_ap=t2 - t1, cmc=t3 - t2, mAP=m, cmc1=float(c[0]))
+    with contextlib.redirect_stdout(sys.stderr):      # the reference prints a scikit-learn version note to stdout
+        t0 = time.perf_counter()
+        dist = M.compute_dist(q, d["g"], type="euclidean")
+        t1 = time.perf_counter()
+        m = M.mean_ap(dist, **ids)
+        t2 = time.perf_counter()
+        c = M.cmc(dist, topk=10, separate_camera_set=False, single_gallery_shot=False, first_match_break=True, **ids) \
+            if kind == "reference" else M.cmc(dist, topk=10, first_match_break=True, **ids)
+        t3 = time.perf_counter()
+    return dict(total=t3 - t0, dist=t1 - t0, mean_ap=t2 - t1, cmc=t3 - t2, mAP=m, cmc1=float(c[0]), kind=kind)
+
+
+def cpu_sample_text(nq_s, nq, ng):
+    kind, _, path = cpu_impl()
+    what = ("the UNMODIFIED reference functions compute_dist / mean_ap / cmc of %s" % os.path.relpath(path, ROOT)
+            if kind == "reference" else "oracle/pps_oracle.py (numpy sgemm + argsort + sklearn AP, as reid_dataset_evaluator.py:244-439)")
+    return "first %d of %d queries x full %d-row gallery per pass; %s" % (nq_s, nq, ng, what)
 
 
 def run_reference(args):
@@ -215,10 +251,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "market1501-shaped 3368x19732x2048 fp32 (BASELINE configs[1])", "nq": cfg["nq"],
                    "ng": cfg["ng"], "dim": cfg["dim"], "sample": "first %d queries x full gallery per step" % nq_s},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "first %d of %d queries x full %d-row gallery per step; oracle/pps_oracle.py "
-                                   "(numpy sgemm + argsort + sklearn AP, as reid_dataset_evaluator.py:244-439)" %
-                                   (nq_s, cfg["nq"], cfg["ng"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": last["kind"],
+                         "sample": cpu_sample_text(nq_s, cfg["nq"], cfg["ng"]),
                          "split_s": {k: last[k] for k in ("dist", "mean_ap", "cmc")}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -228,8 +262,134 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# sub-records: large galleries (BASELINE configs[3] / configs[4]) and the D = 8 064 shape
+# ------------------------------------------------------------------------------------------------
+def timed_passes(torch, engine, q, g, steps, warmup, world, dev):
+    """ms per pass of engine.run(q, g): CUDA events on the launching stream, barrier + synchronize on both sides, max over
+    ranks; also the distance-GEMM launch times (events the engine records around its distance calls)."""
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+    res = None
+    for _ in range(warmup):
+        res = engine.run(q, g)
+    barrier()
+    engine.kernel_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        res = engine.run(q, g)
+    e1.record()
+    barrier()
+    gemm = [a.elapsed_time(b) for a, b in engine.kernel_events]
+    engine.kernel_events = None
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t[0]), res, (float(np.sum(gemm)) / steps if gemm else None)
+
+
+def oracle_rows_device_gallery(torch, q_rows_host, ids_global, shard_iter):
+    """Oracle distance rows [n_sel, ng] of a gallery that only exists on the device: every block is brought to the host,
+    cast to float32 and goes through the CPU compute_dist (reference arithmetic)."""
+    from oracle import pps_oracle as O
+    ng = len(ids_global)
+    out = np.empty((q_rows_host.shape[0], ng), dtype=np.float32)
+    for col0, block in shard_iter:
+        gh = block.float().cpu().numpy()
+        out[:, col0:col0 + gh.shape[0]] = O.compute_dist(q_rows_host, gh)
+    return out
+
+
+def bench_large_gallery(torch, evaluator, synthetic, args, name, ng, dtype_name, world, rank, dev, group, peaks, steps, warmup,
+                        n_check):
+    """Top-100 retrieval + exact positive ranks over a gallery of `ng` rows sharded over the `world` GPUs of the run
+    (strong scaling).  Returns the sub-record (rank 0) or None."""
+    from oracle import parity as P
+    nq, dim, topk, sigma = 3368, 2048, 100, 4.0
+    tdt = torch.float16 if dtype_name == "fp16" else torch.float32
+    qid, qcam, gid, gcam = synthetic.make_distractor_ids(nq, ng)
+    row0, ngl = evaluator.gallery_shard(ng, rank, world)
+    q = synthetic.make_features_device(qid, dim, 750, sigma, 7, dev, tdt)
+    g = synthetic.make_features_device(gid[row0:row0 + ngl], dim, 750, sigma, 1000 + rank, dev, tdt)
+    eng = evaluator.RankEngine(qid, gid, qcam, gcam, nq=nq, ng_local=ngl, dim=dim, gallery_offset=row0, precision=args.precision,
+                               topk=topk, group=group, device=dev, in_dtype=tdt)
+    n0 = evaluator._lib.launch_count()
+    ms, res, gemm_ms = timed_passes(torch, eng, q, g, steps, warmup, world, dev)
+    launches = (evaluator._lib.launch_count() - n0) / float(steps + warmup)
+    rec = None
+    if rank == 0:
+        pairs = float(nq) * float(ng)
+        tf = 2.0 * dim * pairs / (ms * 1e-3) / 1e12
+        rec = {"workload": name, "nq": nq, "ng": ng, "dim": dim, "dtype": dtype_name, "topk": topk, "n_gpus": world,
+               "scaling": "strong", "rows_per_gpu": ngl, "blocks_per_gpu": len(eng._chunk_list()), "steps": steps,
+               "ms_per_pass": ms, "pairs_per_s": pairs / (ms * 1e-3), "algorithmic_tflops": tf,
+               "frac_of_sustained_bf16_all_gpus": tf / (peaks["tf_sustained"] * world),
+               "dist_gemm_ms_per_pass_rank0": gemm_ms, "gpu_launches_per_pass_rank0": launches,
+               "mAP": res.mean_ap(), "cmc1": float(res.cmc(10, True)[0])}
+        # oracle check: a query slice x the WHOLE gallery, regenerated shard by shard on this GPU and ranked on the host
+        del g
+        sel = np.arange(0, nq, nq // n_check)[:n_check]
+        qh = q[torch.from_numpy(sel).to(dev)].float().cpu().numpy()
+
+        def blocks():
+            for r in range(world):
+                r0, rows = evaluator.gallery_shard(ng, r, world)
+                for b0, blk in synthetic.iter_features_device(gid[r0:r0 + rows], dim, 750, sigma, 1000 + r, dev, tdt):
+                    yield r0 + b0, blk
+        t0 = time.perf_counter()
+        dist = oracle_rows_device_gallery(torch, qh, gid, blocks())
+        chk = P.subset_check(res, sel, dist, qid, qcam, gid, gcam, topk=topk)
+        chk["seconds"] = time.perf_counter() - t0
+        chk["what"] = "oracle (CPU compute_dist on float32 casts + count-based AP / first match / top-%d) on %d queries x all %d rows" % (
+            topk, len(sel), ng)
+        rec["oracle_check"] = chk
+    del eng
+    torch.cuda.empty_cache()
+    return rec
+
+
+def bench_dim8064(torch, evaluator, synthetic, args, dev, peaks):
+    """the Market shape at D = 8 064 = 63 x 128 (reid_heads.py:95-101 concat width), one GPU."""
+    from oracle import parity as P
+    from oracle import pps_oracle as O
+    cfg = dict(synthetic.CONFIGS[WORKLOAD])
+    nq, ng, dim = cfg["nq"], cfg["ng"], 8064
+    rs = np.random.RandomState(0)
+    qid = rs.randint(1, cfg["n_ids"] + 1, size=nq).astype(np.int64)
+    qcam = rs.randint(0, cfg["n_cams"], size=nq).astype(np.int64)
+    gid = np.concatenate([rs.randint(1, cfg["n_ids"] + 1, size=ng - cfg["n_distractors"]),
+                          np.zeros(cfg["n_distractors"], dtype=np.int64)])[rs.permutation(ng)].astype(np.int64)
+    gcam = rs.randint(0, cfg["n_cams"], size=ng).astype(np.int64)
+    sigma = 4.0 * 2.0                                   # 4x the dimensions of the D = 2048 set: same mid-range mAP
+    q = synthetic.make_features_device(qid, dim, cfg["n_ids"], sigma, 7, dev, torch.float32)
+    g = synthetic.make_features_device(gid, dim, cfg["n_ids"], sigma, 8, dev, torch.float32)
+    eng = evaluator.RankEngine(qid, gid, qcam, gcam, nq=nq, ng_local=ng, dim=dim, precision=args.precision, device=dev)
+    eng.use_c_path = False                              # the generic path records events around the distance launch
+    ms, res, gemm_ms = timed_passes(torch, eng, q, g, 20, 3, 1, dev)
+    flops = 2.0 * dim * nq * ng
+    sel = np.arange(0, nq, nq // 64)[:64]
+    dist = O.compute_dist(q[torch.from_numpy(sel).to(dev)].cpu().numpy(), g.cpu().numpy())
+    chk = P.subset_check(res, sel, dist, qid, qcam, gid, gcam)
+    terms = 1 if args.precision == "bf16x1" else (6 if args.precision == "bf16x6" else 3)
+    return {"workload": "market1501-shaped %dx%dx%d fp32 (real reid_feature_concat width)" % (nq, ng, dim), "ms_per_pass": ms,
+            "pairs_per_s": nq * float(ng) / (ms * 1e-3), "mAP": res.mean_ap(), "oracle_check": chk,
+            "roofline": {"kernel": "dist_tc2_kernel", "bound": "tensor", "ms_per_launch": gemm_ms,
+                         "achieved": flops / (gemm_ms * 1e-3) / 1e12, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": flops / (gemm_ms * 1e-3) / 1e12 / peaks["tf_sustained"],
+                         "tensor_pipe_frac": terms * flops / (gemm_ms * 1e-3) / 1e12 / peaks["tf_sustained"],
+                         "algorithmic_flops_per_pair": 2 * dim}}
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def synthetic_mod():
+    from pps_b200 import synthetic
+    return synthetic
+
+
 def run_ours(args):
     import torch
     import pps_b200
@@ -342,20 +502,56 @@ def run_ours(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms_total, e2e_s = float(t[0]), float(t[1])
 
+    # ---- N > 1: the sharded result against the oracle on a 64-query slice of the GLOBAL gallery ----
+    checks = {}
+    if world > 1 and rank == 0 and not args.no_checks:
+        from oracle import parity as P
+        from oracle import pps_oracle as O
+        sel = np.arange(0, nq, nq // 64)[:64]
+        g_all = np.concatenate([d["shard"](r) for r in range(world)])
+        chk = P.subset_check(res, sel, O.compute_dist(d["q"][sel], g_all), d["qid"], d["qcam"], d["gid"], d["gcam"], topk=args.topk)
+        chk["what"] = "oracle (CPU compute_dist + count-based AP / first match) on 64 queries x all %d rows of the %d shards" % (ng, world)
+        checks["sharded_vs_oracle"] = chk
+        del g_all
+
+    # ---- sub-records: the >= 1M-row galleries north_star's scaling target names, and D = 8 064 ----
+    h2d = (q_host.numel() + g_host.numel()) * 4
+    engine = q_dev = g_dev = g_host = None
+    release_contexts = getattr(evaluator, "release_host_contexts", None)
+    if release_contexts:
+        release_contexts()
+    torch.cuda.empty_cache()
+    large = None
+    if not args.no_large_gallery:
+        large = {}
+        for key, name, rows, dt, st, wu, nchk in (
+                ("config3", "BASELINE configs[3]: Market-1501 + 500k distractors, fp32", args.c3_rows, "fp32", 5, 2, 64),
+                ("config4", "BASELINE configs[4]: 10M-row gallery, 2048-d fp16", args.c4_rows, "fp16", 3, 1, 32)):
+            if rows <= 0:
+                continue
+            rec = bench_large_gallery(torch, evaluator, synthetic_mod(), args, name, rows, dt, world, rank, dev, group, peaks,
+                                      st, wu, nchk)
+            if rank == 0:
+                large[key] = rec
+    dim8064 = None
+    if world == 1 and not args.no_dim8064:
+        dim8064 = bench_dim8064(torch, evaluator, synthetic_mod(), args, dev, peaks)
+
     if rank == 0:
         ms_step = ms_total / args.steps
         value = pairs_step / (ms_step * 1e-3)
         gemm_avg_ms = float(np.mean(gemm_ms)) if gemm_ms else None
         flops_alg = 2.0 * dim * float(nq) * float(ngl)               # per launch (this rank's block)
-        terms = {"bf16x1": 1, "bf16x3": 3, "bf16x6": 6}[args.precision]
+        terms = {"bf16x1": 1, "bf16x3": 3, "bf16x6": 6, "f16x3": 3}[args.precision]
         roofline = None
         if gemm_avg_ms:
             achieved = flops_alg / (gemm_avg_ms * 1e-3) / 1e12
             roofline = {"kernel": "dist_tc2_kernel", "bound": "tensor", "achieved": achieved,
                         "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-                        "traffic": load_traffic("dist_tc2_kernel@%dx%dx%d/%s" % (nq, ngl, dim, args.precision)),
+                        "traffic": load_traffic("dist_tc2_kernel@%dx%dx%d/%s" % (nq, ngl, dim, args.precision)) or
+                                   load_traffic("dist_tc2_kernel@%dx%dx%d/bf16x3" % (nq, ngl, dim)),
                         "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_d_dist_gemm.md); algorithmic = %d" %
-                                        int((nq + ngl) * dim * 2 * (2 if args.precision == "bf16x3" else 1) + nq * ngl * 4),
+                                        int((nq + ngl) * dim * 2 * (2 if args.precision in ("bf16x3", "f16x3") else 1) + nq * ngl * 4),
                         "peak_source": peaks["source"] + " (sustained bf16)",
                         "ms_per_launch": gemm_avg_ms, "share_of_step": gemm_avg_ms / ms_step,
                         "tensor_pipe_issued_tflops": achieved * terms,
@@ -365,7 +561,7 @@ def run_ours(args):
         # the HBM-bound kernels of the step, from the same phase events (algorithmic bytes / device time)
         kernels = None
         if phases:
-            n_planes = {"bf16x1": 1, "bf16x3": 2, "bf16x6": 3}[args.precision]
+            n_planes = {"bf16x1": 1, "bf16x3": 2, "bf16x6": 3, "f16x3": 2}[args.precision]
             split_b = (nq + ngl) * dim * 4.0 + (nq + ngl) * dim * 2.0 * n_planes
             count_b = 4.0 * nq * ngl
             kernels = {
@@ -377,12 +573,12 @@ def run_ours(args):
                                       "frac": count_b / phases["rank_count"] / 1e6 / peaks["hbm"],
                                       "traffic": load_traffic("rank_count_kernel@%dx%d" % (nq, ngl))},
             }
-        h2d = (q_host.numel() + g_host.numel()) * 4
         d2h = nq * (8 + 1 + 4)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16x3-split fp32 (fp32 accumulate)" if args.precision == "bf16x3" else args.precision,
+            "vs_baseline": None, "dtype": {"bf16x3": "bf16x3-split fp32 (fp32 accumulate)",
+                                           "f16x3": "f16x3-split fp32 (two scaled fp16 planes, fp32 accumulate)"}.get(args.precision, args.precision),
             "data": "synthetic",
             "config": {"workload": "market1501-shaped %dx%dx%d fp32 (BASELINE configs[1]%s)" %
                                    (nq, ng, dim, "" if world == 1 else ", gallery sharded %d rows/GPU" % ngl),
@@ -399,6 +595,9 @@ def run_ours(args):
             "phases_ms": phases,
             "kernels": kernels,
             "pooling": pooling,
+            "large_gallery": large,
+            "dim8064": dim8064,
+            "checks": checks,
             "result": {"mAP": mAP, "cmc1": float(cmc[0]), "cmc5": float(cmc[4]), "cmc10": float(cmc[9]),
                        "mAP_trapezoid_sklearn_0_18_1": mAP_trap},
         }
@@ -407,19 +606,33 @@ def run_ours(args):
             nq_s = min(nq, args.cpu_sample)
             r = cpu_eval(dd, nq_s)
             line["cpu_baseline"] = {"value": nq_s * float(ng) / r["total"], "unit": UNIT, "cores": os.cpu_count() or 1,
-                                    "kind": "port",
-                                    "sample": "first %d of %d queries x full %d-row gallery, one pass; oracle/pps_oracle.py" %
-                                              (nq_s, nq, ng),
+                                    "kind": r["kind"], "sample": cpu_sample_text(nq_s, nq, ng),
                                     "split_s": {k: r[k] for k in ("dist", "mean_ap", "cmc")}, "mAP_on_sample": r["mAP"]}
             if nq_s == nq:
                 line["result"]["mAP_cpu"] = r["mAP"]
                 line["result"]["mAP_abs_diff"] = abs(r["mAP"] - mAP)
         else:
             line["cpu_baseline"] = None
+        failed = []
+        if line["result"].get("mAP_abs_diff") is not None and line["result"]["mAP_abs_diff"] > 1e-6:
+            failed.append("headline mAP differs from the CPU reference by %.3g" % line["result"]["mAP_abs_diff"])
+        for name_, c in list(checks.items()) + [(k, (v or {}).get("oracle_check")) for k, v in (large or {}).items()] + \
+                [("dim8064", (dim8064 or {}).get("oracle_check"))]:
+            if c is not None and not c.get("ok", True):
+                failed.append("%s: %s" % (name_, "; ".join(c.get("errors", []))))
+        line["parity_ok"] = not failed
+        if failed:
+            line["parity_failures"] = failed
         print(json.dumps(line))
+        rc = 0 if not failed else 3
+    else:
+        rc = 0
     if world > 1:
+        t = torch.tensor([rc], dtype=torch.int32, device=dev)
+        torch.distributed.broadcast(t, src=0)
+        rc = int(t[0])
         torch.distributed.destroy_process_group()
-    return 0
+    return rc
 
 
 def bench_pooling(torch, pps_b200, _lib, peaks, dev, args):
@@ -456,7 +669,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x1", "bf16x3", "bf16x6"])
+    ap.add_argument("--precision", default="f16x3", choices=["bf16x1", "bf16x3", "bf16x6", "f16x3"])
     ap.add_argument("--topk", type=int, default=0)
     ap.add_argument("--gallery-per-gpu", type=int, default=None)
     ap.add_argument("--dim", type=int, default=None)
@@ -465,6 +678,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pooling", action="store_true")
     ap.add_argument("--pool-images", type=int, default=1024)
+    ap.add_argument("--no-large-gallery", action="store_true")
+    ap.add_argument("--c3-rows", type=int, default=519732, help="gallery rows of the configs[3] sub-record (0 = skip)")
+    ap.add_argument("--c4-rows", type=int, default=10_000_000, help="gallery rows of the configs[4] sub-record (0 = skip)")
+    ap.add_argument("--no-dim8064", action="store_true")
+    ap.add_argument("--no-checks", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

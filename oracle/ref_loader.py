@@ -1,9 +1,11 @@
-"""Load the UNMODIFIED reference evaluator from /root/reference (authoring container only).
+"""Load the UNMODIFIED reference evaluator: from /root/reference where it exists (authoring container), else from
+the staged copy under baseline/_ref/ (git-ignored, NOT gpurun-ignored: it travels to the GPU box, where
+/root/reference does not exist).  ``stage()`` - called by ``__graft_entry__.build()`` in the authoring container -
+copies the one file byte for byte; nothing of the reference enters the repository's history.
 
 ``reid_dataset_evaluator.py`` imports pycocotools and detectron.* at module top (:19-24), none
 of which ``compute_dist`` / ``cmc`` / ``mean_ap`` touch; empty stub modules satisfy those
-imports, then the file is executed from where it lies.  Nothing is copied.  The GPU box has
-no /root/reference: there only the committed fixtures (tests/golden/) are used.
+imports, then the file is executed from where it lies.
 """
 from __future__ import annotations
 
@@ -13,11 +15,28 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("PPS_REFERENCE_ROOT", "/root/reference")
-EVALUATOR = os.path.join(REFERENCE_ROOT, "detectron", "datasets", "reid_dataset_evaluator.py")
+_REL = os.path.join("detectron", "datasets", "reid_dataset_evaluator.py")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+STAGED = os.path.join(STAGED_ROOT, _REL)
+EVALUATOR = os.path.join(REFERENCE_ROOT, _REL)
+if not os.path.exists(EVALUATOR) and os.path.exists(STAGED):
+    EVALUATOR = STAGED
 
 
 def available() -> bool:
     return os.path.exists(EVALUATOR)
+
+
+def stage() -> bool:
+    """Copy the unmodified evaluator file from /root/reference to baseline/_ref/ (no-op without /root/reference).
+    Returns True if a staged copy exists afterwards."""
+    import shutil
+    src = os.path.join(REFERENCE_ROOT, _REL)
+    if os.path.exists(src):
+        os.makedirs(os.path.dirname(STAGED), exist_ok=True)
+        if not os.path.exists(STAGED) or open(src, "rb").read() != open(STAGED, "rb").read():
+            shutil.copyfile(src, STAGED)
+    return os.path.exists(STAGED)
 
 
 def load():

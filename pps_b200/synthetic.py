@@ -69,20 +69,28 @@ def make_distractor_ids(nq, ng, n_real=16932, n_ids=750, n_cams=6, seed=0):
     return qid, qcam, gid, gcam
 
 
-def make_features_device(ids, dim, n_ids, sigma, seed, device, dtype, block_rows=65536):
+def iter_features_device(ids, dim, n_ids, sigma, seed, device, dtype, block_rows=65536):
     """Identity-model features generated ON THE DEVICE in row blocks (a 41 GB gallery never exists on the host):
     centers (seed 1234, shared by queries and gallery) + sigma * noise (``seed``), L2-normalised, cast to ``dtype``.
-    The result depends only on (ids, seed), so a gallery shard can be generated on its own with ``seed`` = shard seed."""
+    Yields (row0, block).  The values depend only on (ids, seed, block_rows), so a gallery shard can be generated - or
+    regenerated block by block for a check - on its own."""
     import torch
     gen = torch.Generator(device=device).manual_seed(1234)
     centers = torch.randn((n_ids + 1, dim), device=device, generator=gen)
     centers[0] = 0
     g = torch.Generator(device=device).manual_seed(int(seed))
-    out = torch.empty((len(ids), dim), dtype=dtype, device=device)
     ids_t = torch.from_numpy(np.ascontiguousarray(ids)).to(device)
     for r0 in range(0, len(ids), block_rows):
         sl = ids_t[r0:r0 + block_rows]
         x = centers[sl] + sigma * torch.randn((len(sl), dim), device=device, generator=g)
         x = x / x.norm(dim=1, keepdim=True)
-        out[r0:r0 + block_rows] = x.to(dtype)
+        yield r0, x.to(dtype)
+
+
+def make_features_device(ids, dim, n_ids, sigma, seed, device, dtype, block_rows=65536):
+    """All blocks of iter_features_device in one [len(ids), dim] tensor."""
+    import torch
+    out = torch.empty((len(ids), dim), dtype=dtype, device=device)
+    for r0, x in iter_features_device(ids, dim, n_ids, sigma, seed, device, dtype, block_rows):
+        out[r0:r0 + x.shape[0]] = x
     return out
