@@ -42,6 +42,8 @@ extern "C" {
 #define PPS_ERR_UNSUPPORTED     -5  /* valid request this build does not implement */
 #define PPS_ERR_WORKSPACE       -6  /* workspace too small                         */
 #define PPS_ERR_NO_VALID_QUERY  -7  /* reid_dataset_evaluator.py:358-359           */
+#define PPS_ERR_TOPK_OVERFLOW   -8  /* pps_pass_end: a top-k candidate buffer ran over; repeat the pass with
+                                       PPS_PASS_NO_EPILOGUE_TOPK (every rank of a sharded run gets this code) */
 
 int         pps_abi_version(void);
 const char* pps_strerror(int code);
@@ -436,6 +438,40 @@ int pps_rank_thresholds(pps_ctx* ctx, const int32_t* d_cnt_all, int rank, void* 
                       long long* n_pairs, int32_t** d_exchange, long long* n_words);
 int pps_rank_count_local(pps_ctx* ctx, void* stream, uint32_t** d_counters, long long* n_counters);
 int pps_rank_end(pps_ctx* ctx, int cmc_topk, void* stream, double* out_map, double* out_cmc,
+                 double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,
+                 int32_t* out_topk_index, float* out_topk_dist);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2g — one ranking pass over a gallery of ANY size, optionally sharded over several GPUs (BASELINE configs[3] /
+ *           configs[4]; replaces the reference's multi-GPU test path detectron/utils/subprocess.py:39-103 +
+ *           core/test_engine.py:205-213, which shards images over processes and pickles results).
+ *
+ * d_q [nq, dim] and d_g [ng_local, dim] are contiguous device rows (dtype PPS_DTYPE_F32 or _F16); d_g is this
+ * rank's block of the gallery starting at global row gallery_offset.  d_gid / d_gcam are the GLOBAL id / camera vectors
+ * [ng_global] (replicated, like the queries): every rank builds the same pair lists from them (hash pre-filter of
+ * the rows that can match + brute-force sweeps), so no pair metadata is exchanged.  The local rows are processed in
+ * distance blocks of at most max_block_bytes (nq x rows x 4); with topk > 0 the first block is kept short and later
+ * blocks take their top-k candidates in the distance epilogue.
+ *   pps_pass_begin   -> *d_x1 [*n_x1 int32 words]: the thresholds (float bits; pairs of other shards are 0).
+ *                       Sharded: all-reduce(SUM, int32) it over the ranks.
+ *   pps_pass_count   -> *d_x2 [*x2_bytes]: [top-k keys | counters | flags] of this rank.
+ *                       Sharded: all-gather it into d_gathered [world][*x2_bytes].
+ *   pps_pass_end     reduces / merges the gathered buffers (own kernels), finalises, copies the results to the host
+ *                    like pps_rank_end; d_gathered = NULL when world == 1.
+ * Two collectives per pass, identical on every rank whatever its shard looks like (also an empty one).  The pair-list
+ * kernels run on a stream of the ctx, everything else on `stream`; pps_pass_begin blocks the host only on 4-byte
+ * read-backs that arrive while the first distance block is running.  Phase timing (pps_ctx_set_timing) reports the
+ * SUMS over the pass: split, dist_gemm, rank_count (sweeps + merges), finalize. */
+#define PPS_PASS_NO_EPILOGUE_TOPK 1   /* flags: every block takes the one-read sweep (the fallback after TOPK_OVERFLOW) */
+#define PPS_PASS_TKCAP(n) (((n) & 0xffff) << 8)   /* flags: candidate-buffer entries per query (default / maximum 2048) */
+int pps_pass_begin(pps_ctx* ctx, const void* d_q, long long nq, const void* d_g, long long ng_local, int dim, int dtype,
+                   const int64_t* d_query_ids, const int64_t* d_query_cams,
+                   const int64_t* d_gallery_ids, const int64_t* d_gallery_cams, long long ng_global,
+                   long long gallery_offset, int world, int rank, int precision, int topk,
+                   long long max_block_bytes, int flags, void* stream,
+                   int32_t** d_x1, long long* n_x1);
+int pps_pass_count(pps_ctx* ctx, void* stream, void** d_x2, long long* x2_bytes);
+int pps_pass_end(pps_ctx* ctx, const void* d_gathered, int cmc_topk, void* stream, double* out_map, double* out_cmc,
                  double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,
                  int32_t* out_topk_index, float* out_topk_dist);
 

@@ -22,6 +22,8 @@ PPS_ERR_CUDA = -4
 PPS_ERR_UNSUPPORTED = -5
 PPS_ERR_WORKSPACE = -6
 PPS_ERR_NO_VALID_QUERY = -7
+PPS_ERR_TOPK_OVERFLOW = -8
+PASS_NO_EPILOGUE_TOPK = 1
 
 POOL_AVG_MAX = 0
 POOL_MAX_AVE = 1
@@ -115,6 +117,10 @@ SIGNATURES = {
     "pps_rank_thresholds": (_i, [_vp, _vp, _i, _vp, C.POINTER(_ll), C.POINTER(_vp), C.POINTER(_ll)]),
     "pps_rank_count_local": (_i, [_vp, _vp, C.POINTER(_vp), C.POINTER(_ll)]),
     "pps_rank_end": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_pass_begin": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _i, _i, _i, _ll, _i, _vp,
+                            C.POINTER(_vp), C.POINTER(_ll)]),
+    "pps_pass_count": (_i, [_vp, _vp, C.POINTER(_vp), C.POINTER(_ll)]),
+    "pps_pass_end": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_ctx_set_timing": (_i, [_vp, _i]),
     "pps_ctx_phase_ms": (_i, [_vp, _vp]),
     "pps_evaluate_host": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i,

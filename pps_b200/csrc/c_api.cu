@@ -67,6 +67,7 @@ extern "C" const char* pps_strerror(int code) {
     case PPS_ERR_UNSUPPORTED: return "request not supported by this build";
     case PPS_ERR_WORKSPACE: return "workspace too small";
     case PPS_ERR_NO_VALID_QUERY: return "No valid query";
+    case PPS_ERR_TOPK_OVERFLOW: return "top-k candidate buffer overflow: repeat the pass with PPS_PASS_NO_EPILOGUE_TOPK";
     default: return "unknown error code";
   }
 }
@@ -116,87 +117,7 @@ extern "C" int pps_pairs_fill(const int64_t* query_ids, const int64_t* query_cam
   return PPS_OK;
 }
 
-// ------------------------------------------------------------------------------------
-// evaluation context + pps_evaluate_host[_ctx]
-// ------------------------------------------------------------------------------------
-namespace {
-
-struct GrowBuf {                       // device buffer that only ever grows
-  void* p = nullptr;
-  size_t cap = 0;
-  int ensure(size_t bytes) {
-    if (bytes <= cap) return PPS_OK;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
-    const size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc"); }
-    cap = want;
-    return PPS_OK;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-  template <class T> T* as() const { return static_cast<T*>(p); }
-};
-
-struct PinBuf {                        // pinned host staging, grow-only
-  void* p = nullptr;
-  size_t cap = 0;
-  int ensure(size_t bytes) {
-    if (bytes <= cap) return PPS_OK;
-    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-    cudaError_t e = cudaMallocHost(&p, bytes + 256);
-    if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMallocHost"); }
-    cap = bytes + 256;
-    return PPS_OK;
-  }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-  template <class T> T* as() const { return static_cast<T*>(p); }
-};
-
-constexpr int kMaxSlabs = 64;
-
-#define PPS_TRY(expr) do { int _rc = (expr); if (_rc != PPS_OK) return _rc; } while (0)
-
-}  // namespace
-
-namespace {
-struct EvalShape {
-  long long nq, ng /*rows of the local gallery block (and of its id arrays)*/, col0 /*its first global row*/, ldd;
-  int dim, kpad, planes, precision, topk;
-  int split_planes;      // `planes` argument of pps_split_rows: planes, or 2 | PPS_SPLIT_F16_SCALED for PPS_PREC_F16X3
-};
-struct Staging {   // pinned: totals, per-query results
-  int32_t* totals; double* ap; int32_t* first; uint8_t* valid;
-};
-}  // namespace
-
-struct pps_ctx {
-  int device = 0;
-  cudaStream_t copy_s = nullptr, comp_s = nullptr, side_s = nullptr;
-  cudaEvent_t ev_slab[kMaxSlabs] = {};
-  cudaEvent_t ev_totals = nullptr, ev_in = nullptr, ev_pairs = nullptr;
-  GrowBuf qf, gf, qs, gs, qn, gn, dist, ids, pair_ws, pair_off, totals, pair_q, pair_pos, xbuf, counters,
-      ap, valid, first, topk, tki, tkd;
-  PinBuf h_small;      // totals + per-query results
-  // state of the evaluation in flight (pps_rank_begin .. pps_rank_end)
-  EvalShape cur = {};
-  Staging st = {};
-  const int64_t *d_qid = nullptr, *d_qcam = nullptr, *d_gid = nullptr, *d_gcam = nullptr;
-  const float *d_q = nullptr, *d_g = nullptr;
-  long long n_pairs = 0;
-  int max_pairs = 0;
-  int world = 1;
-  int32_t* local_cnt = nullptr;                 // inside pair_ws
-  // exchange buffer xbuf = [pair_d bits (E) | pair_g (E) | pair_pos as int32 (E)], E = n_pairs
-  float* pair_d() const { return xbuf.as<float>(); }
-  int32_t* pair_g() const { return xbuf.as<int32_t>() + n_pairs; }
-  int32_t* pair_pos32() const { return xbuf.as<int32_t>() + 2 * n_pairs; }
-  cudaStream_t ext_pair_s = nullptr;            // caller-provided stream for the pair kernels (sharded runs)
-  cudaStream_t pair_stream(cudaStream_t cs) const { return ext_pair_s ? ext_pair_s : (world == 1 ? side_s : cs); }
-  // optional phase timing of pps_evaluate_device_ctx (events on the caller's stream)
-  bool timing = false;
-  cudaEvent_t ev_phase[PPS_N_PHASES + 1] = {};
-  float phase_ms[PPS_N_PHASES] = {};
-};
+#include "ctx.cuh"
 
 namespace {
 inline void mark(pps_ctx* c, int i, cudaStream_t s) {
@@ -238,6 +159,7 @@ extern "C" int pps_ctx_destroy(pps_ctx* c) {
                      &c->valid, &c->first, &c->topk, &c->tki, &c->tkd};
   for (GrowBuf* b : bufs) b->release();
   c->h_small.release();
+  c->pass.release();
   for (int i = 0; i < kMaxSlabs; ++i) if (c->ev_slab[i]) cudaEventDestroy(c->ev_slab[i]);
   if (c->ev_totals) cudaEventDestroy(c->ev_totals);
   if (c->ev_in) cudaEventDestroy(c->ev_in);

@@ -553,6 +553,7 @@ class RankEngine:
         if group is None and len(self.gi) != self.ngl:
             raise RuntimeError("g_feats has %d rows but %d gallery ids" % (self.ngl, len(self.gi)))
         self.offset, self.group = int(gallery_offset), group
+        self.max_block_bytes = int(max_block_bytes)
         self.topk, self.topk_filtered, self.want_neg_before = int(topk), topk_filtered, want_neg_before
         self.is_f16 = in_dtype == torch.float16
         self.prec = _lib.PREC_F16X1 if self.is_f16 else _prec_code(precision)
@@ -580,7 +581,10 @@ class RankEngine:
             self.pairs = DevicePairs(self.qi, self.qc, self.gi, self.gc, dev)
         self._pair_cap = 0
         self.kernel_events = None        # bench.py: list collecting (start, stop) events around the distance GEMM
-        self.use_c_path = True           # one gallery block per rank: run the pass through the C step functions
+        self.use_c_path = True           # one device, one block, no top-k: the whole evaluation is ONE C call
+        self.use_c_pass = True           # everything else (several blocks, top-k, sharded): pps_pass_begin / _count / _end
+        self.tk_cap = 0                  # test hook: top-k candidate entries per query of the C pass (0 = default 2048)
+        self._gathered = None
         self._cnt_all = None
         self._side = None
         self.h2d_bytes = 0
@@ -704,6 +708,58 @@ class RankEngine:
         if rc != _lib.PPS_ERR_NO_VALID_QUERY:
             _lib.check(rc, "pps_rank_end")
         return RankResult(ap, valid, first, None, None, ti, td)
+
+    def _run_pass(self, q, g):
+        """The pass driven from C (csrc/pass.cu): pair lists from the global id vectors, blocks, top-k admission, and - for
+        a sharded gallery - exactly two collectives: all-reduce(SUM) of the thresholds, all-gather of
+        [top-k keys | counters | flags] (reduced / merged by the library's own kernels in pps_pass_end)."""
+        torch, lib = self.torch, self.lib
+        nq, topk = self.nq, self.topk
+        p = self.pairs
+        ctx = _host_ctx(self.dev.index or 0)
+        s = _lib.stream_ptr()
+        sharded = self.group is not None
+        world, rank = 1, 0
+        if sharded:
+            import torch.distributed as dist_mod
+            world, rank = dist_mod.get_world_size(self.group), dist_mod.get_rank(self.group)
+        flags = (0 if self.fused_topk else _lib.PASS_NO_EPILOGUE_TOPK) | ((int(self.tk_cap) & 0xffff) << 8)
+        for attempt in (0, 1):
+            d_x1, n_x1 = C.c_void_p(0), C.c_longlong(0)
+            _lib.check(lib.pps_pass_begin(ctx, _lib.ptr(q), nq, _lib.ptr(g) if self.ngl else None, self.ngl, self.dim, self.in_code,
+                                          _lib.ptr(p.qid), _lib.ptr(p.qcam), _lib.ptr(p.gid), _lib.ptr(p.gcam), len(self.gi),
+                                          self.offset, world, rank, self.prec, topk, self.max_block_bytes, flags, s,
+                                          C.byref(d_x1), C.byref(n_x1)), "pps_pass_begin")
+            if sharded and n_x1.value:
+                x1 = _wrap_device(torch, d_x1.value, n_x1.value, "<i4", torch.int32, self.dev)
+                dist_mod.all_reduce(x1, op=dist_mod.ReduceOp.SUM, group=self.group)
+            d_x2, nb = C.c_void_p(0), C.c_longlong(0)
+            _lib.check(lib.pps_pass_count(ctx, s, C.byref(d_x2), C.byref(nb)), "pps_pass_count")
+            gathered = None
+            if sharded:
+                packed = _wrap_device(torch, d_x2.value, nb.value, "|u1", torch.uint8, self.dev)
+                if self._gathered is None or self._gathered.numel() != world * nb.value:
+                    self._gathered = torch.empty(world * nb.value, dtype=torch.uint8, device=self.dev)
+                gathered = self._gathered
+                dist_mod.all_gather_into_tensor(gathered, packed, group=self.group)
+            out_map = C.c_double(0.0)
+            out_cmc = np.zeros(10, dtype=np.float64)
+            ap = np.zeros(nq, dtype=np.float64)
+            valid = np.zeros(nq, dtype=np.uint8)
+            first = np.zeros(nq, dtype=np.int32)
+            ti = np.zeros((nq, topk), dtype=np.int32) if topk else None
+            td = np.zeros((nq, topk), dtype=np.float32) if topk else None
+            rc = lib.pps_pass_end(ctx, _lib.ptr(gathered), 10, s, C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc),
+                                  _lib.ptr(ap), _lib.ptr(valid), _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
+            self.used_fused_topk = bool(topk and not (flags & _lib.PASS_NO_EPILOGUE_TOPK))
+            if rc == _lib.PPS_ERR_TOPK_OVERFLOW and attempt == 0:
+                # a candidate buffer ran over (adversarial column order): every rank sees the same flag (it travels in the
+                # gathered buffers), so every rank repeats the pass with the one-read sweep
+                flags |= _lib.PASS_NO_EPILOGUE_TOPK
+                continue
+            if rc != _lib.PPS_ERR_NO_VALID_QUERY:
+                _lib.check(rc, "pps_pass_end")
+            return RankResult(ap, valid, first, None, None, ti, td)
 
     def _split(self, feats, rows, planes_buf, sq_buf):
         if planes_buf is self.g_planes:
@@ -849,14 +905,16 @@ class RankEngine:
         if self.group is not None:
             import torch.distributed as dist_mod
         nq = self.nq
-        if (self.use_c_path and self.n_chunks == 1 and not self.want_neg_before and not self.is_f16
-                and self.topk_filtered and nq > 0 and self.ngl > 0 and self.kernel_events is None
-                and (self.group is None or self.topk == 0)
-                and q.is_contiguous() and g.is_contiguous() and DIST_KERNEL_FLAGS == 0):
-            if torch.cuda.current_device() == (self.dev.index or 0):
-                return self._run_resident_c(q, g)
+        # Which path runs depends only on options that are the same on every rank of a sharded run (never on the shard).
+        plain = (not self.want_neg_before and self.topk_filtered and nq > 0 and self.kernel_events is None
+                 and not self.fused_rank and DIST_KERNEL_FLAGS == 0 and q.is_contiguous() and g.is_contiguous())
+        if (plain and self.use_c_path and self.group is None and self.n_chunks == 1 and self.topk == 0 and not self.is_f16
+                and self.ngl > 0):
             with torch.cuda.device(self.dev):
                 return self._run_resident_c(q, g)
+        if plain and self.use_c_pass:
+            with torch.cuda.device(self.dev):
+                return self._run_pass(q, g)
         with torch.cuda.device(self.dev):
             pairs = self.pairs.begin()          # junk mask / matches from the resident ids, on the device
             key = self.key
@@ -917,7 +975,17 @@ class RankEngine:
                     self._distance(rows)
                 _rank_block(lib, self.block, self.ldd, nq, rows, self.offset + r0, pairs, pair_d, cnt_le, cnt_first,
                             False, True, key, self.topk, self.topk_filtered)
-            if epi_topk and len(chunks) > 1 and int(self._tk[3].item()) != 0:
+            overflow = False
+            may_epi = bool(self.fused_topk and self.topk and DIST_KERNEL_FLAGS == 0)    # the same on every rank
+            if may_epi and (epi_topk or self.group is not None):
+                # the decision to repeat must be the same on every rank (shards differ, so the flags do too): the flag is
+                # max-reduced, and whether this exchange happens depends on options only, never on the shard
+                flag = self._tk[3] if (epi_topk and len(chunks) > 1) else torch.zeros(1, dtype=torch.int32, device=self.dev)
+                if self.group is not None:
+                    flag = flag.clone()
+                    dist_mod.all_reduce(flag, op=dist_mod.ReduceOp.MAX, group=self.group)
+                overflow = int(flag.item()) != 0
+            if overflow:
                 # a candidate buffer ran over (adversarial column order): repeat the pass with the one-read sweep
                 self.fused_topk = False
                 try:

@@ -109,6 +109,7 @@ def test_compacted_threshold_pass_equals_full_sweep(golden):
             eng = evaluator.RankEngine(d["qid"], d["gid"], d["qcam"], d["gcam"], nq=q.shape[0], ng_local=g.shape[0],
                                        dim=q.shape[1], topk=7, want_neg_before=True, max_block_bytes=q.shape[0] * 256 * 4)
             eng.compact_thresholds = compact
+            eng.use_c_pass = False                      # (the launch-by-launch Python path has both forms)
             assert eng.n_chunks > 1
             out.append(eng.run(q, g))
             if compact:
@@ -537,6 +538,7 @@ def test_topk_admission_in_distance_epilogue(golden):
                 eng = evaluator.RankEngine(d["qid"], d["gid"], d["qcam"], d["gcam"], nq=q.shape[0], ng_local=g.shape[0],
                                            dim=q.shape[1], topk=13, topk_filtered=filtered, max_block_bytes=q.shape[0] * 256 * 4)
                 eng.fused_topk = fused
+                eng.use_c_pass = False                  # (tests/test_gpu_pass.py covers the C-driven pass)
                 assert eng.n_chunks > 1
                 out.append(eng.run(q, g))
                 assert eng.used_fused_topk == fused
@@ -554,6 +556,7 @@ def test_topk_admission_in_distance_epilogue(golden):
     eng = evaluator.RankEngine(d["qid"], gid, d["qcam"], gcam, nq=q.shape[0], ng_local=g.shape[0], dim=q.shape[1], topk=13,
                                max_block_bytes=q.shape[0] * 256 * 4)
     eng.TOPK_CAND_CAP = 4
+    eng.use_c_pass = False
     got = eng.run(q, g)
     assert eng.fused_topk and not eng.used_fused_topk                    # the repeat ran without the epilogue path
     np.testing.assert_array_equal(got.topk_index, want.topk_index)
