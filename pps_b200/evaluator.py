@@ -424,7 +424,8 @@ def compute_dist(array1, array2, type="euclidean", precision: str = DEFAULT_PREC
     'euclidean' -> sqrt(max(0, |a|^2 + |b|^2 - 2ab)).  'cosine' -> the reference calls an undefined
     ``normalize`` (NameError, :259-260); what it intends — rows L2-normalised as
     detectron/core/test_engine.py:52-55 does, then a.b^T (a similarity) — is what this returns.
-    numpy in -> numpy out; CUDA tensor in -> CUDA tensor out.
+    numpy in -> numpy out; CUDA tensor in -> CUDA tensor out (a [m1, m2] view whose row stride is m2 rounded up to a
+    multiple of 4).
     """
     assert type in ["cosine", "euclidean"]
     torch = _torch()
@@ -447,7 +448,10 @@ def compute_dist(array1, array2, type="euclidean", precision: str = DEFAULT_PREC
                 return out
             a, b = unit_rows(a), unit_rows(b)
         flags = _lib.DIST_DOT if type == "cosine" else 0
-        out = torch.empty((m1, m2), dtype=torch.float32, device=a.device)
+        # row stride padded to a multiple of 4 floats (16 bytes): what the 2-CTA kernel's TMA store needs - an odd stride
+        # would silently select the single-CTA kernel, whose accumulation order (and last bits) differ from the ranking path
+        buf = torch.empty((m1, (m2 + 3) // 4 * 4), dtype=torch.float32, device=a.device)
+        out = buf[:, :m2]
         if m1 and m2:
             if prec == _lib.PREC_FP32:
                 a32, b32 = a.float().contiguous(), b.float().contiguous()
@@ -458,7 +462,7 @@ def compute_dist(array1, array2, type="euclidean", precision: str = DEFAULT_PREC
                 _lib.check(lib.pps_row_sqnorm(_lib.ptr(b32), _lib.DTYPE_F32, m2, dim, dim, _lib.ptr(bn),
                                               _lib.stream_ptr()), "pps_row_sqnorm")
                 _lib.check(lib.pps_dist_fp32(_lib.ptr(a32), dim, _lib.ptr(an), m1, _lib.ptr(b32), dim, _lib.ptr(bn),
-                                             m2, dim, flags, _lib.ptr(out), m2, _lib.stream_ptr()), "pps_dist_fp32")
+                                             m2, dim, flags, _lib.ptr(out), int(out.stride(0)), _lib.stream_ptr()), "pps_dist_fp32")
             else:
                 planes = _lib.PLANES_FOR[prec]
                 scaled = prec == _lib.PREC_F16X3 and a.dtype == torch.float32 and b.dtype == torch.float32
