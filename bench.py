@@ -403,6 +403,9 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: keep this rank (and, by first touch, its pinned staging buffers) on the GPU's NUMA node
+    from pps_b200 import numa
+    numa_info = numa.bind_to_gpu_node(local_rank) if (world > 1 and not args.no_numa_bind) else {"bound": False, "reason": "single GPU"}
     group = None
     if world > 1:
         import torch.distributed as dist
@@ -589,8 +592,9 @@ def run_ours(args):
             "e2e": {"value": pairs_step * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "api": "pps_evaluate_host (C ABI, pinned host buffers)" if world == 1 and args.topk == 0
-                           else "RankEngine.run_host (pinned host -> device + sharded path)"},
+                           else "RankEngine.run_host (C pass with pps_pass_set_host_input: slab-pipelined upload of the shard from pinned, NUMA-local host rows)"},
             "gpu_launches": int(launches),
+            "numa": numa_info,
             "clocks": sampler.summary(),
             "roofline": roofline,
             "phases_ms": phases,
@@ -684,6 +688,7 @@ def main():
     ap.add_argument("--c4-rows", type=int, default=10_000_000, help="gallery rows of the configs[4] sub-record (0 = skip)")
     ap.add_argument("--no-dim8064", action="store_true")
     ap.add_argument("--no-checks", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

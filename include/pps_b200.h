@@ -470,6 +470,11 @@ int pps_pass_begin(pps_ctx* ctx, const void* d_q, long long nq, const void* d_g,
                    long long gallery_offset, int world, int rank, int precision, int topk,
                    long long max_block_bytes, int flags, void* stream,
                    int32_t** d_x1, long long* n_x1);
+/* Host sources of the NEXT pps_pass_begin only: its d_q / d_g arguments are then device STAGING buffers the call fills
+ * from these host rows (pinned for full PCIe bandwidth) - the queries on `stream`, the gallery on a copy stream of the
+ * ctx block by block, or in ~8 row slabs when the shard is one block, so that the split + distance of what has arrived
+ * overlap the rest of the upload (the multi-GPU form of pps_evaluate_host_ctx).  NULL leaves a buffer as it is. */
+int pps_pass_set_host_input(pps_ctx* ctx, const void* h_q, const void* h_g);
 int pps_pass_count(pps_ctx* ctx, void* stream, void** d_x2, long long* x2_bytes);
 int pps_pass_end(pps_ctx* ctx, const void* d_gathered, int cmc_topk, void* stream, double* out_map, double* out_cmc,
                  double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,

@@ -119,6 +119,7 @@ SIGNATURES = {
     "pps_rank_end": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_pass_begin": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _i, _i, _i, _ll, _i, _vp,
                             C.POINTER(_vp), C.POINTER(_ll)]),
+    "pps_pass_set_host_input": (_i, [_vp, _vp, _vp]),
     "pps_pass_count": (_i, [_vp, _vp, C.POINTER(_vp), C.POINTER(_ll)]),
     "pps_pass_end": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_ctx_set_timing": (_i, [_vp, _i]),

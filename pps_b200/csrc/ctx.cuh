@@ -65,6 +65,8 @@ struct PassState {
   int max_pairs = 0, n_blocks = 0, tk_cap = 2048;
   bool prefilter = false, g_inplace = false, epi_topk = false;
   const void *d_q = nullptr, *d_g = nullptr;
+  const void *h_q = nullptr, *h_g = nullptr;      // host sources of the NEXT pass (pps_pass_set_host_input), else null
+  bool g_from_host = false;
   const int64_t *d_qid = nullptr, *d_qcam = nullptr, *d_gid = nullptr, *d_gcam = nullptr;
   long long blk_row0[kPassMaxBlocks], blk_rows[kPassMaxBlocks];
   size_t packed_bytes = 0;

@@ -115,10 +115,11 @@ struct TimedLaunch {          // CUDA events around one launch when phase timing
 };
 
 // operand split of gallery rows [r0, r0 + rows) of the local shard -> (planes pointer, sqnorm pointer) for the GEMM
-int split_block(pps_ctx* c, long long r0, long long rows, cudaStream_t cs, const void** planes_out) {
+int split_block(pps_ctx* c, int blk, long long r0, long long rows, cudaStream_t cs, const void** planes_out) {
   PassState& p = c->pass;
   const size_t esz = p.dtype == PPS_DTYPE_F16 ? 2 : 4;
   const unsigned char* src = static_cast<const unsigned char*>(p.d_g) + (size_t)r0 * p.dim * esz;
+  if (p.g_from_host && blk >= 0) PPS_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_slab[blk], 0));   // this block's rows have arrived
   TimedLaunch t(c, cs, 1);
   if (p.g_inplace) {         // fp16 rows that already are a K-major operand plane: only the row norms
     *planes_out = src;
@@ -227,14 +228,70 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
     PPS_CUDA_TRY(cudaEventRecord(p.ev_a, ss));
   }
 
+  // ---- host input (pps_pass_set_host_input): d_q / d_g are staging buffers this call fills.  The gallery goes up on the
+  // copy stream - one block after the other, or, for a shard that is one block, in ~8 row slabs whose split + distance
+  // (each writing its column range of the block) overlap the copy of the next slab, as pps_evaluate_host_ctx does ----
+  const size_t esz_in = dtype == PPS_DTYPE_F16 ? 2 : 4;
+  const void* h_q = p.h_q;
+  const void* h_g = p.h_g;
+  p.h_q = p.h_g = nullptr;
+  p.g_from_host = false;
+  if (h_q) PPS_CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(d_q), h_q, (size_t)nq * dim * esz_in, cudaMemcpyHostToDevice, cs));
+  bool slabbed = false;
+  if (h_g && ng_local > 0) {
+    unsigned char* dg = static_cast<unsigned char*>(const_cast<void*>(d_g));
+    const unsigned char* hg = static_cast<const unsigned char*>(h_g);
+    PPS_CUDA_TRY(cudaStreamWaitEvent(c->copy_s, c->ev_in, 0));
+    if (p.n_blocks == 1) {
+      slabbed = true;
+    } else if (p.n_blocks <= kMaxSlabs) {
+      p.g_from_host = true;
+      for (int b = 0; b < p.n_blocks; ++b) {
+        const size_t off = (size_t)p.blk_row0[b] * dim * esz_in;
+        PPS_CUDA_TRY(cudaMemcpyAsync(dg + off, hg + off, (size_t)p.blk_rows[b] * dim * esz_in, cudaMemcpyHostToDevice, c->copy_s));
+        PPS_CUDA_TRY(cudaEventRecord(c->ev_slab[b], c->copy_s));
+      }
+    } else {
+      PPS_CUDA_TRY(cudaMemcpyAsync(dg, hg, (size_t)ng_local * dim * esz_in, cudaMemcpyHostToDevice, cs));
+    }
+  }
+
   // ---- main stream: queries, first block (nothing here needs the pair lists) ----
   {
     TimedLaunch t(c, cs, 1);
     PPS_TRY(pps_split_rows(d_q, dtype, nq, dim, dim, p.split_planes, p.qs.p, p.qn.as<float>(), cs));
   }
-  if (p.n_blocks > 0) {
+  if (slabbed) {
+    unsigned char* dg = static_cast<unsigned char*>(const_cast<void*>(d_g));
+    const unsigned char* hg = static_cast<const unsigned char*>(h_g);
+    long long slab = ((ng_local + 7) / 8 + 255) & ~255LL;
+    if (slab < 1024) slab = 1024;
+    while ((ng_local + slab - 1) / slab > kMaxSlabs) slab *= 2;
+    int si = 0;
+    for (long long r0 = 0; r0 < ng_local; r0 += slab, ++si) {
+      const long long nr = std::min(slab, ng_local - r0);
+      const size_t off = (size_t)r0 * dim * esz_in;
+      PPS_CUDA_TRY(cudaMemcpyAsync(dg + off, hg + off, (size_t)nr * dim * esz_in, cudaMemcpyHostToDevice, c->copy_s));
+      PPS_CUDA_TRY(cudaEventRecord(c->ev_slab[si], c->copy_s));
+      PPS_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_slab[si], 0));
+      const void* bp;
+      {
+        TimedLaunch t(c, cs, 1);
+        if (p.g_inplace) {
+          bp = dg + off;
+          PPS_TRY(pps_row_sqnorm(dg + off, PPS_DTYPE_F16, nr, dim, dim, p.gn.as<float>() + r0, cs));
+        } else {
+          bp = p.gs.as<unsigned char>() + (size_t)r0 * p.kpad * 2;
+          PPS_TRY(pps_split_rows_slab(dg, dtype, r0, nr, ng_local, dim, dim, p.split_planes, p.gs.p, p.gn.as<float>(), cs));
+        }
+      }
+      TimedLaunch t(c, cs, 2);
+      PPS_TRY(pps_dist_tc(p.qs.p, p.qn.as<float>(), nq, p.planes, 0, bp, p.gn.as<float>() + r0, nr, p.planes, ng_local, dim,
+                          precision, world > 1 ? PPS_DIST_RESERVE_SM_PAIR : 0, p.dist.as<float>() + r0, p.ldd, cs));
+    }
+  } else if (p.n_blocks > 0) {
     const void* gp = nullptr;
-    PPS_TRY(split_block(c, p.blk_row0[0], p.blk_rows[0], cs, &gp));
+    PPS_TRY(split_block(c, 0, p.blk_row0[0], p.blk_rows[0], cs, &gp));
     PPS_TRY(distance_block(c, gp, p.blk_rows[0], p.offset + p.blk_row0[0], false, cs));
   }
 
@@ -302,6 +359,8 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
     PPS_TRY(pps_rank_gather(p.dist.as<float>(), p.ldd, nq, p.blk_rows[0], p.offset, p.pair_q.as<int32_t>(),
                             p.pair_g.as<int32_t>(), p.n_pairs, p.pair_d.as<float>(), cs));
   } else if (p.n_rows > 0) {
+    if (p.g_from_host)       // the compacted rows come from all over the shard: the whole upload must have landed
+      PPS_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_slab[p.n_blocks - 1], 0));
     const long long tcols = std::min<long long>(p.n_rows, kThreshCols);
     const long long ldt = (tcols + 3) / 4 * 4;
     PPS_TRY(p.tdist.ensure((size_t)nq * ldt * 4));
@@ -355,7 +414,7 @@ extern "C" int pps_pass_count(pps_ctx* c, void* stream, void** d_x2, long long* 
       continue;
     }
     const void* gp = nullptr;
-    PPS_TRY(split_block(c, r0, rows, cs, &gp));
+    PPS_TRY(split_block(c, b, r0, rows, cs, &gp));
     if (p.epi_topk) {
       if (b == 1)
         PPS_TRY(pps_topk_bound(reinterpret_cast<const uint64_t*>(p.keys()), p.nq, p.topk, p.tk_bound.as<uint32_t>(),
@@ -452,5 +511,15 @@ extern "C" int pps_pass_end(pps_ctx* c, const void* d_gathered, int cmc_topk, vo
     run += hist[(size_t)k];
     out_cmc[k] = run / (double)n_valid;
   }
+  return PPS_OK;
+}
+
+// Host sources of the NEXT pps_pass_begin: its d_q / d_g arguments are then device STAGING buffers the call fills from
+// these (pinned) host rows - queries on `stream`, the gallery on the ctx's copy stream, block by block (or slab by slab
+// when the shard is one block), overlapping the distance of what has already arrived.  NULL keeps a buffer as it is.
+extern "C" int pps_pass_set_host_input(pps_ctx* c, const void* h_q, const void* h_g) {
+  if (!c) return PPS_ERR_INVALID_ARG;
+  c->pass.h_q = h_q;
+  c->pass.h_g = h_g;
   return PPS_OK;
 }

@@ -129,10 +129,10 @@ __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_kernel(const void
 // 11 significant bits, so p0 + p1 holds 22 bits of every element (bf16 planes: 16) at the same two-plane cost, and
 // the scaling keeps p1 out of the fp16 subnormals.  The distance epilogue multiplies the accumulator by the two
 // inverse scales - exact, they are powers of two.  out_sqnorm[row] = |x|^2, out_sqnorm[rows + row] = 1 / s.
-// The first 16 float4 of a lane (k < 2048) stay in registers between the max pass and the split pass; longer rows
-// re-read their tail (L1 / L2).
-constexpr int kF16Cache4 = 16;
-
+// Two streaming passes over the row (max + norm, then split); the second one hits L1 / L2.  Keeping the row in registers
+// between the passes (kF16Cache4 = 16: 98 registers, 16 warps per SM) measured SLOWER: 2.9 TB/s against 4.6-5.1 TB/s
+// (profiles/r02_notes.md).
+template <int kF16Cache4>
 __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_f16s_kernel(const float* __restrict__ feats, long long row_begin,
                                                                             long long row_end, long long rows, int dim,
                                                                             long long ld, int kpad,
@@ -162,14 +162,25 @@ __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_f16s_kernel(const
     acc += (double)t.x * (double)t.x + (double)t.y * (double)t.y + (double)t.z * (double)t.z + (double)t.w * (double)t.w;
     mx = fmaxf(mx, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
   };
-  float4 cache[kF16Cache4];
+  float4 cache[kF16Cache4 > 0 ? kF16Cache4 : 1];
 #pragma unroll
   for (int u = 0; u < kF16Cache4; ++u) {
     const int k = lane * 4 + u * 128;
     cache[u] = k < kpad ? load4(k, true) : make_float4(0.f, 0.f, 0.f, 0.f);
     note(cache[u]);
   }
-  for (int k = lane * 4 + kF16Cache4 * 128; k < kpad; k += 128) note(load4(k, false));
+  {
+    // rows (or row tails) that are not held in registers: streamed with four loads in flight, re-read by the split pass
+    int k = lane * 4 + kF16Cache4 * 128;
+    for (; k + 3 * 128 < kpad; k += 4 * 128) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = load4(k + u * 128, false);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) note(t[u]);
+    }
+    for (; k < kpad; k += 128) note(load4(k, false));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -205,7 +216,17 @@ __global__ void __launch_bounds__(32 * kSplitWarps) split_rows_f16s_kernel(const
     const int k = lane * 4 + u * 128;
     if (k < kpad) emit(k, cache[u]);
   }
-  for (int k = lane * 4 + kF16Cache4 * 128; k < kpad; k += 128) emit(k, load4(k, false));
+  {
+    int k = lane * 4 + kF16Cache4 * 128;
+    for (; k + 3 * 128 < kpad; k += 4 * 128) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = load4(k + u * 128, false);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) emit(k + u * 128, t[u]);
+    }
+    for (; k < kpad; k += 128) emit(k, load4(k, false));
+  }
   if (lane == 0 && out_sqnorm) {
     out_sqnorm[row] = (float)acc;
     out_sqnorm[rows + row] = inv;
@@ -295,8 +316,8 @@ static int split_dispatch(const void* feats, int dtype, long long row0, long lon
     split_rows_kernel<1, true><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm, row_index, index_base);
   } else if (dtype == PPS_DTYPE_F32 && (planes & PPS_SPLIT_F16_SCALED)) {
     if ((planes & ~PPS_SPLIT_F16_SCALED) != 2 || !out_planes || !out_sqnorm) return PPS_ERR_INVALID_ARG;
-    split_rows_f16s_kernel<<<grid, block, 0, st>>>(static_cast<const float*>(feats), row0, row0 + nrows, rows, dim, ld, kpad,
-                                                   static_cast<__half*>(out_planes), out_sqnorm, row_index, index_base);
+    split_rows_f16s_kernel<0><<<grid, block, 0, st>>>(static_cast<const float*>(feats), row0, row0 + nrows, rows, dim, ld, kpad,
+                                                      static_cast<__half*>(out_planes), out_sqnorm, row_index, index_base);
   } else if (dtype == PPS_DTYPE_F32) {
     switch (planes) {
       case 1: split_rows_kernel<1, false><<<grid, block, 0, st>>>(feats, row0, row0 + nrows, rows, dim, ld, kpad, out_planes, out_sqnorm, row_index, index_base); break;

@@ -589,6 +589,7 @@ class RankEngine:
         self.use_c_pass = True           # everything else (several blocks, top-k, sharded): pps_pass_begin / _count / _end
         self.tk_cap = 0                  # test hook: top-k candidate entries per query of the C pass (0 = default 2048)
         self._gathered = None
+        self._stage = None               # device staging of run_host
         self._cnt_all = None
         self._side = None
         self.h2d_bytes = 0
@@ -1013,13 +1014,26 @@ class RankEngine:
                               negb.cpu().numpy() if negb is not None else None, pairs, ti, td)
 
     def run_host(self, q_host, g_host) -> RankResult:
-        """Host (ideally pinned) feature tensors in: the H2D copies are part of the call."""
+        """Host (ideally pinned) feature tensors in: the H2D copies are part of the call.  Through the C pass the gallery
+        goes up block by block (slab by slab when the shard is one block) on a copy stream, overlapping the split +
+        distance of the rows that have already arrived (pps_pass_set_host_input)."""
         torch = self.torch
+        want = torch.float16 if self.is_f16 else torch.float32
+        for t, shape, name in ((q_host, (self.nq, self.dim), "q"), (g_host, (self.ngl, self.dim), "g")):
+            if t.is_cuda or t.dtype != want or tuple(t.shape) != shape or not t.is_contiguous():
+                raise RuntimeError("RankEngine.run_host: %s must be a contiguous host %s tensor of shape %s" % (name, want, shape))
+        self.h2d_bytes = q_host.numel() * q_host.element_size() + g_host.numel() * g_host.element_size()
         with torch.cuda.device(self.dev):
-            q = q_host.to(self.dev, non_blocking=True)
-            g = g_host.to(self.dev, non_blocking=True)
-            self.h2d_bytes = q_host.numel() * q_host.element_size() + g_host.numel() * g_host.element_size()
-            return self.run(q, g)
+            plain = (not self.want_neg_before and self.topk_filtered and self.nq > 0 and self.kernel_events is None
+                     and not self.fused_rank and DIST_KERNEL_FLAGS == 0 and self.use_c_pass)
+            if not plain:
+                return self.run(q_host.to(self.dev, non_blocking=True), g_host.to(self.dev, non_blocking=True))
+            if self._stage is None:
+                self._stage = (torch.empty((self.nq, self.dim), dtype=want, device=self.dev),
+                               torch.empty((max(self.ngl, 1), self.dim), dtype=want, device=self.dev))
+            _lib.check(self.lib.pps_pass_set_host_input(_host_ctx(self.dev.index or 0), _lib.ptr(q_host),
+                                                        _lib.ptr(g_host) if self.ngl else None), "pps_pass_set_host_input")
+            return self._run_pass(self._stage[0], self._stage[1][:self.ngl])
 
 
 def plan_blocks(ng_local, block_rows, topk=0, cand_cap=2048):

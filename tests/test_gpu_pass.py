@@ -168,3 +168,39 @@ def test_pass_argument_errors():
     assert lib.pps_pass_end(h, None, 10, s, None, None, None, None, None, None, None) == _lib.PPS_ERR_INVALID_ARG
     assert bad() == 0
     lib.pps_ctx_destroy(h)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "fp16"])
+def test_pass_host_input_equals_resident(golden, dtype):
+    """RankEngine.run_host: pinned host rows -> staging buffers filled by pps_pass_begin (slabs of a one-block shard,
+    whole blocks otherwise) == the pass on resident tensors, bit for bit; repeated calls reuse the staging."""
+    import torch
+    from pps_b200 import evaluator
+    d = golden("many_pos")
+    tdt = torch.float16 if dtype == "fp16" else torch.float32
+    qh, gh = torch.from_numpy(d["q"]).to(tdt).pin_memory(), torch.from_numpy(d["g"]).to(tdt).pin_memory()
+    q, g = qh.cuda(), gh.cuda()
+    for block_bytes in (8 << 30, q.shape[0] * 256 * 4):
+        for topk in (0, 9):
+            eng = _engine(evaluator, d, q, g, topk=topk, max_block_bytes=block_bytes, in_dtype=tdt)
+            eng.use_c_path = False
+            want = eng.run(q, g)
+            _same(eng.run_host(qh, gh), want, topk)
+            _same(eng.run_host(qh, gh), want, topk)
+    # a large single block: several slabs
+    from pps_b200 import synthetic
+    dd = synthetic.make_reid_set(nq=300, ng=20000, dim=256, n_ids=60, n_cams=4, n_distractors=3000, sigma=3.0, seed=5)
+    qh, gh = torch.from_numpy(dd["q"]).to(tdt).pin_memory(), torch.from_numpy(dd["g"]).to(tdt).pin_memory()
+    q, g = qh.cuda(), gh.cuda()
+    eng = _engine(evaluator, dd, q, g, topk=5, in_dtype=tdt)
+    eng.use_c_path = False
+    _same(eng.run_host(qh, gh), eng.run(q, g), 5)
+    with pytest.raises(RuntimeError, match="run_host"):
+        eng.run_host(q, gh)
+
+
+def test_numa_helper_is_best_effort():
+    from pps_b200 import numa
+    info = numa.bind_to_gpu_node(0)
+    assert info["device"] == 0 and ("reason" in info or info["bound"])
+    assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
