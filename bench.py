@@ -277,14 +277,20 @@ def timed_passes(torch, engine, q, g, steps, warmup, world, dev):
     barrier()
     engine.set_phase_timing(True)          # the C pass sums the device time of its distance launches per pass
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    gemm = []
+    gemm, phases = [], {}
     e0.record()
     for _ in range(steps):
         res = engine.run(q, g)
-        gemm.append(engine.last_phase_ms()["dist_gemm"])
+        ph = engine.last_phase_ms()
+        gemm.append(ph["dist_gemm"])
+        for k_, v_ in ph.items():
+            phases[k_] = phases.get(k_, 0.0) + v_ / steps
     e1.record()
     barrier()
     engine.set_phase_timing(False)
+    engine.last_pass_phases = {"split": phases.get("split"), "dist_gemm": phases.get("dist_gemm"), "rank_count_and_merge": phases.get("rank_count"),
+                               "finalize": phases.get("finalize"), "host_wait_pair_lists": phases.get("pairs_enqueue"),
+                               "host_wait_final_sync": phases.get("d2h")}
     t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -328,6 +334,7 @@ def bench_large_gallery(torch, evaluator, synthetic, args, name, ng, dtype_name,
                "ms_per_pass": ms, "pairs_per_s": pairs / (ms * 1e-3), "algorithmic_tflops": tf,
                "frac_of_sustained_bf16_all_gpus": tf / (peaks["tf_sustained"] * world),
                "dist_gemm_ms_per_pass_rank0": gemm_ms, "gpu_launches_per_pass_rank0": launches,
+               "phase_sums_ms_rank0": getattr(eng, "last_pass_phases", None),
                "mAP": res.mean_ap(), "cmc1": float(res.cmc(10, True)[0])}
         # oracle check: a query slice x the WHOLE gallery, regenerated shard by shard on this GPU and ranked on the host
         del g

@@ -206,6 +206,16 @@ __device__ __forceinline__ void tma_load_3d_2cta(void* smem_dst, const CUtensorM
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// the same load delivered to every CTA of `cta_mask` (same shared-memory offset in each); the bytes are signalled on the
+// mbarrier at `mbar_cluster_addr`'s offset in the pair leader of every destination CTA
+__device__ __forceinline__ void tma_load_3d_2cta_mcast(void* smem_dst, const CUtensorMap* tmap, uint32_t mbar_cluster_addr,
+                                                       uint16_t cta_mask, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5, %6}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar_cluster_addr), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                 uint32_t accumulate) {
   asm volatile(

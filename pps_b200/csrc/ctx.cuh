@@ -76,6 +76,7 @@ struct PassState {
   cudaEvent_t ev_a = nullptr, ev_rows = nullptr;
   cudaEvent_t ev_t[kPassTimedLaunches][2] = {};
   int n_timed = 0, timed_kind[kPassTimedLaunches] = {};
+  float host_wait_ms[4] = {};
   void release() {
     GrowBuf* bufs[] = {&qs, &qn, &gs, &gn, &dist, &tdist, &ts, &tn, &pair_ws, &pair_off, &totals, &pair_q, &pair_g, &pair_pos,
                        &pair_d, &packed, &pf_ws, &cand_rows, &cand_gid, &cand_gcam, &gp_rows, &pair_col, &gp_ws, &tk_bound,

@@ -16,6 +16,7 @@
 //              (2 x 256 TMEM columns) so the epilogue of tile t overlaps the mainloop of t+1.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace pps {
@@ -305,11 +306,14 @@ struct TileWalk {
   }
 };
 
-template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Gemm2Args ga,
-                const __grid_constant__ RankFuse rf) {
+// CL4 = true: a cluster of FOUR CTAs = two CTA pairs that work on two vertically adjacent 256-row m tiles of the SAME n
+// tile.  Each CTA still loads its own 128 A rows; the B halves are loaded ONCE per cluster - by the CTAs of pair 0, with
+// TMA .multicast::cluster into the CTA of the same parity in pair 1 - so the L2 -> SM traffic of B halves.  For the
+// single-plane (fp16 / bf16x1) product, whose tiles are used by one term only and which therefore sits at the chip's
+// L2 -> SM delivery limit instead of at the tensor pipe, that is 25 % fewer bytes per MMA.
+template <int BN, int EPI, bool CL4>
+__device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                                              const Gemm2Args& ga, const RankFuse& rf) {
   extern __shared__ __align__(1024) unsigned char smem[];   // SWIZZLE_128B tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   constexpr int kBTile = (BN / 2) * kBK * 2;                 // this CTA's half of a B plane tile
@@ -329,8 +333,12 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const GemmArgs& g = ga.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const long long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const uint32_t crank = cluster_ctarank();                 // rank in the cluster (0..1, or 0..3 with CL4)
+  const uint32_t rank = crank & 1u;                         // rank in the CTA pair
+  const uint32_t lead = crank & ~1u;                        // cluster rank of this pair's leader
+  const int pair_row0 = CL4 ? (int)(crank >> 1) * 256 : 0;  // this pair's rows inside the cluster's m tile
+  constexpr int kClusterRows = CL4 ? 512 : 256;
+  const long long pair = CL4 ? (blockIdx.x >> 2) : (blockIdx.x >> 1), npairs = CL4 ? (gridDim.x >> 2) : (gridDim.x >> 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -338,7 +346,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (EPI != EPI_RANK) tma_prefetch_desc(&tmO);
     for (int s = 0; s < kMaxStages2; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL4 ? 2 : 1);   // CL4: a slot also receives the other pair's B half, so both pairs' MMAs free it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -361,17 +369,25 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t it = 0;
       TileWalk<EPI> w(ga, pair, npairs);
       while (w.next()) {
-        const int m0 = (int)(w.grp * ga.a_group_rows) + w.m_tile * 256 + (int)rank * kT2Rows;
+        const int m0 = (int)(w.grp * ga.a_group_rows) + w.m_tile * kClusterRows + pair_row0 + (int)rank * kT2Rows;
         const int n0 = (int)(w.grp * ga.b_group_rows) + w.n_tile * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < g.kblocks; ++kb, ++it) {
           const uint32_t s = it % stages, ph = (it / stages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           if (rank == 0) mbar_expect_tx(&full[s], 2u * stage_bytes);
-          const uint32_t full0 = map_to_cta(smem_u32(&full[s]), 0);
+          const uint32_t full0 = map_to_cta(smem_u32(&full[s]), lead);
           unsigned char* slot = smem + (size_t)s * stage_bytes;
           for (int p = 0; p < planes; ++p) tma_load_3d_2cta(slot + p * kTile2Bytes, &tmA, full0, kb * kBK, m0, p);
-          for (int p = 0; p < planes; ++p)
-            tma_load_3d_2cta(slot + planes * kTile2Bytes + p * kBTile, &tmB, full0, kb * kBK, n0, p);
+          if (!CL4) {
+            for (int p = 0; p < planes; ++p)
+              tma_load_3d_2cta(slot + planes * kTile2Bytes + p * kBTile, &tmB, full0, kb * kBK, n0, p);
+          } else if (crank < 2) {
+            // pair 0 loads the B halves for the whole cluster: CTA r and CTA r + 2 receive the same half, each signalling
+            // the full barrier of its own pair leader (the barrier address is relative to the destination's pair)
+            const uint16_t mask = (uint16_t)(0x5u << rank);
+            for (int p = 0; p < planes; ++p)
+              tma_load_3d_2cta_mcast(slot + planes * kTile2Bytes + p * kBTile, &tmB, full0, mask, kb * kBK, n0, p);
+          }
         }
       }
     }
@@ -397,9 +413,9 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int k = 0; k < kBK / 16; ++k)
               tc_mma_f16_2cta(d_tmem, adesc + 2u * k, bdesc + 2u * k, g.idesc, (kb | term | k) ? 1u : 0u);
           }
-          tc_commit_2cta(&empty[s], 3);          // both CTAs' slots reusable once these MMAs retire
+          tc_commit_2cta(&empty[s], CL4 ? 0xF : 3);   // the slots (of every CTA that holds a tile these MMAs read) are reusable
         }
-        tc_commit_2cta(&tfull[as], 3);           // accumulator complete in both CTAs
+        tc_commit_2cta(&tfull[as], (uint16_t)(3u << lead));   // accumulator complete in both CTAs of this pair
       }
     }
   } else {
@@ -425,7 +441,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     long long tab_base = 0;                     // element offset of (row group, j = 0, this row) in the global tables
     TileWalk<EPI> w(ga, pair, npairs);
     for (; w.next(); ++acc_it) {
-      const int m0 = w.m_tile * 256 + (int)rank * kT2Rows;                          // output row (within the group's rows)
+      const int m0 = w.m_tile * kClusterRows + pair_row0 + (int)rank * kT2Rows;       // output row (within the group's rows)
       const int n0 = (int)(w.grp * ga.out_group_cols) + w.n_tile * BN;              // output column
       const int n_end = EPI == EPI_AFFINE_RELU ? (int)((w.grp + 1) * ga.out_group_cols) : (int)g.m2;   // first column not ours
       const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
@@ -599,7 +615,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       __syncwarp();
       if (lane == 0) {
         if (rank == 0) mbar_arrive(&tempty[as]);
-        else mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[as]), 0));
+        else mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[as]), lead));
       }
       if (scaled) asm volatile("bar.sync 1, 128;" ::: "memory");   // every warp is done with bn / sc of this tile
       if (EPI == EPI_RANK && (w.run_end || ++tiles_since_flush == 255)) {
@@ -628,6 +644,22 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, 512);
   }
+}
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Gemm2Args ga,
+                const __grid_constant__ RankFuse rf) {
+  dist_tc2_body<BN, EPI, false>(tmA, tmB, tmO, ga, rf);
+}
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kGemmThreads, 1)
+dist_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Gemm2Args ga,
+                const __grid_constant__ RankFuse rf) {
+  dist_tc2_body<BN, EPI, true>(tmA, tmB, tmO, ga, rf);
 }
 
 // ------------------------------------------------------------------------------------
@@ -825,6 +857,49 @@ static int dist_tc_impl(const void* a_planes, const float* a_sqnorm, long long m
       PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc2_kernel<256, EPI_DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)kGemm2Smem));
       configured2_dev = dev;
+    }
+    // single-plane products (fp16 inputs, bf16x1) with at least two m tiles: clusters of four CTAs, B halves multicast
+    static const bool env_no_cluster4 = getenv("PPS_NO_CLUSTER4") != nullptr;       // kill switch / A-B measurements
+    if (need == 1 && m1 > 256 && !(flags & PPS_DIST_NO_CLUSTER4) && !env_no_cluster4 && sms >= 4) {
+      static thread_local int cfg4_dev = -1;
+      static thread_local int max_clusters[2] = {0, 0};
+      if (cfg4_dev != dev) {
+        PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc4_kernel<256, EPI_DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kGemm2Smem));
+        PPS_CUDA_TRY(cudaFuncSetAttribute(dist_tc4_kernel<256, EPI_DIST_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kGemm2Smem));
+        for (int v = 0; v < 2; ++v) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3((unsigned)(sms / 4 * 4));
+          cfg.blockDim = dim3(kGemmThreads);
+          cfg.dynamicSmemBytes = kGemm2Smem;
+          cudaLaunchAttribute at;
+          at.id = cudaLaunchAttributeClusterDimension;
+          at.val.clusterDim.x = 4; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+          cfg.attrs = &at; cfg.numAttrs = 1;
+          int n = 0;
+          cudaError_t e = v == 0 ? cudaOccupancyMaxActiveClusters(&n, dist_tc4_kernel<256, EPI_DIST>, &cfg)
+                                 : cudaOccupancyMaxActiveClusters(&n, dist_tc4_kernel<256, EPI_DIST_TOPK>, &cfg);
+          if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+          max_clusters[v] = n;
+        }
+        cfg4_dev = dev;
+      }
+      const int mc = max_clusters[topk ? 1 : 0];
+      if (mc > 0) {
+        ga.g.m_tiles = (int)((m1 + 511) / 512);
+        const long long tiles4 = (long long)ga.g.m_tiles * ga.g.n_tiles;
+        long long clusters = tiles4 < mc ? tiles4 : mc;
+        if ((flags & PPS_DIST_RESERVE_SM_PAIR) && clusters == mc && clusters > 4) clusters -= 1;
+        if (topk) {
+          dist_tc4_kernel<256, EPI_DIST_TOPK><<<(unsigned)(4 * clusters), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga, *topk);
+          PPS_LAUNCH_CHECK("dist_tc4_kernel<topk>");
+        } else {
+          dist_tc4_kernel<256, EPI_DIST><<<(unsigned)(4 * clusters), kGemmThreads, kGemm2Smem, st>>>(tmA, tmB, tmO, ga, RankFuse{});
+          PPS_LAUNCH_CHECK("dist_tc4_kernel");
+        }
+        return PPS_OK;
+      }
     }
     const long long tiles2 = (long long)ga.g.m_tiles * ga.g.n_tiles;
     long long slots = sms / 2;

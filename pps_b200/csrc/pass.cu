@@ -13,6 +13,7 @@
 // With world == 1 there is nothing to exchange and the three calls just run back to back.
 #include "ctx.cuh"
 
+#include <chrono>
 #include <cmath>
 
 namespace pps {
@@ -100,6 +101,15 @@ int plan_blocks(PassState& p, bool short_first) {
   return PPS_OK;
 }
 
+// host time spent blocked in a wait (phase timing on): where the pass stalls the CPU
+struct HostWait {
+  pps_ctx* c; int slot; std::chrono::steady_clock::time_point t0;
+  HostWait(pps_ctx* c_, int slot_) : c(c_), slot(slot_), t0(std::chrono::steady_clock::now()) {}
+  ~HostWait() {
+    if (c->timing) c->pass.host_wait_ms[slot] += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+
 struct TimedLaunch {          // CUDA events around one launch when phase timing is on
   pps_ctx* c; cudaStream_t s; int slot;
   TimedLaunch(pps_ctx* c_, cudaStream_t s_, int kind) : c(c_), s(s_), slot(-1) {
@@ -174,6 +184,7 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
   p.d_q = d_q; p.d_g = d_g; p.d_qid = d_qid; p.d_qcam = d_qcam; p.d_gid = d_gid; p.d_gcam = d_gcam;
   p.g_inplace = dtype == PPS_DTYPE_F16 && (dim % 64) == 0 && (reinterpret_cast<uintptr_t>(d_g) & 15u) == 0;
   p.n_timed = 0;
+  for (float& w : p.host_wait_ms) w = 0.f;
   p.tk_cap = (flags >> 8) & 0xffff;                    // PPS_PASS_TKCAP(n): candidate buffer entries per query (tests)
   if (p.tk_cap <= 0 || p.tk_cap > kTkCap) p.tk_cap = kTkCap;
   if (!p.ev_a) PPS_CUDA_TRY(cudaEventCreateWithFlags(&p.ev_a, cudaEventDisableTiming));
@@ -300,7 +311,10 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
   const int64_t* sweep_gcam = d_gcam;
   long long sweep_rows = ng_global;
   if (p.prefilter) {
-    PPS_CUDA_TRY(cudaEventSynchronize(p.ev_a));
+    {
+      HostWait hw(c, 0);
+      PPS_CUDA_TRY(cudaEventSynchronize(p.ev_a));
+    }
     p.n_cand = h_tot[2];
     sweep_gid = p.cand_gid.as<int64_t>(); sweep_gcam = p.cand_gcam.as<int64_t>(); sweep_rows = p.n_cand;
   }
@@ -309,7 +323,10 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
                                  p.totals.as<int32_t>(), ss));
   PPS_CUDA_TRY(cudaMemcpyAsync(h_tot, p.totals.p, 8, cudaMemcpyDeviceToHost, ss));
   PPS_CUDA_TRY(cudaEventRecord(c->ev_totals, ss));
-  PPS_CUDA_TRY(cudaEventSynchronize(c->ev_totals));
+  {
+    HostWait hw(c, 1);
+    PPS_CUDA_TRY(cudaEventSynchronize(c->ev_totals));
+  }
   p.n_pairs = h_tot[0];
   p.max_pairs = h_tot[1];
   const size_t np1 = (size_t)std::max<long long>(p.n_pairs, 1);
@@ -348,7 +365,10 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
                                    p.pair_col.as<int32_t>(), p.totals.as<int32_t>() + 3, ss));
     PPS_CUDA_TRY(cudaMemcpyAsync(h_tot + 3, p.totals.as<int32_t>() + 3, 4, cudaMemcpyDeviceToHost, ss));
     PPS_CUDA_TRY(cudaEventRecord(p.ev_rows, ss));
-    PPS_CUDA_TRY(cudaEventSynchronize(p.ev_rows));
+    {
+      HostWait hw(c, 2);
+      PPS_CUDA_TRY(cudaEventSynchronize(p.ev_rows));
+    }
     p.n_rows = h_tot[3];
   }
   PPS_CUDA_TRY(cudaEventRecord(c->ev_pairs, ss));
@@ -482,7 +502,10 @@ extern "C" int pps_pass_end(pps_ctx* c, const void* d_gathered, int cmc_topk, vo
     PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_index, p.tki.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
   if (topk > 0 && out_topk_dist)
     PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_dist, p.tkd.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
-  PPS_CUDA_TRY(cudaStreamSynchronize(cs));
+  {
+    HostWait hw(c, 3);
+    PPS_CUDA_TRY(cudaStreamSynchronize(cs));
+  }
   p.active = false;
   if (c->timing) {                      // phase sums of this pass: 1 split, 2 distance, 4 counting / merge, 5 finalize
     for (int i = 0; i < PPS_N_PHASES; ++i) c->phase_ms[i] = 0.f;
@@ -490,6 +513,10 @@ extern "C" int pps_pass_end(pps_ctx* c, const void* d_gathered, int cmc_topk, vo
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, p.ev_t[i][0], p.ev_t[i][1]) == cudaSuccess) c->phase_ms[p.timed_kind[i]] += ms;
     }
+    // host-side stalls of this pass: 0 candidate count + pair totals + compacted-row count (pps_pass_begin), 3 unused,
+    // 6 the final synchronise of pps_pass_end
+    c->phase_ms[0] = p.host_wait_ms[0] + p.host_wait_ms[1] + p.host_wait_ms[2];
+    c->phase_ms[6] = p.host_wait_ms[3];
   }
   if (st.totals[4] != 0) return PPS_ERR_TOPK_OVERFLOW;     // identical on every rank (the flags were summed)
   double ap_sum = 0.0;

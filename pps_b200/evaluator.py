@@ -524,9 +524,20 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
+_WRAPPED = {}
+
+
 def _wrap_device(torch, ptr, n, typestr, dtype, device):
-    t = torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
-    assert t.dtype == dtype and t.data_ptr() == ptr
+    """torch tensor aliasing `n` elements of library-owned device memory (cached: the buffers of a ctx are grow-only, so the
+    same (pointer, length) comes back pass after pass and the __cuda_array_interface__ round trip is paid once)."""
+    key = (int(ptr), int(n), typestr, str(device))
+    t = _WRAPPED.get(key)
+    if t is None:
+        if len(_WRAPPED) > 64:
+            _WRAPPED.clear()
+        t = torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
+        assert t.dtype == dtype and t.data_ptr() == ptr
+        _WRAPPED[key] = t
     return t
 
 

@@ -187,3 +187,41 @@ def test_f16x3_row_scaling_covers_the_dynamic_range():
         assert np.max(np.abs(got - exact) / scale) < 4 * max(np.max(np.abs(ref - exact) / scale), 1e-7), kernel
         keep = np.ones(270, bool); keep[5] = False
         np.testing.assert_allclose(cos[:, keep], O.compute_dist(a, b[keep], type="cosine"), rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("m1,m2,dim", [(257, 255, 64), (512, 1000, 192), (513, 300, 2048), (1300, 2049, 320), (3368, 700, 128)])
+def test_cluster4_multicast_kernel_equals_two_cta_kernel(m1, m2, dim):
+    """Single-plane products (fp16 inputs) with more than one m tile run on clusters of FOUR CTAs whose two CTA pairs share
+    the B tile by TMA multicast (dist_tc4_kernel).  Same MMAs in the same order as the 2-CTA kernel: identical bits, with
+    and without the top-k admission epilogue; against float64 at the fp16-product level."""
+    import torch
+    from pps_b200 import _lib, evaluator
+    lib = _lib.load()
+    rs = np.random.RandomState(m1 + m2)
+    a = torch.from_numpy(rs.randn(m1, dim).astype(np.float16)).cuda()
+    b = torch.from_numpy(rs.randn(m2, dim).astype(np.float16)).cuda()
+    sa, sb = evaluator.SplitOperand(a, 1), evaluator.SplitOperand(b, 1)
+    ld = (m2 + 3) // 4 * 4
+    out = {}
+    for name, flags in (("cl4", 0), ("cl2", _lib.DIST_NO_CLUSTER4)):
+        d = torch.zeros((m1, ld), dtype=torch.float32, device="cuda")
+        _lib.check(lib.pps_dist_tc(_lib.ptr(sa.planes), _lib.ptr(sa.sqnorm), m1, 1, 0, _lib.ptr(sb.planes), _lib.ptr(sb.sqnorm), m2, 1, 0,
+                                   dim, _lib.PREC_F16X1, flags, _lib.ptr(d), ld, _lib.stream_ptr()), "pps_dist_tc")
+        out[name] = d[:, :m2].cpu().numpy()
+    np.testing.assert_array_equal(out["cl4"], out["cl2"])
+    np.testing.assert_allclose(out["cl4"], _f64_dist(a.float().cpu().numpy(), b.float().cpu().numpy()), rtol=1e-4, atol=1e-4)
+    # admission epilogue: unbounded state -> every column of every row is a candidate until the buffer is full
+    k, cap = 4, 64
+    bound = torch.full((m1,), -1, dtype=torch.int32, device="cuda")           # 0xffffffff: unbounded
+    res = {}
+    for name, flags in (("cl4", 0), ("cl2", _lib.DIST_NO_CLUSTER4)):
+        cnt = torch.zeros(m1, dtype=torch.int32, device="cuda")
+        cand = torch.zeros((m1, cap), dtype=torch.int64, device="cuda")
+        d = torch.zeros((m1, ld), dtype=torch.float32, device="cuda")
+        _lib.check(lib.pps_dist_topk_tc(_lib.ptr(sa.planes), _lib.ptr(sa.sqnorm), m1, 1, 0, _lib.ptr(sb.planes), _lib.ptr(sb.sqnorm), m2,
+                                        1, 0, dim, _lib.PREC_F16X1, flags, _lib.ptr(d), ld, 1000, _lib.ptr(bound), _lib.ptr(cnt),
+                                        _lib.ptr(cand), cap, _lib.stream_ptr()), "pps_dist_topk_tc")
+        res[name] = (d[:, :m2].cpu().numpy(), cnt.cpu().numpy())
+    np.testing.assert_array_equal(res["cl4"][0], out["cl2"])
+    np.testing.assert_array_equal(res["cl4"][1], np.full(m1, m2))
+    np.testing.assert_array_equal(res["cl2"][1], np.full(m1, m2))
