@@ -43,7 +43,7 @@ PREC_FP32 = 32
 DIST_SQUARED = 1
 DIST_DOT = 2
 DIST_KERNEL_1CTA = 0x100
-DIST_NO_CLUSTER4 = 0x400
+DIST_CLUSTER4 = 0x400
 
 TOPK_MAX = 128
 N_PHASES = 7

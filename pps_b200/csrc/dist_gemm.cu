@@ -858,9 +858,12 @@ static int dist_tc_impl(const void* a_planes, const float* a_sqnorm, long long m
                                         (int)kGemm2Smem));
       configured2_dev = dev;
     }
-    // single-plane products (fp16 inputs, bf16x1) with at least two m tiles: clusters of four CTAs, B halves multicast
-    static const bool env_no_cluster4 = getenv("PPS_NO_CLUSTER4") != nullptr;       // kill switch / A-B measurements
-    if (need == 1 && m1 > 256 && !(flags & PPS_DIST_NO_CLUSTER4) && !env_no_cluster4 && sms >= 4) {
+    // Opt-in (PPS_DIST_CLUSTER4, or PPS_CLUSTER4=1 in the environment): clusters of four CTAs whose two pairs share the B
+    // halves by TMA multicast.  Bit-identical, 25 % fewer L2 reads - and measured SLOWER on B200 (10 M x 2048 fp16: 149.7 vs
+    // 141.1 ms of distance kernels per pass): the single-plane product is bound by what each SM can take in, which multicast
+    // does not change, and 4-CTA clusters leave 12 of the 148 SMs idle.  Kept for the record and for other shapes.
+    static const bool env_cluster4 = getenv("PPS_CLUSTER4") != nullptr;
+    if (need == 1 && m1 > 256 && ((flags & PPS_DIST_CLUSTER4) || env_cluster4) && sms >= 4) {
       static thread_local int cfg4_dev = -1;
       static thread_local int max_clusters[2] = {0, 0};
       if (cfg4_dev != dev) {

@@ -144,7 +144,7 @@ __device__ __noinline__ void topk_admit(float d, unsigned long long gcol, unsign
 constexpr int kCandC = 2048;
 
 template <bool TOPK>
-__global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 12) rank_count_kernel(const float* __restrict__ dist, long long ldd,
+__global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 16) rank_count_kernel(const float* __restrict__ dist, long long ldd,
                                                                      long long ncols, long long col0, long long seg,
                                                                      const int32_t* __restrict__ pair_off,
                                                                      const int32_t* __restrict__ pair_g,
@@ -164,8 +164,6 @@ __global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 12) rank_count_kernel(
   __shared__ uint32_t hist[kNB];          // bit 31: the bin holds a threshold
   __shared__ uint32_t binfo[kNB];         // (index of the bin's first threshold << 16) | thresholds in the bin
   __shared__ uint32_t part[kCntThreads];
-  __shared__ uint32_t dump[64];           // per lane: [0, 32) sink of the elements beyond the last bin, [32, 64) count of
-                                          // the elements below every threshold
   __shared__ int s_np, s_nj;
   __shared__ uint32_t s_below, s_first_cnt;
   __shared__ unsigned long long cand[TOPK ? kCandC : 1];
@@ -187,7 +185,6 @@ __global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 12) rank_count_kernel(
     sg[i] = pair_pos[e0 + i] ? pair_g[e0 + i] : -1;
   }
   for (int i = tid; i < kNB; i += kCntThreads) { hist[i] = 0; binfo[i] = 0; }
-  if (tid < 64) dump[tid] = 0;
   unsigned long long* state = nullptr;
   if (TOPK) {
     state = topk_key + (long long)q * k;
@@ -246,49 +243,22 @@ __global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 12) rank_count_kernel(
 
   unsigned long long bound = ~0ull;                        // TOPK: key of the current k-th best (sampled per half pass)
   int* app_ctr = s_app;                                    // TOPK: this half pass's append counter
-  // Per element, straight-line: key, one compare for "below every threshold", bin, ONE predicated shared-memory atomic.
-  // The atomic returns the bin's flag (bit 31: the bin holds thresholds); the flags of a batch of elements are collected in
-  // a bit mask and the few flagged elements take the exact path AFTER the batch, so the hot loop has no reconvergence
-  // points and all its atomics are in flight together.
-  const int key_lo = count_on ? key_min : 0x7fffffff;      // (no thresholds: everything is "below", nothing is binned)
-  const uint32_t hist_addr = smem_u32(hist), dump_addr = smem_u32(&dump[lane]);
-  auto classify = [&](float d) -> uint32_t {
+  auto visit = [&](float d, long long col) {
     const int key = fkey(d);
-    const bool lt = key < key_lo;
-    const unsigned b = ((unsigned)key - (unsigned)key_lo) >> shift;
-    // ONE unconditional shared-memory atomic, no branch (ptxas turns a predicated atomic with a result into a branch +
-    // reconvergence point): elements beyond the last bin hit this lane's private dump word, elements below every
-    // threshold its private "below" counter (neither is ever flagged)
-    uint32_t addr = b < (unsigned)kNB ? hist_addr + (b << 2) : dump_addr;
-    addr = lt ? dump_addr + 128u : addr;
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
-    return old >> 31;
-  };
-  auto exact_path = [&](float d, long long col) {          // the element's bin holds thresholds: exact comparison
-    const unsigned b = ((unsigned)fkey(d) - (unsigned)key_lo) >> shift;
-    const uint32_t info = binfo[b];
-    const int first = (int)(info >> 16), cnt = (int)(info & 0xffffu);
-    int j = 0;
-    while (j < cnt && thr[first + j] < d) ++j;
-    if (j < cnt) atomicAdd(&exact[first + j], 1u);
-    if (d == dstar) tie_corr += ((col0 + col) < gstar ? 1u : 0u) - 1u;
-  };
-  auto visit4 = [&](const float4& t, long long cu) {       // four consecutive columns
-    uint32_t f = classify(t.x);
-    f = (f << 1) | classify(t.y);
-    f = (f << 1) | classify(t.z);
-    f = (f << 1) | classify(t.w);
-    return f;
-  };
-  auto exact4 = [&](uint32_t f, const float4& t, long long cu) {
-    if (f & 8u) exact_path(t.x, cu);
-    if (f & 4u) exact_path(t.y, cu + 1);
-    if (f & 2u) exact_path(t.z, cu + 2);
-    if (f & 1u) exact_path(t.w, cu + 3);
-  };
-  auto visit = [&](float d, long long col) {               // scalar tails
-    if (classify(d)) exact_path(d, col);
+    const bool lt = key < key_min;
+    below += lt ? 1u : 0u;
+    const unsigned b = ((unsigned)key - (unsigned)key_min) >> shift;
+    if (count_on && !lt && b < (unsigned)kNB) {
+      const uint32_t old = atomicAdd(&hist[b], 1u);
+      if (old & 0x80000000u) {                             // the bin holds thresholds: exact comparison
+        const uint32_t info = binfo[b];
+        const int first = (int)(info >> 16), cnt = (int)(info & 0xffffu);
+        int j = 0;
+        while (j < cnt && thr[first + j] < d) ++j;
+        if (j < cnt) atomicAdd(&exact[first + j], 1u);
+        if (d == dstar) tie_corr += ((col0 + col) < gstar ? 1u : 0u) - 1u;
+      }
+    }
   };
 
   if (TOPK) {
@@ -319,8 +289,7 @@ __global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 12) rank_count_kernel(
           const long long cu = base + u * kStep + 4LL * tid;
           const uint32_t bh = (uint32_t)(bound >> 32);
           if (vec && cu + 3 < c_end) {
-            const uint32_t f4 = visit4(v[u], cu);
-            if (f4) exact4(f4, v[u], cu);
+            visit(v[u].x, cu); visit(v[u].y, cu + 1); visit(v[u].z, cu + 2); visit(v[u].w, cu + 3);
             const float dv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
             if ((__float_as_uint(dv[0]) <= bh) | (__float_as_uint(dv[1]) <= bh) | (__float_as_uint(dv[2]) <= bh) |
                 (__float_as_uint(dv[3]) <= bh)) {
@@ -377,19 +346,15 @@ __global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 12) rank_count_kernel(
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(reinterpret_cast<const float4*>(drow + c + u * kStep));
-      uint32_t f[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) f[u] = visit4(v[u], c + u * kStep);
-      if (f[0] | f[1] | f[2] | f[3]) {                      // a few % of the elements sit in a bin with thresholds
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (f[u]) exact4(f[u], v[u], c + u * kStep);
+      for (int u = 0; u < 4; ++u) {
+        const long long cu = c + u * kStep;
+        visit(v[u].x, cu); visit(v[u].y, cu + 1); visit(v[u].z, cu + 2); visit(v[u].w, cu + 3);
       }
     }
     for (; c < c4_end; c += kStep) {
       const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(drow + c));
-      const uint32_t f = visit4(v, c);
-      if (f) exact4(f, v, c);
+      visit(v.x, c); visit(v.y, c + 1); visit(v.z, c + 2); visit(v.w, c + 3);
     }
     for (c = c4_end + tid; c < c_end; c += kCntThreads) visit(drow[c], c);
   } else {
@@ -398,15 +363,15 @@ __global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 12) rank_count_kernel(
 
   // --- reductions: below, tie correction, exclusive prefix of the histogram ---
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tie_corr += __shfl_xor_sync(0xffffffffu, tie_corr, o);
-  if (lane == 0 && tie_corr) atomicAdd(&s_first_cnt, tie_corr);
-  __syncthreads();
-  if (tid < 32) {
-    below = dump[32 + tid];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-    if (tid == 0) s_below = below;
+  for (int o = 16; o > 0; o >>= 1) {
+    below += __shfl_xor_sync(0xffffffffu, below, o);
+    tie_corr += __shfl_xor_sync(0xffffffffu, tie_corr, o);
   }
+  if (lane == 0) {
+    if (below) atomicAdd(&s_below, below);
+    if (tie_corr) atomicAdd(&s_first_cnt, tie_corr);
+  }
+  __syncthreads();
   constexpr int kPer = kNB / kCntThreads;                  // 8 consecutive bins per thread
   uint32_t local[kPer], sum = 0;
 #pragma unroll

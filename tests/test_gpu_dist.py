@@ -191,9 +191,9 @@ def test_f16x3_row_scaling_covers_the_dynamic_range():
 
 @pytest.mark.parametrize("m1,m2,dim", [(257, 255, 64), (512, 1000, 192), (513, 300, 2048), (1300, 2049, 320), (3368, 700, 128)])
 def test_cluster4_multicast_kernel_equals_two_cta_kernel(m1, m2, dim):
-    """Single-plane products (fp16 inputs) with more than one m tile run on clusters of FOUR CTAs whose two CTA pairs share
-    the B tile by TMA multicast (dist_tc4_kernel).  Same MMAs in the same order as the 2-CTA kernel: identical bits, with
-    and without the top-k admission epilogue; against float64 at the fp16-product level."""
+    """The opt-in cluster-of-4 variant for single-plane products (PPS_DIST_CLUSTER4: two CTA pairs share the B tile by TMA
+    multicast, dist_tc4_kernel).  Same MMAs in the same order as the 2-CTA kernel: identical bits, with and without the
+    top-k admission epilogue; against float64 at the fp16-product level."""
     import torch
     from pps_b200 import _lib, evaluator
     lib = _lib.load()
@@ -203,7 +203,7 @@ def test_cluster4_multicast_kernel_equals_two_cta_kernel(m1, m2, dim):
     sa, sb = evaluator.SplitOperand(a, 1), evaluator.SplitOperand(b, 1)
     ld = (m2 + 3) // 4 * 4
     out = {}
-    for name, flags in (("cl4", 0), ("cl2", _lib.DIST_NO_CLUSTER4)):
+    for name, flags in (("cl4", _lib.DIST_CLUSTER4), ("cl2", 0)):
         d = torch.zeros((m1, ld), dtype=torch.float32, device="cuda")
         _lib.check(lib.pps_dist_tc(_lib.ptr(sa.planes), _lib.ptr(sa.sqnorm), m1, 1, 0, _lib.ptr(sb.planes), _lib.ptr(sb.sqnorm), m2, 1, 0,
                                    dim, _lib.PREC_F16X1, flags, _lib.ptr(d), ld, _lib.stream_ptr()), "pps_dist_tc")
@@ -214,7 +214,7 @@ def test_cluster4_multicast_kernel_equals_two_cta_kernel(m1, m2, dim):
     k, cap = 4, 64
     bound = torch.full((m1,), -1, dtype=torch.int32, device="cuda")           # 0xffffffff: unbounded
     res = {}
-    for name, flags in (("cl4", 0), ("cl2", _lib.DIST_NO_CLUSTER4)):
+    for name, flags in (("cl4", _lib.DIST_CLUSTER4), ("cl2", 0)):
         cnt = torch.zeros(m1, dtype=torch.int32, device="cuda")
         cand = torch.zeros((m1, cap), dtype=torch.int64, device="cuda")
         d = torch.zeros((m1, ld), dtype=torch.float32, device="cuda")
