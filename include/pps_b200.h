@@ -582,13 +582,6 @@ int pps_rerank_jaccard(const int32_t* q_idx, const float* q_val, const int32_t* 
 /* instrumentation: number of kernels this library has launched in this process
  * (bench.py reports the delta over the timed region as `gpu_launches`). */
 unsigned long long pps_kernel_launch_count(void);
-/* instrumentation: the tile schedule of the 2-CTA distance kernel replayed on the host - out[i] = {group, m tile,
- * n tile | run_start << 30 | run_end << 31} for the i-th tile of CTA pair `pair` of `npairs` (rank_order != 0: the walk of
- * the counting-epilogue variant, which keeps one m tile per pair); returns the tile count.  Used by the CPU tests to
- * check that every tile is visited exactly once. */
-long long pps_debug_tile_walk(int rank_order, int m_tiles, int n_tiles, int groups, long long npairs, long long pair,
-                              int32_t* out, long long cap);
-
 #ifdef __cplusplus
 }
 #endif

@@ -142,7 +142,6 @@ SIGNATURES = {
     "pps_rerank_invert": (_i, [_vp, _vp, _vp, _i, _ll, _ll, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_rerank_jaccard": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _ll, _ll, _vp, _ll, C.c_float, _vp, _ll, _vp]),
     "pps_kernel_launch_count": (C.c_ulonglong, []),
-    "pps_debug_tile_walk": (_ll, [_i, _i, _i, _i, _ll, _ll, _vp, _ll]),
 }
 
 _lock = threading.Lock()

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libpps_b200.so")
 SOURCES = ["pps_pool.cu", "split_prep.cu", "dist_gemm.cu", "pairs.cu", "rank.cu", "triplet.cu", "rerank.cu", "c_api.cu", "pass.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ctx.cuh"), os.path.join(os.path.dirname(HERE), "include", "pps_b200.h")]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dist_tiles.cuh"), os.path.join(os.path.dirname(HERE), "include", "pps_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -81,6 +81,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print("\n".join(log))
     return LIB_PATH
+
+
+TEST_HOOKS_PATH = os.path.join(OUT_DIR, "libpps_b200_testhooks.so")
+
+
+def build_test_hooks(force: bool = False) -> str:
+    """TEST-ONLY library (csrc/test_hooks.cu: the host replay of the distance kernels' tile schedule); never loaded by the
+    product.  Returns its path."""
+    src = os.path.join(CSRC, "test_hooks.cu")
+    deps = [src] + [h for h in HEADERS if os.path.exists(h)]
+    if (not force and os.path.exists(TEST_HOOKS_PATH)
+            and all(os.path.getmtime(d) <= os.path.getmtime(TEST_HOOKS_PATH) for d in deps)):
+        return TEST_HOOKS_PATH
+    nvcc = nvcc_path()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build the test hooks")
+    os.makedirs(OUT_DIR, exist_ok=True)
+    tmp = TEST_HOOKS_PATH + ".tmp.%d" % os.getpid()
+    proc = subprocess.run([nvcc] + NVCC_FLAGS + ["-shared", "-o", tmp, "test_hooks.cu"], cwd=CSRC, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed on test_hooks.cu:\n%s" % proc.stdout)
+    os.replace(tmp, TEST_HOOKS_PATH)
+    return TEST_HOOKS_PATH
 
 
 if __name__ == "__main__":

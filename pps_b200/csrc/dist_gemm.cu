@@ -15,6 +15,7 @@
 //   warps 2-5: epilogue, 128 threads = 128 TMEM lanes (rows); double-buffered accumulators
 //              (2 x 256 TMEM columns) so the epilogue of tile t overlaps the mainloop of t+1.
 #include "common.cuh"
+#include "dist_tiles.cuh"
 
 #include <cstdlib>
 #include <mutex>
@@ -29,25 +30,7 @@ constexpr int kABytes = kBM * kBK * 2;               // 16 KB
 constexpr int kBBytes = kBN * kBK * 2;               // 32 KB
 constexpr int kStageBytesG = kABytes + kBBytes;      // 48 KB
 constexpr int kGemmThreads = 192;
-constexpr int kMaxTerms = 6;
 constexpr size_t kGemmSmem = 1024 /*align slack*/ + (size_t)kGemmStages * kStageBytesG + 256 /*barriers*/;
-
-struct GemmArgs {
-  long long m1, m2;
-  int kblocks;                // ceil(K / 64)
-  int nterms;
-  int term_a[kMaxTerms];      // plane of A used by term t
-  int term_b[kMaxTerms];
-  uint32_t idesc;
-  const float* a_sqnorm;
-  const float* b_sqnorm;
-  const float* a_scale;       // PPS_PREC_F16X3: inverse power-of-two row scales of the operands (else nullptr)
-  const float* b_scale;
-  float* out;
-  long long ldo;
-  int flags;
-  int m_tiles, n_tiles;
-};
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 dist_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -220,91 +203,6 @@ constexpr int kMaxStages2 = 6;
 constexpr int kOutChunkBytes = 32 * 32 * 4;                 // one warp's 32 x 32 fp32 staging tile
 constexpr int kOutStageBytes = 4 * 2 * kOutChunkBytes;      // 4 epilogue warps, double-buffered
 constexpr size_t kGemm2Smem = (size_t)kRing2Bytes + kOutStageBytes + 2 * 256 * 4 /*|b|^2 or alpha/beta*/ + 256 /*barriers*/;
-
-struct Gemm2Args {
-  GemmArgs g;
-  int planes;       // planes of each operand loaded per k-block (1..3)
-  int stages;       // ring depth = ring bytes / stage bytes
-  // grouped form (embedding head): `groups` independent products; group grp uses A rows [grp*a_group_rows, ...),
-  // B rows [grp*b_group_rows, ...) and writes output columns [grp*out_group_cols, ...).  Distance: groups = 1.
-  int groups;
-  long long a_group_rows, b_group_rows, out_group_cols;
-};
-
-// Fused ranking epilogue (EPI_RANK): the distance tile never leaves the SM.  Per element one lower-bound search
-// among the row's sorted positive distances (shared memory, [threshold][row] so that bank = row for every
-// thread whatever it searches) and one increment of a thread-private 16-bit histogram counter.
-struct RankFuse {
-  const float* thr_tab;     // [row groups of 128][p_cap][128] ascending positive distances of each query, +inf padded
-  uint32_t* cnt_tab;        // same shape: #{columns whose lower bound among the row's thresholds is j}
-  const float* dstar;       // [rows] nearest positive distance (NaN: the query has no positive)
-  const int32_t* gstar;     // [rows] its global gallery index
-  uint32_t* cnt_first;      // [rows] += -#{d == d*} + #{d == d*, column < g*}   (mod 2^32)
-  long long col0;           // global gallery index of column 0 of this block
-  int p_cap;                // thresholds per row in the tables (multiple of 8, <= 64)
-  // EPI_DIST_TOPK: admission of top-k candidates while the distance block is being written
-  const uint32_t* tk_bound; // [rows] distance bits of the current k-th best of each query (0xffffffff: unbounded)
-  uint32_t* tk_cnt;         // [rows] candidates appended so far (may run past tk_cap: the excess is dropped and detected)
-  unsigned long long* tk_cand;   // [rows][tk_cap] keys (distance bits << 32 | global gallery index)
-  int tk_cap;
-};
-
-constexpr int EPI_DIST = 0;          // |a|^2 + |b|^2 - 2ab, clamp, sqrt (or squared / raw dot by flags) -> matrix
-constexpr int EPI_AFFINE_RELU = 1;   // max(0, dot * alpha[col] + beta[col])   (a_sqnorm = alpha, b_sqnorm = beta)
-constexpr int EPI_RANK = 2;          // distance as EPI_DIST, consumed by the counting epilogue; no matrix
-constexpr int EPI_DIST_TOPK = 3;     // EPI_DIST + one compare per element against the row's top-k admission bound
-
-// Tile order.  EPI_DIST / EPI_AFFINE_RELU: tile t = pair, pair + npairs, ... with the m index fastest, so that the
-// CTA pairs running concurrently share B tiles in L2.  EPI_RANK: every CTA pair keeps ONE m tile (its rows'
-// thresholds and counters stay in shared memory) and walks a contiguous range of n tiles; the pairs that own the
-// other m tiles walk the same n range at the same pace, which keeps the L2 sharing of B.  With more m tiles than
-// pairs the schedule repeats per "superblock" of npairs m tiles.
-template <int EPI>
-struct TileWalk {
-  long long t, tiles, tiles_per_group, npairs, pair;
-  int m_tiles, n_tiles;
-  int sb, n_sb, n_cur, n_stop;
-  // outputs
-  long long grp;
-  int m_tile, n_tile;
-  bool run_start, run_end;
-
-  __host__ __device__ TileWalk(const Gemm2Args& ga, long long pair_, long long npairs_) {
-    pair = pair_; npairs = npairs_;
-    m_tiles = ga.g.m_tiles; n_tiles = ga.g.n_tiles;
-    tiles_per_group = (long long)m_tiles * n_tiles;
-    tiles = tiles_per_group * ga.groups;
-    t = pair - npairs;
-    sb = -1; n_sb = (int)((m_tiles + npairs - 1) / npairs); n_cur = 0; n_stop = 0;
-    grp = 0; m_tile = 0; n_tile = 0; run_start = run_end = false;
-  }
-  __host__ __device__ bool next() {
-    if (EPI != EPI_RANK) {
-      t += npairs;
-      if (t >= tiles) return false;
-      grp = t / tiles_per_group;
-      const long long tt = t % tiles_per_group;
-      m_tile = (int)(tt % m_tiles);
-      n_tile = (int)(tt / m_tiles);
-      return true;
-    }
-    run_start = false;
-    while (n_cur >= n_stop) {                     // next superblock with a non-empty range for this pair
-      if (++sb >= n_sb) return false;
-      const long long m0 = (long long)sb * npairs;
-      const long long mt = (m_tiles - m0) < npairs ? (m_tiles - m0) : npairs;
-      const long long ml = pair % mt, i = pair / mt;
-      const long long owners = npairs / mt + (ml < npairs % mt ? 1 : 0);
-      m_tile = (int)(m0 + ml);
-      n_cur = (int)((long long)n_tiles * i / owners);
-      n_stop = (int)((long long)n_tiles * (i + 1) / owners);
-      run_start = true;
-    }
-    n_tile = n_cur++;
-    run_end = n_cur >= n_stop;
-    return true;
-  }
-};
 
 // CL4 = true: a cluster of FOUR CTAs = two CTA pairs that work on two vertically adjacent 256-row m tiles of the SAME n
 // tile.  Each CTA still loads its own 128 A rows; the B halves are loaded ONCE per cluster - by the CTAs of pair 0, with
@@ -1139,31 +1037,4 @@ extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, lon
       tmA, tmB, tmA /*no output map*/, ga, rf);
   PPS_LAUNCH_CHECK("dist_tc2_kernel<rank>");
   return PPS_OK;
-}
-
-// Instrumentation: the tile schedule of the 2-CTA kernel, replayed on the host (the same TileWalk the producer, MMA and
-// epilogue warps run).  out[i] = {group, m tile, n tile | run_start << 30 | run_end << 31} for the i-th tile of CTA pair
-// `pair` out of `npairs`; returns the number of tiles (also when it exceeds cap).  rank_order != 0: the EPI_RANK walk.
-extern "C" long long pps_debug_tile_walk(int rank_order, int m_tiles, int n_tiles, int groups, long long npairs,
-                                         long long pair, int32_t* out, long long cap) {
-  if (m_tiles < 0 || n_tiles < 0 || groups < 1 || npairs < 1 || pair < 0 || pair >= npairs) return PPS_ERR_INVALID_ARG;
-  Gemm2Args ga{};
-  ga.g.m_tiles = m_tiles; ga.g.n_tiles = n_tiles; ga.groups = groups;
-  long long n = 0;
-  auto emit = [&](long long grp, int m, int nt, bool rs, bool re) {
-    if (out && n < cap) {
-      out[3 * n + 0] = (int32_t)grp;
-      out[3 * n + 1] = m;
-      out[3 * n + 2] = (int32_t)((uint32_t)nt | (rs ? 0x40000000u : 0u) | (re ? 0x80000000u : 0u));
-    }
-    ++n;
-  };
-  if (rank_order) {
-    TileWalk<EPI_RANK> w(ga, pair, npairs);
-    while (w.next()) emit(w.grp, w.m_tile, w.n_tile, w.run_start, w.run_end);
-  } else {
-    TileWalk<EPI_DIST> w(ga, pair, npairs);
-    while (w.next()) emit(w.grp, w.m_tile, w.n_tile, false, false);
-  }
-  return n;
 }

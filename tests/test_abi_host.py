@@ -248,10 +248,16 @@ def test_host_partition_helpers_properties():
 
 
 def test_tile_schedules_visit_every_tile_exactly_once():
-    """The persistent tile walks of the 2-CTA distance kernel (replayed on the host by pps_debug_tile_walk): over all
-    CTA pairs every (group, m, n) tile appears exactly once; in the counting-epilogue order a pair's runs keep one m
-    tile, their n tiles are consecutive and run_start / run_end bracket them."""
-    lib = _lib.load()
+    """The persistent tile walks of the 2-CTA distance kernel (replayed on the host by pps_test_tile_walk of the TEST-ONLY
+    library csrc/test_hooks.cu - the product ABI exports no instrumentation): over all CTA pairs every (group, m, n) tile
+    appears exactly once; in the counting-epilogue order a pair's runs keep one m tile, their n tiles are consecutive
+    and run_start / run_end bracket them."""
+    import ctypes
+    from pps_b200 import build as _build
+    hooks = ctypes.CDLL(_build.build_test_hooks())
+    hooks.pps_test_tile_walk.restype = ctypes.c_longlong
+    hooks.pps_test_tile_walk.argtypes = [ctypes.c_int] * 4 + [ctypes.c_longlong] * 2 + [ctypes.c_void_p, ctypes.c_longlong]
+    assert not hasattr(_lib.load(), "pps_debug_tile_walk") and not hasattr(_lib.load(), "pps_test_tile_walk")
     rs = np.random.RandomState(0)
     shapes = [(14, 78, 1, 74), (14, 2490, 1, 74), (1, 1, 1, 1), (3, 5, 1, 74), (100, 7, 1, 74), (75, 3, 1, 74), (1, 500, 1, 8),
               (91, 63, 1, 74)] + [(int(rs.randint(1, 200)), int(rs.randint(1, 300)), 1, int(rs.randint(1, 80))) for _ in range(40)]
@@ -262,7 +268,7 @@ def test_tile_schedules_visit_every_tile_exactly_once():
             total = m_tiles * n_tiles * groups
             buf = np.zeros((total + 1, 3), dtype=np.int32)
             for pair in range(npairs):
-                cnt = int(lib.pps_debug_tile_walk(rank_order, m_tiles, n_tiles, groups, npairs, pair, _lib.ptr(buf), total + 1))
+                cnt = int(hooks.pps_test_tile_walk(rank_order, m_tiles, n_tiles, groups, npairs, pair, _lib.ptr(buf), total + 1))
                 assert 0 <= cnt <= total
                 prev = None
                 for i in range(cnt):
