@@ -60,7 +60,7 @@ def env_int(name, default):
 
 def load_traffic(key):
     """Measured DRAM bytes per launch of a kernel at a given shape (ncu capture summarised under profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(path) as f:
             return json.load(f).get(key)
@@ -561,7 +561,7 @@ def run_ours(args):
                         "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                         "traffic": load_traffic("dist_tc2_kernel@%dx%dx%d/%s" % (nq, ngl, dim, args.precision)) or
                                    load_traffic("dist_tc2_kernel@%dx%dx%d/bf16x3" % (nq, ngl, dim)),
-                        "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_d_dist_gemm.md); algorithmic = %d" %
+                        "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/r02_e_kernels.md); algorithmic = %d" %
                                         int((nq + ngl) * dim * 2 * (2 if args.precision in ("bf16x3", "f16x3") else 1) + nq * ngl * 4),
                         "peak_source": peaks["source"] + " (sustained bf16)",
                         "ms_per_launch": gemm_avg_ms, "share_of_step": gemm_avg_ms / ms_step,

@@ -202,16 +202,40 @@ static void pair_segments(long long ng, long long* seg, int* nseg) {
 // [row_lo, row_hi) of this gallery shard; pair e of query q then sits at column
 // gp_off[rep(q)] + (e - pair_off[q]) - lo(q) of the product.
 // ------------------------------------------------------------------------------------
+// The representative of a query = the lowest query index carrying the same id.  All queries of one id share one gallery
+// list, so the id is identified by the list's first gallery row g0: an open-addressing table keyed by g0 (claimed with one
+// atomicCAS on the key itself) collects the minimum query index per id - O(nq) instead of the O(nq^2) scan over earlier
+// queries this kernel started with (270 us at 3 368 queries, ncu launch list profiles/r02_e_launches.md).
+__global__ void compact_hash_insert_kernel(int nq, const int32_t* __restrict__ pair_off, const int32_t* __restrict__ pair_g,
+                                           int32_t* __restrict__ keys, int32_t* __restrict__ vals, uint32_t mask) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int e0 = pair_off[q];
+  if (pair_off[q + 1] == e0) return;                      // no pair at all: the query is its own representative
+  const int32_t g0 = pair_g[e0];
+  uint32_t s = ((uint32_t)g0 * 0x9E3779B1u) & mask;
+  while (true) {
+    const int32_t old = atomicCAS(&keys[s], -1, g0);
+    if (old == -1 || old == g0) { atomicMin(&vals[s], q); return; }
+    s = (s + 1) & mask;
+  }
+}
+
 __global__ void compact_rep_kernel(const int64_t* __restrict__ qid, int nq, const int32_t* __restrict__ pair_off,
                                    const int32_t* __restrict__ pair_g, int row_lo, int row_hi,
+                                   const int32_t* __restrict__ keys, const int32_t* __restrict__ vals, uint32_t mask,
                                    int32_t* __restrict__ rep, int32_t* __restrict__ lo_out, int32_t* __restrict__ cnt) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
-  const int64_t id = qid[q];
   int r = q;
-  for (int j = 0; j < q; ++j)
-    if (qid[j] == id) { r = j; break; }
+  if (pair_off[q + 1] > pair_off[q]) {
+    const int32_t g0 = pair_g[pair_off[q]];
+    uint32_t s = ((uint32_t)g0 * 0x9E3779B1u) & mask;
+    while (keys[s] != g0) s = (s + 1) & mask;             // present: inserted by compact_hash_insert_kernel
+    r = vals[s];
+  }
   rep[q] = r;
+  (void)qid;
   // the pair list is ascending in the gallery index: the rows of the window are one sub-range
   const int e0 = pair_off[q], e1 = pair_off[q + 1];
   int a = e0, b = e1;
@@ -532,9 +556,15 @@ extern "C" int pps_pairs_fill_device(const int64_t* query_ids, const int64_t* qu
 }
 
 // ---- compacted same-id gallery for the threshold pass (see compact_rep_kernel) ----
+static uint32_t compact_slots(long long nq) {
+  uint32_t n = 64;
+  while ((long long)n < 2 * nq) n <<= 1;
+  return n;
+}
+
 extern "C" long long pps_pairs_compact_workspace_bytes(long long nq) {
-  if (nq < 0) return PPS_ERR_INVALID_ARG;
-  return (4 * (nq > 0 ? nq : 1) + 4) * 4;
+  if (nq < 0 || nq > 0x3fffffffLL) return PPS_ERR_INVALID_ARG;
+  return (4 * (nq > 0 ? nq : 1) + 4) * 4 + (long long)compact_slots(nq) * 8;     // rep, lo, cnt, gp_off | hash keys, values
 }
 
 extern "C" int pps_pairs_compact_rows(const int64_t* query_ids, long long nq, const int32_t* pair_off,
@@ -554,8 +584,15 @@ extern "C" int pps_pairs_compact_rows(const int64_t* query_ids, long long nq, co
   int32_t* lo = rep + nq;
   int32_t* cnt = lo + nq;
   int32_t* gp_off = cnt + nq;
+  const uint32_t slots = compact_slots(nq);
+  int32_t* keys = gp_off + nq + 4;
+  int32_t* vals = keys + slots;
+  PPS_CUDA_TRY(cudaMemsetAsync(keys, 0xFF, (size_t)slots * 4, st));      // -1: empty
+  PPS_CUDA_TRY(cudaMemsetAsync(vals, 0x7F, (size_t)slots * 4, st));      // 0x7f7f7f7f: above every query index
+  compact_hash_insert_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>((int)nq, pair_off, pair_g, keys, vals, slots - 1);
+  PPS_LAUNCH_CHECK("compact_hash_insert_kernel");
   compact_rep_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(query_ids, (int)nq, pair_off, pair_g, (int)row_lo,
-                                                                   (int)row_hi, rep, lo, cnt);
+                                                                   (int)row_hi, keys, vals, slots - 1, rep, lo, cnt);
   PPS_LAUNCH_CHECK("compact_rep_kernel");
   compact_scan_kernel<<<1, 1024, 0, st>>>(rep, cnt, (int)nq, gp_off, n_rows);
   PPS_LAUNCH_CHECK("compact_scan_kernel");
