@@ -600,6 +600,7 @@ class RankEngine:
         self.use_c_pass = True           # everything else (several blocks, top-k, sharded): pps_pass_begin / _count / _end
         self.tk_cap = 0                  # test hook: top-k candidate entries per query of the C pass (0 = default 2048)
         self._gathered = None
+        self.trace = None                # list collecting (name, cuda event, host time) marks of _run_pass when set
         self._stage = None               # device staging of run_host
         self._cnt_all = None
         self._side = None
@@ -740,17 +741,29 @@ class RankEngine:
             import torch.distributed as dist_mod
             world, rank = dist_mod.get_world_size(self.group), dist_mod.get_rank(self.group)
         flags = (0 if self.fused_topk else _lib.PASS_NO_EPILOGUE_TOPK) | ((int(self.tk_cap) & 0xffff) << 8)
+        tr = self.trace                  # optional: CUDA events + host clocks around the segments of the pass (tools/pass_trace.py)
+        import time as _time
+
+        def mark(name):
+            if tr is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                tr.append((name, ev, _time.perf_counter()))
         for attempt in (0, 1):
+            mark("start")
             d_x1, n_x1 = C.c_void_p(0), C.c_longlong(0)
             _lib.check(lib.pps_pass_begin(ctx, _lib.ptr(q), nq, _lib.ptr(g) if self.ngl else None, self.ngl, self.dim, self.in_code,
                                           _lib.ptr(p.qid), _lib.ptr(p.qcam), _lib.ptr(p.gid), _lib.ptr(p.gcam), len(self.gi),
                                           self.offset, world, rank, self.prec, topk, self.max_block_bytes, flags, s,
                                           C.byref(d_x1), C.byref(n_x1)), "pps_pass_begin")
+            mark("begin_done")
             if sharded and n_x1.value:
                 x1 = _wrap_device(torch, d_x1.value, n_x1.value, "<i4", torch.int32, self.dev)
                 dist_mod.all_reduce(x1, op=dist_mod.ReduceOp.SUM, group=self.group)
+            mark("x1_done")
             d_x2, nb = C.c_void_p(0), C.c_longlong(0)
             _lib.check(lib.pps_pass_count(ctx, s, C.byref(d_x2), C.byref(nb)), "pps_pass_count")
+            mark("count_done")
             gathered = None
             if sharded:
                 packed = _wrap_device(torch, d_x2.value, nb.value, "|u1", torch.uint8, self.dev)
@@ -758,6 +771,7 @@ class RankEngine:
                     self._gathered = torch.empty(world * nb.value, dtype=torch.uint8, device=self.dev)
                 gathered = self._gathered
                 dist_mod.all_gather_into_tensor(gathered, packed, group=self.group)
+            mark("x2_done")
             out_map = C.c_double(0.0)
             out_cmc = np.zeros(10, dtype=np.float64)
             ap = np.zeros(nq, dtype=np.float64)
@@ -767,6 +781,7 @@ class RankEngine:
             td = np.zeros((nq, topk), dtype=np.float32) if topk else None
             rc = lib.pps_pass_end(ctx, _lib.ptr(gathered), 10, s, C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc),
                                   _lib.ptr(ap), _lib.ptr(valid), _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
+            mark("end_done")
             self.used_fused_topk = bool(topk and not (flags & _lib.PASS_NO_EPILOGUE_TOPK))
             if rc == _lib.PPS_ERR_TOPK_OVERFLOW and attempt == 0:
                 # a candidate buffer ran over (adversarial column order): every rank sees the same flag (it travels in the
