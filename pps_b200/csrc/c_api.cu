@@ -67,6 +67,7 @@ extern "C" const char* pps_strerror(int code) {
     case PPS_ERR_UNSUPPORTED: return "request not supported by this build";
     case PPS_ERR_WORKSPACE: return "workspace too small";
     case PPS_ERR_NO_VALID_QUERY: return "No valid query";
+    case PPS_ERR_PASS_RESIZE: return "a speculative size bound of the pass was too small: repeat it with PPS_PASS_SIZING";
     case PPS_ERR_TOPK_OVERFLOW: return "top-k candidate buffer overflow: repeat the pass with PPS_PASS_NO_EPILOGUE_TOPK";
     default: return "unknown error code";
   }

@@ -55,6 +55,23 @@ struct Staging {   // pinned: totals, per-query results
   int32_t* totals; double* ap; int32_t* first; uint8_t* valid;
 };
 
+// Device-count forms of a few entry points (pairs.cu, rank.cu), used by the speculative pass: sizes are host UPPER BOUNDS,
+// the actual counts are read on the device, so nothing has to come back to the host mid-pass.
+int pairs_count_device_ex(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng_cap, void* workspace,
+                          int32_t* pair_off, int32_t* totals, void* stream, const int32_t* ng_dev);
+int pairs_fill_device_ex(const int64_t* query_ids, const int64_t* query_cams, long long nq, const int64_t* gallery_ids,
+                         const int64_t* gallery_cams, long long ng_cap, const void* workspace, int32_t* pair_q, int32_t* pair_g,
+                         uint8_t* pair_pos, float* zero_f32, uint32_t* zero_u32, uint32_t* zero_per_query, long long capacity,
+                         void* stream, const int32_t* ng_dev);
+int pairs_remap_ex(int32_t* pair_g, long long n_cap, const int32_t* cand_rows, long long offset, void* stream,
+                   const int32_t* n_dev);
+int pairs_compact_rows_ex(const int64_t* query_ids, long long nq, const int32_t* pair_off, const int32_t* pair_q,
+                          const int32_t* pair_g, long long n_pairs, long long row_lo, long long row_hi, void* workspace,
+                          int32_t* gp_rows, int32_t* pair_col, int32_t* n_rows, void* stream, const int32_t* n_pairs_dev,
+                          long long rows_cap);
+int rank_gather_ex(const float* dist, long long ldd, long long nq, long long ncols, long long col0, const int32_t* pair_q,
+                   const int32_t* pair_g, long long n_pairs, float* pair_d, void* stream, const int32_t* n_dev);
+
 // State of a multi-block / sharded pass (pass.cu: pps_pass_begin .. pps_pass_end)
 constexpr int kPassMaxBlocks = 4096;
 constexpr int kPassTimedLaunches = 256;
@@ -77,6 +94,11 @@ struct PassState {
   cudaEvent_t ev_t[kPassTimedLaunches][2] = {};
   int n_timed = 0, timed_kind[kPassTimedLaunches] = {};
   float host_wait_ms[4] = {};
+  // sizes of the last pass that read its counts back (the key they belong to), used as upper bounds by the next one
+  struct Hints { bool valid = false; long long nq = 0, ng_global = 0, ngl = 0, offset = 0, mbb = 0; int dim = 0, dtype = 0, topk = 0,
+                 world = 0, precision = 0; long long n_cand = 0, n_pairs = 0, n_rows = 0; int max_pairs = 0; } hints;
+  bool speculative = false;
+  long long cap_cand = 0, cap_rows = 0;
   void release() {
     GrowBuf* bufs[] = {&qs, &qn, &gs, &gn, &dist, &tdist, &ts, &tn, &pair_ws, &pair_off, &totals, &pair_q, &pair_g, &pair_pos,
                        &pair_d, &packed, &pf_ws, &cand_rows, &cand_gid, &cand_gcam, &gp_rows, &pair_col, &gp_ws, &tk_bound,

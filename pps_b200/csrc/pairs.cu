@@ -34,7 +34,9 @@ pairs_sweep_kernel(const int64_t* __restrict__ qid, const int64_t* __restrict__ 
                    long long g_offset /*global index of local gallery row 0*/, int32_t* __restrict__ pair_q,
                    int32_t* __restrict__ pair_g, uint8_t* __restrict__ pair_pos, int32_t* __restrict__ pair_pos32,
                    float* __restrict__ zero_f32, uint32_t* __restrict__ zero_u32,
-                   uint32_t* __restrict__ zero_per_query, long long capacity) {
+                   uint32_t* __restrict__ zero_per_query, long long capacity,
+                   const int32_t* __restrict__ ng_dev /*optional: rows actually present (<= ng), read on the device*/) {
+  if (ng_dev) ng = min(ng, (long long)*ng_dev);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * kPairQPerCta + warp * kPairQPerWarp;
   const int s = blockIdx.y;
@@ -290,7 +292,9 @@ __global__ void compact_fill_kernel(const int32_t* __restrict__ pair_off, const 
                                     const int32_t* __restrict__ pair_g, long long n_pairs,
                                     const int32_t* __restrict__ rep, const int32_t* __restrict__ lo,
                                     const int32_t* __restrict__ cnt, const int32_t* __restrict__ gp_off,
-                                    int32_t* __restrict__ gp_rows, int32_t* __restrict__ pair_col) {
+                                    int32_t* __restrict__ gp_rows, int32_t* __restrict__ pair_col,
+                                    const int32_t* __restrict__ n_dev) {
+  if (n_dev) n_pairs = min(n_pairs, (long long)*n_dev);
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_pairs) return;
   const int q = pair_q[e];
@@ -434,9 +438,17 @@ __global__ void __launch_bounds__(1024) prefilter_scan_kernel(int32_t* __restric
 }
 
 __global__ void pairs_remap_kernel(int32_t* __restrict__ pair_g, long long n, const int32_t* __restrict__ cand_rows,
-                                   long long offset) {
+                                   long long offset, const int32_t* __restrict__ n_dev) {
+  if (n_dev) n = min(n, (long long)*n_dev);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) pair_g[i] = (int32_t)(cand_rows[pair_g[i]] + offset);
+}
+
+// rows [*n_rows, cap) of the compacted row list := a valid row (the product over `cap` columns then reads real memory; the
+// columns beyond *n_rows are never gathered)
+__global__ void compact_pad_kernel(int32_t* __restrict__ gp_rows, const int32_t* __restrict__ n_rows, long long cap, int32_t pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap && i >= (long long)*n_rows) gp_rows[i] = pad;
 }
 
 }  // namespace pps
@@ -456,8 +468,9 @@ extern "C" long long pps_pairs_workspace_bytes(long long nq, long long ng) {
   return ws_ints(nq, ng, nullptr) * 4;
 }
 
-extern "C" int pps_pairs_local_count(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
-                                     void* workspace, int32_t** local_cnt, void* stream) {
+namespace pps {
+int pairs_local_count_ex(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng, void* workspace,
+                         int32_t** local_cnt, void* stream, const int32_t* ng_dev) {
   if (nq < 0 || ng < 0 || nq > 0x7fffffffLL || ng > 0x7fffffffLL) return PPS_ERR_INVALID_ARG;
   if (!workspace) return PPS_ERR_INVALID_ARG;
   if (nq > 0 && ng > 0 && (!query_ids || !gallery_ids)) return PPS_ERR_INVALID_ARG;
@@ -476,11 +489,17 @@ extern "C" int pps_pairs_local_count(const int64_t* query_ids, long long nq, con
   const dim3 grid((unsigned)((nq + kPairQPerCta - 1) / kPairQPerCta), (unsigned)nseg);
   pairs_sweep_kernel<false><<<grid, 32 * kPairWarps, 0, st>>>(query_ids, nullptr, (int)nq, gallery_ids, nullptr, ng, seg,
                                                               nseg, seg_cnt, nullptr, 0, nullptr, nullptr, nullptr,
-                                                              nullptr, nullptr, nullptr, nullptr, 0);
+                                                              nullptr, nullptr, nullptr, nullptr, 0, ng_dev);
   PPS_LAUNCH_CHECK("pairs_sweep_kernel<count>");
   pairs_rowsum_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(seg_cnt, (int)nq, nseg, lc);
   PPS_LAUNCH_CHECK("pairs_rowsum_kernel");
   return PPS_OK;
+}
+}  // namespace pps
+
+extern "C" int pps_pairs_local_count(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
+                                     void* workspace, int32_t** local_cnt, void* stream) {
+  return pairs_local_count_ex(query_ids, nq, gallery_ids, ng, workspace, local_cnt, stream, nullptr);
 }
 
 extern "C" int pps_pairs_offsets(const int32_t* cnt_all, int world, int rank, long long nq, long long ng_local,
@@ -496,11 +515,11 @@ extern "C" int pps_pairs_offsets(const int32_t* cnt_all, int world, int rank, lo
   return PPS_OK;
 }
 
-extern "C" int pps_pairs_fill_local(const int64_t* query_ids, const int64_t* query_cams, long long nq,
-                                    const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
-                                    long long gallery_offset, const void* workspace, int32_t* pair_q, int32_t* pair_g,
-                                    uint8_t* pair_pos, int32_t* pair_pos32, float* zero_f32, uint32_t* zero_u32,
-                                    uint32_t* zero_per_query, long long capacity, void* stream) {
+namespace pps {
+int pairs_fill_local_ex(const int64_t* query_ids, const int64_t* query_cams, long long nq, const int64_t* gallery_ids,
+                        const int64_t* gallery_cams, long long ng, long long gallery_offset, const void* workspace,
+                        int32_t* pair_q, int32_t* pair_g, uint8_t* pair_pos, int32_t* pair_pos32, float* zero_f32,
+                        uint32_t* zero_u32, uint32_t* zero_per_query, long long capacity, void* stream, const int32_t* ng_dev) {
   if (nq < 0 || ng < 0 || nq > 0x7fffffffLL || ng > 0x7fffffffLL || capacity < 0 || gallery_offset < 0 ||
       gallery_offset + ng > 0x7fffffffLL)
     return PPS_ERR_INVALID_ARG;
@@ -521,9 +540,30 @@ extern "C" int pps_pairs_fill_local(const int64_t* query_ids, const int64_t* que
   pairs_sweep_kernel<true><<<grid, 32 * kPairWarps, 0, st>>>(query_ids, query_cams, (int)nq, gallery_ids, gallery_cams, ng,
                                                              seg, nseg, seg_cnt, my_base, gallery_offset, pair_q, pair_g,
                                                              pair_pos, pair_pos32, zero_f32, zero_u32, zero_per_query,
-                                                             capacity);
+                                                             capacity, ng_dev);
   PPS_LAUNCH_CHECK("pairs_sweep_kernel<fill>");
   return PPS_OK;
+}
+
+// the device-count forms used by the speculative (sync-free) pass: sizes are host upper bounds, the actual counts are read
+// on the device
+int pairs_remap_ex(int32_t* pair_g, long long n_cap, const int32_t* cand_rows, long long offset, void* stream,
+                   const int32_t* n_dev) {
+  if (n_cap <= 0) return PPS_OK;
+  pairs_remap_kernel<<<(unsigned)((n_cap + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(pair_g, n_cap, cand_rows,
+                                                                                                     offset, n_dev);
+  PPS_LAUNCH_CHECK("pairs_remap_kernel");
+  return PPS_OK;
+}
+}  // namespace pps
+
+extern "C" int pps_pairs_fill_local(const int64_t* query_ids, const int64_t* query_cams, long long nq,
+                                    const int64_t* gallery_ids, const int64_t* gallery_cams, long long ng,
+                                    long long gallery_offset, const void* workspace, int32_t* pair_q, int32_t* pair_g,
+                                    uint8_t* pair_pos, int32_t* pair_pos32, float* zero_f32, uint32_t* zero_u32,
+                                    uint32_t* zero_per_query, long long capacity, void* stream) {
+  return pairs_fill_local_ex(query_ids, query_cams, nq, gallery_ids, gallery_cams, ng, gallery_offset, workspace, pair_q, pair_g,
+                             pair_pos, pair_pos32, zero_f32, zero_u32, zero_per_query, capacity, stream, nullptr);
 }
 
 extern "C" int pps_pairs_unpack_pos(const int32_t* pair_pos32, long long n_pairs, uint8_t* pair_pos, void* stream) {
@@ -535,6 +575,24 @@ extern "C" int pps_pairs_unpack_pos(const int32_t* pair_pos32, long long n_pairs
   PPS_LAUNCH_CHECK("pairs_unpack_pos_kernel");
   return PPS_OK;
 }
+
+namespace pps {
+int pairs_count_device_ex(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng_cap, void* workspace,
+                          int32_t* pair_off, int32_t* totals, void* stream, const int32_t* ng_dev) {
+  if (!pair_off || !totals) return PPS_ERR_INVALID_ARG;
+  int32_t* lc = nullptr;
+  int rc = pairs_local_count_ex(query_ids, nq, gallery_ids, ng_cap, workspace, &lc, stream, ng_dev);
+  if (rc != PPS_OK) return rc;
+  return pps_pairs_offsets(lc, 1, 0, nq, ng_cap, workspace, pair_off, totals, stream);
+}
+int pairs_fill_device_ex(const int64_t* query_ids, const int64_t* query_cams, long long nq, const int64_t* gallery_ids,
+                         const int64_t* gallery_cams, long long ng_cap, const void* workspace, int32_t* pair_q, int32_t* pair_g,
+                         uint8_t* pair_pos, float* zero_f32, uint32_t* zero_u32, uint32_t* zero_per_query, long long capacity,
+                         void* stream, const int32_t* ng_dev) {
+  return pairs_fill_local_ex(query_ids, query_cams, nq, gallery_ids, gallery_cams, ng_cap, 0, workspace, pair_q, pair_g,
+                             pair_pos, nullptr, zero_f32, zero_u32, zero_per_query, capacity, stream, ng_dev);
+}
+}  // namespace pps
 
 // ---- single-block convenience forms (whole gallery on one device) ----
 extern "C" int pps_pairs_count_device(const int64_t* query_ids, long long nq, const int64_t* gallery_ids, long long ng,
@@ -567,10 +625,11 @@ extern "C" long long pps_pairs_compact_workspace_bytes(long long nq) {
   return (4 * (nq > 0 ? nq : 1) + 4) * 4 + (long long)compact_slots(nq) * 8;     // rep, lo, cnt, gp_off | hash keys, values
 }
 
-extern "C" int pps_pairs_compact_rows(const int64_t* query_ids, long long nq, const int32_t* pair_off,
-                                      const int32_t* pair_q, const int32_t* pair_g, long long n_pairs, long long row_lo,
-                                      long long row_hi, void* workspace, int32_t* gp_rows, int32_t* pair_col,
-                                      int32_t* n_rows, void* stream) {
+namespace pps {
+int pairs_compact_rows_ex(const int64_t* query_ids, long long nq, const int32_t* pair_off, const int32_t* pair_q,
+                          const int32_t* pair_g, long long n_pairs, long long row_lo, long long row_hi, void* workspace,
+                          int32_t* gp_rows, int32_t* pair_col, int32_t* n_rows, void* stream, const int32_t* n_pairs_dev,
+                          long long rows_cap /*> 0: pad gp_rows [*n_rows, rows_cap) with row_lo*/) {
   if (nq < 0 || n_pairs < 0 || row_lo < 0 || row_hi < row_lo || nq > 0x7fffffffLL || row_hi > 0x7fffffffLL)
     return PPS_ERR_INVALID_ARG;
   if (!n_rows) return PPS_ERR_INVALID_ARG;
@@ -597,9 +656,22 @@ extern "C" int pps_pairs_compact_rows(const int64_t* query_ids, long long nq, co
   compact_scan_kernel<<<1, 1024, 0, st>>>(rep, cnt, (int)nq, gp_off, n_rows);
   PPS_LAUNCH_CHECK("compact_scan_kernel");
   compact_fill_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(pair_off, pair_q, pair_g, n_pairs, rep, lo, cnt,
-                                                                         gp_off, gp_rows, pair_col);
+                                                                         gp_off, gp_rows, pair_col, n_pairs_dev);
   PPS_LAUNCH_CHECK("compact_fill_kernel");
+  if (rows_cap > 0) {
+    compact_pad_kernel<<<(unsigned)((rows_cap + 255) / 256), 256, 0, st>>>(gp_rows, n_rows, rows_cap, (int32_t)row_lo);
+    PPS_LAUNCH_CHECK("compact_pad_kernel");
+  }
   return PPS_OK;
+}
+}  // namespace pps
+
+extern "C" int pps_pairs_compact_rows(const int64_t* query_ids, long long nq, const int32_t* pair_off,
+                                      const int32_t* pair_q, const int32_t* pair_g, long long n_pairs, long long row_lo,
+                                      long long row_hi, void* workspace, int32_t* gp_rows, int32_t* pair_col,
+                                      int32_t* n_rows, void* stream) {
+  return pairs_compact_rows_ex(query_ids, nq, pair_off, pair_q, pair_g, n_pairs, row_lo, row_hi, workspace, gp_rows, pair_col,
+                               n_rows, stream, nullptr, 0);
 }
 
 // ---- candidate pre-filter (see qset_build_kernel) ----
@@ -653,7 +725,7 @@ extern "C" int pps_pairs_remap(int32_t* pair_g, long long n_pairs, const int32_t
   if (n_pairs == 0) return PPS_OK;
   if (!pair_g || !cand_rows) return PPS_ERR_INVALID_ARG;
   pairs_remap_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(pair_g, n_pairs,
-                                                                                                       cand_rows, offset);
+                                                                                                       cand_rows, offset, nullptr);
   PPS_LAUNCH_CHECK("pairs_remap_kernel");
   return PPS_OK;
 }

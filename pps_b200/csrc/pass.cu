@@ -69,6 +69,21 @@ __global__ void pass_or_flag_kernel(const int32_t* __restrict__ src, uint32_t* _
   if (threadIdx.x == 0 && blockIdx.x == 0 && *src) *dst = 1u;
 }
 
+__global__ void pass_clamp_offsets_kernel(int32_t* __restrict__ pair_off, long long n, int32_t cap) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && pair_off[i] > cap) pair_off[i] = cap;
+}
+
+// speculative pass: did every actual count stay inside the bound the pass was laid out for?  flags[1] != 0 -> repeat
+__global__ void pass_check_bounds_kernel(const int32_t* __restrict__ tot, int32_t cap_pairs, int32_t cap_maxp, int32_t cap_cand,
+                                         int32_t cap_rows, uint32_t* __restrict__ flag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const bool bad = tot[0] > cap_pairs || tot[1] > cap_maxp || (cap_cand >= 0 && tot[2] > cap_cand) ||
+                     (cap_rows >= 0 && tot[3] > cap_rows);
+    if (bad) *flag = 1u;
+  }
+}
+
 }  // namespace pps
 
 using namespace pps;
@@ -86,7 +101,7 @@ int plan_blocks(PassState& p, bool short_first) {
   long long first = std::min(block_rows, ngl);
   if (short_first && p.topk > 0) {
     long long want = (long long)(2.2 * p.topk * (double)std::min(block_rows, ngl) / kTkCap);   // planned for the default cap
-    want = std::max<long long>(32768, (want + 255) / 256 * 256);
+    want = std::max<long long>(8192, (want + 255) / 256 * 256);
     if (ngl >= 4 * want) first = std::min(first, want);
   }
   long long r0 = 0, rows = first;
@@ -294,29 +309,54 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
     PPS_TRY(split_block(c, 0, p.blk_row0[0], p.blk_rows[0], cs, &gp0));
   }
 
-  // ---- pair lists (three 4-byte read-backs size them; the kernels in between take a few tens of microseconds) ----
+  // ---- pair lists.  SIZING pass (the first one for a shape, or after an overflow): three 4-byte read-backs size the
+  // lists.  SPECULATIVE pass (every later one): the sizes of the sizing pass are used as upper bounds, the actual counts
+  // are read by the kernels on the device, nothing comes back to the host until the results do - the CPU runs ahead of
+  // the GPU for the whole pass - and pps_pass_end checks the bounds (PPS_ERR_PASS_RESIZE -> the caller repeats the pass
+  // as a sizing pass).  The lists are global, so every rank of a sharded run takes the same decision. ----
+  PassState::Hints& hn = p.hints;
+  p.speculative = !(flags & PPS_PASS_SIZING) && hn.valid && hn.nq == nq && hn.ng_global == ng_global && hn.ngl == ng_local &&
+                  hn.offset == gallery_offset && hn.mbb == max_block_bytes && hn.dim == dim && hn.dtype == dtype &&
+                  hn.topk == topk && hn.world == world && hn.precision == precision;
+  const bool spec = p.speculative;
+  int32_t* d_tot = p.totals.as<int32_t>();          // [0] n_pairs [1] max_pairs [2] n_cand [3] n_rows
   const int64_t* sweep_gid = d_gid;
   const int64_t* sweep_gcam = d_gcam;
   long long sweep_rows = ng_global;
+  const int32_t* dn_cand = nullptr;
   if (p.prefilter) {
-    {
-      HostWait hw(c, 0);
-      PPS_CUDA_TRY(cudaEventSynchronize(p.ev_a));
+    if (spec) {
+      p.cap_cand = std::min<long long>(ng_global, (hn.n_cand + 1023) / 1024 * 1024);
+    } else {
+      {
+        HostWait hw(c, 0);
+        PPS_CUDA_TRY(cudaEventSynchronize(p.ev_a));
+      }
+      p.n_cand = h_tot[2];
+      p.cap_cand = p.n_cand;
     }
-    p.n_cand = h_tot[2];
-    sweep_gid = p.cand_gid.as<int64_t>(); sweep_gcam = p.cand_gcam.as<int64_t>(); sweep_rows = p.n_cand;
+    sweep_gid = p.cand_gid.as<int64_t>(); sweep_gcam = p.cand_gcam.as<int64_t>(); sweep_rows = p.cap_cand;
+    dn_cand = d_tot + 2;
   }
   PPS_TRY(p.pair_ws.ensure((size_t)std::max<long long>(pps_pairs_workspace_bytes(nq, sweep_rows), 16)));
-  PPS_TRY(pps_pairs_count_device(d_qid, nq, sweep_gid, sweep_rows, p.pair_ws.p, p.pair_off.as<int32_t>(),
-                                 p.totals.as<int32_t>(), ss));
-  PPS_CUDA_TRY(cudaMemcpyAsync(h_tot, p.totals.p, 8, cudaMemcpyDeviceToHost, ss));
-  PPS_CUDA_TRY(cudaEventRecord(c->ev_totals, ss));
-  {
-    HostWait hw(c, 1);
-    PPS_CUDA_TRY(cudaEventSynchronize(c->ev_totals));
+  PPS_TRY(pairs_count_device_ex(d_qid, nq, sweep_gid, sweep_rows, p.pair_ws.p, p.pair_off.as<int32_t>(), d_tot, ss, dn_cand));
+  if (spec) {
+    p.n_pairs = hn.n_pairs > 0 ? (hn.n_pairs + hn.n_pairs / 8 + 1023) / 1024 * 1024 : 0;     // capacity (layout) of this pass
+    p.max_pairs = hn.max_pairs > 0 ? (hn.max_pairs + 8 + 15) / 16 * 16 : 0;
+    // lists that outgrew the capacity are cut (memory safety); pps_pass_end reports it and the pass is repeated
+    pass_clamp_offsets_kernel<<<(unsigned)((nq + 1 + 255) / 256), 256, 0, ss>>>(p.pair_off.as<int32_t>(), nq + 1, (int32_t)p.n_pairs);
+    PPS_LAUNCH_CHECK("pass_clamp_offsets_kernel");
+  } else {
+    PPS_CUDA_TRY(cudaMemcpyAsync(h_tot, d_tot, 8, cudaMemcpyDeviceToHost, ss));
+    PPS_CUDA_TRY(cudaEventRecord(c->ev_totals, ss));
+    {
+      HostWait hw(c, 1);
+      PPS_CUDA_TRY(cudaEventSynchronize(c->ev_totals));
+    }
+    p.n_pairs = h_tot[0];
+    p.max_pairs = h_tot[1];
   }
-  p.n_pairs = h_tot[0];
-  p.max_pairs = h_tot[1];
+  const int32_t* dn_pairs = spec ? d_tot : nullptr;
   const size_t np1 = (size_t)std::max<long long>(p.n_pairs, 1);
   PPS_TRY(p.pair_q.ensure(np1 * 4));
   PPS_TRY(p.pair_g.ensure(np1 * 4));
@@ -324,14 +364,23 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
   PPS_TRY(p.pair_d.ensure(np1 * 4));
   p.packed_bytes = ((size_t)nq * topk * 8 + p.counter_words() * 4 + 15) & ~(size_t)15;
   PPS_TRY(p.packed.ensure(p.packed_bytes));
-  // the fill zero-fills pair_d, cnt_le and cnt_first of the slots it writes (= all of them: the lists are global)
-  PPS_CUDA_TRY(cudaMemsetAsync(p.flags_dev(), 0, 8, ss));
-  if (p.n_pairs == 0) PPS_CUDA_TRY(cudaMemsetAsync(p.cnt_first(), 0, (size_t)nq * 4, ss));
-  PPS_TRY(pps_pairs_fill_device(d_qid, d_qcam, nq, sweep_gid, sweep_gcam, sweep_rows, p.pair_ws.p, p.pair_q.as<int32_t>(),
-                                p.pair_g.as<int32_t>(), p.pair_pos.as<uint8_t>(), p.pair_d.as<float>(), p.cnt_le(),
-                                p.cnt_first(), p.n_pairs, ss));
+  // the fill zero-fills pair_d, cnt_le and cnt_first of the slots it writes (a sizing pass: all of them, the lists are
+  // global; a speculative pass exchanges whole capacities, so they are cleared in full first)
+  if (spec) {
+    PPS_CUDA_TRY(cudaMemsetAsync(p.pair_d.p, 0, np1 * 4, ss));
+    PPS_CUDA_TRY(cudaMemsetAsync(p.cnt_first(), 0, p.counter_words() * 4, ss));
+    PPS_CUDA_TRY(cudaMemsetAsync(p.pair_q.p, 0xFF, np1 * 4, ss));          // unused slots: query -1 (skipped by the gathers)
+    PPS_CUDA_TRY(cudaMemsetAsync(p.pair_pos.p, 0, np1, ss));
+    PPS_CUDA_TRY(cudaMemsetAsync(p.pair_g.p, 0, np1 * 4, ss));
+  } else {
+    PPS_CUDA_TRY(cudaMemsetAsync(p.flags_dev(), 0, 8, ss));
+    if (p.n_pairs == 0) PPS_CUDA_TRY(cudaMemsetAsync(p.cnt_first(), 0, (size_t)nq * 4, ss));
+  }
+  PPS_TRY(pairs_fill_device_ex(d_qid, d_qcam, nq, sweep_gid, sweep_gcam, sweep_rows, p.pair_ws.p, p.pair_q.as<int32_t>(),
+                               p.pair_g.as<int32_t>(), p.pair_pos.as<uint8_t>(), p.pair_d.as<float>(), p.cnt_le(),
+                               p.cnt_first(), p.n_pairs, ss, dn_cand));
   if (p.prefilter && p.n_pairs > 0)
-    PPS_TRY(pps_pairs_remap(p.pair_g.as<int32_t>(), p.n_pairs, p.cand_rows.as<int32_t>(), 0, ss));
+    PPS_TRY(pairs_remap_ex(p.pair_g.as<int32_t>(), p.n_pairs, p.cand_rows.as<int32_t>(), 0, ss, dn_pairs));
   if (topk > 0) {
     PPS_TRY(pps_topk_init(reinterpret_cast<uint64_t*>(p.keys()), nq, topk, ss));
     if (p.epi_topk) {
@@ -344,20 +393,32 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
   }
   // several blocks: the thresholds come from one product with the compacted same-id rows of this shard
   p.n_rows = 0;
+  p.cap_rows = 0;
+  PPS_CUDA_TRY(cudaMemsetAsync(d_tot + 3, 0, 4, ss));
   if (p.n_blocks > 1 && p.n_pairs > 0) {
-    PPS_TRY(p.gp_rows.ensure(np1 * 4));
-    PPS_TRY(p.pair_col.ensure(np1 * 4));
     PPS_TRY(p.gp_ws.ensure((size_t)pps_pairs_compact_workspace_bytes(nq)));
-    PPS_TRY(pps_pairs_compact_rows(d_qid, nq, p.pair_off.as<int32_t>(), p.pair_q.as<int32_t>(), p.pair_g.as<int32_t>(),
-                                   p.n_pairs, p.offset, p.offset + p.ngl, p.gp_ws.p, p.gp_rows.as<int32_t>(),
-                                   p.pair_col.as<int32_t>(), p.totals.as<int32_t>() + 3, ss));
-    PPS_CUDA_TRY(cudaMemcpyAsync(h_tot + 3, p.totals.as<int32_t>() + 3, 4, cudaMemcpyDeviceToHost, ss));
-    PPS_CUDA_TRY(cudaEventRecord(p.ev_rows, ss));
-    {
-      HostWait hw(c, 2);
-      PPS_CUDA_TRY(cudaEventSynchronize(p.ev_rows));
+    if (spec) p.cap_rows = hn.n_rows > 0 ? std::min<long long>((hn.n_rows + 255) / 256 * 256, std::max<long long>(p.ngl, 1)) : 0;
+    PPS_TRY(p.gp_rows.ensure(std::max(np1, (size_t)p.cap_rows) * 4));
+    PPS_TRY(p.pair_col.ensure(np1 * 4));
+    PPS_TRY(pairs_compact_rows_ex(d_qid, nq, p.pair_off.as<int32_t>(), p.pair_q.as<int32_t>(), p.pair_g.as<int32_t>(),
+                                  p.n_pairs, p.offset, p.offset + p.ngl, p.gp_ws.p, p.gp_rows.as<int32_t>(),
+                                  p.pair_col.as<int32_t>(), d_tot + 3, ss, dn_pairs, spec ? p.cap_rows : 0));
+    if (spec) {
+      p.n_rows = p.cap_rows;
+    } else {
+      PPS_CUDA_TRY(cudaMemcpyAsync(h_tot + 3, d_tot + 3, 4, cudaMemcpyDeviceToHost, ss));
+      PPS_CUDA_TRY(cudaEventRecord(p.ev_rows, ss));
+      {
+        HostWait hw(c, 2);
+        PPS_CUDA_TRY(cudaEventSynchronize(p.ev_rows));
+      }
+      p.n_rows = h_tot[3];
     }
-    p.n_rows = h_tot[3];
+  }
+  if (!spec) {     // what the next pass of this shape may assume
+    hn.valid = true; hn.nq = nq; hn.ng_global = ng_global; hn.ngl = ng_local; hn.offset = gallery_offset; hn.mbb = max_block_bytes;
+    hn.dim = dim; hn.dtype = dtype; hn.topk = topk; hn.world = world; hn.precision = precision;
+    hn.n_cand = p.prefilter ? p.n_cand : 0; hn.n_pairs = p.n_pairs; hn.max_pairs = p.max_pairs; hn.n_rows = p.n_rows;
   }
   PPS_CUDA_TRY(cudaEventRecord(c->ev_pairs, ss));
 
@@ -391,8 +452,8 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
 
   // ---- thresholds ----
   if (p.n_pairs > 0 && p.n_blocks == 1) {
-    PPS_TRY(pps_rank_gather(p.dist.as<float>(), p.ldd, nq, p.blk_rows[0], p.offset, p.pair_q.as<int32_t>(),
-                            p.pair_g.as<int32_t>(), p.n_pairs, p.pair_d.as<float>(), cs));
+    PPS_TRY(rank_gather_ex(p.dist.as<float>(), p.ldd, nq, p.blk_rows[0], p.offset, p.pair_q.as<int32_t>(),
+                           p.pair_g.as<int32_t>(), p.n_pairs, p.pair_d.as<float>(), cs, dn_pairs));
   } else if (p.n_rows > 0) {
     if (p.g_from_host)       // the compacted rows come from all over the shard: the whole upload must have landed
       PPS_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_slab[p.n_blocks - 1], 0));
@@ -415,8 +476,8 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
         PPS_TRY(pps_dist_tc(p.qs.p, p.qn.as<float>(), nq, p.planes, 0, p.ts.p, p.tn.as<float>(), rows, p.planes, 0, dim,
                             precision, 0, p.tdist.as<float>(), ldt, cs));
       }
-      PPS_TRY(pps_rank_gather(p.tdist.as<float>(), ldt, nq, rows, c0, p.pair_q.as<int32_t>(), p.pair_col.as<int32_t>(),
-                              p.n_pairs, p.pair_d.as<float>(), cs));
+      PPS_TRY(rank_gather_ex(p.tdist.as<float>(), ldt, nq, rows, c0, p.pair_q.as<int32_t>(), p.pair_col.as<int32_t>(),
+                             p.n_pairs, p.pair_d.as<float>(), cs, dn_pairs));
     }
   }
   p.active = true;
@@ -425,11 +486,18 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
   return PPS_OK;
 }
 
-extern "C" int pps_pass_count(pps_ctx* c, void* stream, void** d_x2, long long* x2_bytes) {
+extern "C" int pps_pass_count(pps_ctx* c, const void* d_gathered_x1, void* stream, void** d_x2, long long* x2_bytes) {
   if (!c || !c->pass.active) return PPS_ERR_INVALID_ARG;
   PassState& p = c->pass;
+  if (p.world > 1 && p.n_pairs > 0 && !d_gathered_x1) return PPS_ERR_INVALID_ARG;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   const bool have_pairs = p.n_pairs > 0;
+  if (p.world > 1 && have_pairs) {     // thresholds: every pair lives on one shard, the others hold 0 -> the sum is exact
+    pass_reduce_counters_kernel<<<(unsigned)((p.n_pairs + 255) / 256), 256, 0, cs>>>(
+        static_cast<const unsigned char*>(d_gathered_x1), (size_t)p.n_pairs * 4, 0, p.world, p.n_pairs,
+        p.pair_d.as<uint32_t>());
+    PPS_LAUNCH_CHECK("pass_reduce_counters_kernel");
+  }
   auto count_block = [&](long long rows, long long col0, bool with_topk) -> int {
     TimedLaunch t(c, cs, 4);
     if (with_topk)
@@ -465,6 +533,12 @@ extern "C" int pps_pass_count(pps_ctx* c, void* stream, void** d_x2, long long* 
       PPS_TRY(distance_block(c, gp, rows, col0, false, cs));
       PPS_TRY(count_block(rows, col0, p.topk > 0));
     }
+  }
+  if (p.speculative) {                 // bounds of the speculative layout -> flags[1] (summed over ranks by the exchange)
+    pass_check_bounds_kernel<<<1, 32, 0, cs>>>(p.totals.as<int32_t>(), (int32_t)p.n_pairs, (int32_t)p.max_pairs,
+                                               p.prefilter ? (int32_t)p.cap_cand : -1,
+                                               p.n_blocks > 1 ? (int32_t)p.cap_rows : -1, p.flags_dev() + 1);
+    PPS_LAUNCH_CHECK("pass_check_bounds_kernel");
   }
   if (p.epi_topk) {                    // candidate-buffer overflow of any block -> flags[0]
     pass_or_flag_kernel<<<1, 32, 0, cs>>>(p.small.as<int32_t>(), p.flags_dev());
@@ -512,7 +586,7 @@ extern "C" int pps_pass_end(pps_ctx* c, const void* d_gathered, int cmc_topk, vo
   PPS_CUDA_TRY(cudaMemcpyAsync(st.ap, p.ap.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, cs));
   PPS_CUDA_TRY(cudaMemcpyAsync(st.first, p.first.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, cs));
   PPS_CUDA_TRY(cudaMemcpyAsync(st.valid, p.valid.p, (size_t)nq, cudaMemcpyDeviceToHost, cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(st.totals + 4, p.flags_dev(), 4, cudaMemcpyDeviceToHost, cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(st.totals + 4, p.flags_dev(), 8, cudaMemcpyDeviceToHost, cs));
   if (topk > 0 && out_topk_index)
     PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_index, p.tki.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
   if (topk > 0 && out_topk_dist)
@@ -532,6 +606,10 @@ extern "C" int pps_pass_end(pps_ctx* c, const void* d_gathered, int cmc_topk, vo
     // 6 the final synchronise of pps_pass_end
     c->phase_ms[0] = p.host_wait_ms[0] + p.host_wait_ms[1] + p.host_wait_ms[2];
     c->phase_ms[6] = p.host_wait_ms[3];
+  }
+  if (st.totals[5] != 0) {             // a speculative bound was too small somewhere: identical on every rank (flags are summed)
+    p.hints.valid = false;
+    return PPS_ERR_PASS_RESIZE;
   }
   if (st.totals[4] != 0) return PPS_ERR_TOPK_OVERFLOW;     // identical on every rank (the flags were summed)
   double ap_sum = 0.0;

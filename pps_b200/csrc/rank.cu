@@ -94,7 +94,8 @@ __device__ __noinline__ int select_k_smallest(unsigned long long* a, int k, int 
 // ------------------------------------------------------------------------------------
 __global__ void rank_gather_kernel(const float* __restrict__ dist, long long ldd, long long ncols, long long col0,
                                    const int32_t* __restrict__ pair_q, const int32_t* __restrict__ pair_g,
-                                   long long n_pairs, float* __restrict__ pair_d) {
+                                   long long n_pairs, float* __restrict__ pair_d, const int32_t* __restrict__ n_dev) {
+  if (n_dev) n_pairs = min(n_pairs, (long long)*n_dev);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_pairs;
        e += (long long)gridDim.x * blockDim.x) {
     const int q = pair_q[e];
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(kCntThreads, TOPK ? 6 : 16) rank_count_kernel(
   // --- positives of this query, rank-sorted by (distance, gallery index) into thr[] ---
   // stage the pair list in shared memory first (coalesced): the O(P^2) ranking must not chase global latency
   if (tid == 0) { s_np = 0; s_nj = 0; s_below = 0; s_first_cnt = 0; }
-  const int npair = e1 - e0;
+  const int npair = min(e1 - e0, maxp);       // (maxp may be a speculative bound: a longer list is cut - safely - and the
+                                              // caller, who checks the real maximum afterwards, repeats the pass)
   for (int i = tid; i < npair; i += kCntThreads) {
     sd[i] = pair_d[e0 + i];
     sg[i] = pair_pos[e0 + i] ? pair_g[e0 + i] : -1;
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(kCntThreads) topk_merge_kernel(unsigned long l
                                                                  const int32_t* __restrict__ pair_off,
                                                                  const int32_t* __restrict__ pair_g,
                                                                  const uint8_t* __restrict__ pair_pos, int filtered,
-                                                                 int* __restrict__ overflow) {
+                                                                 int* __restrict__ overflow, int sj_cap) {
   extern __shared__ int32_t sj_dyn[];                    // junk gallery indices of this query
   __shared__ unsigned long long cand[kCandC];
   __shared__ int s_n, s_nj;
@@ -657,10 +659,13 @@ __global__ void __launch_bounds__(kCntThreads) topk_merge_kernel(unsigned long l
   if (filtered && pair_off) {
     const int e0 = pair_off[q], e1 = pair_off[q + 1];
     for (int e = e0 + tid; e < e1; e += kCntThreads)
-      if (!pair_pos[e]) sj_dyn[atomicAdd(&s_nj, 1)] = pair_g[e];
+      if (!pair_pos[e]) {
+        const int slot = atomicAdd(&s_nj, 1);
+        if (slot < sj_cap) sj_dyn[slot] = pair_g[e];       // (sj_cap may be a speculative bound, see rank_count_kernel)
+      }
   }
   __syncthreads();
-  const int nj = s_nj;
+  const int nj = min(s_nj, sj_cap);
   const unsigned long long* src = tk_cand + (long long)q * tk_cap;
   int fill = k;
   for (int base = 0; base < cnt;) {
@@ -782,18 +787,25 @@ __global__ void __launch_bounds__(128) rank_finalize_trapezoid_kernel(long long 
 
 using namespace pps;
 
-extern "C" int pps_rank_gather(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
-                               const int32_t* pair_q, const int32_t* pair_g, long long n_pairs, float* pair_d,
-                               void* stream) {
+namespace pps {
+int rank_gather_ex(const float* dist, long long ldd, long long nq, long long ncols, long long col0, const int32_t* pair_q,
+                   const int32_t* pair_g, long long n_pairs, float* pair_d, void* stream, const int32_t* n_dev) {
   if (nq < 0 || ncols < 0 || n_pairs < 0 || ldd < ncols) return PPS_ERR_INVALID_ARG;
   if (n_pairs == 0 || ncols == 0 || nq == 0) return PPS_OK;
   if (!dist || !pair_q || !pair_g || !pair_d) return PPS_ERR_INVALID_ARG;
   const long long blocks = (n_pairs + 255) / 256;
   if (blocks > 0x7fffffffLL) return PPS_ERR_UNSUPPORTED;
   rank_gather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dist, ldd, ncols, col0, pair_q,
-                                                                                      pair_g, n_pairs, pair_d);
+                                                                                      pair_g, n_pairs, pair_d, n_dev);
   PPS_LAUNCH_CHECK("rank_gather_kernel");
   return PPS_OK;
+}
+}  // namespace pps
+
+extern "C" int pps_rank_gather(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
+                               const int32_t* pair_q, const int32_t* pair_g, long long n_pairs, float* pair_d,
+                               void* stream) {
+  return rank_gather_ex(dist, ldd, nq, ncols, col0, pair_q, pair_g, n_pairs, pair_d, stream, nullptr);
 }
 
 static int rank_count_launch(const float* dist, long long ldd, long long nq, long long ncols, long long col0,
@@ -977,7 +989,8 @@ extern "C" int pps_topk_merge(uint64_t* topk_key, long long nq, int k, const uin
   }
   topk_merge_kernel<<<(unsigned)nq, kCntThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<unsigned long long*>(topk_key), k, reinterpret_cast<const unsigned long long*>(tk_cand), tk_cap, tk_cnt,
-      tk_bound, filt ? pair_off : nullptr, pair_g, pair_pos, filt ? 1 : 0, overflow);
+      tk_bound, filt ? pair_off : nullptr, pair_g, pair_pos, filt ? 1 : 0, overflow,
+      max_pairs_per_query > 0 ? max_pairs_per_query : 1);
   PPS_LAUNCH_CHECK("topk_merge_kernel");
   return PPS_OK;
 }

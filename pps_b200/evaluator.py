@@ -600,6 +600,8 @@ class RankEngine:
         self.use_c_pass = True           # everything else (several blocks, top-k, sharded): pps_pass_begin / _count / _end
         self.tk_cap = 0                  # test hook: top-k candidate entries per query of the C pass (0 = default 2048)
         self._gathered = None
+        self._gathered_x1 = None
+        self._res_ring, self._res_turn = None, 0
         self.trace = None                # list collecting (name, cuda event, host time) marks of _run_pass when set
         self._stage = None               # device staging of run_host
         self._cnt_all = None
@@ -749,7 +751,7 @@ class RankEngine:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 tr.append((name, ev, _time.perf_counter()))
-        for attempt in (0, 1):
+        for attempt in (0, 1, 2):
             mark("start")
             d_x1, n_x1 = C.c_void_p(0), C.c_longlong(0)
             _lib.check(lib.pps_pass_begin(ctx, _lib.ptr(q), nq, _lib.ptr(g) if self.ngl else None, self.ngl, self.dim, self.in_code,
@@ -757,12 +759,16 @@ class RankEngine:
                                           self.offset, world, rank, self.prec, topk, self.max_block_bytes, flags, s,
                                           C.byref(d_x1), C.byref(n_x1)), "pps_pass_begin")
             mark("begin_done")
+            g1 = None
             if sharded and n_x1.value:
                 x1 = _wrap_device(torch, d_x1.value, n_x1.value, "<i4", torch.int32, self.dev)
-                dist_mod.all_reduce(x1, op=dist_mod.ReduceOp.SUM, group=self.group)
+                if self._gathered_x1 is None or self._gathered_x1.numel() != world * n_x1.value:
+                    self._gathered_x1 = torch.empty(world * n_x1.value, dtype=torch.int32, device=self.dev)
+                g1 = self._gathered_x1
+                dist_mod.all_gather_into_tensor(g1, x1, group=self.group)
             mark("x1_done")
             d_x2, nb = C.c_void_p(0), C.c_longlong(0)
-            _lib.check(lib.pps_pass_count(ctx, s, C.byref(d_x2), C.byref(nb)), "pps_pass_count")
+            _lib.check(lib.pps_pass_count(ctx, _lib.ptr(g1), s, C.byref(d_x2), C.byref(nb)), "pps_pass_count")
             mark("count_done")
             gathered = None
             if sharded:
@@ -777,13 +783,25 @@ class RankEngine:
             ap = np.zeros(nq, dtype=np.float64)
             valid = np.zeros(nq, dtype=np.uint8)
             first = np.zeros(nq, dtype=np.int32)
-            ti = np.zeros((nq, topk), dtype=np.int32) if topk else None
-            td = np.zeros((nq, topk), dtype=np.float32) if topk else None
+            ti = td = None
+            if topk:
+                # the top-k lists (MBs) come back into PINNED arrays: a device -> pageable copy runs at a fraction of the
+                # PCIe rate.  Two sets, used alternately: a result stays valid until the second-next pass of this engine.
+                if self._res_ring is None:
+                    mk = lambda dt: torch.empty((max(nq, 1), topk), dtype=dt).pin_memory()
+                    self._res_ring = [(mk(torch.int32), mk(torch.float32)) for _ in range(2)]
+                self._res_turn ^= 1
+                ti, td = (t.numpy()[:nq] for t in self._res_ring[self._res_turn])
             rc = lib.pps_pass_end(ctx, _lib.ptr(gathered), 10, s, C.cast(C.byref(out_map), C.c_void_p), _lib.ptr(out_cmc),
                                   _lib.ptr(ap), _lib.ptr(valid), _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
             mark("end_done")
             self.used_fused_topk = bool(topk and not (flags & _lib.PASS_NO_EPILOGUE_TOPK))
-            if rc == _lib.PPS_ERR_TOPK_OVERFLOW and attempt == 0:
+            if rc == _lib.PPS_ERR_PASS_RESIZE and not (flags & _lib.PASS_SIZING):
+                # the speculative size bounds (taken from the last sizing pass of this shape) were too small - the ids
+                # changed: every rank sees the same flag and repeats the pass as a sizing pass
+                flags |= _lib.PASS_SIZING
+                continue
+            if rc == _lib.PPS_ERR_TOPK_OVERFLOW and not (flags & _lib.PASS_NO_EPILOGUE_TOPK):
                 # a candidate buffer ran over (adversarial column order): every rank sees the same flag (it travels in the
                 # gathered buffers), so every rank repeats the pass with the one-read sweep
                 flags |= _lib.PASS_NO_EPILOGUE_TOPK

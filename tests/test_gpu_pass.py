@@ -88,13 +88,12 @@ def _emulated_sharded_pass(torch, lib, _lib, evaluator, d, q, g_full, world, top
                                       _lib.ptr(qcam), _lib.ptr(gid), _lib.ptr(gcam), ng, row0, world, r, prec, topk, block_bytes,
                                       0, s, C.byref(d_x1), C.byref(n_x1)), "begin")
         x1s.append(evaluator._wrap_device(torch, d_x1.value, max(n_x1.value, 1), "<i4", torch.int32, dev)[:n_x1.value])
-    total = torch.stack(x1s).sum(dim=0, dtype=torch.int32)           # all-reduce(SUM)
-    for x in x1s:
-        x.copy_(total)
+    assert len({int(x.numel()) for x in x1s}) == 1
+    g1 = torch.cat(x1s).contiguous() if x1s[0].numel() else None      # all-gather of the thresholds
     packed = []
     for h in ctxs:
         d_x2, nb = C.c_void_p(0), C.c_longlong(0)
-        _lib.check(lib.pps_pass_count(h, s, C.byref(d_x2), C.byref(nb)), "count")
+        _lib.check(lib.pps_pass_count(h, _lib.ptr(g1), s, C.byref(d_x2), C.byref(nb)), "count")
         packed.append(evaluator._wrap_device(torch, d_x2.value, nb.value, "|u1", torch.uint8, dev))
     assert len({int(p.numel()) for p in packed}) == 1
     gathered = torch.cat(packed).contiguous()                        # all-gather
@@ -164,7 +163,7 @@ def test_pass_argument_errors():
     assert bad(rank=1) == _lib.PPS_ERR_INVALID_ARG
     assert bad(topk=1000) == _lib.PPS_ERR_INVALID_ARG
     assert bad(prec=_lib.PREC_FP32) == _lib.PPS_ERR_INVALID_ARG
-    assert lib.pps_pass_count(h, s, None, None) == _lib.PPS_ERR_INVALID_ARG      # no pass in flight
+    assert lib.pps_pass_count(h, None, s, None, None) == _lib.PPS_ERR_INVALID_ARG      # no pass in flight
     assert lib.pps_pass_end(h, None, 10, s, None, None, None, None, None, None, None) == _lib.PPS_ERR_INVALID_ARG
     assert bad() == 0
     lib.pps_ctx_destroy(h)
@@ -204,3 +203,34 @@ def test_numa_helper_is_best_effort():
     info = numa.bind_to_gpu_node(0)
     assert info["device"] == 0 and ("reason" in info or info["bound"])
     assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+
+
+def test_speculative_pass_resizes_when_the_ids_change():
+    """The second pass of a shape lays its buffers out for the sizes of the first (no mid-pass read-back).  When the ids
+    change under it - more pairs, longer lists, more candidate rows - the bound check fails, pps_pass_end says
+    PPS_ERR_PASS_RESIZE, and the engine repeats the pass as a sizing pass: results as if nothing had happened."""
+    import torch
+    from pps_b200 import evaluator, synthetic
+    rs = np.random.RandomState(3)
+    nq, ng, dim = 300, 40000, 128
+    q = torch.from_numpy(rs.randn(nq, dim).astype(np.float32)).cuda()
+    g = torch.from_numpy(rs.randn(ng, dim).astype(np.float32)).cuda()
+    qcam, gcam = rs.randint(0, 3, nq), rs.randint(0, 3, ng)
+    qid = rs.randint(1, 60, nq)
+    few = np.where(rs.rand(ng) < 0.02, rs.randint(1, 60, ng), 0)          # ~2 % of the rows carry a query id
+    many = np.where(rs.rand(ng) < 0.30, rs.randint(1, 60, ng), 0)         # 15x more pairs, candidates, list lengths
+    for topk, bb in ((0, 8 << 30), (7, nq * 4096 * 4)):
+        outs = {}
+        for name, gid in (("few", few), ("many", many), ("few_again", few)):
+            eng = evaluator.RankEngine(qid, gid, qcam, gcam, nq=nq, ng_local=ng, dim=dim, topk=topk, max_block_bytes=bb)
+            eng.use_c_path = False
+            a = eng.run(q, g)
+            b = eng.run(q, g)                                             # speculative on the sizes of the pass before
+            ref = evaluator.RankEngine(qid, gid, qcam, gcam, nq=nq, ng_local=ng, dim=dim, topk=topk, max_block_bytes=bb)
+            ref.use_c_pass = ref.use_c_path = False
+            want = ref.run(q, g)
+            _same(a, want, topk)
+            _same(b, want, topk)
+            outs[name] = a
+        assert not np.array_equal(outs["few"].ap, outs["many"].ap)
+        np.testing.assert_array_equal(outs["few"].ap, outs["few_again"].ap)
