@@ -319,10 +319,20 @@ def rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams, want
         raise RuntimeError("ap_definition must be 'step' or 'trapezoid'")
     torch = _torch()
     lib = _lib.load()
+    if getattr(distmat, "dtype", None) in (np.float64, torch.float64):
+        # the reference ranks whatever dtype it is given; this path ranks float32, and distinct float64 distances can
+        # collapse into float32 ties (tie-grouped AP / first-match rank would then differ)
+        import warnings
+        warnings.warn("rank_distmat: float64 distances are ranked as float32 (values closer than 2^-24 relative become ties)",
+                      RuntimeWarning, stacklevel=3)
     dist, _ = _as_cuda_f32(distmat, "distmat")
     if dist.dtype != torch.float32:
         dist = dist.float()
     m, n = int(dist.shape[0]), int(dist.shape[1])
+    if topk and dist.numel() and bool((dist < 0).any()):
+        # top-k keys order by the bits of a NON-NEGATIVE float; the counting half handles any sign
+        raise RuntimeError("rank_distmat: top-k needs non-negative distances (got negative entries, e.g. a negated similarity); "
+                           "shift the matrix or call it with topk=0")
     with torch.cuda.device(dist.device):
         pairs = DevicePairs(query_ids, query_cams, gallery_ids, gallery_cams, dist.device)
         if pairs.nq != m or pairs.ng != n:
@@ -1260,8 +1270,12 @@ def evaluate_arrays(all_feats, ids, cams, marks, precision: str = DEFAULT_PRECIS
 
 def evaluate(json_dataset, all_feats, output_dir=None, precision: str = DEFAULT_PRECISION, verbose: bool = True,
              to_re_rank: bool = False):
-    """reid_dataset_evaluator.py:29-209.  ``to_re_rank`` is the reference's ``cfg.REID.RERANK`` (:30; there it
-    defaults to True through the config, here the caller passes it).
+    """reid_dataset_evaluator.py:29-209.  ``to_re_rank`` is the reference's ``cfg.REID.RERANK`` (:30).
+
+    NOTE - the one behavioural default that differs from an unconfigured reference: there ``cfg.REID.RERANK`` defaults
+    to True (detectron/core/config.py:1022), so a bare ``evaluate(json_dataset, all_feats, output_dir)`` returns the
+    RE-RANKED scores; here there is no global cfg, ``to_re_rank`` defaults to False and the caller passes the value of
+    its ``cfg.REID.RERANK`` (``python -m pps_b200.dataset_io --rerank`` on the command line).
 
     ``json_dataset`` only needs ``get_roidb(gt=True)`` returning entries with 'image' and 'mark'.
     """
