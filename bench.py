@@ -486,6 +486,11 @@ def run_ours(args):
         engine.set_phase_timing(False)
         gemm_ms = [phase_sum["dist_gemm"] / args.steps]
         phases = {k: v / args.steps for k, v in phase_sum.items()}
+        if not engine.use_c_path or world > 1:
+            # the C pass reports SUMS per pass: split, dist_gemm, rank_count, finalize; two of the slots carry host stalls
+            phases = {"split": phases["split"], "dist_gemm": phases["dist_gemm"], "rank_count": phases["rank_count"],
+                      "finalize": phases["finalize"], "host_wait_pair_lists": phases["pairs_enqueue"],
+                      "host_wait_final_sync": phases["d2h"]}
     else:
         gemm_ms = [a.elapsed_time(b) for a, b in engine.kernel_events]
         engine.kernel_events = None

@@ -101,7 +101,7 @@ int plan_blocks(PassState& p, bool short_first) {
   long long first = std::min(block_rows, ngl);
   if (short_first && p.topk > 0) {
     long long want = (long long)(2.2 * p.topk * (double)std::min(block_rows, ngl) / kTkCap);   // planned for the default cap
-    want = std::max<long long>(8192, (want + 255) / 256 * 256);
+    want = std::max<long long>(16384, (want + 255) / 256 * 256);   // (8 192: the weak bound floods the epilogue admission; 32 768: the sweep itself dominates a 65 k-row shard)
     if (ngl >= 4 * want) first = std::min(first, want);
   }
   long long r0 = 0, rows = first;

@@ -606,7 +606,8 @@ class RankEngine:
             self.pairs = DevicePairs(self.qi, self.qc, self.gi, self.gc, dev)
         self._pair_cap = 0
         self.kernel_events = None        # bench.py: list collecting (start, stop) events around the distance GEMM
-        self.use_c_path = True           # one device, one block, no top-k: the whole evaluation is ONE C call
+        self.use_c_path = False          # True: one device, one block, no top-k through the single C call pps_evaluate_device_ctx
+                                         # (round 1's fast path; the speculative pass below measured faster: 0.864 vs 0.883 ms)
         self.use_c_pass = True           # everything else (several blocks, top-k, sharded): pps_pass_begin / _count / _end
         self.tk_cap = 0                  # test hook: top-k candidate entries per query of the C pass (0 = default 2048)
         self._gathered = None

@@ -234,3 +234,18 @@ def test_speculative_pass_resizes_when_the_ids_change():
             outs[name] = a
         assert not np.array_equal(outs["few"].ap, outs["many"].ap)
         np.testing.assert_array_equal(outs["few"].ap, outs["few_again"].ap)
+
+
+@pytest.mark.parametrize("name", ["small_mid", "dup_ties", "some_invalid"])
+def test_single_call_path_equals_pass(golden, name):
+    """pps_evaluate_device_ctx (round 1's one-call path for one device / one block / no top-k, `use_c_path`) and the pass
+    produce the same bits."""
+    import torch
+    from pps_b200 import evaluator
+    d = golden(name)
+    q, g = torch.from_numpy(d["q"]).cuda(), torch.from_numpy(d["g"]).cuda()
+    one = _engine(evaluator, d, q, g)
+    one.use_c_path = True
+    two = _engine(evaluator, d, q, g)
+    assert not two.use_c_path and two.use_c_pass
+    _same(one.run(q, g), two.run(q, g), 0)
