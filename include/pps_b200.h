@@ -169,6 +169,9 @@ int pps_split_rows_gather(const void* feats, int dtype, const int32_t* row_index
 #define PPS_DIST_KERNEL_1CTA 0x100   /* use the single-CTA 128x256 kernel instead of the 2-CTA 256x256 one */
 #define PPS_DIST_CLUSTER4 0x400        /* single-plane products: clusters of 4 CTAs whose two CTA pairs share the B tile by TMA
                                           multicast (bit-identical; 25 % less L2 -> SM traffic but measured slower, opt-in) */
+#define PPS_DIST_SEPARATE_SMALL 0x800  /* multi-term precisions: the cross terms accumulate in a TMEM buffer of their own and are
+                                          added in the epilogue - the large accumulator then sees a third of the MMA steps
+                                          (the tensor core truncates ~1 ulp of the accumulator per step) */
 #define PPS_DIST_RESERVE_SM_PAIR 0x200 /* persistent grid leaves one SM pair idle: the kernel fills the shared memory
                                           of every SM it runs on, so a concurrent NCCL / pair-list kernel on another
                                           stream could otherwise only start when it ends */

@@ -46,6 +46,7 @@ DIST_SQUARED = 1
 DIST_DOT = 2
 DIST_KERNEL_1CTA = 0x100
 DIST_CLUSTER4 = 0x400
+DIST_SEPARATE_SMALL = 0x800
 
 TOPK_MAX = 128
 N_PHASES = 7

@@ -294,8 +294,16 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
     if (rank == 0 && lane == 0) {
       uint32_t it = 0, acc_it = 0;
       TileWalk<EPI> w(ga, pair, npairs);
+      // sep_small: the leading term p0.p0 accumulates in columns [0, 256), every cross term in columns [256, 512) and
+      // the epilogue adds the two.  The tensor core truncates ~1 ulp OF THE ACCUMULATOR per MMA step; the cross terms are
+      // 2^-11 of the leading one, so in a buffer of their own their 2/3 of the steps cost nothing, and the large
+      // accumulator sees K/16 steps instead of 3K/16.  Price: no second buffer to overlap the epilogue with the next tile.
+      const bool sep = ga.sep_small != 0;
+      int first_small = -1;
+      for (int term = 0; term < g.nterms; ++term)
+        if (first_small < 0 && (g.term_a[term] | g.term_b[term]) != 0) first_small = term;
       for (; w.next(); ++acc_it) {
-        const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        const uint32_t as = sep ? 0u : (acc_it & 1u), aph = sep ? (acc_it & 1u) : ((acc_it >> 1) & 1u);
         mbar_wait(&tempty[as], aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -307,9 +315,12 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
           for (int term = 0; term < g.nterms; ++term) {
             const uint64_t adesc = umma_desc_k_sw128(slot + g.term_a[term] * kTile2Bytes);
             const uint64_t bdesc = umma_desc_k_sw128(slot + planes * kTile2Bytes + g.term_b[term] * kBTile);
+            const bool small = sep && (g.term_a[term] | g.term_b[term]) != 0;
+            const uint32_t d_term = small ? tmem_base + 256u : d_tmem;
+            const bool first = sep ? (kb == 0 && (small ? term == first_small : true)) : (kb == 0 && term == 0);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
-              tc_mma_f16_2cta(d_tmem, adesc + 2u * k, bdesc + 2u * k, g.idesc, (kb | term | k) ? 1u : 0u);
+              tc_mma_f16_2cta(d_term, adesc + 2u * k, bdesc + 2u * k, g.idesc, (first && k == 0) ? 0u : 1u);
           }
           tc_commit_2cta(&empty[s], CL4 ? 0xF : 3);   // the slots (of every CTA that holds a tile these MMAs read) are reusable
         }
@@ -342,7 +353,8 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
       const int m0 = w.m_tile * kClusterRows + pair_row0 + (int)rank * kT2Rows;       // output row (within the group's rows)
       const int n0 = (int)(w.grp * ga.out_group_cols) + w.n_tile * BN;              // output column
       const int n_end = EPI == EPI_AFFINE_RELU ? (int)((w.grp + 1) * ga.out_group_cols) : (int)g.m2;   // first column not ours
-      const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+      const bool sep = (EPI == EPI_DIST || EPI == EPI_DIST_TOPK) && ga.sep_small != 0;
+      const uint32_t as = sep ? 0u : (acc_it & 1u), aph = sep ? (acc_it & 1u) : ((acc_it >> 1) & 1u);
       const long long gi = (long long)m0 + row;
       if (EPI == EPI_RANK && w.run_start) {
         // this thread's row of the threshold table -> shared memory (only this thread ever reads it), counters = 0
@@ -363,7 +375,7 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
       // (scaled operands: |b|^2 and the column scales share the two buffers, so they are single-buffered and a
       // second barrier at the end of the tile keeps a fast warp from refilling them early)
       const bool scaled = EPI != EPI_AFFINE_RELU && EPI != EPI_RANK && g.a_scale != nullptr;
-      float* bn = bn_s + (scaled ? 0 : as * 256);
+      float* bn = bn_s + (scaled ? 0 : as * 256);      // (sep: as == 0 for every tile, the end-of-tile barrier below protects it)
       const float* sc_s = bn_s + 256;
       if (EPI == EPI_AFFINE_RELU) {
         const long long gj = (long long)n0 + etid;            // BN == 128 == number of epilogue threads
@@ -449,6 +461,13 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
           }
         } else {
           unsigned char* buf = my_stage + (chunk_it & 1u) * kOutChunkBytes;
+          if (sep) {                               // + the cross terms from their own accumulator
+            uint32_t r2[32];
+            tmem_ld_32x32(tbase + 256u + c, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__fadd_rn(__uint_as_float(r[e]), __uint_as_float(r2[e])));
+          }
           bulk_wait_group_read<1>();               // the store that last read this buffer has drained it
           __syncwarp();
           tmem_ld_wait();
@@ -515,7 +534,7 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
         if (rank == 0) mbar_arrive(&tempty[as]);
         else mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[as]), lead));
       }
-      if (scaled) asm volatile("bar.sync 1, 128;" ::: "memory");   // every warp is done with bn / sc of this tile
+      if (scaled || sep) asm volatile("bar.sync 1, 128;" ::: "memory");   // every warp is done with bn / sc of this tile
       if (EPI == EPI_RANK && (w.run_end || ++tiles_since_flush == 255)) {
         // counters -> global table at the end of the run (a handful of CTA pairs share a row: atomics), and every 255
         // tiles in between so that no 16-bit counter can wrap
@@ -730,6 +749,8 @@ static int dist_tc_impl(const void* a_planes, const float* a_sqnorm, long long m
     ga.g.n_tiles = (int)((m2 + 255) / 256);
     ga.g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     ga.planes = need;
+    static const int env_sep = [] { const char* e = getenv("PPS_SEPARATE_SMALL"); return e ? atoi(e) : -1; }();
+    ga.sep_small = (g.nterms > 1 && (env_sep >= 0 ? env_sep != 0 : (flags & PPS_DIST_SEPARATE_SMALL) != 0)) ? 1 : 0;
     ga.stages = kRing2Bytes / (2 * need * kTile2Bytes);
     if (ga.stages > kMaxStages2) ga.stages = kMaxStages2;
     ga.groups = 1; ga.a_group_rows = 0; ga.b_group_rows = 0; ga.out_group_cols = 0;
@@ -927,6 +948,7 @@ extern "C" int pps_embed_tc(const void* x_planes /*[planes][K*N][kpad]*/, int x_
   g.m_tiles = (int)((N + 255) / 256);
   g.n_tiles = 1;
   ga.planes = need;
+  ga.sep_small = 0;
   ga.stages = kRing2Bytes / (need * (kTile2Bytes + 64 * kBK * 2));
   if (ga.stages > kMaxStages2) ga.stages = kMaxStages2;
   ga.groups = K; ga.a_group_rows = N; ga.b_group_rows = E; ga.out_group_cols = E;
@@ -1005,6 +1027,7 @@ extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, lon
   g.m_tiles = (int)((m1 + 255) / 256);
   g.n_tiles = (int)((m2 + 255) / 256);
   ga.planes = need;
+  ga.sep_small = 0;
   ga.groups = 1; ga.a_group_rows = 0; ga.b_group_rows = 0; ga.out_group_cols = 0;
   // shared memory: ring | thresholds [p_cap][128] f32 | counters [p_cap/2][128] u32 | |b|^2 [2][256] | barriers
   const int stage_bytes = 2 * need * kTile2Bytes;

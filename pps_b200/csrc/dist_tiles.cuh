@@ -29,6 +29,7 @@ struct GemmArgs {
 struct Gemm2Args {
   GemmArgs g;
   int planes;       // planes of each operand loaded per k-block (1..3)
+  int sep_small;    // 1: the cross terms (every term but p0.p0) accumulate in a TMEM buffer of their own (see dist_gemm.cu)
   int stages;       // ring depth = ring bytes / stage bytes
   // grouped form (embedding head): `groups` independent products; group grp uses A rows [grp*a_group_rows, ...),
   // B rows [grp*b_group_rows, ...) and writes output columns [grp*out_group_cols, ...).  Distance: groups = 1.
