@@ -172,6 +172,8 @@ int pps_split_rows_gather(const void* feats, int dtype, const int32_t* row_index
 #define PPS_DIST_SEPARATE_SMALL 0x800  /* multi-term precisions: the cross terms accumulate in a TMEM buffer of their own and are
                                           added in the epilogue - the large accumulator then sees a third of the MMA steps
                                           (the tensor core truncates ~1 ulp of the accumulator per step) */
+#define PPS_DIST_SQRT_RN 0x1000        /* correctly rounded square root in the epilogue (what np.sqrt gives) instead of the
+                                          hardware approximation */
 #define PPS_DIST_RESERVE_SM_PAIR 0x200 /* persistent grid leaves one SM pair idle: the kernel fills the shared memory
                                           of every SM it runs on, so a concurrent NCCL / pair-list kernel on another
                                           stream could otherwise only start when it ends */

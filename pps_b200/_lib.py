@@ -47,6 +47,7 @@ DIST_DOT = 2
 DIST_KERNEL_1CTA = 0x100
 DIST_CLUSTER4 = 0x400
 DIST_SEPARATE_SMALL = 0x800
+DIST_SQRT_RN = 0x1000
 
 TOPK_MAX = 128
 N_PHASES = 7

@@ -338,6 +338,7 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
     uint32_t acc_it = 0, chunk_it = 0;
     const bool want_sq = (g.flags & PPS_DIST_SQUARED) != 0;
     const bool want_dot = (g.flags & PPS_DIST_DOT) != 0;
+    const bool sqrt_rn = (g.flags & PPS_DIST_SQRT_RN) != 0;     // correctly rounded sqrt (the reference's np.sqrt) instead of MUFU
     unsigned char* my_stage = stage_out + (size_t)lane_grp * (2 * kOutChunkBytes);
     const uint32_t swz = (uint32_t)(lane & 7);
     // EPI_RANK per-row state
@@ -499,7 +500,7 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
                 // with scaled operands sc = -2 / (s_a s_b) and sc * dot is the same exact product)
                 float d2 = __fadd_rn(__fmaf_rn(sc[e], dot, an), bb[e]);
                 d2 = fmaxf(d2, 0.f);
-                v[e] = want_sq ? d2 : sqrt_approx(d2);
+                v[e] = want_sq ? d2 : (sqrt_rn ? __fsqrt_rn(d2) : sqrt_approx(d2));
               }
             }
             *reinterpret_cast<float4*>(buf + lane * 128 + (((uint32_t)j ^ swz) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
@@ -750,6 +751,8 @@ static int dist_tc_impl(const void* a_planes, const float* a_sqnorm, long long m
     ga.g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     ga.planes = need;
     static const int env_sep = [] { const char* e = getenv("PPS_SEPARATE_SMALL"); return e ? atoi(e) : -1; }();
+    static const int env_sqrt = [] { const char* e = getenv("PPS_SQRT_RN"); return e ? atoi(e) : -1; }();
+    if (env_sqrt >= 0) ga.g.flags = env_sqrt ? (ga.g.flags | PPS_DIST_SQRT_RN) : (ga.g.flags & ~PPS_DIST_SQRT_RN);
     ga.sep_small = (g.nterms > 1 && (env_sep >= 0 ? env_sep != 0 : (flags & PPS_DIST_SEPARATE_SMALL) != 0)) ? 1 : 0;
     ga.stages = kRing2Bytes / (2 * need * kTile2Bytes);
     if (ga.stages > kMaxStages2) ga.stages = kMaxStages2;
