@@ -185,9 +185,9 @@ def mean_ap(distmat, query_ids, gallery_ids, query_cams, gallery_cams, average=T
 
 
 def cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk=100, first_match_break=False,
-        average=True, stable=False):
-    """:283-363 for the flag combination the evaluator uses (separate_camera_set=False,
-    single_gallery_shot=False).  ``stable=True`` sorts ties by gallery index (the reference's
+        average=True, stable=False, separate_camera_set=False):
+    """:283-363 with single_gallery_shot=False (the evaluator also fixes separate_camera_set=False, :35-37; True removes
+    EVERY gallery item of the query's camera, :329-331).  ``stable=True`` sorts ties by gallery index (the reference's
     np.argsort is unstable, so tie order there is implementation-defined)."""
     m, n = distmat.shape
     order = np.argsort(distmat, axis=1, kind="stable" if stable else None)
@@ -197,6 +197,8 @@ def cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk=100, fir
     for i in range(m):
         idx = order[i]
         keep = valid_mask(query_ids[i], query_cams[i], gallery_ids[idx], gallery_cams[idx])
+        if separate_camera_set:
+            keep = keep & (gallery_cams[idx] != query_cams[i])
         hits = (gallery_ids[idx] == query_ids[i])[keep]
         if not np.any(hits):
             continue

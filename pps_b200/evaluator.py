@@ -500,17 +500,49 @@ def cmc(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_cams
         separate_camera_set=False, single_gallery_shot=False, first_match_break=False, average=True):
     """reid_dataset_evaluator.py:283-363.
 
-    ``separate_camera_set`` / ``single_gallery_shot`` are the two branches the reference never
-    reaches (its single_gallery_shot branch calls ``np.bool`` and random sampling, :274-279,334-347);
-    they raise here instead of silently computing something else.
+    ``separate_camera_set=True`` (:329-331) removes EVERY gallery item taken by the query's camera, whatever its id: the
+    queries are grouped by camera and each group is ranked against the columns of the other cameras (nothing is junk
+    then).  ``single_gallery_shot=True`` is the one branch that is not provided: it averages 100 np.random.choice draws
+    per query and calls the removed ``np.bool`` (:274-279, :334-347) - it does not run in the reference either under the
+    installed numpy - and the evaluator never selects it (:35-37).
     """
     _ensure_arrays(distmat, query_ids, gallery_ids, query_cams, gallery_cams)
-    if separate_camera_set or single_gallery_shot:
-        raise NotImplementedError("cmc: separate_camera_set / single_gallery_shot are not on the PPS eval path "
-                                  "(reid_dataset_evaluator.py:35-37 fixes both to False)")
+    if single_gallery_shot:
+        raise NotImplementedError("cmc: single_gallery_shot is not on the PPS eval path (reid_dataset_evaluator.py:35-37 fixes "
+                                  "it to False; the branch draws random samples and calls the removed np.bool)")
+    if separate_camera_set:
+        return _cmc_separate_camera_set(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk, first_match_break,
+                                        average)
     res = rank_distmat(distmat, query_ids, gallery_ids, query_cams, gallery_cams,
                        want_neg_before=not first_match_break)
     return res.cmc(topk=topk, first_match_break=first_match_break, average=average)
+
+
+def _cmc_separate_camera_set(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk, first_match_break, average):
+    torch = _torch()
+    dist, _ = _as_cuda_f32(distmat, "distmat")
+    qi, qc = _ids64(query_ids, "query_ids"), _ids64(query_cams, "query_cams")
+    gi, gc = _ids64(gallery_ids, "gallery_ids"), _ids64(gallery_cams, "gallery_cams")
+    m = int(dist.shape[0])
+    if len(qi) != m or len(gi) != int(dist.shape[1]):
+        raise RuntimeError("distmat shape %s does not match %d query / %d gallery ids" % (tuple(dist.shape), len(qi), len(gi)))
+    ret = np.zeros([m, topk])
+    is_valid = np.zeros(m)
+    for cam in np.unique(qc):
+        rows = np.nonzero(qc == cam)[0]
+        cols = np.nonzero(gc != cam)[0]
+        if len(cols) == 0:
+            continue
+        sub = dist[torch.from_numpy(rows).to(dist.device)][:, torch.from_numpy(cols).to(dist.device)].contiguous()
+        res = rank_distmat(sub, qi[rows], gi[cols], qc[rows], gc[cols], want_neg_before=not first_match_break)
+        ret[rows] = res.cmc_matrix(topk, first_match_break)
+        is_valid[rows] = res.is_valid
+    num_valid = int(is_valid.sum())
+    if num_valid == 0:
+        raise RuntimeError("No valid query")                 # :358-359
+    if average:
+        return np.sum(ret, axis=0) / num_valid
+    return ret, is_valid
 
 
 def mean_ap(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_cams=None, average=True,

@@ -592,3 +592,19 @@ def test_trapezoid_ap_definition(golden, name):
     step = pps_b200.mean_ap(d["dist"], **ids)
     trap = pps_b200.mean_ap(d["dist"], ap_definition="trapezoid", **ids)
     assert abs(step - float(d["mAP"])) < 1e-12 and trap != step
+
+
+@pytest.mark.parametrize("name", ["small_mid", "ragged_dim", "many_pos", "some_invalid"])
+def test_cmc_separate_camera_set(golden, name):
+    """The cmc branch the reference's evaluate() never selects but its signature offers (:329-331): every gallery item of
+    the query's camera is removed.  Pinned to the unmodified reference; single_gallery_shot stays NotImplemented."""
+    import pps_b200
+    d, s = golden(name), golden("cmc_sep_" + name)
+    ids = _ids(d)
+    np.testing.assert_allclose(pps_b200.cmc(d["dist"], topk=10, separate_camera_set=True, first_match_break=True, **ids), s["cmc_fmb"], atol=1e-12)
+    np.testing.assert_allclose(pps_b200.cmc(d["dist"], topk=20, separate_camera_set=True, first_match_break=False, **ids), s["cmc_all"], atol=1e-12)
+    rows, valid = pps_b200.cmc(d["dist"], topk=10, separate_camera_set=True, first_match_break=True, average=False, **ids)
+    np.testing.assert_array_equal(rows, s["cmc_rows"])
+    np.testing.assert_array_equal(valid, s["cmc_valid"])
+    with pytest.raises(NotImplementedError):
+        pps_b200.cmc(d["dist"], single_gallery_shot=True, **ids)

@@ -193,3 +193,16 @@ def test_pool_gradient_restatement_equals_finite_differences():
                 xm[idx] -= eps
                 num[idx] = (f(xp) - f(xm)) / (2 * eps)
             np.testing.assert_allclose(g, num, rtol=0, atol=1e-6 * max(1.0, np.abs(num).max()))
+
+
+@pytest.mark.parametrize("name", ["small_mid", "ragged_dim", "many_pos", "some_invalid"])
+def test_cmc_separate_camera_set_matches_reference_fixture(golden, name):
+    """cmc(separate_camera_set=True) (reid_dataset_evaluator.py:329-331) against the unmodified reference
+    (tests/golden/cmc_sep_*.npz, oracle/make_golden_cmc_sep.py)."""
+    d, s = golden(name), golden("cmc_sep_" + name)
+    ids = dict(query_ids=d["qid"], gallery_ids=d["gid"], query_cams=d["qcam"], gallery_cams=d["gcam"])
+    np.testing.assert_allclose(O.cmc(d["dist"], topk=10, first_match_break=True, separate_camera_set=True, **ids), s["cmc_fmb"], atol=1e-12)
+    np.testing.assert_allclose(O.cmc(d["dist"], topk=20, first_match_break=False, separate_camera_set=True, **ids), s["cmc_all"], atol=1e-12)
+    rows, valid = O.cmc(d["dist"], topk=10, first_match_break=True, separate_camera_set=True, average=False, **ids)
+    np.testing.assert_array_equal(rows, s["cmc_rows"])
+    np.testing.assert_array_equal(valid, s["cmc_valid"])
