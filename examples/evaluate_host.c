@@ -50,7 +50,7 @@ int main(void) {
   int32_t* first = malloc(4 * nq);
   int32_t* top_idx = malloc(4 * nq * topk);
   float* top_d = malloc(4 * nq * topk);
-  const int rc = pps_evaluate_host(q, nq, g, ng, dim, qid, qcam, gid, gcam, PPS_PREC_BF16X3, /*cmc_topk=*/10, topk,
+  const int rc = pps_evaluate_host(q, nq, g, ng, dim, qid, qcam, gid, gcam, PPS_PREC_F16X3, /*cmc_topk=*/10, topk,
                                    /*device=*/0, &map, cmc, ap, valid, first, top_idx, top_d);
   if (rc != PPS_OK) {
     fprintf(stderr, "pps_evaluate_host: %s (%s)\n", pps_strerror(rc), pps_last_cuda_error());

@@ -462,8 +462,6 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
     PPS_TRY(p.tdist.ensure((size_t)nq * ldt * 4));
     PPS_TRY(p.ts.ensure((size_t)pps_split_bytes(tcols, dim, p.planes)));
     PPS_TRY(p.tn.ensure((size_t)tcols * 8));
-    const size_t esz = dtype == PPS_DTYPE_F16 ? 2 : 4;
-    (void)esz;
     for (long long c0 = 0; c0 < p.n_rows; c0 += tcols) {
       const long long rows = std::min(tcols, p.n_rows - c0);
       {

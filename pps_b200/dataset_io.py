@@ -5,7 +5,7 @@ order); the roidb comes from a COCO-format json (detectron/datasets/json_dataset
 ``image`` = file name ``{pid:08d}_{cam:04d}_{k:08d}.jpg`` (tools/dataset/transform_market1501.py:60), ``mark`` of the
 image's single annotation (0 query / 1 gallery / 2 multi-query, json_dataset.py:188-189).
 
-    python -m pps_b200.dataset_io --features features.npy --annotations market1501_test.json [--precision bf16x3]
+    python -m pps_b200.dataset_io --features features.npy --annotations market1501_test.json [--precision f16x3]
 """
 from __future__ import annotations
 
@@ -52,7 +52,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description="CMC / mAP of cached re-ID features on B200 (PPS evaluate())")
     ap.add_argument("--features", required=True, help="features.npy written by the reference's test engine")
     ap.add_argument("--annotations", required=True, help="COCO-style json of the test split (with per-annotation 'mark')")
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x1", "bf16x3", "bf16x6"])
+    ap.add_argument("--precision", default="f16x3", choices=["bf16x1", "bf16x3", "bf16x6", "f16x3"])
     ap.add_argument("--rerank", action="store_true", help="k-reciprocal re-ranking (the reference's cfg.REID.RERANK)")
     ap.add_argument("--output", default=None, help="write the result dict as json here")
     args = ap.parse_args(argv)

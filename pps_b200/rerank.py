@@ -93,7 +93,7 @@ def re_ranking(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3):
     return out.cpu().numpy() if qg_np else out
 
 
-def re_ranking_from_features(q_feats, g_feats, k1=20, k2=6, lambda_value=0.3, precision="bf16x3"):
+def re_ranking_from_features(q_feats, g_feats, k1=20, k2=6, lambda_value=0.3, precision="f16x3"):
     """The re-ranked query x gallery distance straight from features: the three ``compute_dist`` calls of evaluate()
     (:165-171) are one [n, n] tensor-core product of the stacked features with themselves."""
     torch = _torch()
