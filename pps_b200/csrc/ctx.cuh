@@ -87,6 +87,7 @@ struct PassState {
   const int64_t *d_qid = nullptr, *d_qcam = nullptr, *d_gid = nullptr, *d_gcam = nullptr;
   long long blk_row0[kPassMaxBlocks], blk_rows[kPassMaxBlocks];
   size_t packed_bytes = 0;
+  size_t res_bytes = 0, res_first_off = 0, res_valid_off = 0, res_flags_off = 0;   // layout of the per-query result buffer (ap)
   // buffers
   GrowBuf qs, qn, gs, gn, dist, tdist, ts, tn, pair_ws, pair_off, totals, pair_q, pair_g, pair_pos, pair_d, packed, pf_ws,
       cand_rows, cand_gid, cand_gcam, gp_rows, pair_col, gp_ws, tk_bound, tk_cnt, tk_cand, small, ap, valid, first, tki, tkd;

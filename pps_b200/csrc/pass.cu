@@ -69,6 +69,10 @@ __global__ void pass_or_flag_kernel(const int32_t* __restrict__ src, uint32_t* _
   if (threadIdx.x == 0 && blockIdx.x == 0 && *src) *dst = 1u;
 }
 
+__global__ void pass_copy_flags_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+  if (threadIdx.x < 2 && blockIdx.x == 0) dst[threadIdx.x] = src[threadIdx.x];
+}
+
 __global__ void pass_clamp_offsets_kernel(int32_t* __restrict__ pair_off, long long n, int32_t cap) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && pair_off[i] > cap) pair_off[i] = cap;
@@ -227,16 +231,19 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
   PPS_TRY(p.dist.ensure((size_t)nq * p.ldd * 4));
   PPS_TRY(p.pair_off.ensure(((size_t)nq + 1) * 4));
   PPS_TRY(p.totals.ensure(64));
-  PPS_TRY(p.ap.ensure((size_t)nq * 8));
-  PPS_TRY(p.valid.ensure((size_t)nq));
-  PPS_TRY(p.first.ensure((size_t)nq * 4));
+  // per-query results: ONE device buffer [ap f64 | first i32 | valid u8 | pad | flags 2 x u32] mirrored by the pinned
+  // staging, so that they come back in a single copy (each small D2H copy costs ~8 us of stream time)
   const size_t off_ap = 64, off_first = off_ap + (size_t)nq * 8, off_valid = off_first + (size_t)nq * 4;
-  PPS_TRY(c->h_small.ensure(off_valid + (size_t)nq));
+  const size_t off_flags = (off_valid + (size_t)nq + 7) & ~(size_t)7;
+  p.res_bytes = off_flags + 8 - off_ap;
+  PPS_TRY(p.ap.ensure(p.res_bytes));
+  PPS_TRY(c->h_small.ensure(off_flags + 8));
   unsigned char* hb = c->h_small.as<unsigned char>();
   c->st.totals = reinterpret_cast<int32_t*>(hb);
   c->st.ap = reinterpret_cast<double*>(hb + off_ap);
   c->st.first = reinterpret_cast<int32_t*>(hb + off_first);
   c->st.valid = hb + off_valid;
+  p.res_first_off = off_first - off_ap; p.res_valid_off = off_valid - off_ap; p.res_flags_off = off_flags - off_ap;
   int32_t* h_tot = c->st.totals;           // [0] n_pairs [1] max_pairs [2] n_cand [3] n_rows [4] flags
 
   // ---- the ids are valid on `cs`; the pair-list work runs on the side stream ----
@@ -572,8 +579,11 @@ extern "C" int pps_pass_end(pps_ctx* c, const void* d_gathered, int cmc_topk, vo
   {
     TimedLaunch t(c, cs, 5);
     PPS_TRY(pps_rank_finalize(nq, p.pair_off.as<int32_t>(), p.pair_g.as<int32_t>(), p.pair_pos.as<uint8_t>(),
-                              p.pair_d.as<float>(), p.cnt_le(), p.cnt_first(), p.ap.as<double>(), p.valid.as<uint8_t>(),
-                              p.first.as<int32_t>(), nullptr, cs));
+                              p.pair_d.as<float>(), p.cnt_le(), p.cnt_first(), p.ap.as<double>(),
+                              p.ap.as<uint8_t>() + p.res_valid_off,
+                              reinterpret_cast<int32_t*>(p.ap.as<unsigned char>() + p.res_first_off), nullptr, cs));
+    pass_copy_flags_kernel<<<1, 32, 0, cs>>>(p.flags_dev(), reinterpret_cast<uint32_t*>(p.ap.as<unsigned char>() + p.res_flags_off));
+    PPS_LAUNCH_CHECK("pass_copy_flags_kernel");
     if (topk > 0) {
       PPS_TRY(p.tki.ensure((size_t)nq * topk * 4));
       PPS_TRY(p.tkd.ensure((size_t)nq * topk * 4));
@@ -581,10 +591,7 @@ extern "C" int pps_pass_end(pps_ctx* c, const void* d_gathered, int cmc_topk, vo
     }
   }
   const Staging& st = c->st;
-  PPS_CUDA_TRY(cudaMemcpyAsync(st.ap, p.ap.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(st.first, p.first.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(st.valid, p.valid.p, (size_t)nq, cudaMemcpyDeviceToHost, cs));
-  PPS_CUDA_TRY(cudaMemcpyAsync(st.totals + 4, p.flags_dev(), 8, cudaMemcpyDeviceToHost, cs));
+  PPS_CUDA_TRY(cudaMemcpyAsync(st.ap, p.ap.p, p.res_bytes, cudaMemcpyDeviceToHost, cs));
   if (topk > 0 && out_topk_index)
     PPS_CUDA_TRY(cudaMemcpyAsync(out_topk_index, p.tki.p, (size_t)nq * topk * 4, cudaMemcpyDeviceToHost, cs));
   if (topk > 0 && out_topk_dist)
@@ -605,11 +612,12 @@ extern "C" int pps_pass_end(pps_ctx* c, const void* d_gathered, int cmc_topk, vo
     c->phase_ms[0] = p.host_wait_ms[0] + p.host_wait_ms[1] + p.host_wait_ms[2];
     c->phase_ms[6] = p.host_wait_ms[3];
   }
-  if (st.totals[5] != 0) {             // a speculative bound was too small somewhere: identical on every rank (flags are summed)
+  const uint32_t* h_flags = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(st.ap) + p.res_flags_off);
+  if (h_flags[1] != 0) {               // a speculative bound was too small somewhere: identical on every rank (flags are summed)
     p.hints.valid = false;
     return PPS_ERR_PASS_RESIZE;
   }
-  if (st.totals[4] != 0) return PPS_ERR_TOPK_OVERFLOW;     // identical on every rank (the flags were summed)
+  if (h_flags[0] != 0) return PPS_ERR_TOPK_OVERFLOW;       // identical on every rank (the flags were summed)
   double ap_sum = 0.0;
   long long n_valid = 0;
   std::vector<double> hist((size_t)std::max(cmc_topk, 1), 0.0);
