@@ -19,6 +19,8 @@
  *   mAP       detectron/datasets/reid_dataset_evaluator.py:366-439  mean_ap
  *   CMC       detectron/datasets/reid_dataset_evaluator.py:283-363  cmc
  *   evaluate  detectron/datasets/reid_dataset_evaluator.py:29-125   evaluate (single query)
+ *   gradient  the op idiom of detectron/ops/pairwise_distance_op.cc:14-24 (GetGradientDefs)   pps_pool_bwd
+ *   multi-GPU detectron/utils/subprocess.py:39-103 + core/test_engine.py:205-213             pps_pass_*
  */
 #ifndef PPS_B200_H_
 #define PPS_B200_H_
