@@ -341,6 +341,14 @@ int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, long long m1, 
                      int dim, int precision, int flags, long long col0, int p_cap,
                      const float* thr_tab, uint32_t* cnt_tab, const float* dstar, const int32_t* gstar,
                      uint32_t* cnt_first, void* stream);
+/* pps_dist_rank_tc + the top-k admission of pps_dist_topk_tc in the same epilogue (tk_cand == NULL: none): the form the
+ * multi-block pass uses for single-plane operands, so that no block after the first is ever written or re-read. */
+int pps_dist_rank_topk_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n, long long a_plane_rows,
+                          const void* b_planes, const float* b_sqnorm, long long m2, int b_planes_n, long long b_plane_rows,
+                          int dim, int precision, int flags, long long col0, int p_cap,
+                          const float* thr_tab, uint32_t* cnt_tab, const float* dstar, const int32_t* gstar,
+                          uint32_t* cnt_first, const uint32_t* tk_bound, uint32_t* tk_cnt, uint64_t* tk_cand, int tk_cap,
+                          void* stream);
 int pps_rank_tab_finish(long long nq, int p_cap, const int32_t* tpair_tab, const uint32_t* cnt_tab,
                         uint32_t* cnt_le, void* stream);
 
@@ -480,6 +488,8 @@ int pps_rank_end(pps_ctx* ctx, int cmc_topk, void* stream, double* out_map, doub
                                          read the actual counts on the device and the host never waits mid-pass;
                                          pps_pass_end returns PPS_ERR_PASS_RESIZE when a bound was too small (different ids) */
 #define PPS_PASS_NO_EPILOGUE_TOPK 1   /* flags: every block takes the one-read sweep (the fallback after TOPK_OVERFLOW) */
+#define PPS_PASS_NO_FUSED_COUNT 4     /* flags: blocks after the first are written and counted by pps_rank_count even where the
+                                         counting epilogue (pps_dist_rank_topk_tc) applies (A/B measurements, tests) */
 #define PPS_PASS_TKCAP(n) (((n) & 0xffff) << 8)   /* flags: candidate-buffer entries per query (default / maximum 2048) */
 int pps_pass_begin(pps_ctx* ctx, const void* d_q, long long nq, const void* d_g, long long ng_local, int dim, int dtype,
                    const int64_t* d_query_ids, const int64_t* d_query_cams,
@@ -492,6 +502,10 @@ int pps_pass_begin(pps_ctx* ctx, const void* d_q, long long nq, const void* d_g,
  * ctx block by block, or in ~8 row slabs when the shard is one block, so that the split + distance of what has arrived
  * overlap the rest of the upload (the multi-GPU form of pps_evaluate_host_ctx).  NULL leaves a buffer as it is. */
 int pps_pass_set_host_input(pps_ctx* ctx, const void* h_q, const void* h_g);
+/* What the last pps_pass_begin of this context decided: which = 0 number of blocks of the local shard, 1 whether the blocks
+ * after the first take the counting epilogue (pps_dist_rank_topk_tc: nothing written), 2 whether the layout is speculative,
+ * 3 thresholds per query in the epilogue tables, 4 whether top-k candidates are admitted in the distance epilogue. */
+long long pps_pass_stat(const pps_ctx* ctx, int which);
 int pps_pass_count(pps_ctx* ctx, const void* d_gathered_x1, void* stream, void** d_x2, long long* x2_bytes);
 int pps_pass_end(pps_ctx* ctx, const void* d_gathered, int cmc_topk, void* stream, double* out_map, double* out_cmc,
                  double* out_ap, uint8_t* out_valid, int32_t* out_first_rank,

@@ -26,6 +26,7 @@ PPS_ERR_TOPK_OVERFLOW = -8
 PPS_ERR_PASS_RESIZE = -9
 PASS_NO_EPILOGUE_TOPK = 1
 PASS_SIZING = 2
+PASS_NO_FUSED_COUNT = 4
 
 POOL_AVG_MAX = 0
 POOL_MAX_AVE = 1
@@ -101,6 +102,8 @@ SIGNATURES = {
     "pps_rank_tab_prep": (_i, [_ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_dist_rank_tc": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp, _ll, _i, _ll, _i, _i, _i, _ll, _i,
                               _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pps_dist_rank_topk_tc": (_i, [_vp, _vp, _ll, _i, _ll, _vp, _vp, _ll, _i, _ll, _i, _i, _i, _ll, _i,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pps_rank_tab_finish": (_i, [_ll, _i, _vp, _vp, _vp, _vp]),
     "pps_rank_count_eq": (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _i, _vp, _vp]),
     "pps_rank_finalize_trapezoid": (_i, [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -125,6 +128,7 @@ SIGNATURES = {
     "pps_pass_begin": (_i, [_vp, _vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _ll, _ll, _i, _i, _i, _i, _ll, _i, _vp,
                             C.POINTER(_vp), C.POINTER(_ll)]),
     "pps_pass_set_host_input": (_i, [_vp, _vp, _vp]),
+    "pps_pass_stat": (_ll, [_vp, _i]),
     "pps_pass_count": (_i, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_ll)]),
     "pps_pass_end": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pps_ctx_set_timing": (_i, [_vp, _i]),

@@ -107,6 +107,15 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_group_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// shared-memory accesses by 32-bit shared-space address (the counting epilogue of dist_gemm.cu: base + byte offset)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void red_shared_add_u32(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

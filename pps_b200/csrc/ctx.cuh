@@ -81,6 +81,8 @@ struct PassState {
   int dim = 0, kpad = 0, dtype = 0, planes = 0, split_planes = 0, precision = 0, topk = 0, world = 1, rank = 0, flags = 0;
   int max_pairs = 0, n_blocks = 0, tk_cap = 2048;
   bool prefilter = false, g_inplace = false, epi_topk = false;
+  bool fused = false;            // blocks after the first: counting (+ admission) in the distance epilogue, nothing written
+  int p_cap = 0;                 // thresholds per query in the tables of the counting epilogue
   const void *d_q = nullptr, *d_g = nullptr;
   const void *h_q = nullptr, *h_g = nullptr;      // host sources of the NEXT pass (pps_pass_set_host_input), else null
   bool g_from_host = false;
@@ -90,7 +92,8 @@ struct PassState {
   size_t res_bytes = 0, res_first_off = 0, res_valid_off = 0, res_flags_off = 0;   // layout of the per-query result buffer (ap)
   // buffers
   GrowBuf qs, qn, gs, gn, dist, tdist, ts, tn, pair_ws, pair_off, totals, pair_q, pair_g, pair_pos, pair_d, packed, pf_ws,
-      cand_rows, cand_gid, cand_gcam, gp_rows, pair_col, gp_ws, tk_bound, tk_cnt, tk_cand, small, ap, valid, first, tki, tkd;
+      cand_rows, cand_gid, cand_gcam, gp_rows, pair_col, gp_ws, tk_bound, tk_cnt, tk_cand, small, ap, valid, first, tki, tkd,
+      thr_tab, tpair_tab, cnt_tab, dstar, gstar;
   cudaEvent_t ev_a = nullptr, ev_rows = nullptr;
   cudaEvent_t ev_t[kPassTimedLaunches][2] = {};
   int n_timed = 0, timed_kind[kPassTimedLaunches] = {};
@@ -103,7 +106,7 @@ struct PassState {
   void release() {
     GrowBuf* bufs[] = {&qs, &qn, &gs, &gn, &dist, &tdist, &ts, &tn, &pair_ws, &pair_off, &totals, &pair_q, &pair_g, &pair_pos,
                        &pair_d, &packed, &pf_ws, &cand_rows, &cand_gid, &cand_gcam, &gp_rows, &pair_col, &gp_ws, &tk_bound,
-                       &tk_cnt, &tk_cand, &small, &ap, &valid, &first, &tki, &tkd};
+                       &tk_cnt, &tk_cand, &small, &ap, &valid, &first, &tki, &tkd, &thr_tab, &tpair_tab, &cnt_tab, &dstar, &gstar};
     for (GrowBuf* b : bufs) b->release();
     if (ev_a) cudaEventDestroy(ev_a);
     if (ev_rows) cudaEventDestroy(ev_rows);

@@ -30,6 +30,11 @@ constexpr int kABytes = kBM * kBK * 2;               // 16 KB
 constexpr int kBBytes = kBN * kBK * 2;               // 32 KB
 constexpr int kStageBytesG = kABytes + kBBytes;      // 48 KB
 constexpr int kGemmThreads = 192;
+// the counting epilogue runs on EIGHT epilogue warps: two per TMEM lane group, each taking one 128-column half of the tile.
+// With one warp per scheduler every dependent instruction of its ~30-instruction-per-element search cost its full latency
+// and the epilogue (46 k cycles per tile) stuck out from under the single-plane mainloop (35 k).
+constexpr int kRankThreads = 64 + 8 * 32;
+template <int EPI> constexpr int gemm2_threads() { return EPI == EPI_RANK ? kRankThreads : kGemmThreads; }
 constexpr size_t kGemmSmem = 1024 /*align slack*/ + (size_t)kGemmStages * kStageBytesG + 256 /*barriers*/;
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -221,8 +226,8 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
   unsigned char* after_ring = smem + (EPI == EPI_RANK ? (size_t)stages * stage_bytes : (size_t)kRing2Bytes);
   unsigned char* stage_out = after_ring;
   float* thr_s = reinterpret_cast<float*>(after_ring);                               // [p_cap][128]
-  uint32_t* cnt_s = reinterpret_cast<uint32_t*>(after_ring + (size_t)rf.p_cap * 512); // [p_cap / 2][128], two u16 per word
-  float* bn_s = reinterpret_cast<float*>(after_ring + (EPI == EPI_RANK ? (size_t)rf.p_cap * 768 : (size_t)kOutStageBytes));
+  uint32_t* cnt_s = reinterpret_cast<uint32_t*>(after_ring + (size_t)rf.p_cap * 512); // [p_cap + 1][128]; row p_cap takes what is not counted
+  float* bn_s = reinterpret_cast<float*>(after_ring + (EPI == EPI_RANK ? (size_t)rf.p_cap * 1024 + 512 : (size_t)kOutStageBytes));
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(bn_s) + 2 * 256 * 4);
   uint64_t* empty = full + kMaxStages2;
   uint64_t* tfull = empty + kMaxStages2;      // [2]
@@ -230,6 +235,8 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const GemmArgs& g = ga.g;
+  constexpr int kEpiWarps = EPI == EPI_RANK ? 8 : 4;
+  constexpr int kEpiThreads = kEpiWarps * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();                 // rank in the cluster (0..1, or 0..3 with CL4)
   const uint32_t rank = crank & 1u;                         // rank in the CTA pair
@@ -248,7 +255,7 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 8);   // 4 epilogue warps x 2 CTAs
+      mbar_init(&tempty[s], 2 * kEpiWarps);   // the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -332,9 +339,10 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
     // EPI_DIST / EPI_AFFINE_RELU: TMEM -> registers (thread = row) -> value -> 128B-swizzled staging tile in shared
     // memory -> one TMA store per 32 x 32 chunk (coalesced, clipped at the matrix edges by the tensor map).
     // EPI_RANK: TMEM -> registers -> distance -> lower bound among the row's thresholds -> private counter.
-    const int lane_grp = warp & 3;
+    const int lane_grp = warp & 3;              // the TMEM lanes a warp may read: 32 * (warp % 4) ..
     const int row = lane_grp * 32 + lane;
-    const int etid = (int)threadIdx.x - 64;     // 0..127 among the epilogue threads
+    const int etid = (int)threadIdx.x - 64;     // 0 .. kEpiThreads - 1 among the epilogue threads
+    const int col_half = EPI == EPI_RANK ? ((warp - 2) >> 2) : 0;    // EPI_RANK: which 128 columns of the tile this warp takes
     uint32_t acc_it = 0, chunk_it = 0;
     const bool want_sq = (g.flags & PPS_DIST_SQUARED) != 0;
     const bool want_dot = (g.flags & PPS_DIST_DOT) != 0;
@@ -347,7 +355,8 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
     long long gstar = 0;
     uint32_t tie_corr = 0;
     float piv1 = 0.f, piv2a = 0.f, piv2b = 0.f; // thresholds probed by the first two search levels
-    int tiles_since_flush = 0;                  // a 16-bit counter takes <= 256 increments per tile
+    uint32_t rk_bound = 0u;                     // top-k admission bound of this row (EPI_RANK with candidate lists)
+    const bool rk_admit = EPI == EPI_RANK && rf.tk_cand != nullptr;
     long long tab_base = 0;                     // element offset of (row group, j = 0, this row) in the global tables
     TileWalk<EPI> w(ga, pair, npairs);
     for (; w.next(); ++acc_it) {
@@ -358,14 +367,17 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
       const uint32_t as = sep ? 0u : (acc_it & 1u), aph = sep ? (acc_it & 1u) : ((acc_it >> 1) & 1u);
       const long long gi = (long long)m0 + row;
       if (EPI == EPI_RANK && w.run_start) {
-        // this thread's row of the threshold table -> shared memory (only this thread ever reads it), counters = 0
+        // this row of the threshold table -> shared memory.  The two threads of a row (one per column half) write the same
+        // values and each reads after its own writes; the counters are zero here: zeroed at kernel start, re-zeroed by every
+        // flush, and the barrier before a flush keeps this block behind the last use of the previous run's tables
         tab_base = ((long long)(m0 >> 7) * p_cap) * 128 + row;
         for (int j = 0; j < p_cap; ++j) thr_s[j * 128 + row] = __ldg(rf.thr_tab + tab_base + (long long)j * 128);
-        for (int j = 0; j < p_cap / 2; ++j) cnt_s[j * 128 + row] = 0u;
+        if (acc_it == 0)
+          for (int j = col_half; j < p_cap; j += 2) cnt_s[j * 128 + row] = 0u;
         dstar = gi < g.m1 ? __ldg(rf.dstar + gi) : __int_as_float(0x7fc00000);
         gstar = gi < g.m1 ? (long long)__ldg(rf.gstar + gi) : 0;
+        rk_bound = (rf.tk_cand != nullptr && gi < g.m1) ? __ldg(rf.tk_bound + gi) : 0u;
         tie_corr = 0;
-        tiles_since_flush = 0;
         const int h1 = p_cap >> 1, h2 = (p_cap - h1) >> 1;
         piv1 = thr_s[(h1 - 1) * 128 + row];
         piv2a = thr_s[(h2 - 1) * 128 + row];
@@ -386,14 +398,14 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
         const long long gj = (long long)n0 + etid;
         if (!want_dot) {
           bn[etid] = gj < g.m2 ? __ldg(g.b_sqnorm + gj) : 0.f;
-          if (BN > 128) bn[etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_sqnorm + gj + 128) : 0.f;
+          if (BN > kEpiThreads) bn[etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_sqnorm + gj + 128) : 0.f;
         }
         if (scaled) {
           bn_s[256 + etid] = gj < g.m2 ? __ldg(g.b_scale + gj) : 0.f;
           if (BN > 128) bn_s[256 + etid + 128] = gj + 128 < g.m2 ? __ldg(g.b_scale + gj + 128) : 0.f;
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       const float an = (EPI != EPI_AFFINE_RELU && gi < g.m1 && !want_dot) ? __ldg(g.a_sqnorm + gi) : 0.f;
       const float cs = (scaled && gi < g.m1) ? -2.f * __ldg(g.a_scale + gi) : -2.f;    // -2 / s_a
       uint32_t tk_bound = 0u;                  // EPI_DIST_TOPK: nothing is admitted for padding rows
@@ -401,8 +413,9 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + as * BN + ((uint32_t)(lane_grp * 32) << 16);
+      const int c_first = EPI == EPI_RANK ? col_half * 128 : 0, c_stop = EPI == EPI_RANK ? c_first + 128 : BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32, ++chunk_it) {
+      for (int c = c_first; c < c_stop; c += 32, ++chunk_it) {
         uint32_t r[32];
         tmem_ld_32x32(tbase + c, r);
         if (EPI == EPI_RANK) {
@@ -423,42 +436,67 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
               d[4 * j + e] = want_sq ? d2 : sqrt_approx(d2);
             }
           }
-          // lower bound of every element among this row's thresholds: 32 independent searches per step, the first
-          // two levels against pivots held in registers
-          int lo[32];
+          // lower bound of every element among this row's thresholds: 32 independent searches per step, the first two
+          // levels against pivots held in registers.  The position is kept as the BYTE offset of (threshold lo, this row)
+          // in the [threshold][row] tables, so that a probe is one LDS at (uniform base + offset) and the counter of the
+          // result sits at the same offset of the counter table.
+          uint32_t off[32];
           const int half1 = p_cap >> 1, half2 = (p_cap - half1) >> 1;
+          const uint32_t row_off = (uint32_t)row * 4u, h1o = (uint32_t)half1 * 512u, h2o = (uint32_t)half2 * 512u;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const bool up = piv1 < d[e];
-            lo[e] = up ? half1 : 0;
-            lo[e] += ((up ? piv2b : piv2a) < d[e]) ? half2 : 0;
+            off[e] = row_off + (up ? h1o : 0u);
+            off[e] += ((up ? piv2b : piv2a) < d[e]) ? h2o : 0u;
           }
+          const uint32_t thr_base = smem_u32(thr_s);
           int len = p_cap - half1 - half2;
           while (len > 1) {
             const int half = len >> 1;
-            const float* probe = thr_s + (half - 1) * 128 + row;
+            const uint32_t probe = thr_base + (uint32_t)(half - 1) * 512u, step = (uint32_t)half * 512u;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) lo[e] += (probe[lo[e] * 128] < d[e]) ? half : 0;
+            for (int e = 0; e < 32; ++e) off[e] += (lds_f32(probe + off[e]) < d[e]) ? step : 0u;
             len -= half;
           }
           bool tie = false;
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            lo[e] += (thr_s[lo[e] * 128 + row] < d[e]) ? 1 : 0;
+            off[e] += (lds_f32(thr_base + off[e]) < d[e]) ? 512u : 0u;
             tie |= (d[e] == dstar);
           }
-          // one fire-and-forget shared-memory add per element on the thread's own 16-bit counter (no read-back, so no
-          // dependent chain); columns past the block end and elements beyond every threshold add nothing
+          // one fire-and-forget shared-memory add per element (no read-back, so no dependent chain).  An element beyond every
+          // threshold lands in row p_cap of the counter table, which nobody reads; so do the columns past the block's end.
+          const uint32_t cnt_base = smem_u32(cnt_s);
+          if (valid_cols >= 32) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int b = min(lo[e], p_cap - 1);             // branch-free: an uncounted element adds 0
-            const uint32_t inc = (e < valid_cols && lo[e] < p_cap) ? (1u << ((b & 1) << 4)) : 0u;
-            atomicAdd(cnt_s + (b >> 1) * 128 + row, inc);
+            for (int e = 0; e < 32; ++e) red_shared_add_u32(cnt_base + off[e], 1u);
+          } else {
+            const uint32_t dump = row_off + (uint32_t)p_cap * 512u;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) red_shared_add_u32(cnt_base + (e < valid_cols ? off[e] : dump), 1u);
           }
           if (tie) {                                         // exact ties with the nearest positive: rare
 #pragma unroll                                               // (unrolled: a runtime index would push d[] to local memory)
             for (int e = 0; e < 32; ++e)
               if (e < valid_cols && d[e] == dstar) tie_corr += ((colg + e) < gstar ? 1u : 0u) - 1u;
+          }
+          if (rk_admit) {
+            // top-k admission, as EPI_DIST_TOPK: one compare per element against the row's k-th best so far (distances
+            // are >= 0: their bits order like the values); almost never true once a bound exists
+            bool hit = false;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) hit |= __float_as_uint(d[e]) <= rk_bound;
+            if (hit && gi < g.m1) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                if (__float_as_uint(d[e]) <= rk_bound && e < valid_cols) {
+                  const uint32_t slot = atomicAdd(rf.tk_cnt + gi, 1u);
+                  if (slot < (uint32_t)rf.tk_cap)
+                    rf.tk_cand[(long long)gi * rf.tk_cap + slot] =
+                        ((unsigned long long)__float_as_uint(d[e]) << 32) | (unsigned long long)(uint32_t)(colg + e);
+                }
+              }
+            }
           }
         } else {
           unsigned char* buf = my_stage + (chunk_it & 1u) * kOutChunkBytes;
@@ -535,22 +573,19 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
         if (rank == 0) mbar_arrive(&tempty[as]);
         else mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[as]), lead));
       }
-      if (scaled || sep) asm volatile("bar.sync 1, 128;" ::: "memory");   // every warp is done with bn / sc of this tile
-      if (EPI == EPI_RANK && (w.run_end || ++tiles_since_flush == 255)) {
-        // counters -> global table at the end of the run (a handful of CTA pairs share a row: atomics), and every 255
-        // tiles in between so that no 16-bit counter can wrap
-        tiles_since_flush = 0;
-        for (int j = 0; j < p_cap / 2; ++j) {
+      if (scaled || sep) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // every warp is done with bn / sc of this tile
+      if (EPI == EPI_RANK && w.run_end) {
+        // counters -> global table at the end of the run (a handful of CTA pairs share a row: atomics).  Both threads of a
+        // row must be done with the tile first; each then flushes (and re-zeroes) every other counter.
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        for (int j = col_half; j < p_cap; j += 2) {
           const uint32_t v = cnt_s[j * 128 + row];
           if (v) {
             cnt_s[j * 128 + row] = 0u;
-            if (gi < g.m1) {
-              if (v & 0xffffu) atomicAdd(rf.cnt_tab + tab_base + (long long)(2 * j) * 128, v & 0xffffu);
-              if (v >> 16) atomicAdd(rf.cnt_tab + tab_base + (long long)(2 * j + 1) * 128, v >> 16);
-            }
+            if (gi < g.m1) atomicAdd(rf.cnt_tab + tab_base + (long long)j * 128, v);
           }
         }
-        if (w.run_end && gi < g.m1 && tie_corr) atomicAdd(rf.cnt_first + gi, tie_corr);
+        if (gi < g.m1 && tie_corr) atomicAdd(rf.cnt_first + gi, tie_corr);
       }
     }
     if (EPI != EPI_RANK) bulk_wait_group_read<0>();
@@ -565,7 +600,7 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
 }
 
 template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm2_threads<EPI>(), 1)
 dist_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ Gemm2Args ga,
                 const __grid_constant__ RankFuse rf) {
@@ -994,12 +1029,14 @@ extern "C" int pps_embed_tc(const void* x_planes /*[planes][K*N][kpad]*/, int x_
 // are already known (pps_rank_tab_prep).  The [m1, m2] distance block is never written: the epilogue turns every
 // distance into one increment of cnt_tab and, for exact ties with the nearest positive, of cnt_first.
 // ------------------------------------------------------------------------------------
-extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
-                                long long a_plane_rows, const void* b_planes, const float* b_sqnorm, long long m2,
-                                int b_planes_n, long long b_plane_rows, int dim, int precision, int flags,
-                                long long col0, int p_cap, const float* thr_tab, uint32_t* cnt_tab, const float* dstar,
-                                const int32_t* gstar, uint32_t* cnt_first, void* stream) {
+extern "C" int pps_dist_rank_topk_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
+                                     long long a_plane_rows, const void* b_planes, const float* b_sqnorm, long long m2,
+                                     int b_planes_n, long long b_plane_rows, int dim, int precision, int flags,
+                                     long long col0, int p_cap, const float* thr_tab, uint32_t* cnt_tab, const float* dstar,
+                                     const int32_t* gstar, uint32_t* cnt_first, const uint32_t* tk_bound, uint32_t* tk_cnt,
+                                     uint64_t* tk_cand, int tk_cap, void* stream) {
   if (m1 < 0 || m2 < 0 || dim <= 0 || col0 < 0) return PPS_ERR_INVALID_ARG;
+  if (tk_cand && (!tk_bound || !tk_cnt || tk_cap <= 0)) return PPS_ERR_INVALID_ARG;
   if (p_cap < 8 || p_cap > 64 || (p_cap & 7)) return PPS_ERR_INVALID_ARG;
   if (flags & ~PPS_DIST_SQUARED) return PPS_ERR_INVALID_ARG;
   if (a_plane_rows == 0) a_plane_rows = m1;
@@ -1032,9 +1069,9 @@ extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, lon
   ga.planes = need;
   ga.sep_small = 0;
   ga.groups = 1; ga.a_group_rows = 0; ga.b_group_rows = 0; ga.out_group_cols = 0;
-  // shared memory: ring | thresholds [p_cap][128] f32 | counters [p_cap/2][128] u32 | |b|^2 [2][256] | barriers
+  // shared memory: ring | thresholds [p_cap][128] f32 | counters [p_cap + 1][128] u32 | |b|^2 [2][256] | barriers
   const int stage_bytes = 2 * need * kTile2Bytes;
-  const int tail = p_cap * 768 + 2 * 256 * 4 + 256;
+  const int tail = p_cap * 1024 + 512 + 2 * 256 * 4 + 256;
   int stages = (227 * 1024 - tail) / stage_bytes;
   if (stages > kMaxStages2) stages = kMaxStages2;
   if (stages < 2) return PPS_ERR_UNSUPPORTED;
@@ -1048,6 +1085,8 @@ extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, lon
   RankFuse rf;
   rf.thr_tab = thr_tab; rf.cnt_tab = cnt_tab; rf.dstar = dstar; rf.gstar = gstar; rf.cnt_first = cnt_first;
   rf.col0 = col0; rf.p_cap = p_cap;
+  rf.tk_bound = tk_cand ? tk_bound : nullptr; rf.tk_cnt = tk_cand ? tk_cnt : nullptr;
+  rf.tk_cand = reinterpret_cast<unsigned long long*>(tk_cand); rf.tk_cap = tk_cand ? tk_cap : 0;
   static thread_local int configured_dev = -1;
   int dev = 0;
   PPS_CUDA_TRY(cudaGetDevice(&dev));
@@ -1059,8 +1098,18 @@ extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, lon
   const long long tiles = (long long)g.m_tiles * g.n_tiles;
   const long long slots = sms / 2;
   const long long pairs = tiles < slots ? tiles : slots;
-  dist_tc2_kernel<256, EPI_RANK><<<(unsigned)(2 * pairs), kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+  dist_tc2_kernel<256, EPI_RANK><<<(unsigned)(2 * pairs), kRankThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       tmA, tmB, tmA /*no output map*/, ga, rf);
   PPS_LAUNCH_CHECK("dist_tc2_kernel<rank>");
   return PPS_OK;
+}
+
+extern "C" int pps_dist_rank_tc(const void* a_planes, const float* a_sqnorm, long long m1, int a_planes_n,
+                                long long a_plane_rows, const void* b_planes, const float* b_sqnorm, long long m2,
+                                int b_planes_n, long long b_plane_rows, int dim, int precision, int flags,
+                                long long col0, int p_cap, const float* thr_tab, uint32_t* cnt_tab, const float* dstar,
+                                const int32_t* gstar, uint32_t* cnt_first, void* stream) {
+  return pps_dist_rank_topk_tc(a_planes, a_sqnorm, m1, a_planes_n, a_plane_rows, b_planes, b_sqnorm, m2, b_planes_n,
+                               b_plane_rows, dim, precision, flags, col0, p_cap, thr_tab, cnt_tab, dstar, gstar, cnt_first,
+                               nullptr, nullptr, nullptr, 0, stream);
 }

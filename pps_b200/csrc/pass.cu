@@ -365,6 +365,17 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
   }
   const int32_t* dn_pairs = spec ? d_tot : nullptr;
   const size_t np1 = (size_t)std::max<long long>(p.n_pairs, 1);
+  // single-plane operands, several blocks: the blocks after the first take the counting epilogue (+ admission) and are never
+  // written.  (With a 2-plane split the threshold tables would cost the operand ring a stage, and the 3-term mainloop
+  // gains nothing from a lighter epilogue: those keep block + count kernel.)
+  {
+    const int need = spec ? hn.max_pairs + 8 : p.max_pairs;
+    p.fused = p.n_blocks > 1 && p.planes == 1 && p.n_pairs > 0 && need <= 64 && !(flags & PPS_PASS_NO_FUSED_COUNT) &&
+              (topk == 0 || p.epi_topk);
+    p.p_cap = std::max(8, (need + 7) / 8 * 8);
+  }
+  PPS_TRY(p.small.ensure(16));
+  PPS_CUDA_TRY(cudaMemsetAsync(p.small.p, 0, 16, ss));
   PPS_TRY(p.pair_q.ensure(np1 * 4));
   PPS_TRY(p.pair_g.ensure(np1 * 4));
   PPS_TRY(p.pair_pos.ensure(np1));
@@ -394,8 +405,6 @@ extern "C" int pps_pass_begin(pps_ctx* c, const void* d_q, long long nq, const v
       PPS_TRY(p.tk_bound.ensure((size_t)nq * 4));
       PPS_TRY(p.tk_cnt.ensure((size_t)nq * 4));
       PPS_TRY(p.tk_cand.ensure((size_t)nq * p.tk_cap * 8));
-      PPS_TRY(p.small.ensure(16));
-      PPS_CUDA_TRY(cudaMemsetAsync(p.small.p, 0, 16, ss));
     }
   }
   // several blocks: the thresholds come from one product with the compacted same-id rows of this shard
@@ -515,6 +524,18 @@ extern "C" int pps_pass_count(pps_ctx* c, const void* d_gathered_x1, void* strea
     return pps_rank_count(p.dist.as<float>(), p.ldd, p.nq, rows, col0, p.pair_off.as<int32_t>(), p.pair_g.as<int32_t>(),
                           p.pair_pos.as<uint8_t>(), p.pair_d.as<float>(), p.max_pairs, p.cnt_le(), p.cnt_first(), cs);
   };
+  if (p.fused) {                       // tables of the counting epilogue from the (now global) thresholds
+    const size_t elems = (size_t)pps_rank_tab_elems(p.nq, p.p_cap);
+    PPS_TRY(p.thr_tab.ensure(elems * 4));
+    PPS_TRY(p.tpair_tab.ensure(elems * 4));
+    PPS_TRY(p.cnt_tab.ensure(elems * 4));
+    PPS_TRY(p.dstar.ensure((size_t)p.nq * 4));
+    PPS_TRY(p.gstar.ensure((size_t)p.nq * 4));
+    TimedLaunch t(c, cs, 4);
+    PPS_TRY(pps_rank_tab_prep(p.nq, p.pair_off.as<int32_t>(), p.pair_g.as<int32_t>(), p.pair_pos.as<uint8_t>(),
+                              p.pair_d.as<float>(), p.p_cap, p.thr_tab.as<float>(), p.tpair_tab.as<int32_t>(),
+                              p.cnt_tab.as<uint32_t>(), p.dstar.as<float>(), p.gstar.as<int32_t>(), p.small.as<int32_t>() + 1, cs));
+  }
   for (int b = 0; b < p.n_blocks; ++b) {
     const long long r0 = p.blk_row0[b], rows = p.blk_rows[b], col0 = p.offset + r0;
     if (b == 0) {                      // its distance block was enqueued by pps_pass_begin
@@ -523,7 +544,26 @@ extern "C" int pps_pass_count(pps_ctx* c, const void* d_gathered_x1, void* strea
     }
     const void* gp = nullptr;
     PPS_TRY(split_block(c, b, r0, rows, cs, &gp));
-    if (p.epi_topk) {
+    if (p.fused) {
+      if (p.epi_topk && b == 1)
+        PPS_TRY(pps_topk_bound(reinterpret_cast<const uint64_t*>(p.keys()), p.nq, p.topk, p.tk_bound.as<uint32_t>(),
+                               p.tk_cnt.as<uint32_t>(), cs));
+      {
+        TimedLaunch t(c, cs, 2);
+        PPS_TRY(pps_dist_rank_topk_tc(p.qs.p, p.qn.as<float>(), p.nq, p.planes, 0, gp, p.gn.as<float>(), rows, p.planes, 0,
+                                      p.dim, p.precision, 0, col0, p.p_cap, p.thr_tab.as<float>(), p.cnt_tab.as<uint32_t>(),
+                                      p.dstar.as<float>(), p.gstar.as<int32_t>(), p.cnt_first(),
+                                      p.epi_topk ? p.tk_bound.as<uint32_t>() : nullptr,
+                                      p.epi_topk ? p.tk_cnt.as<uint32_t>() : nullptr,
+                                      p.epi_topk ? p.tk_cand.as<uint64_t>() : nullptr, p.tk_cap, cs));
+      }
+      if (p.epi_topk) {
+        TimedLaunch t(c, cs, 4);
+        PPS_TRY(pps_topk_merge(reinterpret_cast<uint64_t*>(p.keys()), p.nq, p.topk, p.tk_cand.as<uint64_t>(), p.tk_cap,
+                               p.tk_cnt.as<uint32_t>(), p.tk_bound.as<uint32_t>(), p.pair_off.as<int32_t>(),
+                               p.pair_g.as<int32_t>(), p.pair_pos.as<uint8_t>(), p.max_pairs, 1, p.small.as<int32_t>(), cs));
+      }
+    } else if (p.epi_topk) {
       if (b == 1)
         PPS_TRY(pps_topk_bound(reinterpret_cast<const uint64_t*>(p.keys()), p.nq, p.topk, p.tk_bound.as<uint32_t>(),
                                p.tk_cnt.as<uint32_t>(), cs));
@@ -538,6 +578,12 @@ extern "C" int pps_pass_count(pps_ctx* c, const void* d_gathered_x1, void* strea
       PPS_TRY(distance_block(c, gp, rows, col0, false, cs));
       PPS_TRY(count_block(rows, col0, p.topk > 0));
     }
+  }
+  if (p.fused) {                       // counters of the tables -> cnt_le of the pairs; a query with more positives than the
+    TimedLaunch t(c, cs, 4);           // tables hold (only a speculative pass can meet one) -> flags[1]: the pass is repeated
+    PPS_TRY(pps_rank_tab_finish(p.nq, p.p_cap, p.tpair_tab.as<int32_t>(), p.cnt_tab.as<uint32_t>(), p.cnt_le(), cs));
+    pass_or_flag_kernel<<<1, 32, 0, cs>>>(p.small.as<int32_t>() + 1, p.flags_dev() + 1);
+    PPS_LAUNCH_CHECK("pass_or_flag_kernel");
   }
   if (p.speculative) {                 // bounds of the speculative layout -> flags[1] (summed over ranks by the exchange)
     pass_check_bounds_kernel<<<1, 32, 0, cs>>>(p.totals.as<int32_t>(), (int32_t)p.n_pairs, (int32_t)p.max_pairs,
@@ -638,6 +684,21 @@ extern "C" int pps_pass_end(pps_ctx* c, const void* d_gathered, int cmc_topk, vo
     out_cmc[k] = run / (double)n_valid;
   }
   return PPS_OK;
+}
+
+// What the last pps_pass_begin decided (tests, bench records): 0 blocks of the local shard, 1 counting epilogue used for the
+// blocks after the first, 2 speculative layout, 3 thresholds per query in the epilogue tables, 4 top-k admission in the epilogue.
+extern "C" long long pps_pass_stat(const pps_ctx* c, int which) {
+  if (!c) return -1;
+  const PassState& p = c->pass;
+  switch (which) {
+    case 0: return p.n_blocks;
+    case 1: return p.fused ? 1 : 0;
+    case 2: return p.speculative ? 1 : 0;
+    case 3: return p.fused ? p.p_cap : 0;
+    case 4: return p.epi_topk ? 1 : 0;
+    default: return -1;
+  }
 }
 
 // Host sources of the NEXT pps_pass_begin: its d_q / d_g arguments are then device STAGING buffers the call fills from

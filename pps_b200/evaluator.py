@@ -655,6 +655,10 @@ class RankEngine:
         self._c_fixed = {}
         self.fused_topk = True           # blocks after the first: top-k admission in the distance epilogue
         self.used_fused_topk = False
+        self.fused_count = os.environ.get("PPS_NO_FUSED_COUNT", "0") != "1"   # C pass, single-plane operands (fp16 rows), several blocks: counters AND top-k admission
+                                         # in the distance epilogue, so no block after the first is written (pps_dist_rank_topk_tc)
+        self.used_fused_count = False
+        self.pass_blocks = 0
         self._tk = None
         self.fused_rank = False          # counters in the epilogue of the distance kernel (no distance block written):
                                          # bit-identical, saves the block's memory, but measured slower than block +
@@ -786,6 +790,8 @@ class RankEngine:
             import torch.distributed as dist_mod
             world, rank = dist_mod.get_world_size(self.group), dist_mod.get_rank(self.group)
         flags = (0 if self.fused_topk else _lib.PASS_NO_EPILOGUE_TOPK) | ((int(self.tk_cap) & 0xffff) << 8)
+        if not self.fused_count:
+            flags |= _lib.PASS_NO_FUSED_COUNT
         tr = self.trace                  # optional: CUDA events + host clocks around the segments of the pass (tools/pass_trace.py)
         import time as _time
 
@@ -839,6 +845,8 @@ class RankEngine:
                                   _lib.ptr(ap), _lib.ptr(valid), _lib.ptr(first), _lib.ptr(ti), _lib.ptr(td))
             mark("end_done")
             self.used_fused_topk = bool(topk and not (flags & _lib.PASS_NO_EPILOGUE_TOPK))
+            self.used_fused_count = bool(lib.pps_pass_stat(ctx, 1) == 1)
+            self.pass_blocks = int(lib.pps_pass_stat(ctx, 0))      # (the C plan also splits a gallery that fits one block)
             if rc == _lib.PPS_ERR_PASS_RESIZE and not (flags & _lib.PASS_SIZING):
                 # the speculative size bounds (taken from the last sizing pass of this shape) were too small - the ids
                 # changed: every rank sees the same flag and repeats the pass as a sizing pass

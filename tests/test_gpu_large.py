@@ -32,6 +32,15 @@ def _large_case(ng, dtype_name, block_bytes_list, sigma=4.0, n_slice=64):
         eng = evaluator.RankEngine(qid, gid, qcam, gcam, nq=NQ, ng_local=ng, dim=DIM, topk=TOPK, device=dev,
                                    max_block_bytes=bb, in_dtype=tdt)
         results.append((eng.n_chunks, eng.run(q, g)))
+        # fp16 rows are single-plane operands: the blocks after the first take the counting epilogue (never written)
+        assert eng.used_fused_count == (dtype_name == "fp16" and eng.pass_blocks > 1)
+        del eng
+    if dtype_name == "fp16":         # ... and the same blocks written and counted by pps_rank_count give the same bits
+        eng = evaluator.RankEngine(qid, gid, qcam, gcam, nq=NQ, ng_local=ng, dim=DIM, topk=TOPK, device=dev,
+                                   max_block_bytes=block_bytes_list[-1], in_dtype=tdt)
+        eng.fused_count = False
+        results.append((eng.n_chunks, eng.run(q, g)))
+        assert not eng.used_fused_count
         del eng
     assert results[0][0] == 1 and all(n > 1 for n, _ in results[1:]), [n for n, _ in results]
     one = results[0][1]

@@ -249,3 +249,27 @@ def test_single_call_path_equals_pass(golden, name):
     two = _engine(evaluator, d, q, g)
     assert not two.use_c_path and two.use_c_pass
     _same(one.run(q, g), two.run(q, g), 0)
+
+
+@pytest.mark.parametrize("name", ["small_mid", "dup_ties", "some_invalid", "many_pos"])
+@pytest.mark.parametrize("topk", [0, 13])
+def test_counting_epilogue_equals_block_and_count_kernel(golden, name, topk):
+    """fp16 rows (single-plane operands), several blocks: the blocks after the first take the counting epilogue with top-k
+    admission (pps_dist_rank_topk_tc: no distance block is written); PPS_PASS_NO_FUSED_COUNT writes and counts them.  Same
+    bits, on a first (sizing) pass and on the speculative passes after it."""
+    import torch
+    from pps_b200 import evaluator
+    d = golden(name)
+    q, g = torch.from_numpy(d["q"]).cuda().half(), torch.from_numpy(d["g"]).cuda().half()
+    bb = q.shape[0] * 256 * 4
+    ref = _engine(evaluator, d, q, g, topk=topk, max_block_bytes=bb, in_dtype=torch.float16)
+    ref.fused_count = False
+    want = ref.run(q, g)
+    assert not ref.used_fused_count
+    eng = _engine(evaluator, d, q, g, topk=topk, max_block_bytes=bb, in_dtype=torch.float16)
+    for _ in range(3):
+        got = eng.run(q, g)
+        _same(got, want, topk)
+    per_query = np.array([(d["gid"] == i).sum() for i in d["qid"]])
+    # the epilogue tables hold <= 64 thresholds per query (speculative passes plan for 8 more than the last sizing pass saw)
+    assert eng.used_fused_count == (eng.pass_blocks > 1 and 0 < per_query.max() <= 56), (eng.pass_blocks, per_query.max())
