@@ -61,15 +61,23 @@ constexpr int EPI_RANK = 2;          // distance as EPI_DIST, consumed by the co
 constexpr int EPI_DIST_TOPK = 3;     // EPI_DIST + one compare per element against the row's top-k admission bound
 
 // Tile order.  EPI_DIST / EPI_AFFINE_RELU: tile t = pair, pair + npairs, ... with the m index fastest, so that the
-// CTA pairs running concurrently share B tiles in L2.  EPI_RANK: every CTA pair keeps ONE m tile (its rows'
-// thresholds and counters stay in shared memory) and walks a contiguous range of n tiles; the pairs that own the
-// other m tiles walk the same n range at the same pace, which keeps the L2 sharing of B.  With more m tiles than
-// pairs the schedule repeats per "superblock" of npairs m tiles.
+// CTA pairs running concurrently share B tiles in L2.  EPI_RANK: a CTA pair keeps ONE m tile per run (its rows'
+// thresholds and counters stay in shared memory) and walks a contiguous range of n tiles.
+//   npairs >= m_tiles: k = npairs / m_tiles pairs per m tile walk n tiles [0, Na) in k aligned parts - the pairs that own
+//     the other m tiles walk the same n range at the same pace, which keeps the L2 sharing of B - and the X = npairs % m_tiles
+//     pairs left over share the columns [Na, n_tiles) of ALL m tiles (m-major, a few runs each); Na = n_tiles * k * m_tiles /
+//     npairs makes every pair's tile count equal to within one run's rounding.  (Round 1 gave the X pairs to X of the m
+//     tiles: 6 owners against 5 at 14 m tiles x 74 pairs, 5.7 % of the kernel lost to the imbalance.)
+//   npairs < m_tiles: the schedule repeats per "superblock" of npairs m tiles, remainders as in round 1.
 template <int EPI>
 struct TileWalk {
   long long t, tiles, tiles_per_group, npairs, pair;
   int m_tiles, n_tiles;
   int sb, n_sb, n_cur, n_stop;
+  // balanced EPI_RANK schedule (npairs >= m_tiles)
+  bool balanced, extra;
+  int n_first, n_a, n_b;
+  long long lin_cur, lin_first, lin_stop;
   // outputs
   long long grp;
   int m_tile, n_tile;
@@ -83,6 +91,24 @@ struct TileWalk {
     t = pair - npairs;
     sb = -1; n_sb = (int)((m_tiles + npairs - 1) / npairs); n_cur = 0; n_stop = 0;
     grp = 0; m_tile = 0; n_tile = 0; run_start = run_end = false;
+    balanced = false; extra = false; n_first = 0; n_a = n_tiles; n_b = 0; lin_cur = lin_first = lin_stop = 0;
+    if (EPI == EPI_RANK && m_tiles > 0 && npairs >= m_tiles) {
+      balanced = true;
+      const long long k = npairs / m_tiles, aligned = k * m_tiles, x = npairs - aligned;
+      n_a = x == 0 ? n_tiles : (int)(((long long)n_tiles * aligned + npairs - 1) / npairs);
+      n_b = n_tiles - n_a;
+      if (pair < aligned) {
+        m_tile = (int)(pair % m_tiles);
+        const long long i = pair / m_tiles;
+        n_first = n_cur = (int)((long long)n_a * i / k);
+        n_stop = (int)((long long)n_a * (i + 1) / k);
+      } else {
+        extra = true;
+        const long long e = pair - aligned, total = (long long)m_tiles * n_b;
+        lin_first = lin_cur = total * e / x;
+        lin_stop = total * (e + 1) / x;
+      }
+    }
   }
   __host__ __device__ bool next() {
     if (EPI != EPI_RANK) {
@@ -92,6 +118,22 @@ struct TileWalk {
       const long long tt = t % tiles_per_group;
       m_tile = (int)(tt % m_tiles);
       n_tile = (int)(tt / m_tiles);
+      return true;
+    }
+    if (balanced) {
+      if (!extra) {
+        if (n_cur >= n_stop) return false;
+        run_start = n_cur == n_first;
+        n_tile = n_cur++;
+        run_end = n_cur >= n_stop;
+        return true;
+      }
+      if (lin_cur >= lin_stop) return false;
+      m_tile = (int)(lin_cur / n_b);
+      n_tile = n_a + (int)(lin_cur % n_b);
+      run_start = lin_cur == lin_first || n_tile == n_a;
+      ++lin_cur;
+      run_end = lin_cur >= lin_stop || n_tile == n_tiles - 1;
       return true;
     }
     run_start = false;

@@ -287,3 +287,7 @@ def test_tile_schedules_visit_every_tile_exactly_once():
                 if rank_order and cnt:
                     assert prev[2]                                              # the last tile closes its run
             assert len(seen) == total, (m_tiles, n_tiles, groups, npairs, rank_order, len(seen), total)
+            if rank_order and npairs >= m_tiles:
+                # balanced: no pair carries more than the mean + one tile per run (round 1: 498 against 471 at 14 x 2 490 x 74)
+                per_pair = np.bincount(np.array(list(seen.values())), minlength=npairs)
+                assert per_pair.max() <= total / npairs + m_tiles / max(npairs % m_tiles, 1) + 2, (m_tiles, n_tiles, npairs, per_pair.max())
