@@ -15,6 +15,9 @@ Pinning status
     tests/golden/pool_*.npz (oracle/make_golden_pool.py) hold what they return; this file reproduces them bit for
     bit.  The arithmetic inside the six stock operators stays a restatement of their published semantics
     (**parity unpinned** in that sense).
+  * triplet-mining ops: pinned to the reference's own operators - batch_hard_op.cc and
+    pairwise_distance_op.{cc,cu} compiled unmodified against oracle/caffe2_shim (oracle/build_ref_ops.py ->
+    oracle/_ref/libref_reid_ops.so), fixtures tests/golden/triplet_ref_*.npz (oracle/make_golden_triplet.py).
 
 Third-party arithmetic the reference leans on: scikit-learn ``average_precision_score``
 (reid_dataset_evaluator.py:434; the code asks for 0.18.1 at :398-407, the installed 1.9.0
@@ -274,8 +277,11 @@ def topk_filtered(distmat, query_ids, gallery_ids, query_cams, gallery_cams, k):
 
 
 # ------------------------------------------------------------------------------------
-# training-side triplet mining ops — parity unpinned: the reference has no test for them
-# and PairWiseDistance has no CPU implementation (pairwise_distance_op.cc:5-24 holds schema + gradient only)
+# training-side triplet mining ops.  The reference has no test for them and PairWiseDistance has no
+# CPU implementation (pairwise_distance_op.cc:5-24 holds schema + gradient only); these restatements are PINNED to the
+# reference's own operators, compiled unmodified against a small interface shim (oracle/build_ref_ops.py, oracle/ref_ops.py):
+# fixtures tests/golden/triplet_ref_*.npz written by oracle/make_golden_triplet.py (BatchHard here on the CPU,
+# PairWiseDistance on a B200), plus live comparisons wherever the compiled library is present.
 # ------------------------------------------------------------------------------------
 
 
@@ -313,16 +319,20 @@ def batch_hard(xdist, labels):
     return ap, an, ip, inn
 
 
-def batch_hard_grad(idx_p, idx_n, dap, dan):
-    """batch_hard_op.cc:62-123 with the out-of-row writes for idx == -1 left out."""
+def batch_hard_grad(idx_p, idx_n, dap, dan, stray_writes=False):
+    """batch_hard_op.cc:62-123.  The operator stores `dX[a * N + idx]` also when idx stayed -1 (an anchor alone in its class,
+    or a batch of one class): that lands on element (a - 1, N - 1) - the last column of the PREVIOUS row - and, for a = 0,
+    one float before the buffer.  stray_writes=False (what pps_b200 computes): those stores are left out.
+    stray_writes=True: the operator's stores exactly, in its order (the a = 0 store outside the buffer excepted), which is
+    what the compiled reference is compared with."""
     n = len(idx_p)
-    dx = np.zeros((n, n), np.float32)
+    dx = np.zeros(n * n, np.float32)
     for a in range(n):
-        if idx_p[a] >= 0:
-            dx[a, idx_p[a]] = dap[a]
-        if idx_n[a] >= 0:
-            dx[a, idx_n[a]] = dan[a]
-    return dx
+        for idx, val in ((idx_p[a], dap[a]), (idx_n[a], dan[a])):
+            flat = a * n + int(idx)
+            if idx >= 0 or (stray_writes and flat >= 0):
+                dx[flat] = val
+    return dx.reshape(n, n)
 
 
 # ------------------------------------------------------------------------------------

@@ -206,3 +206,76 @@ def test_cmc_separate_camera_set_matches_reference_fixture(golden, name):
     rows, valid = O.cmc(d["dist"], topk=10, first_match_break=True, separate_camera_set=True, average=False, **ids)
     np.testing.assert_array_equal(rows, s["cmc_rows"])
     np.testing.assert_array_equal(valid, s["cmc_valid"])
+
+
+# ---- triplet-mining ops: the restatement against the reference's own operators ----
+def _batch_hard_cases(golden):
+    d = golden("triplet_ref_batch_hard")
+    i = 0
+    while "xd%d" % i in d:
+        yield {k: d["%s%d" % (k, i)] for k in ("xd", "labels", "dap", "dan", "ap", "an", "dx")}
+        i += 1
+
+
+def test_batch_hard_restatement_matches_reference_operator_fixture(golden):
+    """tests/golden/triplet_ref_batch_hard.npz holds what BatchHardOp / BatchHardGradientOp of
+    /root/reference/detectron/ops/batch_hard_op.cc - compiled unmodified (oracle/build_ref_ops.py) - computed; the
+    restatement must reproduce it bit for bit, the operator's stray stores for idx == -1 included."""
+    n_cases = 0
+    for c in _batch_hard_cases(golden):
+        ap, an, ip, inn = O.batch_hard(c["xd"], c["labels"])
+        np.testing.assert_array_equal(ap, c["ap"])
+        np.testing.assert_array_equal(an, c["an"])
+        np.testing.assert_array_equal(O.batch_hard_grad(ip, inn, c["dap"], c["dan"], stray_writes=True), c["dx"])
+        # what the product computes (no stray stores) differs from the operator ONLY in the last column of the row before
+        # an anchor whose search found nothing
+        clean = O.batch_hard_grad(ip, inn, c["dap"], c["dan"])
+        diff = np.argwhere(clean != c["dx"])
+        n = len(ip)
+        allowed = {(a - 1, n - 1) for a in range(1, n) if ip[a] < 0 or inn[a] < 0}
+        assert {tuple(x) for x in diff} <= allowed
+        n_cases += 1
+    assert n_cases >= 6
+
+
+def test_batch_hard_restatement_matches_live_reference_operator():
+    from oracle import ref_ops
+    if not ref_ops.available():
+        pytest.skip("neither /root/reference nor a prebuilt oracle/_ref/libref_reid_ops.so")
+    assert ref_ops.schema("BatchHard") == (2, 2) and ref_ops.schema("BatchHardGradient") == (4, 1)
+    assert ref_ops.schema("PairWiseDistance") == (1, 1) and ref_ops.schema("PairWiseDistanceGradient") == (2, 1)
+    # the gradient wiring the reference registers (batch_hard_op.cc:141-150, pairwise_distance_op.cc:14-24)
+    assert ref_ops.gradient_def("BatchHard", 2, 2) == ("BatchHardGradient", ["I0", "I1", "GO0", "GO1"], ["I0_grad"])
+    assert ref_ops.gradient_def("PairWiseDistance", 1, 1) == ("PairWiseDistanceGradient", ["I0", "GO0"], ["I0_grad"])
+    rs = np.random.RandomState(3)
+    for n, n_ids in [(50, 7), (17, 17), (130, 2), (3, 1)]:
+        xd = np.abs(rs.randn(n, n)).astype(np.float32)
+        xd[:, ::3] = np.round(xd[:, ::3] * 2) / 2
+        labels = rs.randint(0, n_ids, size=n).astype(np.int32)
+        dap, dan = rs.randn(n).astype(np.float32), rs.randn(n).astype(np.float32)
+        ap, an = ref_ops.batch_hard(xd, labels)
+        oap, oan, ip, inn = O.batch_hard(xd, labels)
+        np.testing.assert_array_equal(ap, oap)
+        np.testing.assert_array_equal(an, oan)
+        dx, _ = ref_ops.batch_hard_grad(xd, labels, dap, dan)
+        np.testing.assert_array_equal(dx, O.batch_hard_grad(ip, inn, dap, dan, stray_writes=True))
+    with pytest.raises(RuntimeError, match=r"X.dim32\(0\) == X.dim32\(1\)"):           # CAFFE_ENFORCE_EQ of :16
+        ref_ops.batch_hard(np.zeros((4, 5), np.float32), np.zeros(4, np.int32))
+
+
+def test_pairwise_distance_restatement_matches_reference_operator_fixture(golden):
+    """tests/golden/triplet_ref_pairwise.npz: outputs of the reference's CUDA operators PairWiseDistance /
+    PairWiseDistanceGradient (pairwise_distance_op.cu, compiled unmodified for sm_100a and run on a B200 by
+    `oracle/make_golden_triplet.py --cuda`).  float32 sums in another order (sequential over d there, atomics in the
+    gradient), hence tolerances."""
+    d = golden("triplet_ref_pairwise")
+    i = 0
+    while "x%d" % i in d:
+        x, dz = d["x%d" % i], d["dz%d" % i]
+        z = O.pairwise_distance(x)
+        np.testing.assert_allclose(z, d["z%d" % i], rtol=1e-5, atol=1e-5)
+        assert np.all(np.diag(d["z%d" % i]) == 0)
+        scale = np.abs(d["dx%d" % i]).max() + 1e-6
+        np.testing.assert_allclose(O.pairwise_distance_grad(x, dz), d["dx%d" % i], rtol=1e-4, atol=1e-5 * scale)
+        i += 1
+    assert i >= 5
