@@ -330,7 +330,9 @@ def bench_large_gallery(torch, evaluator, synthetic, args, name, ng, dtype_name,
         pairs = float(nq) * float(ng)
         tf = 2.0 * dim * pairs / (ms * 1e-3) / 1e12
         rec = {"workload": name, "nq": nq, "ng": ng, "dim": dim, "dtype": dtype_name, "topk": topk, "n_gpus": world,
-               "scaling": "strong", "rows_per_gpu": ngl, "blocks_per_gpu": len(eng._chunk_list()), "steps": steps,
+               "scaling": "strong", "rows_per_gpu": ngl, "blocks_per_gpu": eng.pass_blocks or len(eng._chunk_list()),
+               "counting_epilogue": bool(eng.used_fused_count),   # blocks after the first never written (fp16 rows)
+               "steps": steps,
                "ms_per_pass": ms, "pairs_per_s": pairs / (ms * 1e-3), "algorithmic_tflops": tf,
                "frac_of_sustained_bf16_all_gpus": tf / (peaks["tf_sustained"] * world),
                "dist_gemm_ms_per_pass_rank0": gemm_ms, "gpu_launches_per_pass_rank0": launches,
