@@ -32,7 +32,7 @@ def main():
     ap.add_argument("--n-ids", type=int, default=750)
     ap.add_argument("--n-cams", type=int, default=6)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "fp32"])
-    ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--precision", default="f16x3")
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
