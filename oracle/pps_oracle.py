@@ -1,7 +1,8 @@
 """CPU oracle for the PPS retrieval hot path — TEST INFRASTRUCTURE, not product code.
 
 A NumPy restatement of the reference's algorithm, used only as the checker by ``tests/``,
-``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` (plus three study scripts
+under ``tools/`` that measure error margins against it: map_margin_sweep, split_precision_sim, rerank_bench --cpu-images).
 Nothing under ``pps_b200/`` imports it.
 
 Pinning status
