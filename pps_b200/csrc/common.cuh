@@ -116,6 +116,14 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 __device__ __forceinline__ void red_shared_add_u32(uint32_t addr, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -273,7 +273,20 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
     if (lane == 0) {
       uint32_t it = 0;
       TileWalk<EPI> w(ga, pair, npairs);
+      // EPI_RANK progress window (RankFuse::window): see dist_tiles.cuh
+      const bool windowed = EPI == EPI_RANK && rf.window > 0 && w.balanced && !w.extra;
+      uint32_t tile_j = 0;
+      if (windowed && rank == 0 && w.n_cur >= w.n_stop) st_volatile_u32(rf.progress + pair, 0xffffffffu);   // nothing to do: never waited for
       while (w.next()) {
+        if (windowed) {
+          const uint32_t* peers = rf.progress + (long long)w.stream_i * w.m_tiles;
+          for (;;) {
+            uint32_t mn = 0xffffffffu;
+            for (int m = 0; m < w.m_tiles; ++m) mn = min(mn, ld_volatile_u32(peers + m));
+            if (tile_j - min(tile_j, mn) <= (uint32_t)rf.window) break;
+            __nanosleep(200);
+          }
+        }
         const int m0 = (int)(w.grp * ga.a_group_rows) + w.m_tile * kClusterRows + pair_row0 + (int)rank * kT2Rows;
         const int n0 = (int)(w.grp * ga.b_group_rows) + w.n_tile * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < g.kblocks; ++kb, ++it) {
@@ -294,6 +307,8 @@ __device__ __forceinline__ void dist_tc2_body(const CUtensorMap& tmA, const CUte
               tma_load_3d_2cta_mcast(slot + planes * kTile2Bytes + p * kBTile, &tmB, full0, mask, kb * kBK, n0, p);
           }
         }
+        ++tile_j;
+        if (windowed && rank == 0) st_volatile_u32(rf.progress + pair, w.run_end ? 0xffffffffu : tile_j);
       }
     }
   } else if (warp == 1) {
@@ -1087,6 +1102,7 @@ extern "C" int pps_dist_rank_topk_tc(const void* a_planes, const float* a_sqnorm
   rf.col0 = col0; rf.p_cap = p_cap;
   rf.tk_bound = tk_cand ? tk_bound : nullptr; rf.tk_cnt = tk_cand ? tk_cnt : nullptr;
   rf.tk_cand = reinterpret_cast<unsigned long long*>(tk_cand); rf.tk_cap = tk_cand ? tk_cap : 0;
+  rf.progress = nullptr; rf.window = 0;
   static thread_local int configured_dev = -1;
   int dev = 0;
   PPS_CUDA_TRY(cudaGetDevice(&dev));
@@ -1098,6 +1114,17 @@ extern "C" int pps_dist_rank_topk_tc(const void* a_planes, const float* a_sqnorm
   const long long tiles = (long long)g.m_tiles * g.n_tiles;
   const long long slots = sms / 2;
   const long long pairs = tiles < slots ? tiles : slots;
+  {
+    // progress window of the aligned streams (PPS_STREAM_WINDOW = tiles a pair may run ahead of the slowest of its stream)
+    static const int window_env = [] { const char* e = std::getenv("PPS_STREAM_WINDOW"); return e ? std::atoi(e) : 0; }();
+    static thread_local uint32_t* progress_buf[64] = {};
+    if (window_env > 0 && dev >= 0 && dev < 64 && pairs <= 1024) {
+      if (!progress_buf[dev]) PPS_CUDA_TRY(cudaMalloc(&progress_buf[dev], 1024 * sizeof(uint32_t)));
+      PPS_CUDA_TRY(cudaMemsetAsync(progress_buf[dev], 0, (size_t)pairs * sizeof(uint32_t), static_cast<cudaStream_t>(stream)));
+      rf.progress = progress_buf[dev];
+      rf.window = window_env;
+    }
+  }
   dist_tc2_kernel<256, EPI_RANK><<<(unsigned)(2 * pairs), kRankThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       tmA, tmB, tmA /*no output map*/, ga, rf);
   PPS_LAUNCH_CHECK("dist_tc2_kernel<rank>");
